@@ -1,0 +1,222 @@
+/* inferflow_b200.h -- C ABI of the B200-native decode hot path of inferflow/inferflow.
+ *
+ * The reference has NO C-ABI / FFI seam: its operator layer is the
+ * C++ static classes TensorMul (src/tensor/tensor_mul.h:21-57) and TensorOpr
+ * (src/tensor/tensor_opr.h:39-130) called by GpuInferenceWorker
+ * (src/transformer/inference_worker.cc). This header DEFINES the boundary a binding
+ * would use; every entry point names the reference interface it replaces.
+ * INTEGRATION.md shows the TensorMul/TensorOpr-shaped shim a maintainer would add.
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers on the current CUDA device unless named host_*;
+ *    the caller owns all memory; nothing here allocates or synchronises (the reference
+ *    launchers end in cudaDeviceSynchronize, e.g. tensor_mul.cu:709 -- ours are async
+ *    on `stream`, a cudaStream_t passed as void*).
+ *  - element types are the reference's ElementType ids (src/tensor/tensor_common.h:15-42).
+ *  - quantized tensors use the reference's block byte layouts unchanged
+ *    (src/common/quant_types.h:11-174): rows of cx/capacity consecutive blocks.
+ *  - return 0 on success, <0 on error (reference: LogError + return false);
+ *    ifb_last_error() gives the message. There is no CPU fallback: without a CUDA
+ *    device every compute entry returns IFB_E_CUDA.
+ */
+#ifndef INFERFLOW_B200_H
+#define INFERFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IFB_VERSION 100
+
+#define IFB_E_ARG (-1)
+#define IFB_E_TYPE (-2)
+#define IFB_E_CUDA (-3)
+#define IFB_E_STATE (-4)
+#define IFB_E_IO (-5)
+
+typedef void *ifb_stream_t; /* cudaStream_t */
+
+/* ElementType (tensor_common.h:15-42) */
+enum {
+    IFB_F32 = 0, IFB_F16 = 1, IFB_BF16 = 2, IFB_I32 = 3, IFB_I16 = 4, IFB_Q8_GL = 5,
+    IFB_Q8_LOG = 6, IFB_Q8_B32T1 = 7, IFB_Q8_B32T2 = 8, IFB_Q6_B64T1 = 9, IFB_Q5_B64T1 = 10,
+    IFB_Q5_B32T1 = 11, IFB_Q4_B16 = 12, IFB_Q4_B32T1A = 13, IFB_Q4_B32T1B = 14,
+    IFB_Q4_B32T2 = 15, IFB_Q4_B32P8 = 16, IFB_Q4_B64T1 = 17, IFB_Q3H_B64T1 = 18,
+    IFB_Q3_B32T1A = 19, IFB_Q3_B32T1B = 20, IFB_Q2_B32T1A = 21, IFB_Q2_B32T1B = 22
+};
+
+/* ------------------------------------------------------------------ info */
+int32_t ifb_version(void);
+const char *ifb_last_error(void);
+/* TensorCommon::ByteCount / block geometry (tensor_common.cc:162-167, quant_types.h) */
+int32_t ifb_block_capacity(int32_t dtype);
+int32_t ifb_block_bytes(int32_t dtype);
+int64_t ifb_row_bytes(int32_t dtype, int64_t cx);
+/* ini type names ("q4" -> Q4_B32T1A ...), tensor_common.cc:170-204; -1 if unknown */
+int32_t ifb_dtype_from_name(const char *name);
+
+/* plumbing for bindings that hold no CUDA runtime handle of their own (blocking copies) */
+int32_t ifb_memcpy_d2h(void *host, const void *dev, int64_t bytes);
+int32_t ifb_memcpy_h2d(void *dev, const void *host, int64_t bytes);
+int32_t ifb_memcpy_d2h_async(void *host_pinned, const void *dev, int64_t bytes, ifb_stream_t stream);
+int32_t ifb_memcpy_h2d_async(void *dev, const void *host_pinned, int64_t bytes, ifb_stream_t stream);
+int32_t ifb_device_synchronize(void);
+
+/* ------------------------------------------------------------------ codecs
+ * TensorOpr::Quantize(B, A)  (tensor_opr.cu:1623; kernels/tensor_quant.h; the per-block
+ * algorithms are Quantization::QuantizeRow_* in src/common/quantization.h:110-1194).
+ * src fp16 [rows][cx] -> dst blocks [rows][row_bytes]. Codes are bit-exact with the
+ * reference. Q8_B32T2 uses the device algorithm (tensor_quant.h:45-82) as the reference does. */
+int32_t ifb_quantize_rows(int32_t dtype, void *dst, const void *src_f16, int64_t rows, int64_t cx,
+                          ifb_stream_t stream);
+/* TensorOpr::Dequantize(B, A) (tensor_opr.cu; kernels/tensor_quant.h:302-868) -> fp16 */
+int32_t ifb_dequantize_rows(int32_t dtype, void *dst_f16, const void *src, int64_t rows, int64_t cx,
+                            ifb_stream_t stream);
+
+/* ------------------------------------------------------------------ GEMV
+ * TensorMul::Gemv_AX(Y, A, X, Alg3, nullptr, bias) (tensor_mul.h:27, tensor_mul.cu:766):
+ *   y[cy] = W[cy][cx] . x[cx] (+ bias), fp16 out.
+ * x_dtype = IFB_Q8_B32T2 : dp4a path  (kernels/gemv.h:1500-1709; weights Q8_B32T2, Q6_B64T1,
+ *                          Q5_B64T1, Q4_B32T1A/B, Q4_B64T1, Q3H_B64T1)
+ * x_dtype = IFB_F16      : fp16-activation path (kernels/gemv.h:470-1470; any weight type
+ *                          incl. IFB_F16), fp32 accumulation. */
+int32_t ifb_gemv(int32_t w_dtype, void *y_f16, const void *w, int32_t x_dtype, const void *x,
+                 int64_t cy, int64_t cx, const void *bias_f16, ifb_stream_t stream);
+
+/* Fused decode GEMV used by our layer runtime: one launch replaces
+ *   [RmsNorm] -> Quantize(Q8_B32T2) -> 1..3 Gemv_AX sharing x -> [SiLU, Mul] -> [Add residual]
+ * (inference_worker.cc:1038,1442-1444,1555-1571,1726-1900). */
+typedef struct ifb_gemv_desc {
+    int32_t w_dtype;
+    int32_t nseg;            /* 1..3 weight matrices sharing x; outputs are concatenated in y */
+    const void *w[3];
+    int32_t rows[3];
+    const void *w_gate;      /* optional (nseg==1): y = silu(w[0] x) * (w_gate x) */
+    int64_t cx;
+    const void *x_f16;       /* [cx] fp16 */
+    const void *norm_w_f16;  /* optional fused RMSNorm weight [cx] (TensorOpr::RmsNorm, eps 1e-5) */
+    float norm_eps;
+    float norm_base;         /* multi_base */
+    const void *residual_f16;/* optional [sum rows]: y += residual */
+    const void *bias_f16;    /* optional [sum rows] */
+    void *y_f16;             /* [sum rows] */
+    int32_t quantize_x;      /* 1: x -> Q8_B32T2 then dp4a (reference default); 0: fp16 x */
+    int32_t pdl;             /* 1: launch with programmatic stream serialization */
+} ifb_gemv_desc_t;
+int32_t ifb_gemv_fused(const ifb_gemv_desc_t *desc, ifb_stream_t stream);
+
+/* ------------------------------------------------------------------ small ops
+ * TensorOpr::RmsNorm (tensor_opr.cu:557; eps 1e-5 hard-coded at :568) */
+int32_t ifb_rmsnorm(void *y_f16, const void *x_f16, const void *w_f16, int64_t rows, int64_t cols,
+                    float eps, float multi_base, ifb_stream_t stream);
+/* TensorOpr::PositionEmbedding ROPE (tensor_opr.cu:693-760): x [tokens][heads][head_dim] in place,
+ * position of token t = pos0 + t; order 0 = interleaved (llama2.c), 2 = half-split (HF). */
+int32_t ifb_rope(void *x_f16, int32_t tokens, int32_t heads, int32_t head_dim, int32_t rope_dims,
+                 int32_t pos0, float theta, int32_t order, ifb_stream_t stream);
+/* TensorOpr::Activation(SILU) + TensorOpr::Mul  (unary_tensor_opr.h:553, binary_tensor_opr.h) */
+int32_t ifb_silu_mul(void *out_f16, const void *a_f16, const void *b_f16, int64_t n,
+                     ifb_stream_t stream);
+/* TensorOpr::Add */
+int32_t ifb_add(void *c_f16, const void *a_f16, const void *b_f16, int64_t n, ifb_stream_t stream);
+/* greedy token pick on device (replaces the D2H logits copy of SampleTokens,
+ * inference_engine.cc:1986, for the Greedy strategy): first max wins */
+int32_t ifb_argmax(int32_t *out_idx, const void *logits_f16, int64_t n, ifb_stream_t stream);
+
+/* ------------------------------------------------------------------ KV cache + attention
+ * GpuLayerKVCache (src/transformer/kv_cache.cc:104-249). Storage is OURS (head-major, codes
+ * and scales separate) -- the values (int8 code, fp16 scale per 32 dims of a
+ * row) are the reference's. kv_dtype = IFB_F16 or IFB_Q8_B32T2. head_dim % 32 == 0. */
+int64_t ifb_kv_cache_bytes(int32_t kv_dtype, int32_t kv_heads, int32_t head_dim, int32_t max_ctx);
+/* SetKRows+SetVRows: append n_tokens rows (fp16 [n][kv_heads*head_dim]) at position pos0 */
+int32_t ifb_kv_append(int32_t kv_dtype, void *kcache, void *vcache, const void *k_f16,
+                      const void *v_f16, int32_t kv_heads, int32_t head_dim, int32_t max_ctx,
+                      int32_t pos0, int32_t n_tokens, ifb_stream_t stream);
+/* GetKRows / GetVRows: rows pos0..pos0+n as fp16 [n][kv_heads*head_dim] (dequantized) */
+int32_t ifb_kv_get_rows(int32_t kv_dtype, void *out_f16, const void *cache, int32_t kv_heads,
+                        int32_t head_dim, int32_t max_ctx, int32_t pos0, int32_t n,
+                        ifb_stream_t stream);
+/* One decode step of grouped-query attention for one query token: replaces
+ * CalculateProductKQ + SoftMax + Transpose/RepeatKV + Gemm(kqv) + Assign
+ * (inference_worker.cc:1130-1320,1639-1724). q [heads][head_dim] fp16 (after RoPE);
+ * ctx_len = positions 0..ctx_len-1 attended (the new token's K/V must already be appended).
+ * workspace: ifb_attn_workspace_bytes(heads, head_dim) bytes. out [heads*head_dim] fp16. */
+int64_t ifb_attn_workspace_bytes(int32_t heads, int32_t head_dim);
+int32_t ifb_attn_decode(int32_t kv_dtype, void *out_f16, const void *q_f16, const void *kcache,
+                        const void *vcache, int32_t heads, int32_t kv_heads, int32_t head_dim,
+                        int32_t max_ctx, int32_t ctx_len, float kq_scale, void *workspace,
+                        ifb_stream_t stream);
+
+/* ------------------------------------------------------------------ MoE router
+ * HostTensorOpr::BuildRowsForMoE (src/tensor/host_tensor_opr.cc:190-244) on device:
+ * scores fp16 [rows][experts] (softmax over all experts already applied, as in
+ * ProcessGpuLayer_Moe) -> ids int32 [rows][top_k] (-1 = none), weights fp32, counts int32. */
+int32_t ifb_moe_topk(int32_t *ids, float *weights, int32_t *counts, const void *scores_f16,
+                     int32_t rows, int32_t experts, int32_t top_k, int32_t norm_top_k_prob,
+                     ifb_stream_t stream);
+
+/* ------------------------------------------------------------------ model runtime
+ * The per-GPU decode runtime behind GpuInferenceWorker::Run / ProcessGpuLayer
+ * (inference_worker.cc:234-977) for pre-norm llama-family decoders, one instance per GPU
+ * (= per process; ranks of one tensor-parallel group exchange the row-parallel sums through
+ * peer memory, see ifb_model_tp_*). */
+typedef struct ifb_model_spec {
+    int32_t layers, d_model, d_ffn, heads, kv_heads, vocab, max_ctx;
+    int32_t weight_dtype;     /* device_weight_data_type */
+    int32_t kv_dtype;         /* device_kv_cache_data_type: IFB_F16 or IFB_Q8_B32T2 */
+    int32_t lm_head_dtype;    /* IFB_F16 (L > 20, network_builder.cc:829-844) or a quant type */
+    int32_t rope_order;       /* qk_column_order: 0 interleaved, 2 half-split */
+    float rope_theta;
+    float norm_eps;
+    float kq_scale;
+    int32_t tp_rank, tp_size; /* tensor-parallel shard this instance holds (BY_COL/BY_ROW rules,
+                                 network_builder.cc:1373-1406) */
+    int32_t experts, experts_top_k; /* 0 = dense FFN */
+} ifb_model_spec_t;
+
+typedef struct ifb_model ifb_model_t;
+
+/* allocate weights / KV / activations for `spec` on the current device */
+int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *spec);
+void ifb_model_destroy(ifb_model_t *m);
+int64_t ifb_model_weight_bytes(const ifb_model_t *m);   /* quantized bytes read per token */
+int64_t ifb_model_kv_bytes_per_token(const ifb_model_t *m, int32_t ctx_len);
+/* deterministic synthetic weights generated on the device: quant blocks
+ * with uniform codes and |N(0,sigma)| fp16 scales, norms 1.0 */
+int32_t ifb_model_init_synthetic(ifb_model_t *m, uint64_t seed, ifb_stream_t stream);
+/* load one tensor from HOST fp32/fp16 data (DeviceTensorBuilder::Build, device_tensor_builder.cu:
+ * 161-330): quantize on the device to the model's weight type and keep this rank's shard.
+ * name: "tok_embeddings", "output_norm", "output", "layers.N.{attention_norm,wq,wk,wv,wo,
+ * ffn_norm,w1,w2,w3}" ; data is the FULL (unsharded) [rows][cols] matrix */
+int32_t ifb_model_load_tensor(ifb_model_t *m, const char *name, const void *host_data,
+                              int32_t host_dtype, int64_t rows, int64_t cols, ifb_stream_t stream);
+/* reset the KV length (and optionally fill `ctx_len` synthetic rows for benchmarking) */
+int32_t ifb_model_kv_reset(ifb_model_t *m, int32_t ctx_len, int32_t fill_synthetic, uint64_t seed,
+                           ifb_stream_t stream);
+/* One decode step for one sequence at position pos (0-based): embedding row of `token_id`
+ * (or *token_dev if token_id < 0) -> all layers -> logits (fp16 [vocab], device) and greedy
+ * next token (int32, device). Captured as a CUDA graph internally; async on stream. */
+int32_t ifb_model_decode(ifb_model_t *m, int32_t token_id, const int32_t *token_dev, int32_t pos,
+                         ifb_stream_t stream);
+/* replay the step graph from the position / token the previous step left in device memory
+ * (back-to-back generation without host round trips) */
+int32_t ifb_model_decode_next(ifb_model_t *m, ifb_stream_t stream);
+/* raw device pointer of a named tensor ("layers.N.wq", "logits", "layers.N.kcache", ...): tests
+ * and tools read weights / activations back through it */
+int32_t ifb_model_tensor_ptr(ifb_model_t *m, const char *name, void **ptr, int64_t *bytes);
+/* measurement aid: issue only part of a step's kernels, eagerly (bit 0 = the GEMV family,
+ * bit 1 = kv-append + attention, bit 2 = embedding/argmax/advance); returns #launches or <0 */
+int32_t ifb_model_issue_parts(ifb_model_t *m, int32_t parts, ifb_stream_t stream);
+const void *ifb_model_logits(const ifb_model_t *m);      /* device fp16 [vocab] */
+const int32_t *ifb_model_next_token(const ifb_model_t *m); /* device int32 */
+int32_t ifb_model_kernel_launches_per_step(const ifb_model_t *m);
+/* tensor-parallel plumbing: every rank exports the IPC handle of its exchange buffer,
+ * the host side (torch.distributed all_gather / MPI / fork) hands all handles to every rank */
+int32_t ifb_model_tp_export(ifb_model_t *m, void *host_handle_64B);
+int32_t ifb_model_tp_import(ifb_model_t *m, const void *host_handles_64B_each, int32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INFERFLOW_B200_H */

@@ -1,0 +1,510 @@
+// KV cache and single-token grouped-query attention, sm_100a.
+//
+// Replaces GpuLayerKVCache::{SetKRows,SetVRows,GetKRows,GetVRows} (reference
+// src/transformer/kv_cache.cc:104-249) and the attention sub-graph of
+// GpuInferenceWorker::ProcessGpuLayer_Attention (src/transformer/inference_worker.cc:1130-1320,
+// 1587-1724): RoPE on q/k, append, [dequantize whole K prefix -> RepeatKV -> Gemm_Alg2(alpha) ->
+// SoftMax(causal, kq_scale) -> dequantize whole V -> Transpose -> RepeatKV -> Gemm_Alg2 -> Assign].
+//
+// Here: the cache is read IN PLACE exactly once per token (flash-decoding): split over the
+// context, K/V tiles staged global->shared by 1-D TMA bulk copies (cp.async.bulk) behind
+// mbarriers, online softmax in fp32 with warp-shuffle reductions, GQA by sharing the staged
+// tile across the q-heads of the group (no RepeatKV), split partials merged by the last CTA.
+//
+// Cache layout (ours; the VALUES -- int8 code and fp16 scale per 32 consecutive dims of a
+// row -- are the reference's Q8_B32T2 rows, kernels/tensor_quant.h:45-82):
+//   F16      : half [kv_heads][max_ctx][head_dim]
+//   Q8_B32T2 : int8 [kv_heads][max_ctx][head_dim] ++ half [kv_heads][max_ctx][head_dim/32]
+// head-major so that a (head, position-range) tile is ONE contiguous byte range.
+#include "ifb_formats.cuh"
+#include "ifb_kernels.h"
+
+namespace ifb {
+
+constexpr int ATT_CHUNK = 64;    // positions per staged tile
+constexpr int ATT_STAGES = 3;
+constexpr int ATT_THREADS = 128;
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+int64_t kv_cache_bytes(int kv_dtype, int kv_heads, int head_dim, int max_ctx) {
+    int64_t rows = (int64_t)kv_heads * round_up(max_ctx, ATT_CHUNK);
+    if (kv_dtype == DT_F16) return rows * head_dim * 2;
+    if (kv_dtype == DT_Q8_B32T2) return rows * head_dim + rows * (head_dim / 32) * 2;
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------
+// append (+ fused RoPE on q and k)
+// ---------------------------------------------------------------------------------------
+struct KvArgs {
+    int kv_dtype, kv_heads, head_dim, max_ctx_pad, pos0, n_tokens;
+    uint8_t *kcache, *vcache;
+    const __half *k, *v;
+    int rope, rope_order, rope_dims;
+    float rope_theta;
+    __half *q;
+    int q_heads;
+    const int32_t *pos_dev;
+};
+
+__device__ __forceinline__ void rope_rot(float &x0, float &x1, int pos, int i, float theta_scale) {
+    float ang = (float)pos;
+    if (i > 0) ang *= powf(theta_scale, (float)i);
+    float c = cosf(ang), s = sinf(ang);
+    float a = x0 * c - x1 * s, b = x0 * s + x1 * c;
+    x0 = a;
+    x1 = b;
+}
+
+__device__ __forceinline__ void kv_store_row(int kv_dtype, uint8_t *cache, const float *row_smem,
+                                             const __half *row_gmem, int kv_heads, int hd,
+                                             int max_ctx_pad, int pos, int warp, int lane, int nwarps) {
+    const int nblk = kv_heads * hd / 32;
+    int8_t *codes = reinterpret_cast<int8_t *>(cache);
+    __half *scales = reinterpret_cast<__half *>(cache + (int64_t)kv_heads * max_ctx_pad * hd);
+    for (int b = warp; b < nblk; b += nwarps) {
+        int d = b * 32 + lane;  // dim within the row
+        float v = row_smem != nullptr ? row_smem[d] : __half2float(row_gmem[d]);
+        int h = d / hd, dh = d % hd;
+        int64_t base = ((int64_t)h * max_ctx_pad + pos);
+        if (kv_dtype == DT_F16) {
+            reinterpret_cast<__half *>(cache)[base * hd + dh] = __float2half_rn(v);
+        } else {
+            // Tensor_QuantizeQ8_B32T2_Alg2_Kernel (tensor_quant.h:45-82)
+            float m = warp_max(fabsf(v));
+            float scale = __fdiv_rn(m, 127.0f);
+            int q = scale <= 0.000001f ? 0 : (int)roundf(__fdiv_rn(v, scale));
+            q = min(max(q, -128), 127);
+            codes[base * hd + dh] = (int8_t)q;
+            if (lane == 0) scales[base * (hd / 32) + dh / 32] = __float2half_rn(scale);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) kv_append_kernel(const KvArgs a) {
+    extern __shared__ float krow[];  // kv_heads*head_dim floats (RoPE'd K, rounded to half)
+    pdl_launch_dependents();
+    pdl_wait();
+    const int t = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int pos = (a.pos_dev != nullptr ? *a.pos_dev : a.pos0) + t;
+    const int hd = a.head_dim, kvd = a.kv_heads * hd;
+    const __half *k = a.k + (int64_t)t * kvd;
+    const __half *v = a.v + (int64_t)t * kvd;
+    const int rd = a.rope_dims > 0 ? a.rope_dims : hd;
+    const float theta_scale = powf(a.rope_theta, -2.0f / (float)rd);
+
+    for (int i = tid; i < kvd; i += 256) krow[i] = __half2float(k[i]);
+    __syncthreads();
+    if (a.rope) {
+        const int pairs = rd / 2;
+        for (int idx = tid; idx < a.kv_heads * pairs; idx += 256) {
+            int i = idx % pairs, h = idx / pairs;
+            int i0 = a.rope_order == 2 ? i : 2 * i, i1 = a.rope_order == 2 ? i + rd / 2 : 2 * i + 1;
+            float x0 = krow[h * hd + i0], x1 = krow[h * hd + i1];
+            rope_rot(x0, x1, pos, i, theta_scale);
+            krow[h * hd + i0] = round_h(x0);  // PositionEmbedding writes half
+            krow[h * hd + i1] = round_h(x1);
+        }
+        if (a.q != nullptr) {
+            __half *q = a.q + (int64_t)t * a.q_heads * hd;
+            for (int idx = tid; idx < a.q_heads * pairs; idx += 256) {
+                int i = idx % pairs, h = idx / pairs;
+                int i0 = a.rope_order == 2 ? i : 2 * i, i1 = a.rope_order == 2 ? i + rd / 2 : 2 * i + 1;
+                float x0 = __half2float(q[h * hd + i0]), x1 = __half2float(q[h * hd + i1]);
+                rope_rot(x0, x1, pos, i, theta_scale);
+                q[h * hd + i0] = __float2half_rn(x0);
+                q[h * hd + i1] = __float2half_rn(x1);
+            }
+        }
+        __syncthreads();
+    }
+    kv_store_row(a.kv_dtype, a.kcache, krow, nullptr, a.kv_heads, hd, a.max_ctx_pad, pos, warp, lane, 8);
+    kv_store_row(a.kv_dtype, a.vcache, nullptr, v, a.kv_heads, hd, a.max_ctx_pad, pos, warp, lane, 8);
+}
+
+int kv_append(const KvAppend &p, cudaStream_t st) {
+    IFB_CHECK_ARG(p.kv_dtype == DT_F16 || p.kv_dtype == DT_Q8_B32T2,
+                  "kv cache type %d (F16 or Q8_B32T2 only, inference_engine.cc:1702-1704)", p.kv_dtype);
+    IFB_CHECK_ARG(p.head_dim == 32 || p.head_dim == 64 || p.head_dim == 128, "kv: head_dim %d not supported (32/64/128)", p.head_dim);
+    IFB_CHECK_ARG(p.pos_dev != nullptr || (p.pos0 >= 0 && p.pos0 + p.n_tokens <= p.max_ctx),
+                  "kv: rows %d..%d outside max_context_len %d", p.pos0, p.pos0 + p.n_tokens, p.max_ctx);
+    if (p.n_tokens <= 0) return IFB_OK;
+    KvArgs a;
+    a.kv_dtype = p.kv_dtype; a.kv_heads = p.kv_heads; a.head_dim = p.head_dim;
+    a.max_ctx_pad = round_up(p.max_ctx, ATT_CHUNK); a.pos0 = p.pos0; a.n_tokens = p.n_tokens;
+    a.kcache = (uint8_t *)p.kcache; a.vcache = (uint8_t *)p.vcache;
+    a.k = (const __half *)p.k; a.v = (const __half *)p.v;
+    a.rope = p.rope; a.rope_order = p.rope_order; a.rope_dims = p.rope_dims; a.rope_theta = p.rope_theta;
+    a.q = (__half *)p.q; a.q_heads = p.q_heads; a.pos_dev = p.pos_dev;
+    size_t smem = (size_t)p.kv_heads * p.head_dim * sizeof(float);
+    IFB_CHECK_ARG(smem <= 48 * 1024, "kv: kv_dim too large for the append kernel");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.n_tokens); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = p.pdl ? 1 : 0;
+    IFB_CUDA(cudaLaunchKernelEx(&cfg, kv_append_kernel, a));
+    return IFB_OK;
+}
+
+// rows pos0..pos0+n-1 as fp16 [n][kv_heads*head_dim] (GetKRows: dequantized view)
+__global__ void kv_get_rows_kernel(__half *out, const uint8_t *cache, int kv_dtype, int kv_heads,
+                                   int hd, int max_ctx_pad, int pos0, int n) {
+    int64_t total = (int64_t)n * kv_heads * hd;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int d = (int)(i % (kv_heads * hd));
+        int t = (int)(i / (kv_heads * hd));
+        int h = d / hd, dh = d % hd;
+        int64_t base = (int64_t)h * max_ctx_pad + pos0 + t;
+        if (kv_dtype == DT_F16) {
+            out[i] = reinterpret_cast<const __half *>(cache)[base * hd + dh];
+        } else {
+            const int8_t *codes = reinterpret_cast<const int8_t *>(cache);
+            const __half *scales = reinterpret_cast<const __half *>(cache + (int64_t)kv_heads * max_ctx_pad * hd);
+            out[i] = __float2half_rn((float)codes[base * hd + dh] * __half2float(scales[base * (hd / 32) + dh / 32]));
+        }
+    }
+}
+
+int kv_get_rows(int kv_dtype, void *out, const void *cache, int kv_heads, int head_dim, int max_ctx,
+                int pos0, int n, cudaStream_t st) {
+    IFB_CHECK_ARG(kv_dtype == DT_F16 || kv_dtype == DT_Q8_B32T2, "kv cache type %d", kv_dtype);
+    IFB_CHECK_ARG(pos0 >= 0 && n >= 0 && pos0 + n <= max_ctx, "kv: rows outside the cache");
+    if (n == 0) return IFB_OK;
+    kv_get_rows_kernel<<<256, 256, 0, st>>>((__half *)out, (const uint8_t *)cache, kv_dtype, kv_heads,
+                                            head_dim, round_up(max_ctx, ATT_CHUNK), pos0, n);
+    IFB_LAUNCH_CHECK();
+    return IFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// decode attention
+// ---------------------------------------------------------------------------------------
+struct AttnArgs {
+    int heads, kv_heads, max_ctx_pad, ctx_len, nsplit;
+    float softmax_scale;  // 1/sqrt(head_dim)  (= alpha * kq_scale of the reference)
+    __half *out;
+    const __half *q;
+    const uint8_t *kcache, *vcache;
+    float *ws;            // [heads][nsplit][HD+2]
+    unsigned int *counters;  // [kv_heads]
+    const int32_t *pos_dev;
+};
+
+int64_t attn_workspace_bytes(int heads, int head_dim) {
+    // worst-case split count = 2*SMs (one per CTA) ; + counters
+    int64_t max_split = 2 * 160;
+    return (int64_t)heads * max_split * (head_dim + 2) * sizeof(float) + 4096;
+}
+
+// signed byte k of w -> float
+__device__ __forceinline__ float s8f(uint32_t w, int k) {
+    return (float)(int)(int8_t)((w >> (8 * k)) & 0xffu);
+}
+
+template <int HD, int G, bool Q8>
+__global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs a) {
+    constexpr int NB = HD / 32;                       // scale blocks per (pos, head)
+    constexpr int KBYTES = Q8 ? ATT_CHUNK * HD : ATT_CHUNK * HD * 2;
+    constexpr int SBYTES = Q8 ? ATT_CHUNK * NB * 2 : 0;
+    constexpr int STAGE = 2 * (KBYTES + SBYTES);      // K codes, K scales, V codes, V scales
+    constexpr int LPP = HD / 16;                      // lanes per position in the QK phase
+    constexpr int PPW = 32 / LPP;                     // positions per warp iteration
+    constexpr int NW = ATT_THREADS / 32;
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full_bar[ATT_STAGES];
+    __shared__ float s_p[G][ATT_CHUNK];               // scores / probabilities of the chunk
+    __shared__ float s_corr[G], s_m[G], s_l[G];
+    __shared__ __align__(16) float s_q[G][HD / 16][20];   // 16 dims + 4 pad: conflict-free LDS.128
+    __shared__ unsigned int s_last;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kvh = blockIdx.y, split = blockIdx.x;
+
+    if (tid == 0) {
+        for (int i = 0; i < ATT_STAGES; i++) mbar_init(&full_bar[i], 1);
+        mbar_fence_init();
+    }
+    pdl_launch_dependents();
+    pdl_wait();  // q, the new K/V row and the position come from the previous kernels
+    const int ctx = a.pos_dev != nullptr ? (*a.pos_dev + 1) : a.ctx_len;
+    const int nchunks_total = (ctx + ATT_CHUNK - 1) / ATT_CHUNK;
+    const int cps = (nchunks_total + a.nsplit - 1) / a.nsplit;   // chunks per split
+    const int c0 = split * cps, c1 = min(c0 + cps, nchunks_total);
+    const int nch = max(c1 - c0, 0);
+
+    // stage q (scaled) for the G heads of this group
+    for (int i = tid; i < G * HD; i += ATT_THREADS) {
+        int g = i / HD, d = i % HD;
+        s_q[g][d / 16][d % 16] = __half2float(a.q[(int64_t)(kvh * G + g) * HD + d]) * a.softmax_scale;
+    }
+    if (tid < G) { s_m[tid] = -INFINITY; s_l[tid] = 0.f; }
+    __syncthreads();
+
+    const int64_t head_rows = (int64_t)kvh * a.max_ctx_pad;
+    const uint8_t *kc = a.kcache + (Q8 ? head_rows * HD : head_rows * HD * 2);
+    const uint8_t *vc = a.vcache + (Q8 ? head_rows * HD : head_rows * HD * 2);
+    const uint8_t *ks = a.kcache + (int64_t)a.kv_heads * a.max_ctx_pad * HD + head_rows * NB * 2;
+    const uint8_t *vs = a.vcache + (int64_t)a.kv_heads * a.max_ctx_pad * HD + head_rows * NB * 2;
+
+    auto issue = [&](int ci) {  // chunk index within this split -> stage ci % STAGES
+        const int st = ci % ATT_STAGES;
+        uint8_t *dst = smem + (size_t)st * STAGE;
+        const int64_t p0 = (int64_t)(c0 + ci) * ATT_CHUNK;
+        mbar_arrive_expect_tx(&full_bar[st], STAGE);
+        if (Q8) {
+            bulk_g2s(dst, kc + p0 * HD, KBYTES, &full_bar[st]);
+            bulk_g2s(dst + KBYTES, ks + p0 * NB * 2, SBYTES, &full_bar[st]);
+            bulk_g2s(dst + KBYTES + SBYTES, vc + p0 * HD, KBYTES, &full_bar[st]);
+            bulk_g2s(dst + 2 * KBYTES + SBYTES, vs + p0 * NB * 2, SBYTES, &full_bar[st]);
+        } else {
+            bulk_g2s(dst, kc + p0 * HD * 2, KBYTES, &full_bar[st]);
+            bulk_g2s(dst + KBYTES, vc + p0 * HD * 2, KBYTES, &full_bar[st]);
+        }
+    };
+    if (tid == 0)
+        for (int ci = 0; ci < min(nch, ATT_STAGES); ci++) issue(ci);
+
+    float acc[G][4];
+#pragma unroll
+    for (int g = 0; g < G; g++) acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f;
+
+    for (int ci = 0; ci < nch; ci++) {
+        const int st = ci % ATT_STAGES;
+        mbar_wait(&full_bar[st], (ci / ATT_STAGES) & 1);
+        const uint8_t *tK = smem + (size_t)st * STAGE;
+        const uint8_t *tKs = tK + KBYTES;
+        const uint8_t *tV = tK + KBYTES + SBYTES;
+        const uint8_t *tVs = tV + KBYTES;
+        const int pbase = (c0 + ci) * ATT_CHUNK;
+
+        // ---- scores: LPP lanes per position, 16 dims per lane
+        {
+            const int sub = lane % LPP, pl = lane / LPP;
+            for (int pp = warp * PPW + pl; pp < ATT_CHUNK; pp += NW * PPW) {
+                float kf[16];
+                float ksc = 1.f;
+                if (Q8) {
+                    const uint4 w = *reinterpret_cast<const uint4 *>(tK + pp * HD + sub * 16);
+                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+#pragma unroll
+                        for (int k = 0; k < 4; k++) kf[4 * j + k] = s8f(ww[j], k);
+                    ksc = __half2float(reinterpret_cast<const __half *>(tKs)[pp * NB + sub / 2]);
+                } else {
+                    const uint4 w0 = *reinterpret_cast<const uint4 *>(tK + (pp * HD + sub * 16) * 2);
+                    const uint4 w1 = *reinterpret_cast<const uint4 *>(tK + (pp * HD + sub * 16) * 2 + 16);
+                    const __half2 *h0 = reinterpret_cast<const __half2 *>(&w0);
+                    const __half2 *h1 = reinterpret_cast<const __half2 *>(&w1);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float2 f0 = __half22float2(h0[j]), f1 = __half22float2(h1[j]);
+                        kf[2 * j] = f0.x; kf[2 * j + 1] = f0.y;
+                        kf[8 + 2 * j] = f1.x; kf[8 + 2 * j + 1] = f1.y;
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const float4 *qv = reinterpret_cast<const float4 *>(&s_q[g][sub][0]);
+                    float s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float4 qq = qv[j];
+                        s = fmaf(kf[4 * j], qq.x, s);
+                        s = fmaf(kf[4 * j + 1], qq.y, s);
+                        s = fmaf(kf[4 * j + 2], qq.z, s);
+                        s = fmaf(kf[4 * j + 3], qq.w, s);
+                    }
+                    s *= ksc;
+#pragma unroll
+                    for (int o = LPP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (sub == 0) s_p[g][pp] = (pbase + pp < ctx) ? s : -INFINITY;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- online softmax bookkeeping: warp w owns heads g = w, w+NW, ...
+        for (int g = warp; g < G; g += NW) {
+            float v0 = s_p[g][lane], v1 = s_p[g][lane + 32];
+            float cm = warp_max(fmaxf(v0, v1));
+            float m_old = s_m[g], m_new = fmaxf(m_old, cm);
+            float e0 = (v0 == -INFINITY) ? 0.f : __expf(v0 - m_new);
+            float e1 = (v1 == -INFINITY) ? 0.f : __expf(v1 - m_new);
+            float cs = warp_sum(e0 + e1);
+            s_p[g][lane] = e0;
+            s_p[g][lane + 32] = e1;
+            if (lane == 0) {
+                float corr = (m_old == -INFINITY) ? 0.f : __expf(m_old - m_new);
+                s_corr[g] = corr;
+                s_l[g] = s_l[g] * corr + cs;
+                s_m[g] = m_new;
+            }
+        }
+        __syncthreads();
+
+        // ---- P.V: warp w takes positions w, w+NW, ... ; lane owns 4 dims (one code word)
+        {
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const float c = s_corr[g];
+                acc[g][0] *= c; acc[g][1] *= c; acc[g][2] *= c; acc[g][3] *= c;
+            }
+            if (lane < HD / 4) {
+                const int npos = min(ATT_CHUNK, ctx - pbase);
+                for (int pp = warp; pp < npos; pp += NW) {
+                    float vf[4];
+                    if (Q8) {
+                        const uint32_t w = reinterpret_cast<const uint32_t *>(tV + pp * HD)[lane];
+                        const float vsc = __half2float(reinterpret_cast<const __half *>(tVs)[pp * NB + lane / 8]);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) vf[k] = s8f(w, k) * vsc;
+                    } else {
+                        const uint2 w = reinterpret_cast<const uint2 *>(tV + pp * HD * 2)[lane];
+                        float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&w.x));
+                        float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w.y));
+                        vf[0] = f0.x; vf[1] = f0.y; vf[2] = f1.x; vf[3] = f1.y;
+                    }
+#pragma unroll
+                    for (int g = 0; g < G; g++) {
+                        const float p = s_p[g][pp];
+                        acc[g][0] = fmaf(p, vf[0], acc[g][0]);
+                        acc[g][1] = fmaf(p, vf[1], acc[g][1]);
+                        acc[g][2] = fmaf(p, vf[2], acc[g][2]);
+                        acc[g][3] = fmaf(p, vf[3], acc[g][3]);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with this stage (and with s_p)
+        if (tid == 0 && ci + ATT_STAGES < nch) issue(ci + ATT_STAGES);
+    }
+
+    // ---- cross-warp reduction of acc, write the split's partial
+    float *red = reinterpret_cast<float *>(smem);  // reuse the tile ring: [NW][G][HD]
+    if (lane < HD / 4) {
+#pragma unroll
+        for (int g = 0; g < G; g++)
+            *reinterpret_cast<float4 *>(&red[((warp * G) + g) * HD + lane * 4]) =
+                make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
+    }
+    __syncthreads();
+    for (int i = tid; i < G * HD; i += ATT_THREADS) {
+        int g = i / HD, d = i % HD;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; w++) s += red[((w * G) + g) * HD + d];
+        float *o = a.ws + ((int64_t)(kvh * G + g) * a.nsplit + split) * (HD + 2);
+        o[2 + d] = s;
+        if (d == 0) { o[0] = s_m[g]; o[1] = s_l[g]; }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int prev = atomicAdd(&a.counters[kvh], 1u);
+        s_last = (prev == (unsigned)a.nsplit - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last == 0u) return;
+    __threadfence();
+    // ---- the last CTA of this kv head merges the splits (log-sum-exp)
+    for (int i = tid; i < G * HD; i += ATT_THREADS) {
+        int g = i / HD, d = i % HD;
+        const float *base = a.ws + (int64_t)(kvh * G + g) * a.nsplit * (HD + 2);
+        float M = -INFINITY;
+        for (int s = 0; s < a.nsplit; s++) M = fmaxf(M, base[s * (HD + 2)]);
+        float num = 0.f, den = 0.f;
+        for (int s = 0; s < a.nsplit; s++) {
+            const float *o = base + s * (HD + 2);
+            float w = (o[0] == -INFINITY) ? 0.f : __expf(o[0] - M);
+            num = fmaf(w, o[2 + d], num);
+            den = fmaf(w, o[1], den);
+        }
+        a.out[(int64_t)(kvh * G + g) * HD + d] = __float2half_rn(num / den);
+    }
+    if (tid == 0) a.counters[kvh] = 0u;  // ready for the next launch
+}
+
+template <int HD, int G>
+static int attn_launch_t(const AttnArgs &a, int kv_dtype, bool pdl, cudaStream_t st) {
+    const bool q8 = kv_dtype == DT_Q8_B32T2;
+    const int nb = HD / 32;
+    const size_t stage = q8 ? 2 * (ATT_CHUNK * HD + ATT_CHUNK * nb * 2) : 2 * (ATT_CHUNK * HD * 2);
+    size_t smem = ATT_STAGES * stage;
+    const size_t red = (size_t)(ATT_THREADS / 32) * G * HD * sizeof(float);
+    if (smem < red) smem = red;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(a.nsplit, a.kv_heads);
+    cfg.blockDim = dim3(ATT_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    static bool attr_done[2] = {false, false};   // per <HD, G> instantiation
+    if (q8) {
+        auto kern = attn_decode_kernel<HD, G, true>;
+        if (!attr_done[1]) { IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[1] = true; }
+        IFB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    } else {
+        auto kern = attn_decode_kernel<HD, G, false>;
+        if (!attr_done[0]) { IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[0] = true; }
+        IFB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    }
+    return IFB_OK;
+}
+
+template <int HD>
+static int attn_launch_hd(const AttnArgs &a, int group, int kv_dtype, bool pdl, cudaStream_t st) {
+    switch (group) {
+        case 1: return attn_launch_t<HD, 1>(a, kv_dtype, pdl, st);
+        case 2: return attn_launch_t<HD, 2>(a, kv_dtype, pdl, st);
+        case 4: return attn_launch_t<HD, 4>(a, kv_dtype, pdl, st);
+        case 8: return attn_launch_t<HD, 8>(a, kv_dtype, pdl, st);
+        default:
+            set_last_error("attention: heads/kv_heads = %d not in {1,2,4,8}", group);
+            return IFB_ERR_ARG;
+    }
+}
+
+int attn_decode(const AttnDecode &p, cudaStream_t st) {
+    IFB_CHECK_ARG(p.kv_dtype == DT_F16 || p.kv_dtype == DT_Q8_B32T2, "kv cache type %d", p.kv_dtype);
+    IFB_CHECK_ARG(p.kv_heads > 0 && p.heads % p.kv_heads == 0, "attention: heads %d / kv_heads %d", p.heads, p.kv_heads);
+    IFB_CHECK_ARG(p.pos_dev != nullptr || (p.ctx_len >= 1 && p.ctx_len <= p.max_ctx), "attention: ctx_len %d", p.ctx_len);
+    AttnArgs a;
+    a.heads = p.heads; a.kv_heads = p.kv_heads;
+    a.max_ctx_pad = round_up(p.max_ctx, ATT_CHUNK);
+    a.ctx_len = p.ctx_len;
+    a.softmax_scale = 1.0f / sqrtf((float)p.head_dim);   // alpha*kq_scale (inference_worker.cc:1666, softmax s_scale)
+    a.out = (__half *)p.out; a.q = (const __half *)p.q;
+    a.kcache = (const uint8_t *)p.kcache; a.vcache = (const uint8_t *)p.vcache;
+    a.counters = reinterpret_cast<unsigned int *>(p.workspace);
+    a.ws = reinterpret_cast<float *>((uint8_t *)p.workspace + 4096);
+    a.pos_dev = p.pos_dev;
+    // split count: fill ~2 CTAs per SM; with a device-side position (graph replay) size for max_ctx
+    const int ctx_for_split = p.pos_dev != nullptr ? p.max_ctx : p.ctx_len;
+    const int nchunks = (ctx_for_split + ATT_CHUNK - 1) / ATT_CHUNK;
+    int nsplit = (2 * sm_count() + p.kv_heads - 1) / p.kv_heads;
+    if (nsplit > nchunks) nsplit = nchunks;
+    if (nsplit > 2 * 160) nsplit = 2 * 160;
+    if (nsplit < 1) nsplit = 1;
+    a.nsplit = nsplit;
+    const int group = p.heads / p.kv_heads;
+    switch (p.head_dim) {
+        case 32: return attn_launch_hd<32>(a, group, p.kv_dtype, p.pdl, st);
+        case 64: return attn_launch_hd<64>(a, group, p.kv_dtype, p.pdl, st);
+        case 128: return attn_launch_hd<128>(a, group, p.kv_dtype, p.pdl, st);
+        default:
+            set_last_error("attention: head_dim %d not supported (32/64/128)", p.head_dim);
+            return IFB_ERR_ARG;
+    }
+}
+
+}  // namespace ifb

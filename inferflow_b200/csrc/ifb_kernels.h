@@ -1,0 +1,74 @@
+// Internal launch interface between the C ABI (ifb_capi.cu), the model runtime
+// (ifb_model.cu) and the kernels. Not installed; the public surface is include/inferflow_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ifb {
+
+int sm_count();
+
+struct GemvLaunch {
+    int w_dtype = 0;
+    int nseg = 1;
+    const void *w[3] = {nullptr, nullptr, nullptr};
+    int rows[3] = {0, 0, 0};
+    const void *w_gate = nullptr;
+    int64_t cx = 0;
+    const void *x = nullptr;       // fp16 [cx]
+    const void *xq = nullptr;      // or Q8_B32T2 blocks [cx/32*34]
+    const void *norm_w = nullptr;
+    float norm_eps = 1e-5f, norm_base = 0.f;
+    const void *residual = nullptr, *bias = nullptr;
+    void *y = nullptr;
+    int quantize_x = 1;
+    int pdl = 0;
+    int64_t smem_budget = 0;       // bytes of shared memory per CTA (0 = default, 2 CTAs/SM)
+};
+int gemv_launch(const GemvLaunch &g, cudaStream_t st);
+
+int quantize_rows(int dt, void *dst, const void *src_f16, int64_t rows, int64_t cx, cudaStream_t st);
+int dequantize_rows(int dt, void *dst_f16, const void *src, int64_t rows, int64_t cx, cudaStream_t st);
+
+int rmsnorm(void *y, const void *x, const void *w, int64_t rows, int64_t cols, float eps,
+            float multi_base, cudaStream_t st);
+int rope(void *x, int tokens, int heads, int head_dim, int rope_dims, int pos0, float theta,
+         int order, cudaStream_t st);
+int silu_mul(void *out, const void *a, const void *b, int64_t n, cudaStream_t st);
+int add(void *c, const void *a, const void *b, int64_t n, cudaStream_t st);
+int argmax(int32_t *out, const void *logits, int64_t n, cudaStream_t st);
+int embed_row(void *dst_f16, const void *table, int table_dtype, int64_t cols, int token_id,
+              const int32_t *token_dev, cudaStream_t st);
+
+// KV cache (head-major): per K or V buffer
+//   F16      : half  [kv_heads][max_ctx][head_dim]
+//   Q8_B32T2 : int8  [kv_heads][max_ctx][head_dim]  followed by  half scales [kv_heads][max_ctx][head_dim/32]
+int64_t kv_cache_bytes(int kv_dtype, int kv_heads, int head_dim, int max_ctx);
+struct KvAppend {
+    int kv_dtype, kv_heads, head_dim, max_ctx, pos0, n_tokens;
+    void *kcache, *vcache;
+    const void *k, *v;       // fp16 [n][kv_heads*head_dim]
+    // optional fused RoPE on K (and on q, in place) before the append
+    int rope = 0, rope_order = 2, rope_dims = 0;
+    float rope_theta = 10000.f;
+    void *q = nullptr; int q_heads = 0;
+    const int32_t *pos_dev = nullptr;   // position read from device memory (graph replay)
+    int pdl = 0;
+};
+int kv_append(const KvAppend &a, cudaStream_t st);
+int kv_get_rows(int kv_dtype, void *out, const void *cache, int kv_heads, int head_dim, int max_ctx,
+                int pos0, int n, cudaStream_t st);
+int64_t attn_workspace_bytes(int heads, int head_dim);
+struct AttnDecode {
+    int kv_dtype, heads, kv_heads, head_dim, max_ctx, ctx_len;
+    float kq_scale;
+    void *out; const void *q; const void *kcache, *vcache; void *workspace;
+    const int32_t *pos_dev = nullptr;   // ctx_len = *pos_dev + 1 when set (graph replay)
+    int pdl = 0;
+};
+int attn_decode(const AttnDecode &a, cudaStream_t st);
+
+int moe_topk(int32_t *ids, float *weights, int32_t *counts, const void *scores, int rows,
+             int experts, int top_k, int norm, cudaStream_t st);
+
+}  // namespace ifb

@@ -1,0 +1,625 @@
+// Per-GPU decode runtime for pre-norm llama-family decoders.
+//
+// Replaces GpuInferenceWorker::{Run, ProcessPreLayer, ProcessGpuLayer, ProcessGpuLayer_Attention,
+// Attention_CalculateCurQKV, ProcessGpuLayer_FeedForward, ProcessPostLayer}
+// (reference src/transformer/inference_worker.cc:234-977,983-1405,1407-1620,1726-1900,552-640)
+// for batch-1 decode, and the tensor partitioner's placement rules
+// (src/transformer/network_builder.cc:1373-1406: wq/wk/wv/w1/w3 BY_COL = split output rows,
+// wo/w2 BY_ROW = split the contraction dim on block boundaries, norms DUP).
+//
+// Where the reference runs ~60 synchronous launches per layer on the default stream and
+// creates/joins a thread per token, this runtime issues 6 fused kernels per layer, chained
+// with programmatic dependent launch, and replays the whole token as ONE CUDA graph whose
+// position / token inputs live in device memory.
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdlib>
+
+#include "ifb_formats.cuh"
+#include "ifb_kernels.h"
+#include "../../include/inferflow_b200.h"
+
+using namespace ifb;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct LayerW {
+    DevBuf attn_norm, wq, wk, wv, wo, ffn_norm, w1, w2, w3;
+    DevBuf kcache, vcache;
+};
+
+struct ifb_model {
+    ifb_model_spec_t spec;
+    int hd = 0;            // head_dim
+    int heads_l = 0, kv_heads_l = 0, ffn_l = 0;   // this rank's shard
+    int q_dim_l = 0, kv_dim_l = 0;
+    std::vector<LayerW> layers;
+    DevBuf tok_emb, out_norm, lm_head;
+    DevBuf x0, x1, qkv, attn_out, hbuf, logits, attn_ws, scalars;   // scalars: [0]=pos, [1]=token, [2]=next
+    std::vector<void *> allocs;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    bool graph_ready = false;
+    int launches_per_step = 0;
+    int use_pdl = 1;
+    int use_graph = 1;
+    int64_t weight_bytes = 0;
+    // tensor-parallel exchange (peer memory)
+    DevBuf xchg;                    // this rank's exchange buffer
+    std::vector<void *> peer_xchg;  // mapped peer buffers, [tp_size]
+    uint32_t xchg_epoch = 0;
+};
+
+static int dev_alloc(ifb_model *m, DevBuf &b, size_t bytes) {
+    bytes = (bytes + 255) / 256 * 256;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        set_last_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return IFB_ERR_CUDA;
+    }
+    b.p = p;
+    b.bytes = bytes;
+    m->allocs.push_back(p);
+    return IFB_OK;
+}
+
+#define TRY(x)                      \
+    do {                            \
+        int rc_ = (x);              \
+        if (rc_ != IFB_OK) return rc_; \
+    } while (0)
+
+static int64_t wbytes(int dt, int64_t rows, int64_t cols) { return rows * row_bytes(dt, cols); }
+
+extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *spec) {
+    IFB_CHECK_ARG(out != nullptr && spec != nullptr, "model_create: null argument");
+    const ifb_model_spec_t &s = *spec;
+    IFB_CHECK_ARG(s.layers > 0 && s.d_model > 0 && s.heads > 0 && s.kv_heads > 0 && s.vocab > 0,
+                  "model_create: bad hyper-parameters");
+    IFB_CHECK_ARG(s.d_model % s.heads == 0 && s.heads % s.kv_heads == 0, "heads do not divide d_model");
+    const int tp = s.tp_size > 0 ? s.tp_size : 1;
+    // network_builder.cc:1207: heads % ndev == 0 ; kv heads are sharded with them
+    IFB_CHECK_ARG(s.heads % tp == 0 && s.kv_heads % tp == 0 && s.d_ffn % tp == 0,
+                  "tensor parallelism %d does not divide heads %d / kv_heads %d / d_ffn %d", tp,
+                  s.heads, s.kv_heads, s.d_ffn);
+    IFB_CHECK_ARG(s.experts == 0, "MoE layers are not built in this runtime yet");
+    const int wdt = s.weight_dtype;
+    const int wcap = block_capacity(wdt);
+    IFB_CHECK_ARG(wcap > 0 && wdt != DT_F32, "unsupported device_weight_data_type %d", wdt);
+    // BY_ROW split must fall on block boundaries (device_tensor_builder.cu:161-330)
+    IFB_CHECK_ARG((s.d_model / tp) % (wcap > 32 ? wcap : 32) == 0 && (s.d_ffn / tp) % (wcap > 32 ? wcap : 32) == 0,
+                  "BY_ROW shard (d_model/%d=%d, d_ffn/%d=%d) is not a multiple of the block capacity %d",
+                  tp, s.d_model / tp, tp, s.d_ffn / tp, wcap);
+
+    ifb_model *m = new ifb_model();
+    m->spec = s;
+    m->spec.tp_size = tp;
+    m->hd = s.d_model / s.heads;
+    m->heads_l = s.heads / tp;
+    m->kv_heads_l = s.kv_heads / tp;
+    m->ffn_l = s.d_ffn / tp;
+    m->q_dim_l = m->heads_l * m->hd;
+    m->kv_dim_l = m->kv_heads_l * m->hd;
+    const char *e1 = getenv("IFB_NO_PDL");
+    if (e1 && atoi(e1)) m->use_pdl = 0;
+    const char *e2 = getenv("IFB_NO_GRAPH");
+    if (e2 && atoi(e2)) m->use_graph = 0;
+
+    int rc = IFB_OK;
+    auto A = [&](DevBuf &b, size_t bytes) { if (rc == IFB_OK) rc = dev_alloc(m, b, bytes); };
+    const int d = s.d_model;
+    m->layers.resize(s.layers);
+    int64_t wsum = 0;
+    for (auto &L : m->layers) {
+        A(L.attn_norm, d * 2);
+        A(L.ffn_norm, d * 2);
+        A(L.wq, wbytes(wdt, m->q_dim_l, d));
+        A(L.wk, wbytes(wdt, m->kv_dim_l, d));
+        A(L.wv, wbytes(wdt, m->kv_dim_l, d));
+        A(L.wo, wbytes(wdt, d, m->q_dim_l));
+        A(L.w1, wbytes(wdt, m->ffn_l, d));
+        A(L.w3, wbytes(wdt, m->ffn_l, d));
+        A(L.w2, wbytes(wdt, d, m->ffn_l));
+        wsum += wbytes(wdt, m->q_dim_l, d) + 2 * wbytes(wdt, m->kv_dim_l, d) + wbytes(wdt, d, m->q_dim_l) +
+                2 * wbytes(wdt, m->ffn_l, d) + wbytes(wdt, d, m->ffn_l);
+        int64_t kvb = kv_cache_bytes(s.kv_dtype, m->kv_heads_l, m->hd, s.max_ctx);
+        if (kvb < 0 && rc == IFB_OK) { set_last_error("unsupported kv cache type %d", s.kv_dtype); rc = IFB_ERR_TYPE; }
+        A(L.kcache, kvb);
+        A(L.vcache, kvb);
+    }
+    A(m->tok_emb, (size_t)s.vocab * d * 2);
+    A(m->out_norm, d * 2);
+    const int ldt = s.lm_head_dtype;
+    if (rc == IFB_OK && (block_capacity(ldt) <= 0 || ldt == DT_F32)) {
+        set_last_error("unsupported lm_head type %d", ldt);
+        rc = IFB_ERR_TYPE;
+    }
+    A(m->lm_head, wbytes(ldt, s.vocab, d));
+    wsum += wbytes(ldt, s.vocab, d);
+    m->weight_bytes = wsum;
+    A(m->x0, d * 2);
+    A(m->x1, d * 2);
+    A(m->qkv, (size_t)(m->q_dim_l + 2 * m->kv_dim_l) * 2);
+    A(m->attn_out, (size_t)m->q_dim_l * 2);
+    A(m->hbuf, (size_t)m->ffn_l * 2);
+    A(m->logits, (size_t)s.vocab * 2);
+    A(m->attn_ws, attn_workspace_bytes(m->heads_l, m->hd));
+    A(m->scalars, 256);
+    if (rc == IFB_OK) {
+        if (cudaMemset(m->attn_ws.p, 0, m->attn_ws.bytes) != cudaSuccess ||
+            cudaMemset(m->scalars.p, 0, 256) != cudaSuccess) {
+            set_last_error("cudaMemset failed");
+            rc = IFB_ERR_CUDA;
+        }
+        for (auto &L : m->layers) {
+            cudaMemset(L.kcache.p, 0, L.kcache.bytes);
+            cudaMemset(L.vcache.p, 0, L.vcache.bytes);
+        }
+    }
+    if (rc != IFB_OK) {
+        ifb_model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return IFB_OK;
+}
+
+extern "C" void ifb_model_destroy(ifb_model_t *m) {
+    if (!m) return;
+    if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+    if (m->graph) cudaGraphDestroy(m->graph);
+    for (void *p : m->allocs) cudaFree(p);
+    delete m;
+}
+
+extern "C" int64_t ifb_model_weight_bytes(const ifb_model_t *m) { return m ? m->weight_bytes : 0; }
+
+extern "C" int64_t ifb_model_kv_bytes_per_token(const ifb_model_t *m, int32_t ctx_len) {
+    if (!m) return 0;
+    // 2 * L * ctx * (g*e) * kvb   (SURVEY section 8d), this rank's shard
+    double kvb = m->spec.kv_dtype == DT_F16 ? 2.0 : 34.0 / 32.0;
+    return (int64_t)(2.0 * m->spec.layers * (double)ctx_len * m->kv_dim_l * kvb);
+}
+
+// ---------------------------------------------------------------------------------------
+// synthetic weights: generated on the device directly in block form
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float u01(uint64_t h) { return ((h >> 40) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float gauss(uint64_t key) {
+    float u1 = u01(mix64(key)), u2 = u01(mix64(key ^ 0xabcdef1234567ull));
+    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// levels-1 of each format (largest code)
+__device__ __forceinline__ int max_code(int dt) {
+    switch (dt) {
+        case DT_Q8_B32T1: return 255;
+        case DT_Q6_B64T1: return 63;
+        case DT_Q5_B64T1: case DT_Q5_B32T1: return 31;
+        case DT_Q4_B16: case DT_Q4_B32T1A: case DT_Q4_B32T1B: case DT_Q4_B64T1: return 15;
+        case DT_Q3H_B64T1: return 10;
+        case DT_Q3_B32T1A: case DT_Q3_B32T1B: return 7;
+        case DT_Q2_B32T1A: case DT_Q2_B32T1B: return 3;
+        default: return 127;
+    }
+}
+
+// Fill a block-quantized tensor: random code bytes, scale ~ |N(0, sigma)|*2/maxcode, base = -maxcode/2*scale
+// (so dequantized weights are ~uniform in +-|N(0,sigma)|, sigma = 0.02 like N(0,0.02) weights).
+// Q3H needs valid base-11 pairs (P <= 120): its code bytes are generated through the quantizer's packing.
+__global__ void synth_blocks_kernel(uint8_t *dst, int dt, int64_t nblocks, int bb, uint64_t seed, float sigma) {
+    int64_t bi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= nblocks) return;
+    uint8_t *b = dst + bi * bb;
+    uint64_t key = seed * 0x100000001b3ull + (uint64_t)bi;
+    float amp = fabsf(gauss(key)) * sigma + 1e-4f;
+    int mc = max_code(dt);
+    if (dt == DT_Q8_B32T2) {
+        uint16_t sc = f2h_bits(amp / 127.0f);
+        b[0] = sc & 0xff; b[1] = sc >> 8;
+        for (int i = 0; i < 32; i += 8) {
+            uint64_t r = mix64(key * 31 + i);
+            for (int k = 0; k < 8; k++) b[2 + i + k] = (uint8_t)(r >> (8 * k));
+        }
+        return;
+    }
+    float scale = 2.0f * amp / (float)mc, base = -amp;
+    int hdr = 4;
+    if (dt == DT_Q4_B16) {
+        b[0] = (uint8_t)(base * 100 + 100.5f); b[1] = (uint8_t)(scale * 1000 + 0.5f); hdr = 2;
+    } else if (dt == DT_Q5_B32T1) {
+        uint16_t s16 = f2h_bits(scale), b16 = f2h_bits(base);
+        b[0] = s16 & 0xff; b[1] = s16 >> 8; b[2] = b16 & 0xff; b[3] = b16 >> 8;
+    } else {
+        uint16_t s16 = f2h_bits(scale), b16 = f2h_bits(base);
+        b[0] = b16 & 0xff; b[1] = b16 >> 8; b[2] = s16 & 0xff; b[3] = s16 >> 8;
+    }
+    if (dt == DT_Q3H_B64T1) {
+        for (int i = 4; i < 8; i++) b[i] = 0;
+        for (int r = 0; r < 8; r++) {
+            uint64_t rr = mix64(key * 131 + r);
+            int P[4];
+            for (int k = 0; k < 4; k++) P[k] = (int)((rr >> (16 * k)) & 0xffff) % 121;
+            b[16 + 2 * r] = (uint8_t)((P[0] & 15) | ((P[1] & 15) << 4));
+            b[16 + 2 * r + 1] = (uint8_t)((P[2] & 15) | ((P[3] & 15) << 4));
+            b[8 + r] = (uint8_t)(((P[0] >> 4) & 3) | (((P[1] >> 4) & 3) << 2) | (((P[2] >> 4) & 3) << 4) | (((P[3] >> 4) & 3) << 6));
+            int hn = ((P[0] >> 6) & 1) | (((P[1] >> 6) & 1) << 1) | (((P[2] >> 6) & 1) << 2) | (((P[3] >> 6) & 1) << 3);
+            b[4 + r / 2] |= (uint8_t)(hn << ((r & 1) * 4));
+        }
+        return;
+    }
+    for (int i = hdr; i < bb; i += 8) {
+        uint64_t r = mix64(key * 31 + i);
+        for (int k = 0; k < 8 && i + k < bb; k++) b[i + k] = (uint8_t)(r >> (8 * k));
+    }
+}
+
+__global__ void synth_f16_kernel(__half *dst, int64_t n, uint64_t seed, float sigma, float constant, int use_const) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[i] = __float2half_rn(use_const ? constant : gauss(seed * 0x100000001b3ull + (uint64_t)i) * sigma);
+}
+
+static int synth_tensor(void *p, int dt, int64_t rows, int64_t cols, uint64_t seed, float sigma, cudaStream_t st) {
+    if (dt == DT_F16) {
+        int64_t n = rows * cols;
+        synth_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((__half *)p, n, seed, sigma, 0.f, 0);
+    } else {
+        int cap = block_capacity(dt), bb = block_bytes(dt);
+        int64_t nb = rows * (cols / cap);
+        synth_blocks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>((uint8_t *)p, dt, nb, bb, seed, sigma);
+    }
+    IFB_LAUNCH_CHECK();
+    return IFB_OK;
+}
+static int const_f16(void *p, int64_t n, float v, cudaStream_t st) {
+    synth_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((__half *)p, n, 0, 0.f, v, 1);
+    IFB_LAUNCH_CHECK();
+    return IFB_OK;
+}
+
+extern "C" int32_t ifb_model_init_synthetic(ifb_model_t *m, uint64_t seed, ifb_stream_t stream) {
+    IFB_CHECK_ARG(m != nullptr, "null model");
+    cudaStream_t st = (cudaStream_t)stream;
+    const auto &s = m->spec;
+    const int d = s.d_model, wdt = s.weight_dtype;
+    // every shard is generated from (global seed, tensor id, rank) so that runs are reproducible
+    uint64_t sd = seed * 1000003ull + (uint64_t)s.tp_rank * 7919ull;
+    int li = 0;
+    for (auto &L : m->layers) {
+        uint64_t ls = sd + 100ull * (uint64_t)(li + 1);
+        TRY(const_f16(L.attn_norm.p, d, 1.0f, st));
+        TRY(const_f16(L.ffn_norm.p, d, 1.0f, st));
+        TRY(synth_tensor(L.wq.p, wdt, m->q_dim_l, d, ls + 1, 0.02f, st));
+        TRY(synth_tensor(L.wk.p, wdt, m->kv_dim_l, d, ls + 2, 0.02f, st));
+        TRY(synth_tensor(L.wv.p, wdt, m->kv_dim_l, d, ls + 3, 0.02f, st));
+        TRY(synth_tensor(L.wo.p, wdt, d, m->q_dim_l, ls + 4, 0.02f, st));
+        TRY(synth_tensor(L.w1.p, wdt, m->ffn_l, d, ls + 5, 0.02f, st));
+        TRY(synth_tensor(L.w3.p, wdt, m->ffn_l, d, ls + 6, 0.02f, st));
+        TRY(synth_tensor(L.w2.p, wdt, d, m->ffn_l, ls + 7, 0.02f, st));
+        li++;
+    }
+    TRY(synth_tensor(m->tok_emb.p, DT_F16, s.vocab, d, seed * 1000003ull + 11, 1.0f, st));   // same on all ranks
+    TRY(const_f16(m->out_norm.p, d, 1.0f, st));
+    TRY(synth_tensor(m->lm_head.p, s.lm_head_dtype, s.vocab, d, seed * 1000003ull + 13, 0.02f, st));
+    return IFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// KV reset / synthetic fill
+// ---------------------------------------------------------------------------------------
+__global__ void synth_kv_kernel(uint8_t *cache, int kv_dtype, int kv_heads, int hd, int max_ctx_pad,
+                                int ctx, uint64_t seed) {
+    // one warp per (head, pos, block of 32 dims)
+    int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    int nb = hd / 32;
+    int64_t total = (int64_t)kv_heads * ctx * nb;
+    if (wid >= total) return;
+    int blk = (int)(wid % nb);
+    int pos = (int)((wid / nb) % ctx);
+    int h = (int)(wid / ((int64_t)nb * ctx));
+    float v = round_h(gauss(seed + (uint64_t)wid * 32 + lane));
+    int64_t base = (int64_t)h * max_ctx_pad + pos;
+    if (kv_dtype == DT_F16) {
+        reinterpret_cast<__half *>(cache)[base * hd + blk * 32 + lane] = __float2half_rn(v);
+    } else {
+        float mx = warp_max(fabsf(v));
+        float scale = __fdiv_rn(mx, 127.0f);
+        int q = scale <= 0.000001f ? 0 : (int)roundf(__fdiv_rn(v, scale));
+        q = min(max(q, -128), 127);
+        reinterpret_cast<int8_t *>(cache)[base * hd + blk * 32 + lane] = (int8_t)q;
+        if (lane == 0)
+            reinterpret_cast<__half *>(cache + (int64_t)kv_heads * max_ctx_pad * hd)[base * nb + blk] = __float2half_rn(scale);
+    }
+}
+
+extern "C" int32_t ifb_model_kv_reset(ifb_model_t *m, int32_t ctx_len, int32_t fill, uint64_t seed,
+                                      ifb_stream_t stream) {
+    IFB_CHECK_ARG(m != nullptr, "null model");
+    IFB_CHECK_ARG(ctx_len >= 0 && ctx_len <= m->spec.max_ctx, "kv_reset: ctx_len %d outside [0, %d]", ctx_len, m->spec.max_ctx);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fill && ctx_len > 0) {
+        int pad = (m->spec.max_ctx + 63) / 64 * 64;
+        int li = 0;
+        for (auto &L : m->layers) {
+            int64_t warps = (int64_t)m->kv_heads_l * ctx_len * (m->hd / 32);
+            unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+            synth_kv_kernel<<<grid, 256, 0, st>>>((uint8_t *)L.kcache.p, m->spec.kv_dtype, m->kv_heads_l, m->hd, pad, ctx_len, seed + 977ull * li + 1);
+            synth_kv_kernel<<<grid, 256, 0, st>>>((uint8_t *)L.vcache.p, m->spec.kv_dtype, m->kv_heads_l, m->hd, pad, ctx_len, seed + 977ull * li + 500009);
+            li++;
+        }
+        IFB_LAUNCH_CHECK();
+    }
+    return IFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// tensor loading (host data -> fp16 -> quantize on device -> keep this rank's shard)
+// ---------------------------------------------------------------------------------------
+__global__ void f32_to_f16_kernel(__half *dst, const float *src, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+
+// Upload rows [r0, r0+nr) x cols [c0, c0+nc) of a host [rows][cols] matrix as fp16, then quantize to dt.
+static int load_shard(DevBuf &dst, int dt, const void *host, int host_dt, int64_t rows, int64_t cols,
+                      int64_t r0, int64_t nr, int64_t c0, int64_t nc, cudaStream_t st) {
+    const size_t esz = host_dt == DT_F32 ? 4 : 2;
+    IFB_CHECK_ARG(host_dt == DT_F32 || host_dt == DT_F16, "load_tensor: host data must be F32 or F16");
+    IFB_CHECK_ARG(wbytes(dt, nr, nc) <= (int64_t)dst.bytes, "load_tensor: shard %lldx%lld does not fit the device tensor", (long long)nr, (long long)nc);
+    void *staging = nullptr, *half_buf = nullptr;
+    IFB_CUDA(cudaMalloc(&staging, (size_t)nr * nc * esz));
+    cudaError_t e = cudaMemcpy2DAsync(staging, nc * esz, (const uint8_t *)host + ((size_t)r0 * cols + c0) * esz,
+                                      cols * esz, nc * esz, nr, cudaMemcpyHostToDevice, st);
+    int rc = IFB_OK;
+    if (e != cudaSuccess) { set_last_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = IFB_ERR_CUDA; }
+    const void *h16 = staging;
+    if (rc == IFB_OK && host_dt == DT_F32) {
+        if (cudaMalloc(&half_buf, (size_t)nr * nc * 2) != cudaSuccess) { set_last_error("cudaMalloc failed"); rc = IFB_ERR_CUDA; }
+        else {
+            int64_t n = nr * nc;
+            f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((__half *)half_buf, (const float *)staging, n);
+            h16 = half_buf;
+        }
+    }
+    if (rc == IFB_OK) {
+        if (dt == DT_F16) {
+            if (cudaMemcpyAsync(dst.p, h16, (size_t)nr * nc * 2, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { set_last_error("D2D copy failed"); rc = IFB_ERR_CUDA; }
+        } else {
+            rc = quantize_rows(dt, dst.p, h16, nr, nc, st);
+        }
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(staging);
+    if (half_buf) cudaFree(half_buf);
+    return rc;
+}
+
+extern "C" int32_t ifb_model_load_tensor(ifb_model_t *m, const char *name, const void *host, int32_t host_dt,
+                                         int64_t rows, int64_t cols, ifb_stream_t stream) {
+    IFB_CHECK_ARG(m != nullptr && name != nullptr && host != nullptr, "load_tensor: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const auto &s = m->spec;
+    const int tp = s.tp_size, rk = s.tp_rank, d = s.d_model, wdt = s.weight_dtype;
+    std::string n(name);
+    m->graph_ready = m->graph_ready;  // weights are read through fixed pointers: the graph stays valid
+    if (n == "tok_embeddings") return load_shard(m->tok_emb, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
+    if (n == "output_norm") return load_shard(m->out_norm, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
+    if (n == "output") return load_shard(m->lm_head, s.lm_head_dtype, host, host_dt, rows, cols, 0, rows, 0, cols, st);
+    int li = -1;
+    char tn[64] = {0};
+    if (sscanf(name, "layers.%d.%63s", &li, tn) != 2 || li < 0 || li >= s.layers) {
+        set_last_error("load_tensor: unknown tensor '%s'", name);
+        return IFB_ERR_ARG;
+    }
+    LayerW &L = m->layers[li];
+    std::string t(tn);
+    const int hd = m->hd;
+    // DUP
+    if (t == "attention_norm") return load_shard(L.attn_norm, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
+    if (t == "ffn_norm") return load_shard(L.ffn_norm, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
+    // BY_COL (split output rows; heads stay whole)
+    if (t == "wq") { IFB_CHECK_ARG(rows == (int64_t)s.heads * hd && cols == d, "wq shape"); return load_shard(L.wq, wdt, host, host_dt, rows, cols, (int64_t)rk * m->q_dim_l, m->q_dim_l, 0, cols, st); }
+    if (t == "wk") { IFB_CHECK_ARG(rows == (int64_t)s.kv_heads * hd && cols == d, "wk shape"); return load_shard(L.wk, wdt, host, host_dt, rows, cols, (int64_t)rk * m->kv_dim_l, m->kv_dim_l, 0, cols, st); }
+    if (t == "wv") { IFB_CHECK_ARG(rows == (int64_t)s.kv_heads * hd && cols == d, "wv shape"); return load_shard(L.wv, wdt, host, host_dt, rows, cols, (int64_t)rk * m->kv_dim_l, m->kv_dim_l, 0, cols, st); }
+    if (t == "w1") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "w1 shape"); return load_shard(L.w1, wdt, host, host_dt, rows, cols, (int64_t)rk * m->ffn_l, m->ffn_l, 0, cols, st); }
+    if (t == "w3") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "w3 shape"); return load_shard(L.w3, wdt, host, host_dt, rows, cols, (int64_t)rk * m->ffn_l, m->ffn_l, 0, cols, st); }
+    // BY_ROW (split the contraction dimension)
+    if (t == "wo") { IFB_CHECK_ARG(rows == d && cols == (int64_t)s.heads * hd, "wo shape"); return load_shard(L.wo, wdt, host, host_dt, rows, cols, 0, rows, (int64_t)rk * m->q_dim_l, m->q_dim_l, st); }
+    if (t == "w2") { IFB_CHECK_ARG(rows == d && cols == s.d_ffn, "w2 shape"); return load_shard(L.w2, wdt, host, host_dt, rows, cols, 0, rows, (int64_t)rk * m->ffn_l, m->ffn_l, st); }
+    set_last_error("load_tensor: unknown tensor '%s'", name);
+    (void)tp;
+    return IFB_ERR_ARG;
+}
+
+// raw access for tests (read back weights / activations / cache)
+extern "C" int32_t ifb_model_tensor_ptr(ifb_model_t *m, const char *name, void **ptr, int64_t *bytes) {
+    IFB_CHECK_ARG(m && name && ptr && bytes, "tensor_ptr: null argument");
+    std::string n(name);
+    DevBuf *b = nullptr;
+    if (n == "tok_embeddings") b = &m->tok_emb;
+    else if (n == "output_norm") b = &m->out_norm;
+    else if (n == "output") b = &m->lm_head;
+    else if (n == "logits") b = &m->logits;
+    else if (n == "x") b = &m->x0;
+    else if (n == "qkv") b = &m->qkv;
+    else if (n == "attn_out") b = &m->attn_out;
+    else if (n == "scalars") b = &m->scalars;
+    else {
+        int li = -1; char tn[64] = {0};
+        if (sscanf(name, "layers.%d.%63s", &li, tn) == 2 && li >= 0 && li < m->spec.layers) {
+            LayerW &L = m->layers[li];
+            std::string t(tn);
+            if (t == "attention_norm") b = &L.attn_norm; else if (t == "ffn_norm") b = &L.ffn_norm;
+            else if (t == "wq") b = &L.wq; else if (t == "wk") b = &L.wk; else if (t == "wv") b = &L.wv;
+            else if (t == "wo") b = &L.wo; else if (t == "w1") b = &L.w1; else if (t == "w2") b = &L.w2;
+            else if (t == "w3") b = &L.w3; else if (t == "kcache") b = &L.kcache; else if (t == "vcache") b = &L.vcache;
+        }
+    }
+    if (!b) { set_last_error("tensor_ptr: unknown tensor '%s'", name); return IFB_ERR_ARG; }
+    *ptr = b->p;
+    *bytes = (int64_t)b->bytes;
+    return IFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// the decode step
+// ---------------------------------------------------------------------------------------
+__global__ void set_scalars_kernel(int32_t *sc, int pos, int token, const int32_t *token_dev) {
+    sc[0] = pos;
+    sc[1] = token_dev != nullptr ? *token_dev : token;
+}
+// next token + advance the position so the graph can be replayed back-to-back
+__global__ void advance_kernel(int32_t *sc) {
+    sc[0] = sc[0] + 1;
+    sc[1] = sc[2];
+}
+
+enum { PART_GEMV = 1, PART_ATTN = 2, PART_MISC = 4, PART_ALL = 7 };
+static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = PART_ALL) {
+    const auto &s = m->spec;
+    const int d = s.d_model, wdt = s.weight_dtype;
+    const int pdl = m->use_pdl;
+    int32_t *sc = (int32_t *)m->scalars.p;
+    int n = 0;
+    if (parts & PART_MISC) { TRY(embed_row(m->x0.p, m->tok_emb.p, DT_F16, d, 0, sc + 1, st)); n++; }
+    const bool q8 = true;   // enable_full_quant_gemv = true (inference_engine.cc:53-57)
+    auto ax8_ok = [](int dt) {
+        return dt == DT_Q8_B32T2 || dt == DT_Q6_B64T1 || dt == DT_Q5_B64T1 || dt == DT_Q4_B32T1A ||
+               dt == DT_Q4_B32T1B || dt == DT_Q4_B64T1 || dt == DT_Q3H_B64T1;
+    };
+    const int quant_x = (q8 && ax8_ok(wdt)) ? 1 : 0;
+    __half *qkv = (__half *)m->qkv.p;
+    for (auto &L : m->layers) {
+        // --- attention: norm + quantize + wq|wk|wv
+        GemvLaunch g;
+        g.w_dtype = wdt; g.nseg = 3;
+        g.w[0] = L.wq.p; g.w[1] = L.wk.p; g.w[2] = L.wv.p;
+        g.rows[0] = m->q_dim_l; g.rows[1] = m->kv_dim_l; g.rows[2] = m->kv_dim_l;
+        g.cx = d; g.x = m->x0.p; g.norm_w = L.attn_norm.p; g.norm_eps = s.norm_eps;
+        g.y = qkv; g.quantize_x = quant_x; g.pdl = pdl;
+        if (parts & PART_GEMV) { TRY(gemv_launch(g, st)); n++; }
+        // --- RoPE(q,k) + append K,V
+        KvAppend ka;
+        ka.kv_dtype = s.kv_dtype; ka.kv_heads = m->kv_heads_l; ka.head_dim = m->hd; ka.max_ctx = s.max_ctx;
+        ka.pos0 = 0; ka.n_tokens = 1; ka.kcache = L.kcache.p; ka.vcache = L.vcache.p;
+        ka.k = qkv + m->q_dim_l; ka.v = qkv + m->q_dim_l + m->kv_dim_l;
+        ka.rope = 1; ka.rope_order = s.rope_order; ka.rope_dims = 0; ka.rope_theta = s.rope_theta;
+        ka.q = qkv; ka.q_heads = m->heads_l; ka.pos_dev = sc; ka.pdl = pdl;
+        if (parts & PART_ATTN) { TRY(kv_append(ka, st)); n++; }
+        // --- attention over the cache
+        AttnDecode ad;
+        ad.kv_dtype = s.kv_dtype; ad.heads = m->heads_l; ad.kv_heads = m->kv_heads_l; ad.head_dim = m->hd;
+        ad.max_ctx = s.max_ctx; ad.ctx_len = 0; ad.kq_scale = s.kq_scale; ad.out = m->attn_out.p; ad.q = qkv;
+        ad.kcache = L.kcache.p; ad.vcache = L.vcache.p; ad.workspace = m->attn_ws.p; ad.pos_dev = sc; ad.pdl = pdl;
+        if (parts & PART_ATTN) { TRY(attn_decode(ad, st)); n++; }
+        // --- wo + residual
+        GemvLaunch o;
+        o.w_dtype = wdt; o.nseg = 1; o.w[0] = L.wo.p; o.rows[0] = d; o.cx = m->q_dim_l;
+        o.x = m->attn_out.p; o.residual = m->x0.p; o.y = m->x1.p; o.quantize_x = quant_x; o.pdl = pdl;
+        if (parts & PART_GEMV) { TRY(gemv_launch(o, st)); n++; }
+        // --- FFN: norm + quantize + (w1, w3) + SiLU*mul
+        GemvLaunch f;
+        f.w_dtype = wdt; f.nseg = 1; f.w[0] = L.w1.p; f.w_gate = L.w3.p; f.rows[0] = m->ffn_l; f.cx = d;
+        f.x = m->x1.p; f.norm_w = L.ffn_norm.p; f.norm_eps = s.norm_eps; f.y = m->hbuf.p;
+        f.quantize_x = quant_x; f.pdl = pdl;
+        if (parts & PART_GEMV) { TRY(gemv_launch(f, st)); n++; }
+        // --- w2 + residual
+        GemvLaunch w2;
+        w2.w_dtype = wdt; w2.nseg = 1; w2.w[0] = L.w2.p; w2.rows[0] = d; w2.cx = m->ffn_l;
+        w2.x = m->hbuf.p; w2.residual = m->x1.p; w2.y = m->x0.p; w2.quantize_x = quant_x; w2.pdl = pdl;
+        if (parts & PART_GEMV) { TRY(gemv_launch(w2, st)); n++; }
+    }
+    // --- final norm + lm_head (fp16 weights meet an fp16 activation: GemvHalf_AX_Alg3)
+    GemvLaunch h;
+    h.w_dtype = s.lm_head_dtype; h.nseg = 1; h.w[0] = m->lm_head.p; h.rows[0] = s.vocab; h.cx = d;
+    h.x = m->x0.p; h.norm_w = m->out_norm.p; h.norm_eps = s.norm_eps; h.y = m->logits.p;
+    h.quantize_x = (s.lm_head_dtype != DT_F16 && ax8_ok(s.lm_head_dtype)) ? 1 : 0; h.pdl = pdl;
+    if (parts & PART_GEMV) { TRY(gemv_launch(h, st)); n++; }
+    if (parts & PART_MISC) {
+        TRY(argmax(sc + 2, m->logits.p, s.vocab, st)); n++;
+        advance_kernel<<<1, 1, 0, st>>>(sc); n++;
+        IFB_LAUNCH_CHECK();
+    }
+    if (launches) *launches = n;
+    return IFB_OK;
+}
+
+extern "C" int32_t ifb_model_decode(ifb_model_t *m, int32_t token_id, const int32_t *token_dev, int32_t pos,
+                                    ifb_stream_t stream) {
+    IFB_CHECK_ARG(m != nullptr, "null model");
+    IFB_CHECK_ARG(pos >= 0 && pos < m->spec.max_ctx, "decode: position %d outside max_context_len %d", pos, m->spec.max_ctx);
+    IFB_CHECK_ARG(m->spec.tp_size == 1 || !m->peer_xchg.empty(), "decode: tensor-parallel model without imported peer buffers");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pos >= 0 && (token_id >= 0 || token_dev != nullptr)) {
+        set_scalars_kernel<<<1, 1, 0, st>>>((int32_t *)m->scalars.p, pos, token_id, token_id < 0 ? token_dev : nullptr);
+        IFB_LAUNCH_CHECK();
+    }
+    if (!m->use_graph) return issue_step(m, st, &m->launches_per_step);
+    if (!m->graph_ready) {
+        // warm every kernel once outside capture (cudaFuncSetAttribute etc. are not capturable)
+        int32_t saved[4];
+        IFB_CUDA(cudaStreamSynchronize(st));
+        IFB_CUDA(cudaMemcpy(saved, m->scalars.p, sizeof(saved), cudaMemcpyDeviceToHost));
+        TRY(issue_step(m, st, &m->launches_per_step));
+        IFB_CUDA(cudaStreamSynchronize(st));
+        IFB_CUDA(cudaMemcpy(m->scalars.p, saved, sizeof(saved), cudaMemcpyHostToDevice));
+        cudaStream_t cs;
+        IFB_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        IFB_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        int rc = issue_step(m, cs, &m->launches_per_step);
+        cudaError_t e = cudaStreamEndCapture(cs, &m->graph);
+        if (rc != IFB_OK) { cudaStreamDestroy(cs); return rc; }
+        if (e != cudaSuccess) { cudaStreamDestroy(cs); set_last_error("graph capture failed: %s", cudaGetErrorString(e)); return IFB_ERR_CUDA; }
+        IFB_CUDA(cudaGraphInstantiate(&m->graph_exec, m->graph, 0));
+        cudaStreamDestroy(cs);
+        m->graph_ready = true;
+    }
+    IFB_CUDA(cudaGraphLaunch(m->graph_exec, st));
+    return IFB_OK;
+}
+
+// replay without touching the scalars: continues from the position/token the previous step left
+extern "C" int32_t ifb_model_decode_next(ifb_model_t *m, ifb_stream_t stream) {
+    IFB_CHECK_ARG(m != nullptr && (m->graph_ready || !m->use_graph), "decode_next: call ifb_model_decode first");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!m->use_graph) return issue_step(m, st, &m->launches_per_step);
+    IFB_CUDA(cudaGraphLaunch(m->graph_exec, st));
+    return IFB_OK;
+}
+
+// measurement aid: issue only a subset of the step's kernels, eagerly (1 = the GEMV family,
+// 2 = kv-append + attention, 4 = embedding/argmax/advance). Returns the number of launches (>= 0).
+extern "C" int32_t ifb_model_issue_parts(ifb_model_t *m, int32_t parts, ifb_stream_t stream) {
+    IFB_CHECK_ARG(m != nullptr, "null model");
+    int n = 0;
+    int rc = issue_step(m, (cudaStream_t)stream, &n, parts);
+    return rc != IFB_OK ? rc : n;
+}
+
+extern "C" const void *ifb_model_logits(const ifb_model_t *m) { return m ? m->logits.p : nullptr; }
+extern "C" const int32_t *ifb_model_next_token(const ifb_model_t *m) { return m ? (const int32_t *)m->scalars.p + 2 : nullptr; }
+extern "C" int32_t ifb_model_kernel_launches_per_step(const ifb_model_t *m) { return m ? m->launches_per_step : 0; }
+
+extern "C" int32_t ifb_model_tp_export(ifb_model_t *m, void *host_handle) {
+    (void)m; (void)host_handle;
+    set_last_error("tensor-parallel exchange is not built yet");
+    return IFB_ERR_STATE;
+}
+extern "C" int32_t ifb_model_tp_import(ifb_model_t *m, const void *handles, int32_t n) {
+    (void)m; (void)handles; (void)n;
+    set_last_error("tensor-parallel exchange is not built yet");
+    return IFB_ERR_STATE;
+}

@@ -1,0 +1,118 @@
+"""Thin handle on the C++ decode runtime (ifb_model_* in include/inferflow_b200.h)."""
+import ctypes as C
+from dataclasses import dataclass
+
+from .capi import DT, ModelSpecC, check, lib
+
+
+@dataclass
+class ModelSpec:
+    layers: int
+    d_model: int
+    d_ffn: int
+    heads: int
+    kv_heads: int
+    vocab: int
+    max_ctx: int = 2048
+    weight_dtype: int = DT.Q4_B32T1A
+    kv_dtype: int = DT.Q8_B32T2
+    lm_head_dtype: int = DT.F16
+    rope_order: int = 2
+    rope_theta: float = 10000.0
+    norm_eps: float = 1e-5
+    kq_scale: float = 1.0
+    tp_rank: int = 0
+    tp_size: int = 1
+    experts: int = 0
+    experts_top_k: int = 0
+
+    def to_c(self):
+        return ModelSpecC(self.layers, self.d_model, self.d_ffn, self.heads, self.kv_heads, self.vocab,
+                          self.max_ctx, self.weight_dtype, self.kv_dtype, self.lm_head_dtype,
+                          self.rope_order, self.rope_theta, self.norm_eps, self.kq_scale, self.tp_rank,
+                          self.tp_size, self.experts, self.experts_top_k)
+
+
+# shapes of SURVEY.md section 8
+LLAMA2_7B = dict(layers=32, d_model=4096, d_ffn=11008, heads=32, kv_heads=32, vocab=32000)
+LLAMA2_70B = dict(layers=80, d_model=8192, d_ffn=28672, heads=64, kv_heads=8, vocab=32000)
+STORIES_110M = dict(layers=12, d_model=768, d_ffn=2048, heads=12, kv_heads=12, vocab=32000)
+
+
+class Model:
+    def __init__(self, spec: ModelSpec):
+        self.spec = spec
+        self._h = C.c_void_p()
+        c = spec.to_c()
+        check(lib.ifb_model_create(C.byref(self._h), C.byref(c)), "ifb_model_create")
+
+    def close(self):
+        if self._h:
+            lib.ifb_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def weight_bytes(self):
+        return lib.ifb_model_weight_bytes(self._h)
+
+    def kv_bytes_per_token(self, ctx_len):
+        return lib.ifb_model_kv_bytes_per_token(self._h, ctx_len)
+
+    def init_synthetic(self, seed=1234, stream=0):
+        check(lib.ifb_model_init_synthetic(self._h, seed, stream), "ifb_model_init_synthetic")
+
+    def load_tensor(self, name, array, stream=0):
+        import numpy as np
+        a = np.ascontiguousarray(array)
+        dt = {np.dtype(np.float32): DT.F32, np.dtype(np.float16): DT.F16}[a.dtype]
+        rows, cols = (a.shape if a.ndim == 2 else (1, a.shape[0]))
+        check(lib.ifb_model_load_tensor(self._h, name.encode(), a.ctypes.data, dt, rows, cols, stream),
+              f"ifb_model_load_tensor({name})")
+
+    def tensor_ptr(self, name):
+        p = C.c_void_p()
+        n = C.c_int64()
+        check(lib.ifb_model_tensor_ptr(self._h, name.encode(), C.byref(p), C.byref(n)), "ifb_model_tensor_ptr")
+        return p.value, n.value
+
+    def read_tensor(self, name, nbytes=None):
+        """device bytes of a named tensor as a numpy uint8 array (blocking)"""
+        import numpy as np
+        p, n = self.tensor_ptr(name)
+        n = n if nbytes is None else nbytes
+        out = np.empty(n, dtype=np.uint8)
+        check(lib.ifb_memcpy_d2h(out.ctypes.data, p, n), "ifb_memcpy_d2h")
+        return out
+
+    def kv_reset(self, ctx_len=0, fill_synthetic=False, seed=99, stream=0):
+        check(lib.ifb_model_kv_reset(self._h, ctx_len, 1 if fill_synthetic else 0, seed, stream), "ifb_model_kv_reset")
+
+    def decode(self, token_id, pos, stream=0, token_dev=None):
+        check(lib.ifb_model_decode(self._h, token_id, token_dev, pos, stream), "ifb_model_decode")
+
+    def decode_next(self, stream=0):
+        check(lib.ifb_model_decode_next(self._h, stream), "ifb_model_decode_next")
+
+    def issue_parts(self, parts, stream=0):
+        n = lib.ifb_model_issue_parts(self._h, parts, stream)
+        if n < 0:
+            check(n, "ifb_model_issue_parts")
+        return n
+
+    @property
+    def logits_ptr(self):
+        return lib.ifb_model_logits(self._h)
+
+    @property
+    def next_token_ptr(self):
+        return lib.ifb_model_next_token(self._h)
+
+    @property
+    def launches_per_step(self):
+        return lib.ifb_model_kernel_launches_per_step(self._h)

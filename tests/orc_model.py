@@ -1,0 +1,61 @@
+"""Host-side oracle of one llama decode step (TEST INFRASTRUCTURE): the layer schedule of
+GpuInferenceWorker::ProcessGpuLayer (inference_worker.cc:762-977) restated with the oracle's
+operators, every intermediate tensor rounded to fp16 where the reference stores half."""
+import numpy as np
+
+import orc
+
+AX8 = set(orc.AX8_TYPES)
+
+
+class OracleModel:
+    def __init__(self, spec, tensors):
+        """tensors: name -> raw uint8 bytes as stored on the device (reference block layout)"""
+        self.s = spec
+        self.t = tensors
+        self.hd = spec.d_model // spec.heads
+        self.K = [[] for _ in range(spec.layers)]
+        self.V = [[] for _ in range(spec.layers)]
+        self.o = orc.oracle()
+
+    def _gemv(self, name, dt, x, rows, cols):
+        w = self.t[name][: orc.row_bytes(dt, cols) * rows] if dt != orc.F16 else self.t[name][: rows * cols * 2]
+        if dt == orc.F16:
+            return self.o.gemv_f16(w.view(np.float16).reshape(rows, cols), x, rows, cols)
+        if dt in AX8:
+            xq = self.o.quantize(orc.Q8_B32T2, x[None, :])
+            return self.o.gemv_ax8(dt, w, xq, rows, cols)
+        return self.o.gemv_half(dt, w, x, rows, cols)
+
+    def _norm(self, name, x):
+        w = self.t[name][: x.size * 2].view(np.float16).astype(np.float32)
+        return orc.f16(self.o.rmsnorm(x, w, self.s.norm_eps))
+
+    def step(self, token, pos):
+        s, o, hd = self.s, self.o, self.hd
+        d, wdt = s.d_model, s.weight_dtype
+        emb = self.t["tok_embeddings"].view(np.float16).reshape(s.vocab, d)
+        x = emb[token].astype(np.float32)
+        qd, kvd = s.heads * hd, s.kv_heads * hd
+        for l in range(s.layers):
+            p = f"layers.{l}."
+            xn = self._norm(p + "attention_norm", x)
+            q = orc.f16(self._gemv(p + "wq", wdt, xn, qd, d))
+            k = orc.f16(self._gemv(p + "wk", wdt, xn, kvd, d))
+            v = orc.f16(self._gemv(p + "wv", wdt, xn, kvd, d))
+            q = orc.f16(o.rope(q, s.heads, hd, pos, s.rope_theta, s.rope_order)).reshape(-1)
+            k = orc.f16(o.rope(k, s.kv_heads, hd, pos, s.rope_theta, s.rope_order)).reshape(-1)
+            if s.kv_dtype == orc.Q8_B32T2:
+                k = o.dequantize(orc.Q8_B32T2, o.quantize(orc.Q8_B32T2, k[None, :]), kvd)[0]
+                v = o.dequantize(orc.Q8_B32T2, o.quantize(orc.Q8_B32T2, v[None, :]), kvd)[0]
+            assert len(self.K[l]) == pos
+            self.K[l].append(k); self.V[l].append(v)
+            a = orc.f16(o.attn_decode(q, np.stack(self.K[l]), np.stack(self.V[l]), s.heads, s.kv_heads, hd, 1.0, True))
+            x1 = orc.f16(orc.f16(self._gemv(p + "wo", wdt, a, d, qd)) + x)
+            x1n = self._norm(p + "ffn_norm", x1)
+            g = orc.f16(self._gemv(p + "w1", wdt, x1n, s.d_ffn, d))
+            u = orc.f16(self._gemv(p + "w3", wdt, x1n, s.d_ffn, d))
+            h = orc.f16(orc.f16(g / (1.0 + np.exp(-g.astype(np.float64)))) * u)
+            x = orc.f16(orc.f16(self._gemv(p + "w2", wdt, h, d, s.d_ffn)) + x1)
+        xn = self._norm("output_norm", x)
+        return self._gemv("output", s.lm_head_dtype, xn, s.vocab, d)

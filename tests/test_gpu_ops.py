@@ -1,0 +1,364 @@
+"""GPU parity tests (run with -m gpu on a B200): every kernel, called THROUGH THE C ABI
+(ctypes -> libinferflow_b200.so), against the oracle (oracle/oracle.c) on the same seeded inputs.
+
+Bars: bit-exact for quantized bytes, codes, KV rows and expert ids; for fp outputs
+|ours - exact oracle| <= TOL_REL*|oracle| + TOL_ABS*max|oracle| with TOL_REL = 2**-10 (one fp16
+rounding of the output plus fp32 accumulation), as SURVEY.md section 8c sets.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+TOL_REL = 2.0 ** -10
+TOL_ABS = 2.0 ** -10
+
+
+@pytest.fixture(scope="module")
+def ib():
+    import inferflow_b200
+    assert torch.cuda.is_available()
+    torch.cuda.init()
+    torch.zeros(1, device="cuda")
+    return inferflow_b200
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def close(got, want, rel=TOL_REL, abs_=TOL_ABS):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    bound = rel * np.abs(want) + abs_ * np.max(np.abs(want))
+    err = np.abs(got - want)
+    bad = err > bound
+    assert not bad.any(), f"max err {err.max():.3e} (bound {bound[np.argmax(err)]:.3e}), {bad.sum()} of {bad.size} outside"
+
+
+def weights(dt, cy, cx, seed):
+    rng = np.random.default_rng(seed)
+    w = orc.f16(rng.normal(0, 0.02, (cy, cx)))
+    if dt == orc.Q4_B16:
+        w = np.clip(w * 20, -1.4, 1.4)
+    return orc.oracle().quantize(dt, w)
+
+
+# ------------------------------------------------------------------ codecs
+@pytest.mark.parametrize("dt", orc.ALL_QUANT, ids=[orc.NAMES[d] for d in orc.ALL_QUANT])
+def test_quantize_bit_exact(ib, dt):
+    rng = np.random.default_rng(10 + dt)
+    for sigma, rows, cx in ((0.02, 64, 1024), (1.0, 33, 256), (1e-4, 8, 128)):
+        src = orc.f16(rng.normal(0, sigma, (rows, cx)))
+        src[0, :64] = 0.25                      # constant blocks -> scale < 1e-5
+        if dt == orc.Q4_B16:
+            src = np.clip(src, -1.4, 1.4)
+        want = orc.oracle().quantize(dt, src)
+        x = dev(src.astype(np.float16))
+        out = torch.zeros(want.size, dtype=torch.uint8, device="cuda")
+        ib.check(ib.lib.ifb_quantize_rows(dt, ptr(out), ptr(x), rows, cx, None), "quantize")
+        got = out.cpu().numpy().reshape(want.shape)
+        assert np.array_equal(got, want), f"{orc.NAMES[dt]}: {(got != want).sum()} bytes differ"
+
+
+@pytest.mark.parametrize("dt", orc.ALL_QUANT, ids=[orc.NAMES[d] for d in orc.ALL_QUANT])
+def test_dequantize_exact(ib, dt):
+    blocks = weights(dt, 32, 512, 20 + dt)
+    want = orc.oracle().dequantize(dt, blocks, 512).astype(np.float16)
+    b = dev(blocks)
+    out = torch.zeros(32 * 512, dtype=torch.float16, device="cuda")
+    ib.check(ib.lib.ifb_dequantize_rows(dt, ptr(out), ptr(b), 32, 512, None), "dequantize")
+    assert np.array_equal(out.cpu().numpy().reshape(32, 512), want)
+
+
+def test_quantize_golden_fixture(ib):
+    """the committed reference fixtures through the CUDA quantizer (all but the host-flavoured Q8_B32T2)"""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for dt in orc.ALL_QUANT:
+        if dt == orc.Q8_B32T2:
+            continue
+        g = np.load(os.path.join(gold, f"codec_{orc.NAMES[dt]}.npz"))
+        src = g["src"]
+        x = dev(src.astype(np.float16))
+        out = torch.zeros(g["blocks"].size, dtype=torch.uint8, device="cuda")
+        ib.check(ib.lib.ifb_quantize_rows(dt, ptr(out), ptr(x), src.shape[0], src.shape[1], None), "quantize")
+        assert np.array_equal(out.cpu().numpy().reshape(g["blocks"].shape), g["blocks"]), orc.NAMES[dt]
+
+
+# ------------------------------------------------------------------ GEMV
+SHAPES = [(64, 256), (40, 4096), (4096, 4096), (1000, 11008), (72, 288), (128, 768)]
+
+
+def _gemv(ib, dt, w, x_dtype, x_t, cy, cx, bias=None):
+    y = torch.zeros(cy, dtype=torch.float16, device="cuda")
+    wt = dev(w)
+    ib.check(ib.lib.ifb_gemv(dt, ptr(y), ptr(wt), x_dtype, ptr(x_t), cy, cx,
+                             ptr(bias) if bias is not None else None, None), "gemv")
+    torch.cuda.synchronize()
+    return y.cpu().numpy().astype(np.float64)
+
+
+@pytest.mark.parametrize("dt", orc.AX8_TYPES, ids=[orc.NAMES[d] for d in orc.AX8_TYPES])
+@pytest.mark.parametrize("shape", SHAPES, ids=[f"{a}x{b}" for a, b in SHAPES])
+def test_gemv_q8_activation(ib, dt, shape):
+    cy, cx = shape
+    if cx % orc.CAP[dt] or (dt == orc.Q8_B32T2 and cy % 8):
+        pytest.skip("shape not tileable for this block size")
+    w = weights(dt, cy, cx, 30 + dt)
+    rng = np.random.default_rng(31)
+    x = orc.f16(rng.normal(0, 1, cx))
+    xq = orc.oracle().quantize(orc.Q8_B32T2, x[None, :])
+    want = orc.oracle().gemv_ax8(dt, w, xq, cy, cx)
+    got = _gemv(ib, dt, w, orc.Q8_B32T2, dev(xq), cy, cx)
+    close(got, want)
+
+
+@pytest.mark.parametrize("dt", orc.ALL_QUANT, ids=[orc.NAMES[d] for d in orc.ALL_QUANT])
+def test_gemv_f16_activation(ib, dt):
+    cy, cx = 96, 1024
+    w = weights(dt, cy, cx, 40 + dt)
+    x = orc.f16(np.random.default_rng(41).normal(0, 1, cx))
+    want = orc.oracle().gemv_half(dt, w, x, cy, cx)
+    got = _gemv(ib, dt, w, orc.F16, dev(x.astype(np.float16)), cy, cx)
+    close(got, want)
+
+
+@pytest.mark.parametrize("shape", [(64, 256), (32000, 4096), (1000, 288)], ids=["64x256", "lm_head", "1000x288"])
+def test_gemv_f16_weights(ib, shape):
+    cy, cx = shape
+    rng = np.random.default_rng(50)
+    w = rng.normal(0, 0.02, (cy, cx)).astype(np.float16)
+    x = orc.f16(rng.normal(0, 1, cx))
+    want = orc.oracle().gemv_f16(w, x, cy, cx)
+    y = torch.zeros(cy, dtype=torch.float16, device="cuda")
+    wt, xt = dev(w), dev(x.astype(np.float16))
+    ib.check(ib.lib.ifb_gemv(orc.F16, ptr(y), ptr(wt), orc.F16, ptr(xt), cy, cx, None, None), "gemv")
+    close(y.cpu().numpy(), want)
+
+
+def test_gemv_bias_and_errors(ib):
+    cy, cx = 64, 256
+    w = weights(orc.Q4_B32T1A, cy, cx, 60)
+    x = orc.f16(np.random.default_rng(61).normal(0, 1, cx))
+    b = orc.f16(np.random.default_rng(62).normal(0, 1, cy))
+    xq = orc.oracle().quantize(orc.Q8_B32T2, x[None, :])
+    want = orc.f16(orc.f16(orc.oracle().gemv_ax8(orc.Q4_B32T1A, w, xq, cy, cx)) + b)
+    got = _gemv(ib, orc.Q4_B32T1A, w, orc.Q8_B32T2, dev(xq), cy, cx, bias=dev(b.astype(np.float16)))
+    close(got, want, rel=2 ** -9)
+    # unsupported combinations fail loudly (reference: Gemv_AX_QuantQ8 logs "not supported")
+    y = torch.zeros(cy, dtype=torch.float16, device="cuda")
+    rc = ib.lib.ifb_gemv(orc.Q2_B32T1B, ptr(y), ptr(dev(w)), orc.Q8_B32T2, ptr(dev(xq)), cy, cx, None, None)
+    assert rc == -2
+    rc = ib.lib.ifb_gemv(orc.Q4_B32T1A, ptr(y), ptr(dev(w)), orc.F16, ptr(dev(x.astype(np.float16))), 6, cx, None, None)
+    assert rc == -1   # rows not tileable
+
+
+def _fused(ib, dt, segs, cx, x, norm_w=None, gate=None, residual=None, quantize_x=1, pdl=0):
+    from inferflow_b200.capi import GemvDesc
+    d = GemvDesc()
+    d.w_dtype = dt
+    d.nseg = len(segs)
+    keep = []
+    total = 0
+    for i, (w, rows) in enumerate(segs):
+        t = dev(w); keep.append(t)
+        d.w[i] = t.data_ptr(); d.rows[i] = rows; total += rows
+    if gate is not None:
+        g = dev(gate); keep.append(g); d.w_gate = g.data_ptr()
+    d.cx = cx
+    xt = dev(x.astype(np.float16)); keep.append(xt); d.x_f16 = xt.data_ptr()
+    if norm_w is not None:
+        nt = dev(norm_w.astype(np.float16)); keep.append(nt); d.norm_w_f16 = nt.data_ptr()
+    d.norm_eps = 1e-5
+    if residual is not None:
+        rt = dev(residual.astype(np.float16)); keep.append(rt); d.residual_f16 = rt.data_ptr()
+    y = torch.zeros(total, dtype=torch.float16, device="cuda")
+    d.y_f16 = y.data_ptr()
+    d.quantize_x = quantize_x
+    d.pdl = pdl
+    ib.check(ib.lib.ifb_gemv_fused(C.byref(d), None), "gemv_fused")
+    torch.cuda.synchronize()
+    return y.cpu().numpy().astype(np.float64)
+
+
+@pytest.mark.parametrize("dt", [orc.Q4_B32T1A, orc.Q3H_B64T1, orc.Q8_B32T2], ids=["Q4", "Q3H", "Q8"])
+def test_gemv_fused_qkv_norm(ib, dt):
+    """RmsNorm -> Quantize -> wq|wk|wv in one launch (GQA-shaped segments)"""
+    cx = 1024
+    o = orc.oracle()
+    rng = np.random.default_rng(70)
+    x = orc.f16(rng.normal(0, 1, cx))
+    nw = orc.f16(rng.normal(1, 0.1, cx))
+    segs = [(weights(dt, 512, cx, 71), 512), (weights(dt, 128, cx, 72), 128), (weights(dt, 128, cx, 73), 128)]
+    xn = orc.f16(o.rmsnorm(x, nw))
+    xq = o.quantize(orc.Q8_B32T2, xn[None, :])
+    want = np.concatenate([o.gemv_ax8(dt, w, xq, r, cx) for w, r in segs])
+    got = _fused(ib, dt, segs, cx, x, norm_w=nw, pdl=1)
+    close(got, want)
+
+
+def test_gemv_fused_glu_and_residual(ib):
+    dt = orc.Q4_B32T1A
+    o = orc.oracle()
+    cx, f = 512, 1376            # 1376 = 11008/8: a TP-8 shard of the llama-7B FFN
+    rng = np.random.default_rng(80)
+    x = orc.f16(rng.normal(0, 1, cx))
+    nw = orc.f16(rng.normal(1, 0.1, cx))
+    w1, w3 = weights(dt, f, cx, 81), weights(dt, f, cx, 82)
+    xq = o.quantize(orc.Q8_B32T2, orc.f16(o.rmsnorm(x, nw))[None, :])
+    a = orc.f16(o.gemv_ax8(dt, w1, xq, f, cx)); b = orc.f16(o.gemv_ax8(dt, w3, xq, f, cx))
+    silu = orc.f16(a / (1.0 + np.exp(-a.astype(np.float64))))
+    want = orc.f16(silu * b)
+    got = _fused(ib, dt, [(w1, f)], cx, x, norm_w=nw, gate=w3)
+    close(got, want, rel=2 ** -9)
+    # w2 (cx = 1376: 43 blocks per row, not a multiple of the warp) + residual
+    w2 = weights(dt, cx, f, 83)
+    h = orc.f16(want)
+    res = orc.f16(rng.normal(0, 1, cx))
+    hq = o.quantize(orc.Q8_B32T2, h[None, :])
+    want2 = orc.f16(orc.f16(o.gemv_ax8(dt, w2, hq, cx, f)) + res)
+    got2 = _fused(ib, dt, [(w2, cx)], f, h, residual=res)
+    close(got2, want2, rel=2 ** -9)
+
+
+def test_gemv_full_size_linearity(ib):
+    """property at BASELINE size (llama-7B w1 11008x4096, Q4): W(x1) + W(x2) == W applied to both
+    through the fp16-activation path within fp16 rounding; and the dp4a path agrees with the oracle."""
+    dt = orc.Q4_B32T1A
+    cy, cx = 11008, 4096
+    w = weights(dt, cy, cx, 90)
+    rng = np.random.default_rng(91)
+    x = orc.f16(rng.normal(0, 1, cx))
+    xq = orc.oracle().quantize(orc.Q8_B32T2, x[None, :])
+    want = orc.oracle().gemv_ax8(dt, w, xq, cy, cx)
+    got = _gemv(ib, dt, w, orc.Q8_B32T2, dev(xq), cy, cx)
+    close(got, want)
+    # checksum of checksums: sum(y) == (sum_rows W) . x
+    deq = orc.oracle().dequantize(dt, w, cx).astype(np.float64)
+    x8 = orc.oracle().dequantize(orc.Q8_B32T2, xq, cx)[0].astype(np.float64)
+    assert abs(got.sum() - deq.sum(0) @ x8) <= 2 ** -10 * np.abs(deq @ x8).sum()
+
+
+# ------------------------------------------------------------------ small ops
+def test_rmsnorm_rope_silu_add_argmax(ib):
+    o = orc.oracle()
+    rng = np.random.default_rng(100)
+    x = orc.f16(rng.normal(0, 1, (3, 4096)))
+    w = orc.f16(rng.normal(1, 0.1, 4096))
+    y = torch.zeros(3 * 4096, dtype=torch.float16, device="cuda")
+    ib.check(ib.lib.ifb_rmsnorm(ptr(y), ptr(dev(x.astype(np.float16))), ptr(dev(w.astype(np.float16))), 3, 4096, 1e-5, 0.0, None), "rmsnorm")
+    want = np.stack([o.rmsnorm(x[i], w) for i in range(3)])
+    close(y.cpu().numpy().reshape(3, 4096), want)
+
+    for order in (0, 2):
+        q = orc.f16(rng.normal(0, 1, (2, 8, 128)))
+        t = dev(q.astype(np.float16))
+        ib.check(ib.lib.ifb_rope(ptr(t), 2, 8, 128, 0, 1000, 10000.0, order, None), "rope")
+        want = np.stack([o.rope(q[i], 8, 128, 1000 + i, 10000.0, order) for i in range(2)])
+        # sinf/cosf/powf of large angles: device vs libm differ by a few ulp of the ANGLE
+        close(t.cpu().numpy(), want, rel=2 ** -9, abs_=2 ** -9)
+
+    a = orc.f16(rng.normal(0, 2, 11008)); b = orc.f16(rng.normal(0, 1, 11008))
+    out = torch.zeros(11008, dtype=torch.float16, device="cuda")
+    ib.check(ib.lib.ifb_silu_mul(ptr(out), ptr(dev(a.astype(np.float16))), ptr(dev(b.astype(np.float16))), 11008, None), "silu")
+    close(out.cpu().numpy(), o.silu_mul(a, b), rel=2 ** -9)
+    ib.check(ib.lib.ifb_add(ptr(out), ptr(dev(a.astype(np.float16))), ptr(dev(b.astype(np.float16))), 11008, None), "add")
+    assert np.array_equal(out.cpu().numpy(), (a + b).astype(np.float16))
+
+    logits = rng.normal(0, 1, 32000).astype(np.float16)
+    logits[777] = logits[31999] = 9.0      # tie: first wins
+    idx = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ib.check(ib.lib.ifb_argmax(ptr(idx), ptr(dev(logits)), 32000, None), "argmax")
+    assert int(idx.item()) == 777
+
+
+def test_moe_topk_bit_exact(ib):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "moe_topk.npz"))
+    s = dev(g["scores"])
+    rows, experts = g["scores"].shape
+    for k in (1, 2, 4):
+        for norm in (0, 1):
+            ids = torch.zeros(rows * k, dtype=torch.int32, device="cuda")
+            wts = torch.zeros(rows * k, dtype=torch.float32, device="cuda")
+            cnt = torch.zeros(rows, dtype=torch.int32, device="cuda")
+            ib.check(ib.lib.ifb_moe_topk(ptr(ids), ptr(wts), ptr(cnt), ptr(s), rows, experts, k, norm, None), "moe_topk")
+            assert np.array_equal(ids.cpu().numpy().reshape(rows, k), g[f"ids_k{k}_n{norm}"])
+            assert np.array_equal(cnt.cpu().numpy(), g[f"cnt_k{k}_n{norm}"])
+            assert np.array_equal(wts.cpu().numpy().reshape(rows, k), g[f"w_k{k}_n{norm}"])
+
+
+# ------------------------------------------------------------------ KV cache + attention
+def _kv_setup(ib, kv_dt, kv_heads, hd, max_ctx, k_rows, v_rows):
+    nb = ib.lib.ifb_kv_cache_bytes(kv_dt, kv_heads, hd, max_ctx)
+    kc = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+    vc = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+    n = k_rows.shape[0]
+    ib.check(ib.lib.ifb_kv_append(kv_dt, ptr(kc), ptr(vc), ptr(dev(k_rows.astype(np.float16))),
+                                  ptr(dev(v_rows.astype(np.float16))), kv_heads, hd, max_ctx, 0, n, None), "kv_append")
+    return kc, vc
+
+
+@pytest.mark.parametrize("kv_dt", [orc.F16, orc.Q8_B32T2], ids=["F16", "Q8"])
+def test_kv_rows_bit_exact(ib, kv_dt):
+    """SetKRows -> GetKRows round trip equals Quantize -> Dequantize of the reference (row-wise)"""
+    kv_heads, hd, max_ctx, n = 4, 128, 300, 77
+    rng = np.random.default_rng(110)
+    k = orc.f16(rng.normal(0, 1, (n, kv_heads * hd))); v = orc.f16(rng.normal(0, 1, (n, kv_heads * hd)))
+    k[5] = 0.0
+    kc, vc = _kv_setup(ib, kv_dt, kv_heads, hd, max_ctx, k, v)
+    out = torch.zeros(n * kv_heads * hd, dtype=torch.float16, device="cuda")
+    o = orc.oracle()
+    for cache, rows in ((kc, k), (vc, v)):
+        ib.check(ib.lib.ifb_kv_get_rows(kv_dt, ptr(out), ptr(cache), kv_heads, hd, max_ctx, 0, n, None), "kv_get")
+        got = out.cpu().numpy().reshape(n, -1)
+        if kv_dt == orc.F16:
+            want = rows.astype(np.float16)
+        else:
+            want = o.dequantize(orc.Q8_B32T2, o.quantize(orc.Q8_B32T2, rows), kv_heads * hd).astype(np.float16)
+        assert np.array_equal(got, want)
+
+
+CASES = [(32, 32, 128, 1), (32, 32, 128, 63), (32, 32, 128, 64), (32, 32, 128, 65), (32, 32, 128, 500),
+         (32, 32, 128, 2048), (8, 1, 128, 700), (64, 8, 128, 333), (12, 12, 64, 200), (8, 4, 64, 130), (4, 4, 32, 90)]
+
+
+@pytest.mark.parametrize("kv_dt", [orc.F16, orc.Q8_B32T2], ids=["F16", "Q8"])
+@pytest.mark.parametrize("case", CASES, ids=[f"h{h}g{g}d{d}c{c}" for h, g, d, c in CASES])
+def test_attn_decode(ib, kv_dt, case):
+    heads, kv_heads, hd, ctx = case
+    max_ctx = 2048
+    rng = np.random.default_rng(120 + ctx)
+    k = orc.f16(rng.normal(0, 1, (ctx, kv_heads * hd))); v = orc.f16(rng.normal(0, 1, (ctx, kv_heads * hd)))
+    q = orc.f16(rng.normal(0, 1, heads * hd))
+    kc, vc = _kv_setup(ib, kv_dt, kv_heads, hd, max_ctx, k, v)
+    o = orc.oracle()
+    if kv_dt == orc.Q8_B32T2:   # the cache holds the quantized rows: the oracle attends over their dequantization
+        kd = o.dequantize(orc.Q8_B32T2, o.quantize(orc.Q8_B32T2, k), kv_heads * hd)
+        vd = o.dequantize(orc.Q8_B32T2, o.quantize(orc.Q8_B32T2, v), kv_heads * hd)
+    else:
+        kd, vd = k, v
+    want = o.attn_decode(q, kd, vd, heads, kv_heads, hd, 1.0, exact=True)
+    ref_style = o.attn_decode(q, orc.f16(kd), orc.f16(vd), heads, kv_heads, hd, 1.0, exact=False)
+    ws = torch.zeros(ib.lib.ifb_attn_workspace_bytes(heads, hd), dtype=torch.uint8, device="cuda")
+    out = torch.zeros(heads * hd, dtype=torch.float16, device="cuda")
+    for _ in range(2):   # twice: the arrival counters must be left reset
+        ib.check(ib.lib.ifb_attn_decode(kv_dt, ptr(out), ptr(dev(q.astype(np.float16))), ptr(kc), ptr(vc), heads,
+                                        kv_heads, hd, max_ctx, ctx, 1.0, ptr(ws), None), "attn_decode")
+        got = out.cpu().numpy().astype(np.float64)
+        close(got, want, rel=2 ** -9, abs_=2 ** -10)
+    # SURVEY 8c policy: our error against the exact oracle does not exceed the reference's own
+    err_ours = np.abs(got - want).max()
+    err_ref = np.abs(ref_style - want).max()
+    assert err_ours <= max(err_ref, 2 ** -10 * np.abs(want).max())
