@@ -57,70 +57,76 @@ __device__ __forceinline__ void rope_rot(float &x0, float &x1, int pos, int i, f
     x1 = b;
 }
 
-__device__ __forceinline__ void kv_store_row(int kv_dtype, uint8_t *cache, const float *row_smem,
-                                             const __half *row_gmem, int kv_heads, int hd,
-                                             int max_ctx_pad, int pos, int warp, int lane, int nwarps) {
-    const int nblk = kv_heads * hd / 32;
-    int8_t *codes = reinterpret_cast<int8_t *>(cache);
-    __half *scales = reinterpret_cast<__half *>(cache + (int64_t)kv_heads * max_ctx_pad * hd);
-    for (int b = warp; b < nblk; b += nwarps) {
-        int d = b * 32 + lane;  // dim within the row
-        float v = row_smem != nullptr ? row_smem[d] : __half2float(row_gmem[d]);
-        int h = d / hd, dh = d % hd;
-        int64_t base = ((int64_t)h * max_ctx_pad + pos);
-        if (kv_dtype == DT_F16) {
-            reinterpret_cast<__half *>(cache)[base * hd + dh] = __float2half_rn(v);
-        } else {
-            // Tensor_QuantizeQ8_B32T2_Alg2_Kernel (tensor_quant.h:45-82)
-            float m = warp_max(fabsf(v));
-            float scale = __fdiv_rn(m, 127.0f);
-            int q = scale <= 0.000001f ? 0 : (int)roundf(__fdiv_rn(v, scale));
-            q = min(max(q, -128), 127);
-            codes[base * hd + dh] = (int8_t)q;
-            if (lane == 0) scales[base * (hd / 32) + dh / 32] = __float2half_rn(scale);
-        }
+// quantize / store one 32-dim block of a K or V head row: lane = element
+__device__ __forceinline__ void kv_store_block(int kv_dtype, uint8_t *cache, float v, int kv_heads,
+                                               int hd, int max_ctx_pad, int h, int pos, int blk, int lane) {
+    const int64_t base = (int64_t)h * max_ctx_pad + pos;
+    const int dh = blk * 32 + lane;
+    if (kv_dtype == DT_F16) {
+        reinterpret_cast<__half *>(cache)[base * hd + dh] = __float2half_rn(v);
+    } else {
+        // Tensor_QuantizeQ8_B32T2_Alg2_Kernel (tensor_quant.h:45-82)
+        int8_t *codes = reinterpret_cast<int8_t *>(cache);
+        __half *scales = reinterpret_cast<__half *>(cache + (int64_t)kv_heads * max_ctx_pad * hd);
+        const float m = warp_max(fabsf(v));
+        const float scale = __fdiv_rn(m, 127.0f);
+        int q = scale <= 0.000001f ? 0 : (int)roundf(__fdiv_rn(v, scale));
+        q = min(max(q, -128), 127);
+        codes[base * hd + dh] = (int8_t)q;
+        if (lane == 0) scales[base * (hd / 32) + blk] = __float2half_rn(scale);
     }
 }
 
-__global__ void __launch_bounds__(256) kv_append_kernel(const KvArgs a) {
-    extern __shared__ float krow[];  // kv_heads*head_dim floats (RoPE'd K, rounded to half)
+// grid (kv_heads, n_tokens), 128 threads: CTA = one kv head of one token and the q heads of its group
+__global__ void __launch_bounds__(128) kv_append_kernel(const KvArgs a) {
+    __shared__ float s_cos[128], s_sin[128];
+    __shared__ float s_k[256];
     pdl_launch_dependents();
     pdl_wait();
-    const int t = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.x, t = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int pos = (a.pos_dev != nullptr ? *a.pos_dev : a.pos0) + t;
     const int hd = a.head_dim, kvd = a.kv_heads * hd;
-    const __half *k = a.k + (int64_t)t * kvd;
-    const __half *v = a.v + (int64_t)t * kvd;
+    const __half *k = a.k + (int64_t)t * kvd + (int64_t)h * hd;
+    const __half *v = a.v + (int64_t)t * kvd + (int64_t)h * hd;
     const int rd = a.rope_dims > 0 ? a.rope_dims : hd;
-    const float theta_scale = powf(a.rope_theta, -2.0f / (float)rd);
+    const int pairs = rd / 2;
 
-    for (int i = tid; i < kvd; i += 256) krow[i] = __half2float(k[i]);
-    __syncthreads();
+    for (int i = tid; i < hd; i += 128) s_k[i] = __half2float(k[i]);
     if (a.rope) {
-        const int pairs = rd / 2;
-        for (int idx = tid; idx < a.kv_heads * pairs; idx += 256) {
-            int i = idx % pairs, h = idx / pairs;
-            int i0 = a.rope_order == 2 ? i : 2 * i, i1 = a.rope_order == 2 ? i + rd / 2 : 2 * i + 1;
-            float x0 = krow[h * hd + i0], x1 = krow[h * hd + i1];
-            rope_rot(x0, x1, pos, i, theta_scale);
-            krow[h * hd + i0] = round_h(x0);  // PositionEmbedding writes half
-            krow[h * hd + i1] = round_h(x1);
-        }
-        if (a.q != nullptr) {
-            __half *q = a.q + (int64_t)t * a.q_heads * hd;
-            for (int idx = tid; idx < a.q_heads * pairs; idx += 256) {
-                int i = idx % pairs, h = idx / pairs;
-                int i0 = a.rope_order == 2 ? i : 2 * i, i1 = a.rope_order == 2 ? i + rd / 2 : 2 * i + 1;
-                float x0 = __half2float(q[h * hd + i0]), x1 = __half2float(q[h * hd + i1]);
-                rope_rot(x0, x1, pos, i, theta_scale);
-                q[h * hd + i0] = __float2half_rn(x0);
-                q[h * hd + i1] = __float2half_rn(x1);
-            }
+        // angle_i = pos * theta_scale^i, theta_scale = theta^(-2/dims) (unary_tensor_opr.h:666-679,706-719)
+        const float theta_scale = powf(a.rope_theta, -2.0f / (float)rd);
+        for (int i = tid; i < pairs; i += 128) {
+            float ang = (float)pos;
+            if (i > 0) ang *= powf(theta_scale, (float)i);
+            s_cos[i] = cosf(ang);
+            s_sin[i] = sinf(ang);
         }
         __syncthreads();
+        for (int i = tid; i < pairs; i += 128) {
+            const int i0 = a.rope_order == 2 ? i : 2 * i, i1 = a.rope_order == 2 ? i + rd / 2 : 2 * i + 1;
+            const float x0 = s_k[i0], x1 = s_k[i1], c = s_cos[i], sn = s_sin[i];
+            s_k[i0] = round_h(x0 * c - x1 * sn);   // PositionEmbedding writes half
+            s_k[i1] = round_h(x0 * sn + x1 * c);
+        }
+        if (a.q != nullptr) {
+            const int G = a.q_heads / a.kv_heads;
+            __half *q = a.q + (int64_t)t * a.q_heads * hd + (int64_t)h * G * hd;
+            for (int idx = tid; idx < G * pairs; idx += 128) {
+                const int i = idx % pairs, g = idx / pairs;
+                const int i0 = a.rope_order == 2 ? i : 2 * i, i1 = a.rope_order == 2 ? i + rd / 2 : 2 * i + 1;
+                const float x0 = __half2float(q[g * hd + i0]), x1 = __half2float(q[g * hd + i1]);
+                const float c = s_cos[i], sn = s_sin[i];
+                q[g * hd + i0] = __float2half_rn(x0 * c - x1 * sn);
+                q[g * hd + i1] = __float2half_rn(x0 * sn + x1 * c);
+            }
+        }
     }
-    kv_store_row(a.kv_dtype, a.kcache, krow, nullptr, a.kv_heads, hd, a.max_ctx_pad, pos, warp, lane, 8);
-    kv_store_row(a.kv_dtype, a.vcache, nullptr, v, a.kv_heads, hd, a.max_ctx_pad, pos, warp, lane, 8);
+    __syncthreads();
+    const int nb = hd / 32;
+    for (int b = warp; b < 2 * nb; b += 4) {
+        if (b < nb) kv_store_block(a.kv_dtype, a.kcache, s_k[b * 32 + lane], a.kv_heads, hd, a.max_ctx_pad, h, pos, b, lane);
+        else kv_store_block(a.kv_dtype, a.vcache, __half2float(v[(b - nb) * 32 + lane]), a.kv_heads, hd, a.max_ctx_pad, h, pos, b - nb, lane);
+    }
 }
 
 int kv_append(const KvAppend &p, cudaStream_t st) {
@@ -137,10 +143,10 @@ int kv_append(const KvAppend &p, cudaStream_t st) {
     a.k = (const __half *)p.k; a.v = (const __half *)p.v;
     a.rope = p.rope; a.rope_order = p.rope_order; a.rope_dims = p.rope_dims; a.rope_theta = p.rope_theta;
     a.q = (__half *)p.q; a.q_heads = p.q_heads; a.pos_dev = p.pos_dev;
-    size_t smem = (size_t)p.kv_heads * p.head_dim * sizeof(float);
-    IFB_CHECK_ARG(smem <= 48 * 1024, "kv: kv_dim too large for the append kernel");
+    IFB_CHECK_ARG(p.q == nullptr || (p.q_heads > 0 && p.q_heads % p.kv_heads == 0), "kv: q_heads %d / kv_heads %d", p.q_heads, p.kv_heads);
+    IFB_CHECK_ARG(p.n_tokens <= 65535, "kv: too many tokens in one append");
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(p.n_tokens); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(p.kv_heads, p.n_tokens); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -196,14 +202,17 @@ struct AttnArgs {
 
 int64_t attn_workspace_bytes(int heads, int head_dim) {
     // worst-case split count = 2*SMs (one per CTA) ; + counters
-    int64_t max_split = 2 * 160;
+    int64_t max_split = 4 * 160;
     return (int64_t)heads * max_split * (head_dim + 2) * sizeof(float) + 4096;
 }
 
-// signed byte k of w -> float
-__device__ __forceinline__ float s8f(uint32_t w, int k) {
-    return (float)(int)(int8_t)((w >> (8 * k)) & 0xffu);
+// signed byte k of w -> float without I2F: flip the sign bit (u = b + 128), drop the byte into the
+// mantissa of 2^23 with one PRMT, subtract 2^23 + 128. Exact.
+__device__ __forceinline__ float s8f(uint32_t w_biased, int k) {
+    const uint32_t bits = __byte_perm(w_biased, 0x4b000000u, 0x7650u + (uint32_t)k);
+    return __uint_as_float(bits) - 8388736.0f;
 }
+__device__ __forceinline__ uint32_t s8bias(uint32_t w) { return w ^ 0x80808080u; }
 
 template <int HD, int G, bool Q8>
 __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs a) {
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
                 float ksc = 1.f;
                 if (Q8) {
                     const uint4 w = *reinterpret_cast<const uint4 *>(tK + pp * HD + sub * 16);
-                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                    const uint32_t ww[4] = {s8bias(w.x), s8bias(w.y), s8bias(w.z), s8bias(w.w)};
 #pragma unroll
                     for (int j = 0; j < 4; j++)
 #pragma unroll
@@ -360,7 +369,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
                 for (int pp = warp; pp < npos; pp += NW) {
                     float vf[4];
                     if (Q8) {
-                        const uint32_t w = reinterpret_cast<const uint32_t *>(tV + pp * HD)[lane];
+                        const uint32_t w = s8bias(reinterpret_cast<const uint32_t *>(tV + pp * HD)[lane]);
                         const float vsc = __half2float(reinterpret_cast<const __half *>(tVs)[pp * NB + lane / 8]);
 #pragma unroll
                         for (int k = 0; k < 4; k++) vf[k] = s8f(w, k) * vsc;
@@ -491,9 +500,9 @@ int attn_decode(const AttnDecode &p, cudaStream_t st) {
     // split count: fill ~2 CTAs per SM; with a device-side position (graph replay) size for max_ctx
     const int ctx_for_split = p.pos_dev != nullptr ? p.max_ctx : p.ctx_len;
     const int nchunks = (ctx_for_split + ATT_CHUNK - 1) / ATT_CHUNK;
-    int nsplit = (2 * sm_count() + p.kv_heads - 1) / p.kv_heads;
+    int nsplit = (4 * sm_count() + p.kv_heads - 1) / p.kv_heads;
     if (nsplit > nchunks) nsplit = nchunks;
-    if (nsplit > 2 * 160) nsplit = 2 * 160;
+    if (nsplit > 4 * 160) nsplit = 4 * 160;
     if (nsplit < 1) nsplit = 1;
     a.nsplit = nsplit;
     const int group = p.heads / p.kv_heads;

@@ -240,9 +240,9 @@ struct FmtQ3H_B64T1 {
             uint32_t p1 = ((u16 & 0x00f0u) >> 4) | ((m8 & 0x0cu) << 2) | ((h8 & 0x02u) << 5);
             uint32_t p2 = ((u16 & 0x0f00u) >> 8) | (m8 & 0x30u) | ((h8 & 0x04u) << 4);
             uint32_t p3 = ((u16 & 0xf000u) >> 12) | ((m8 & 0xc0u) >> 2) | ((h8 & 0x08u) << 3);
-            // P/11 for P in 0..127 : (P*47)>>9 is exact on that range
-            uint32_t d0 = (p0 * 47u) >> 9, d1 = (p1 * 47u) >> 9, d2 = (p2 * 47u) >> 9,
-                     d3 = (p3 * 47u) >> 9;
+            // P/11 for P in 0..127 : (P*187)>>11 is exact on that range (checked exhaustively in tests)
+            uint32_t d0 = (p0 * 187u) >> 11, d1 = (p1 * 187u) >> 11, d2 = (p2 * 187u) >> 11,
+                     d3 = (p3 * 187u) >> 11;
             uint32_t m0 = p0 - 11u * d0, m1 = p1 - 11u * d1, m2 = p2 - 11u * d2,
                      m3 = p3 - 11u * d3;
             codes[2 * r] = m0 | (d0 << 8) | (m1 << 16) | (d1 << 24);

@@ -60,14 +60,23 @@ __device__ __forceinline__ int x_pos(int e) {
     return g * 8 + (k & 1) * 4 + (k >> 1);
 }
 
-// RMS scale of the whole vector, computed by the 256 consumer threads.
+// RMS scale of the whole vector, computed by the 256 consumer threads (128-bit loads).
 // Tensor_RmsNorm_Kernel (unary_tensor_opr.h:217): scale = 1/sqrt(mean(x^2) + eps)
 __device__ __forceinline__ float rms_scale_256(const __half *x, int cx, float eps, float *red,
                                                int tid) {
+    const uint4 *x4 = reinterpret_cast<const uint4 *>(x);
+    const int ng = cx >> 3;
     float s = 0.f;
-    for (int i = tid; i < cx; i += GEMV_CWARPS * 32) {
-        float v = __half2float(x[i]);
-        s = fmaf(v, v, s);
+#pragma unroll 4
+    for (int g = tid; g < ng; g += GEMV_CWARPS * 32) {
+        const uint4 v = x4[g];
+        const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float2 f = __half22float2(h[k]);
+            s = fmaf(f.x, f.x, s);
+            s = fmaf(f.y, f.y, s);
+        }
     }
     s = warp_sum(s);
     if ((tid & 31) == 0) red[tid >> 5] = s;
@@ -75,13 +84,15 @@ __device__ __forceinline__ float rms_scale_256(const __half *x, int cx, float ep
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < GEMV_CWARPS; i++) t += red[i];
-    float mean = t / (float)cx;
+    const float mean = t / (float)cx;
     return 1.0f / sqrtf(mean + eps);
 }
 
 // Stage x as Q8_B32T2 (codes + fp16-rounded scale + scale*sum(q)) into shared memory.
-// One warp per activation block, lane = element (the reference's alg 2: warp max, scale=max/127,
-// q = roundf(v/scale), scale <= 1e-6 -> 0; tensor_quant.h:45-82).
+// The arithmetic per block of 32 is the reference's alg 2 (tensor_quant.h:45-82): scale =
+// absmax/127, q = roundf(v/scale), scale <= 1e-6 -> 0. Mapping: one thread = 8 consecutive
+// elements (ONE 128-bit load), four neighbouring lanes = one block; all of a thread's loads are
+// issued before any is used, so the prologue costs one memory round trip, not one per block.
 template <bool XSPLIT>
 __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint8_t *xhi,
                                            float2 *xs, float *red, int tid) {
@@ -101,37 +112,106 @@ __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint
         }
         return;
     }
+    const bool norm = a.norm_w != nullptr;
     float rs = 1.f;
-    if (a.norm_w != nullptr) rs = rms_scale_256(a.x, a.cx, a.eps, red, tid);
-    for (int b = warp; b < nxb; b += GEMV_CWARPS) {
-        int i = b * 32 + lane;
-        float v = __half2float(a.x[i]);
-        if (a.norm_w != nullptr) {
-            // v = x*scale*(multi_base + w), stored as half by the reference's RmsNorm
-            v = round_h(v * rs * (a.norm_base + __half2float(a.norm_w[i])));
+    if (norm) rs = rms_scale_256(a.x, a.cx, a.eps, red, tid);
+    const uint4 *x4 = reinterpret_cast<const uint4 *>(a.x);
+    const uint4 *w4 = reinterpret_cast<const uint4 *>(a.norm_w);
+    const int ng = a.cx >> 3;                 // groups of 8 elements; ng % 4 == 0
+    constexpr int KPT = 4;                    // groups per thread per round
+    for (int g0 = 0; g0 < ng; g0 += GEMV_CWARPS * 32 * KPT) {
+        uint4 xv[KPT], wv[KPT];
+#pragma unroll
+        for (int k = 0; k < KPT; k++) {
+            const int g = g0 + k * GEMV_CWARPS * 32 + tid;
+            xv[k] = make_uint4(0, 0, 0, 0);
+            wv[k] = make_uint4(0, 0, 0, 0);
+            if (g < ng) {
+                xv[k] = x4[g];
+                if (norm) wv[k] = w4[g];
+            }
         }
-        float m = warp_max(fabsf(v));
-        float scale = m / 127.0f;
-        int q = scale <= 0.000001f ? 0 : (int)roundf(v / scale);
-        q = min(max(q, -128), 127);
-        int p = x_pos<XSPLIT>(lane);
-        (p < 16 ? xlo + b * 16 + p : xhi + b * 16 + (p - 16))[0] = (uint8_t)(int8_t)q;
-        int qs = __reduce_add_sync(0xffffffffu, q);
-        if (lane == 0) {
-            float s = round_h(scale);  // the GEMV reads the fp16 scale back (gemv.h:1631)
-            xs[b] = make_float2(s, s * (float)qs);
+#pragma unroll
+        for (int k = 0; k < KPT; k++) {
+            const int g = g0 + k * GEMV_CWARPS * 32 + tid;   // a quad of lanes shares one block
+            float v[8];
+            {
+                const __half2 *h = reinterpret_cast<const __half2 *>(&xv[k]);
+                const __half2 *hw = reinterpret_cast<const __half2 *>(&wv[k]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    float2 f = __half22float2(h[i]);
+                    if (norm) {  // v = x*scale*(multi_base + w), stored as half by the reference's RmsNorm
+                        const float2 fw = __half22float2(hw[i]);
+                        f.x = round_h(f.x * rs * (a.norm_base + fw.x));
+                        f.y = round_h(f.y * rs * (a.norm_base + fw.y));
+                    }
+                    v[2 * i] = f.x;
+                    v[2 * i + 1] = f.y;
+                }
+            }
+            float m = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) m = fmaxf(m, fabsf(v[i]));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            const float scale = m / 127.0f;
+            int q[8], qs = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                int t = scale <= 0.000001f ? 0 : (int)roundf(v[i] / scale);
+                q[i] = min(max(t, -128), 127);
+                qs += q[i];
+            }
+            qs += __shfl_xor_sync(0xffffffffu, qs, 1);
+            qs += __shfl_xor_sync(0xffffffffu, qs, 2);
+            if (g < ng) {
+                uint32_t w0, w1;
+                if (XSPLIT) {
+                    w0 = (q[0] & 0xff) | ((q[2] & 0xff) << 8) | ((q[4] & 0xff) << 16) | ((uint32_t)(q[6] & 0xff) << 24);
+                    w1 = (q[1] & 0xff) | ((q[3] & 0xff) << 8) | ((q[5] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
+                } else {
+                    w0 = (q[0] & 0xff) | ((q[1] & 0xff) << 8) | ((q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
+                    w1 = (q[4] & 0xff) | ((q[5] & 0xff) << 8) | ((q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
+                }
+                const int b = g >> 2, j = g & 3;   // block, group-in-block (elements 8j..8j+7 = words 2j,2j+1)
+                uint2 *dst = reinterpret_cast<uint2 *>((j < 2 ? xlo : xhi) + (size_t)b * 16 + (j & 1) * 8);
+                *dst = make_uint2(w0, w1);
+                if (j == 0) {
+                    const float sh = round_h(scale);  // the GEMV reads the fp16 scale back (gemv.h:1631)
+                    xs[b] = make_float2(sh, sh * (float)qs);
+                }
+            }
         }
     }
 }
 
 // Stage x as fp16 (optionally RMS-normalised) for the fp16-activation paths.
 __device__ __forceinline__ void stage_x_f16(const GemvArgs &a, __half *xh, float *red, int tid) {
+    const bool norm = a.norm_w != nullptr;
     float rs = 1.f;
-    if (a.norm_w != nullptr) rs = rms_scale_256(a.x, a.cx, a.eps, red, tid);
-    for (int i = tid; i < a.cx; i += GEMV_CWARPS * 32) {
-        float v = __half2float(a.x[i]);
-        if (a.norm_w != nullptr) v = v * rs * (a.norm_base + __half2float(a.norm_w[i]));
-        xh[i] = __float2half_rn(v);
+    if (norm) rs = rms_scale_256(a.x, a.cx, a.eps, red, tid);
+    const uint4 *x4 = reinterpret_cast<const uint4 *>(a.x);
+    const uint4 *w4 = reinterpret_cast<const uint4 *>(a.norm_w);
+    uint4 *o4 = reinterpret_cast<uint4 *>(xh);
+    const int ng = a.cx >> 3;
+#pragma unroll 4
+    for (int g = tid; g < ng; g += GEMV_CWARPS * 32) {
+        uint4 xv = x4[g];
+        if (norm) {
+            const uint4 wv = w4[g];
+            __half2 *h = reinterpret_cast<__half2 *>(&xv);
+            const __half2 *hw = reinterpret_cast<const __half2 *>(&wv);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float2 f = __half22float2(h[i]);
+                const float2 fw = __half22float2(hw[i]);
+                f.x = f.x * rs * (a.norm_base + fw.x);
+                f.y = f.y * rs * (a.norm_base + fw.y);
+                h[i] = __floats2half2_rn(f.x, f.y);
+            }
+        }
+        o4[g] = xv;
     }
 }
 
@@ -301,6 +381,12 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_stream_kernel(const GemvArg
         for (int r = wl; r < a.R; r += a.wpg) {
             const uint8_t *row = slot + (size_t)r * a.row_bytes;
             float acc, acc2 = 0.f;
+            // lane 0 fetches the epilogue operands while the row is being reduced
+            float res_v = 0.f, bias_v = 0.f;
+            if (lane == 0) {
+                if (a.residual != nullptr) res_v = __half2float(a.residual[out_base + r]);
+                if (a.bias != nullptr) bias_v = __half2float(a.bias[out_base + r]);
+            }
             if (MODE == MODE_Q8) {
                 acc = row_dot_q8<Fmt>(row, a.nblk, (const uint4 *)xlo, (const uint4 *)xhi, xs, lane);
                 if (GLU) acc2 = row_dot_q8<Fmt>(row + mat_bytes, a.nblk, (const uint4 *)xlo,
@@ -315,13 +401,13 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_stream_kernel(const GemvArg
             if (lane == 0) {
                 const int o = out_base + r;
                 float v = round_h(acc);  // the GEMV output tensor is half
-                if (a.bias != nullptr) v = round_h(v + __half2float(a.bias[o]));
+                if (a.bias != nullptr) v = round_h(v + bias_v);
                 if (GLU) {
                     // SiluActivation_Kernel (unary_tensor_opr.h:553) then Mul, each stored as half
                     float g = round_h(v / (1.0f + expf(-v)));
                     v = round_h(g * round_h(acc2));
                 }
-                if (a.residual != nullptr) v = round_h(v + __half2float(a.residual[o]));
+                if (a.residual != nullptr) v = round_h(v + res_v);
                 a.y[o] = __float2half_rn(v);
             }
         }
@@ -402,6 +488,8 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
                   "gemv: cx (%lld) should be a multiple of 32", (long long)g.cx);
     if (dt != DT_F16) IFB_CHECK_ARG(g.cx % cap == 0, "gemv: cx %% block capacity != 0");
     IFB_CHECK_ARG(!(g.w_gate != nullptr && g.nseg != 1), "gemv: GLU needs exactly one segment");
+    IFB_CHECK_ARG((((uintptr_t)g.x | (uintptr_t)g.norm_w) & 15) == 0,
+                  "gemv: x / norm weight must be 16-byte aligned");
 
     int mode;
     if (dt == DT_F16) {

@@ -226,8 +226,7 @@ __global__ void synth_blocks_kernel(uint8_t *dst, int dt, int64_t nblocks, int b
     float amp = fabsf(gauss(key)) * sigma + 1e-4f;
     int mc = max_code(dt);
     if (dt == DT_Q8_B32T2) {
-        uint16_t sc = f2h_bits(amp / 127.0f);
-        b[0] = sc & 0xff; b[1] = sc >> 8;
+        *reinterpret_cast<uint16_t *>(b) = f2h_bits(amp / 127.0f);   // one 16-bit store (see ifb_quantize.cu put16)
         for (int i = 0; i < 32; i += 8) {
             uint64_t r = mix64(key * 31 + i);
             for (int k = 0; k < 8; k++) b[2 + i + k] = (uint8_t)(r >> (8 * k));
@@ -239,11 +238,11 @@ __global__ void synth_blocks_kernel(uint8_t *dst, int dt, int64_t nblocks, int b
     if (dt == DT_Q4_B16) {
         b[0] = (uint8_t)(base * 100 + 100.5f); b[1] = (uint8_t)(scale * 1000 + 0.5f); hdr = 2;
     } else if (dt == DT_Q5_B32T1) {
-        uint16_t s16 = f2h_bits(scale), b16 = f2h_bits(base);
-        b[0] = s16 & 0xff; b[1] = s16 >> 8; b[2] = b16 & 0xff; b[3] = b16 >> 8;
+        *reinterpret_cast<uint16_t *>(b) = f2h_bits(scale);
+        *reinterpret_cast<uint16_t *>(b + 2) = f2h_bits(base);
     } else {
-        uint16_t s16 = f2h_bits(scale), b16 = f2h_bits(base);
-        b[0] = b16 & 0xff; b[1] = b16 >> 8; b[2] = s16 & 0xff; b[3] = s16 >> 8;
+        *reinterpret_cast<uint16_t *>(b) = f2h_bits(base);
+        *reinterpret_cast<uint16_t *>(b + 2) = f2h_bits(scale);
     }
     if (dt == DT_Q3H_B64T1) {
         for (int i = 4; i < 8; i++) b[i] = 0;

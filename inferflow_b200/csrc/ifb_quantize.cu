@@ -38,9 +38,11 @@ __device__ __forceinline__ uint32_t lin_q(float v, const QParams &p, int mode, u
     uint32_t q = (uint32_t)u;  // cvt.rzi.u32.f32 saturates negatives to 0 like the x86 build's range
     return q > maxq ? maxq : q;
 }
+// Block headers sit at even offsets: store fp16 bit patterns with ONE 16-bit store. (Splitting
+// them into two byte stores makes ptxas 12.9 emit F2I.U8.F16 for the low byte -- it converts the
+// half VALUE instead of truncating its bits.)
 __device__ __forceinline__ void put16(uint8_t *p, uint16_t v) {
-    p[0] = (uint8_t)(v & 0xff);
-    p[1] = (uint8_t)(v >> 8);
+    *reinterpret_cast<uint16_t *>(p) = v;
 }
 
 // one thread = one block (load-time path, mirrors the reference's launch shape)
@@ -102,15 +104,17 @@ __global__ void quantize_blocks_kernel(int dt, uint8_t *dst, const __half *src, 
         case DT_Q4_B16: {  // :43-68, :657-708
             float mn = s[0], mx = s[0];
             for (int i = 1; i < 16; i++) { if (mn > s[i]) mn = s[i]; if (mx < s[i]) mx = s[i]; }
-            uint8_t u8 = (uint8_t)((double)__fmul_rn(mn, 100.0f) + 100.01);
+            // float->uint8 of an out-of-range value is UB in C++; the reference as built (x86 cvttsd2si, low byte)
+            // wraps, CUDA's cvt saturates: go through int to reproduce the reference's bytes.
+            uint8_t u8 = (uint8_t)(int)((double)__fmul_rn(mn, 100.0f) + 100.01);
             mn = __fsub_rn(__fdiv_rn((float)(int)(uint32_t)u8, 100.0f), 1.0f);
             QParams p;
             p.mn = mn;
             p.scale = __fdiv_rn(__fsub_rn(mx, mn), 15.0f);
             p.inv = p.scale >= 0.00001f ? __fdiv_rn(1.0f, p.scale) : 0.0f;
             p.base = mn;
-            b[0] = (uint8_t)__fmaf_rn(mn, 100.0f, 100.5f);
-            b[1] = (uint8_t)__fmaf_rn(p.scale, 1000.0f, 0.5f);
+            b[0] = (uint8_t)(int)__fmaf_rn(mn, 100.0f, 100.5f);
+            b[1] = (uint8_t)(int)__fmaf_rn(p.scale, 1000.0f, 0.5f);
             for (int r = 0; r < 8; r++)
                 b[2 + r] = (uint8_t)(lin_q(s[2 * r], p, 0, 15) | (lin_q(s[2 * r + 1], p, 0, 15) << 4));
         } break;

@@ -29,8 +29,23 @@ def ib():
     return inferflow_b200
 
 
+_KEEP = []
+
+
+@pytest.fixture(autouse=True)
+def _keep_alive():
+    """device tensors created with dev() stay allocated until the test ends (a temporary passed as
+    ptr(dev(x)) would otherwise be freed -- and its memory reused -- before the kernel runs)"""
+    _KEEP.clear()
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
+
+
 def dev(a):
-    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    _KEEP.append(t)
+    return t
 
 
 def ptr(t):
@@ -50,7 +65,7 @@ def weights(dt, cy, cx, seed):
     rng = np.random.default_rng(seed)
     w = orc.f16(rng.normal(0, 0.02, (cy, cx)))
     if dt == orc.Q4_B16:
-        w = np.clip(w * 20, -1.4, 1.4)
+        w = orc.f16(np.clip(w * 20, -0.99, 1.4))
     return orc.oracle().quantize(dt, w)
 
 
@@ -62,7 +77,7 @@ def test_quantize_bit_exact(ib, dt):
         src = orc.f16(rng.normal(0, sigma, (rows, cx)))
         src[0, :64] = 0.25                      # constant blocks -> scale < 1e-5
         if dt == orc.Q4_B16:
-            src = np.clip(src, -1.4, 1.4)
+            src = orc.f16(np.clip(src, -0.99, 1.4))   # the format's valid base range
         want = orc.oracle().quantize(dt, src)
         x = dev(src.astype(np.float16))
         out = torch.zeros(want.size, dtype=torch.uint8, device="cuda")
