@@ -22,7 +22,6 @@
 namespace ifb {
 
 constexpr int ATT_CHUNK = 64;    // positions per staged tile
-constexpr int ATT_STAGES = 3;
 constexpr int ATT_THREADS = 128;
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -82,16 +81,15 @@ __global__ void __launch_bounds__(128) kv_append_kernel(const KvArgs a) {
     __shared__ float s_cos[128], s_sin[128];
     __shared__ float s_k[256];
     pdl_launch_dependents();
-    pdl_wait();
     const int h = blockIdx.x, t = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the position is stable before this token's first kernel starts: the rotation table does not
+    // depend on the QKV GEMV and is built while that kernel is still running
     const int pos = (a.pos_dev != nullptr ? *a.pos_dev : a.pos0) + t;
     const int hd = a.head_dim, kvd = a.kv_heads * hd;
     const __half *k = a.k + (int64_t)t * kvd + (int64_t)h * hd;
     const __half *v = a.v + (int64_t)t * kvd + (int64_t)h * hd;
     const int rd = a.rope_dims > 0 ? a.rope_dims : hd;
     const int pairs = rd / 2;
-
-    for (int i = tid; i < hd; i += 128) s_k[i] = __half2float(k[i]);
     if (a.rope) {
         // angle_i = pos * theta_scale^i, theta_scale = theta^(-2/dims) (unary_tensor_opr.h:666-679,706-719)
         const float theta_scale = powf(a.rope_theta, -2.0f / (float)rd);
@@ -101,6 +99,11 @@ __global__ void __launch_bounds__(128) kv_append_kernel(const KvArgs a) {
             s_cos[i] = cosf(ang);
             s_sin[i] = sinf(ang);
         }
+    }
+    pdl_wait();
+
+    for (int i = tid; i < hd; i += 128) s_k[i] = __half2float(k[i]);
+    if (a.rope) {
         __syncthreads();
         for (int i = tid; i < pairs; i += 128) {
             const int i0 = a.rope_order == 2 ? i : 2 * i, i1 = a.rope_order == 2 ? i + rd / 2 : 2 * i + 1;
@@ -198,6 +201,7 @@ struct AttnArgs {
     float *ws;            // [heads][nsplit][HD+2]
     unsigned int *counters;  // [kv_heads]
     const int32_t *pos_dev;
+    unsigned long long *trace;
 };
 
 int64_t attn_workspace_bytes(int heads, int head_dim) {
@@ -214,87 +218,110 @@ __device__ __forceinline__ float s8f(uint32_t w_biased, int k) {
 }
 __device__ __forceinline__ uint32_t s8bias(uint32_t w) { return w ^ 0x80808080u; }
 
+// Each WARP owns whole tiles of 64 positions (its own shared-memory buffer, its own mbarrier, its
+// own online softmax): no block-wide barrier inside the scan. The 4 warps of a CTA merge through
+// shared memory, CTAs of one kv head through the workspace (last CTA merges, log-sum-exp).
 template <int HD, int G, bool Q8>
 __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs a) {
     constexpr int NB = HD / 32;                       // scale blocks per (pos, head)
     constexpr int KBYTES = Q8 ? ATT_CHUNK * HD : ATT_CHUNK * HD * 2;
     constexpr int SBYTES = Q8 ? ATT_CHUNK * NB * 2 : 0;
-    constexpr int STAGE = 2 * (KBYTES + SBYTES);      // K codes, K scales, V codes, V scales
+    constexpr int TILE = 2 * (KBYTES + SBYTES);       // K codes, K scales, V codes, V scales
     constexpr int LPP = HD / 16;                      // lanes per position in the QK phase
     constexpr int PPW = 32 / LPP;                     // positions per warp iteration
     constexpr int NW = ATT_THREADS / 32;
 
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t full_bar[ATT_STAGES];
-    __shared__ float s_p[G][ATT_CHUNK];               // scores / probabilities of the chunk
-    __shared__ float s_corr[G], s_m[G], s_l[G];
+    extern __shared__ __align__(128) uint8_t smem[];  // [NW][TILE]
+    __shared__ uint64_t full_bar[NW];
+    __shared__ float s_p[NW][G][ATT_CHUNK];           // scores / probabilities of the warp's tile
     __shared__ __align__(16) float s_q[G][HD / 16][20];   // 16 dims + 4 pad: conflict-free LDS.128
+    __shared__ float s_ml[NW][G][2];
     __shared__ unsigned int s_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kvh = blockIdx.y, split = blockIdx.x;
 
     if (tid == 0) {
-        for (int i = 0; i < ATT_STAGES; i++) mbar_init(&full_bar[i], 1);
+        for (int i = 0; i < NW; i++) mbar_init(&full_bar[i], 1);
         mbar_fence_init();
     }
+    __syncthreads();
     pdl_launch_dependents();
-    pdl_wait();  // q, the new K/V row and the position come from the previous kernels
+    if (tid == 0) trace_mark(a.trace, 0);
+    // The position was written before this token's first kernel started (it is stable here), and
+    // every cache row except the NEW one (position ctx-1, written by the kv-append kernel just
+    // ahead of us) is older than the previous token: those tiles are fetched BEFORE the grid
+    // dependency resolves, i.e. while the QKV GEMV is still running.
     const int ctx = a.pos_dev != nullptr ? (*a.pos_dev + 1) : a.ctx_len;
     const int nchunks_total = (ctx + ATT_CHUNK - 1) / ATT_CHUNK;
-    const int cps = (nchunks_total + a.nsplit - 1) / a.nsplit;   // chunks per split
+    const int cps = (nchunks_total + a.nsplit - 1) / a.nsplit;   // chunks per CTA
     const int c0 = split * cps, c1 = min(c0 + cps, nchunks_total);
-    const int nch = max(c1 - c0, 0);
-
-    // stage q (scaled) for the G heads of this group
-    for (int i = tid; i < G * HD; i += ATT_THREADS) {
-        int g = i / HD, d = i % HD;
-        s_q[g][d / 16][d % 16] = __half2float(a.q[(int64_t)(kvh * G + g) * HD + d]) * a.softmax_scale;
-    }
-    if (tid < G) { s_m[tid] = -INFINITY; s_l[tid] = 0.f; }
-    __syncthreads();
+    const int new_chunk = (ctx - 1) / ATT_CHUNK;                 // the tile holding the new row
 
     const int64_t head_rows = (int64_t)kvh * a.max_ctx_pad;
     const uint8_t *kc = a.kcache + (Q8 ? head_rows * HD : head_rows * HD * 2);
     const uint8_t *vc = a.vcache + (Q8 ? head_rows * HD : head_rows * HD * 2);
     const uint8_t *ks = a.kcache + (int64_t)a.kv_heads * a.max_ctx_pad * HD + head_rows * NB * 2;
     const uint8_t *vs = a.vcache + (int64_t)a.kv_heads * a.max_ctx_pad * HD + head_rows * NB * 2;
+    uint8_t *tile = smem + (size_t)warp * TILE;
 
-    auto issue = [&](int ci) {  // chunk index within this split -> stage ci % STAGES
-        const int st = ci % ATT_STAGES;
-        uint8_t *dst = smem + (size_t)st * STAGE;
-        const int64_t p0 = (int64_t)(c0 + ci) * ATT_CHUNK;
-        mbar_arrive_expect_tx(&full_bar[st], STAGE);
+    auto issue = [&](int c) {  // tile c of the sequence -> this warp's buffer
+        const int64_t p0 = (int64_t)c * ATT_CHUNK;
+        mbar_arrive_expect_tx(&full_bar[warp], TILE);
         if (Q8) {
-            bulk_g2s(dst, kc + p0 * HD, KBYTES, &full_bar[st]);
-            bulk_g2s(dst + KBYTES, ks + p0 * NB * 2, SBYTES, &full_bar[st]);
-            bulk_g2s(dst + KBYTES + SBYTES, vc + p0 * HD, KBYTES, &full_bar[st]);
-            bulk_g2s(dst + 2 * KBYTES + SBYTES, vs + p0 * NB * 2, SBYTES, &full_bar[st]);
+            bulk_g2s(tile, kc + p0 * HD, KBYTES, &full_bar[warp]);
+            bulk_g2s(tile + KBYTES, ks + p0 * NB * 2, SBYTES, &full_bar[warp]);
+            bulk_g2s(tile + KBYTES + SBYTES, vc + p0 * HD, KBYTES, &full_bar[warp]);
+            bulk_g2s(tile + 2 * KBYTES + SBYTES, vs + p0 * NB * 2, SBYTES, &full_bar[warp]);
         } else {
-            bulk_g2s(dst, kc + p0 * HD * 2, KBYTES, &full_bar[st]);
-            bulk_g2s(dst + KBYTES, vc + p0 * HD * 2, KBYTES, &full_bar[st]);
+            bulk_g2s(tile, kc + p0 * HD * 2, KBYTES, &full_bar[warp]);
+            bulk_g2s(tile + KBYTES, vc + p0 * HD * 2, KBYTES, &full_bar[warp]);
         }
     };
-    if (tid == 0)
-        for (int ci = 0; ci < min(nch, ATT_STAGES); ci++) issue(ci);
+    int c = c0 + warp;                 // this warp's tiles: c0+warp, c0+warp+NW, ...
+    bool issued = false;
+    // prefetch paced to one tile in flight per CTA (warp w goes after warp w-1's tile has landed):
+    // a deep backlog on the SM's memory port would only delay the running kernels' small loads
+    if (lane == 0 && c < c1 && c != new_chunk) {
+        issue(c);
+        issued = true;
+    }
 
-    float acc[G][4];
+    pdl_wait();  // q and the new K/V row come from the previous kernels
+    if (tid == 0) trace_mark(a.trace, 1);
+    if (lane == 0 && c < c1 && !issued) issue(c);
+
+    // stage q (scaled) for the G heads of this group
+    for (int i = tid; i < G * HD; i += ATT_THREADS) {
+        int g = i / HD, d = i % HD;
+        s_q[g][d / 16][d % 16] = __half2float(a.q[(int64_t)(kvh * G + g) * HD + d]) * a.softmax_scale;
+    }
+    __syncthreads();
+
+    float m_run[G], l_run[G], acc[G][4];
 #pragma unroll
-    for (int g = 0; g < G; g++) acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f;
+    for (int g = 0; g < G; g++) {
+        m_run[g] = -INFINITY;
+        l_run[g] = 0.f;
+        acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f;
+    }
 
-    for (int ci = 0; ci < nch; ci++) {
-        const int st = ci % ATT_STAGES;
-        mbar_wait(&full_bar[st], (ci / ATT_STAGES) & 1);
-        const uint8_t *tK = smem + (size_t)st * STAGE;
+    uint32_t phase = 0;
+    for (; c < c1; c += NW) {
+        mbar_wait(&full_bar[warp], phase);
+        phase ^= 1u;
+        if (tid == 0 && c == c0) trace_mark(a.trace, 3);
+        const uint8_t *tK = tile;
         const uint8_t *tKs = tK + KBYTES;
         const uint8_t *tV = tK + KBYTES + SBYTES;
         const uint8_t *tVs = tV + KBYTES;
-        const int pbase = (c0 + ci) * ATT_CHUNK;
+        const int pbase = c * ATT_CHUNK;
 
         // ---- scores: LPP lanes per position, 16 dims per lane
         {
             const int sub = lane % LPP, pl = lane / LPP;
-            for (int pp = warp * PPW + pl; pp < ATT_CHUNK; pp += NW * PPW) {
+#pragma unroll 2
+            for (int pp = pl; pp < ATT_CHUNK; pp += PPW) {
                 float kf[16];
                 float ksc = 1.f;
                 if (Q8) {
@@ -320,97 +347,118 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
 #pragma unroll
                 for (int g = 0; g < G; g++) {
                     const float4 *qv = reinterpret_cast<const float4 *>(&s_q[g][sub][0]);
-                    float s = 0.f;
+                    float s0 = 0.f, s1 = 0.f;   // two chains: halve the dependent-FMA latency
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        float4 qq = qv[j];
-                        s = fmaf(kf[4 * j], qq.x, s);
-                        s = fmaf(kf[4 * j + 1], qq.y, s);
-                        s = fmaf(kf[4 * j + 2], qq.z, s);
-                        s = fmaf(kf[4 * j + 3], qq.w, s);
+                    for (int j = 0; j < 4; j += 2) {
+                        const float4 qa = qv[j], qb = qv[j + 1];
+                        s0 = fmaf(kf[4 * j], qa.x, s0);
+                        s1 = fmaf(kf[4 * j + 4], qb.x, s1);
+                        s0 = fmaf(kf[4 * j + 1], qa.y, s0);
+                        s1 = fmaf(kf[4 * j + 5], qb.y, s1);
+                        s0 = fmaf(kf[4 * j + 2], qa.z, s0);
+                        s1 = fmaf(kf[4 * j + 6], qb.z, s1);
+                        s0 = fmaf(kf[4 * j + 3], qa.w, s0);
+                        s1 = fmaf(kf[4 * j + 7], qb.w, s1);
                     }
-                    s *= ksc;
+                    float sc = (s0 + s1) * ksc;
 #pragma unroll
-                    for (int o = LPP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (sub == 0) s_p[g][pp] = (pbase + pp < ctx) ? s : -INFINITY;
+                    for (int o = LPP / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+                    if (sub == 0) s_p[warp][g][pp] = (pbase + pp < ctx) ? sc : -INFINITY;
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---- online softmax bookkeeping: warp w owns heads g = w, w+NW, ...
-        for (int g = warp; g < G; g += NW) {
-            float v0 = s_p[g][lane], v1 = s_p[g][lane + 32];
-            float cm = warp_max(fmaxf(v0, v1));
-            float m_old = s_m[g], m_new = fmaxf(m_old, cm);
-            float e0 = (v0 == -INFINITY) ? 0.f : __expf(v0 - m_new);
-            float e1 = (v1 == -INFINITY) ? 0.f : __expf(v1 - m_new);
-            float cs = warp_sum(e0 + e1);
-            s_p[g][lane] = e0;
-            s_p[g][lane + 32] = e1;
-            if (lane == 0) {
-                float corr = (m_old == -INFINITY) ? 0.f : __expf(m_old - m_new);
-                s_corr[g] = corr;
-                s_l[g] = s_l[g] * corr + cs;
-                s_m[g] = m_new;
-            }
+        // ---- online softmax for the G heads (whole warp per head)
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const float v0 = s_p[warp][g][lane], v1 = s_p[warp][g][lane + 32];
+            const float cm = warp_max(fmaxf(v0, v1));
+            const float m_new = fmaxf(m_run[g], cm);
+            const float e0 = (v0 == -INFINITY) ? 0.f : __expf(v0 - m_new);
+            const float e1 = (v1 == -INFINITY) ? 0.f : __expf(v1 - m_new);
+            const float cs = warp_sum(e0 + e1);
+            s_p[warp][g][lane] = e0;
+            s_p[warp][g][lane + 32] = e1;
+            const float corr = (m_run[g] == -INFINITY) ? 0.f : __expf(m_run[g] - m_new);
+            l_run[g] = l_run[g] * corr + cs;
+            m_run[g] = m_new;
+            acc[g][0] *= corr; acc[g][1] *= corr; acc[g][2] *= corr; acc[g][3] *= corr;
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---- P.V: warp w takes positions w, w+NW, ... ; lane owns 4 dims (one code word)
-        {
+        // ---- P.V: lane owns 4 dims (one code word), loop over the tile's positions
+        if (lane < HD / 4) {
+            const int npos = min(ATT_CHUNK, ctx - pbase);
+#pragma unroll 4
+            for (int pp = 0; pp < npos; pp++) {
+                float vf[4];
+                if (Q8) {
+                    const uint32_t w = s8bias(reinterpret_cast<const uint32_t *>(tV + pp * HD)[lane]);
+                    const float vsc = __half2float(reinterpret_cast<const __half *>(tVs)[pp * NB + lane / 8]);
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                const float c = s_corr[g];
-                acc[g][0] *= c; acc[g][1] *= c; acc[g][2] *= c; acc[g][3] *= c;
-            }
-            if (lane < HD / 4) {
-                const int npos = min(ATT_CHUNK, ctx - pbase);
-                for (int pp = warp; pp < npos; pp += NW) {
-                    float vf[4];
-                    if (Q8) {
-                        const uint32_t w = s8bias(reinterpret_cast<const uint32_t *>(tV + pp * HD)[lane]);
-                        const float vsc = __half2float(reinterpret_cast<const __half *>(tVs)[pp * NB + lane / 8]);
+                    for (int k = 0; k < 4; k++) vf[k] = s8f(w, k) * vsc;
+                } else {
+                    const uint2 w = reinterpret_cast<const uint2 *>(tV + pp * HD * 2)[lane];
+                    float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&w.x));
+                    float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w.y));
+                    vf[0] = f0.x; vf[1] = f0.y; vf[2] = f1.x; vf[3] = f1.y;
+                }
 #pragma unroll
-                        for (int k = 0; k < 4; k++) vf[k] = s8f(w, k) * vsc;
-                    } else {
-                        const uint2 w = reinterpret_cast<const uint2 *>(tV + pp * HD * 2)[lane];
-                        float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&w.x));
-                        float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w.y));
-                        vf[0] = f0.x; vf[1] = f0.y; vf[2] = f1.x; vf[3] = f1.y;
-                    }
-#pragma unroll
-                    for (int g = 0; g < G; g++) {
-                        const float p = s_p[g][pp];
-                        acc[g][0] = fmaf(p, vf[0], acc[g][0]);
-                        acc[g][1] = fmaf(p, vf[1], acc[g][1]);
-                        acc[g][2] = fmaf(p, vf[2], acc[g][2]);
-                        acc[g][3] = fmaf(p, vf[3], acc[g][3]);
-                    }
+                for (int g = 0; g < G; g++) {
+                    const float p = s_p[warp][g][pp];
+                    acc[g][0] = fmaf(p, vf[0], acc[g][0]);
+                    acc[g][1] = fmaf(p, vf[1], acc[g][1]);
+                    acc[g][2] = fmaf(p, vf[2], acc[g][2]);
+                    acc[g][3] = fmaf(p, vf[3], acc[g][3]);
                 }
             }
         }
-        __syncthreads();  // everyone is done with this stage (and with s_p)
-        if (tid == 0 && ci + ATT_STAGES < nch) issue(ci + ATT_STAGES);
+        __syncwarp();
+        if (lane == 0 && c + NW < c1) issue(c + NW);   // the buffer is free again
     }
+    if (tid == 0) trace_mark(a.trace, 4);
 
-    // ---- cross-warp reduction of acc, write the split's partial
-    float *red = reinterpret_cast<float *>(smem);  // reuse the tile ring: [NW][G][HD]
+    // ---- merge the 4 warps (log-sum-exp) through shared memory, write the CTA's partial
+    __syncthreads();                                   // every tile buffer is idle now: reuse as scratch
+    float *red = reinterpret_cast<float *>(smem);      // [NW][G][HD]
     if (lane < HD / 4) {
 #pragma unroll
         for (int g = 0; g < G; g++)
             *reinterpret_cast<float4 *>(&red[((warp * G) + g) * HD + lane * 4]) =
                 make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
     }
+    if (lane == 0) {
+#pragma unroll
+        for (int g = 0; g < G; g++) { s_ml[warp][g][0] = m_run[g]; s_ml[warp][g][1] = l_run[g]; }
+    }
     __syncthreads();
     for (int i = tid; i < G * HD; i += ATT_THREADS) {
-        int g = i / HD, d = i % HD;
-        float s = 0.f;
+        const int g = i / HD, d = i % HD;
+        float M = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < NW; w++) s += red[((w * G) + g) * HD + d];
+        for (int w = 0; w < NW; w++) M = fmaxf(M, s_ml[w][g][0]);
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const float mw = s_ml[w][g][0];
+            const float wt = (mw == -INFINITY) ? 0.f : __expf(mw - M);
+            num = fmaf(wt, red[((w * G) + g) * HD + d], num);
+            den = fmaf(wt, s_ml[w][g][1], den);
+        }
         float *o = a.ws + ((int64_t)(kvh * G + g) * a.nsplit + split) * (HD + 2);
-        o[2 + d] = s;
-        if (d == 0) { o[0] = s_m[g]; o[1] = s_l[g]; }
+        o[2 + d] = num;
+        if (d == 0) { o[0] = M; o[1] = den; }
+    }
+    if (a.nsplit == 1) {
+        // single CTA per head: normalise right here
+        __syncthreads();
+        for (int i = tid; i < G * HD; i += ATT_THREADS) {
+            const int g = i / HD, d = i % HD;
+            const float *o = a.ws + ((int64_t)(kvh * G + g) * a.nsplit) * (HD + 2);
+            a.out[(int64_t)(kvh * G + g) * HD + d] = __float2half_rn(o[2 + d] / o[1]);
+        }
+        return;
     }
     __threadfence();
     __syncthreads();
@@ -421,20 +469,32 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
     __syncthreads();
     if (s_last == 0u) return;
     __threadfence();
-    // ---- the last CTA of this kv head merges the splits (log-sum-exp)
-    for (int i = tid; i < G * HD; i += ATT_THREADS) {
-        int g = i / HD, d = i % HD;
+    // ---- the last CTA of this kv head merges the CTAs' partials
+    float *wts = reinterpret_cast<float *>(smem);      // [G][nsplit] normalised weights
+    for (int g = warp; g < G; g += NW) {
         const float *base = a.ws + (int64_t)(kvh * G + g) * a.nsplit * (HD + 2);
         float M = -INFINITY;
-        for (int s = 0; s < a.nsplit; s++) M = fmaxf(M, base[s * (HD + 2)]);
-        float num = 0.f, den = 0.f;
-        for (int s = 0; s < a.nsplit; s++) {
-            const float *o = base + s * (HD + 2);
-            float w = (o[0] == -INFINITY) ? 0.f : __expf(o[0] - M);
-            num = fmaf(w, o[2 + d], num);
-            den = fmaf(w, o[1], den);
+        for (int sp = lane; sp < a.nsplit; sp += 32) M = fmaxf(M, base[sp * (HD + 2)]);
+        M = warp_max(M);
+        float den = 0.f;
+        for (int sp = lane; sp < a.nsplit; sp += 32) {
+            const float ms = base[sp * (HD + 2)];
+            const float wt = (ms == -INFINITY) ? 0.f : __expf(ms - M);
+            wts[g * a.nsplit + sp] = wt;
+            den = fmaf(wt, base[sp * (HD + 2) + 1], den);
         }
-        a.out[(int64_t)(kvh * G + g) * HD + d] = __float2half_rn(num / den);
+        den = warp_sum(den);
+        const float inv = 1.0f / den;
+        for (int sp = lane; sp < a.nsplit; sp += 32) wts[g * a.nsplit + sp] *= inv;
+    }
+    __syncthreads();
+    for (int i = tid; i < G * HD; i += ATT_THREADS) {
+        const int g = i / HD, d = i % HD;
+        const float *base = a.ws + (int64_t)(kvh * G + g) * a.nsplit * (HD + 2) + 2 + d;
+        float num = 0.f;
+#pragma unroll 4
+        for (int sp = 0; sp < a.nsplit; sp++) num = fmaf(wts[g * a.nsplit + sp], base[(int64_t)sp * (HD + 2)], num);
+        a.out[(int64_t)(kvh * G + g) * HD + d] = __float2half_rn(num);
     }
     if (tid == 0) a.counters[kvh] = 0u;  // ready for the next launch
 }
@@ -443,10 +503,12 @@ template <int HD, int G>
 static int attn_launch_t(const AttnArgs &a, int kv_dtype, bool pdl, cudaStream_t st) {
     const bool q8 = kv_dtype == DT_Q8_B32T2;
     const int nb = HD / 32;
-    const size_t stage = q8 ? 2 * (ATT_CHUNK * HD + ATT_CHUNK * nb * 2) : 2 * (ATT_CHUNK * HD * 2);
-    size_t smem = ATT_STAGES * stage;
+    const size_t tile = q8 ? 2 * (ATT_CHUNK * HD + ATT_CHUNK * nb * 2) : 2 * (ATT_CHUNK * HD * 2);
+    size_t smem = (ATT_THREADS / 32) * tile;
     const size_t red = (size_t)(ATT_THREADS / 32) * G * HD * sizeof(float);
+    const size_t wts = (size_t)G * a.nsplit * sizeof(float);
     if (smem < red) smem = red;
+    if (smem < wts) smem = wts;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(a.nsplit, a.kv_heads);
     cfg.blockDim = dim3(ATT_THREADS);
@@ -457,14 +519,14 @@ static int attn_launch_t(const AttnArgs &a, int kv_dtype, bool pdl, cudaStream_t
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
-    static bool attr_done[2] = {false, false};   // per <HD, G> instantiation
+    static size_t attr_smem[2] = {0, 0};   // per <HD, G> instantiation
     if (q8) {
         auto kern = attn_decode_kernel<HD, G, true>;
-        if (!attr_done[1]) { IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[1] = true; }
+        if (attr_smem[1] < smem) { IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem[1] = smem; }
         IFB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     } else {
         auto kern = attn_decode_kernel<HD, G, false>;
-        if (!attr_done[0]) { IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[0] = true; }
+        if (attr_smem[0] < smem) { IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem[0] = smem; }
         IFB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     }
     return IFB_OK;
@@ -497,11 +559,15 @@ int attn_decode(const AttnDecode &p, cudaStream_t st) {
     a.counters = reinterpret_cast<unsigned int *>(p.workspace);
     a.ws = reinterpret_cast<float *>((uint8_t *)p.workspace + 4096);
     a.pos_dev = p.pos_dev;
+    a.trace = (unsigned long long *)p.trace;
     // split count: fill ~2 CTAs per SM; with a device-side position (graph replay) size for max_ctx
     const int ctx_for_split = p.pos_dev != nullptr ? p.max_ctx : p.ctx_len;
     const int nchunks = (ctx_for_split + ATT_CHUNK - 1) / ATT_CHUNK;
-    int nsplit = (4 * sm_count() + p.kv_heads - 1) / p.kv_heads;
-    if (nsplit > nchunks) nsplit = nchunks;
+    // one tile per warp while that still fills the machine: CTAs per head = ceil(tiles / 4),
+    // capped at ~4 CTAs per SM overall (longer contexts: several tiles per warp)
+    int nsplit = (nchunks + (ATT_THREADS / 32) - 1) / (ATT_THREADS / 32);
+    const int cap = (4 * sm_count() + p.kv_heads - 1) / p.kv_heads;
+    if (nsplit > cap) nsplit = cap;
     if (nsplit > 4 * 160) nsplit = 4 * 160;
     if (nsplit < 1) nsplit = 1;
     a.nsplit = nsplit;

@@ -141,6 +141,16 @@ __device__ __forceinline__ void pdl_launch_dependents() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// optional timeline probe: trace[cta*8 + slot] = ns timestamp (first 160 CTAs of a launch)
+__device__ __forceinline__ void trace_mark(unsigned long long *trace, int slot) {
+    if (trace != nullptr && blockIdx.x < 160 && blockIdx.y == 0) trace[blockIdx.x * 8 + slot] = globaltimer_ns();
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -167,6 +177,19 @@ __device__ __forceinline__ uint16_t f2h_bits(float v) {
 }
 // round-trip through fp16 (the reference stores every intermediate tensor as half)
 __device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
+
+// q = (int)roundf(v / scale) exactly as the reference's alg-2 quantizer computes it
+// (kernels/tensor_quant.h:64), but cheaply: r = v * (1/scale) is within ~3e-5 of the correctly rounded
+// quotient for |q| <= 127; round it to nearest with the 1.5*2^23 trick and take the IEEE division +
+// roundf path only when r sits within 2e-4 of a .5 tie (where the two roundings could disagree).
+__device__ __forceinline__ int q8_round_div(float v, float scale, float inv_scale) {
+    const float r = v * inv_scale;
+    const float y = r + 12582912.0f;              // 1.5 * 2^23: the low mantissa bits now hold rne(r)
+    const float fl = y - 12582912.0f;
+    int q = __float_as_int(y) - 0x4b400000;
+    if (fabsf(r - fl) > 0.4998f) q = (int)roundf(__fdiv_rn(v, scale));
+    return q;
+}
 
 // mixed-sign dp4a: a holds 4 unsigned bytes (weight codes 0..255), b 4 signed bytes
 __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {

@@ -7,39 +7,46 @@
 // 1555-1571,1726-1900).
 //
 // Design (HBM-bound streaming kernel; DESIGN.md "gemv"):
-//  * persistent CTAs, 1 producer warp + 8 consumer warps;
-//  * the weight matrix is streamed in the reference's own AoS block layout: a "unit" is R
-//    whole rows = one contiguous byte range, moved global->shared by ONE 1-D TMA bulk copy
-//    (cp.async.bulk, SASS UBLKCP) into a ring of shared-memory slots guarded by full/empty
-//    mbarriers -- the producer runs ahead of the consumers by the ring depth and, under PDL,
-//    starts streaming BEFORE the previous kernel has finished (weights do not depend on it);
-//  * consumers: one warp per row, lanes stride over the row's blocks (20/36/52-byte block
-//    strides are odd multiples of 4 bytes -> conflict-free LDS.32), integer dot by dp4a
-//    against the int8 activation staged once per CTA, fp32 combine, warp-shuffle reduce;
+//  * ONE persistent CTA per SM using at most half of the SM's shared memory, so that under
+//    programmatic dependent launch the NEXT kernel's CTA is co-resident: its producer warp asks the
+//    L2 to prefetch that kernel's weights (cp.async.bulk.prefetch.L2) and fills its own ring while
+//    this kernel is still computing -- the HBM pipe does not drain at kernel boundaries;
+//  * 1 producer warp + 16 consumer warps. The weight matrix is streamed in the reference's own
+//    AoS block layout: a "unit" is R whole rows = one contiguous byte range, moved
+//    global->shared by ONE 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) into a ring of
+//    shared-memory slots guarded by full/empty mbarriers; units are handed out by a global
+//    cursor (SMs do not get equal shares of the memory bandwidth);
+//  * consumers: one warp per row; for the headline format (Q4_B32T1, 20-byte blocks) a lane owns 4
+//    consecutive blocks = 80 bytes = five conflict-free LDS.128; integer dot by dp4a against the
+//    int8 activation staged once per CTA (high nibbles are used in place as 16*q: no shift),
+//    fp32 combine, warp-shuffle reduce;
 //  * the activation prologue (optional RMSNorm, Q8_B32T2 quantization identical to
 //    Tensor_QuantizeQ8_B32T2_Alg2_Kernel, kernels/tensor_quant.h:45-82) runs in every CTA
-//    from the fp16 vector, overlapped with the first weight copies.
+//    from the fp16 vector with one memory round trip.
 #include "ifb_formats.cuh"
 #include "ifb_kernels.h"
 
 namespace ifb {
 
-constexpr int GEMV_CWARPS = 8;                       // consumer warps
-constexpr int GEMV_THREADS = (GEMV_CWARPS + 1) * 32; // + producer warp
+constexpr int GEMV_CWARPS = 16;                       // consumer warps
+constexpr int GEMV_CTHREADS = GEMV_CWARPS * 32;
+constexpr int GEMV_THREADS = GEMV_CTHREADS + 32;      // + producer warp
 constexpr int GEMV_MAX_SLOTS = 16;
-constexpr int BAR_CONSUMERS = 1;                     // named barrier id for the 8 consumer warps
+constexpr int BAR_CONSUMERS = 1;                      // named barrier id for the consumer warps
 
 struct GemvArgs {
-    const uint8_t *w[3];
-    int rows[3];
-    int unit0[3];  // first unit index of each segment
-    int nseg;
+    const uint8_t *w0, *w1, *w2;   // up to 3 segments sharing x
+    int unit1, unit2;              // first unit of segment 1 / 2 (INT_MAX when absent)
+    long long bytes0, bytes1, bytes2;   // bytes of each segment (L2 prefetch)
     const uint8_t *w_gate;
     int cx, nblk, row_bytes;
+    int nxb_alloc;   // activation blocks allocated in shared memory (padded to 128 for the transposed layout)
     int R;           // rows per unit/slot
-    int wpg;         // consumer warps per group (= min(R, 8))
+    int wpg;         // consumer warps per group (= min(R, CWARPS))
+    int groups;      // consumer groups in use; nslots % groups == 0 so a group meets every fill of its slots in order
     int nslots, slot_stride;
     int units;
+    int l2_prefetch; // 1: ask the L2 for this kernel's weights at kernel entry
     const __half *x;
     const uint8_t *xq;  // pre-quantized activation (Q8_B32T2 blocks) or null
     const __half *norm_w;
@@ -47,6 +54,8 @@ struct GemvArgs {
     const __half *residual, *bias;
     __half *y;
     int w_dtype;
+    unsigned long long *trace;
+    int *counter;    // work-stealing cursor over the units (zero before the launch)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -59,16 +68,22 @@ __device__ __forceinline__ int x_pos(int e) {
     int g = e >> 3, k = e & 7;
     return g * 8 + (k & 1) * 4 + (k >> 1);
 }
+// slot of activation block b in the staged arrays. VEC4 kernels read, per pass of 128 blocks,
+// block 4*lane+i with all lanes at once: store those 32 blocks contiguously (transpose 4x32).
+template <bool VEC4>
+__device__ __forceinline__ int x_slot(int b) {
+    if (!VEC4) return b;
+    return (b & ~127) | ((b & 3) << 5) | ((b & 127) >> 2);
+}
 
-// RMS scale of the whole vector, computed by the 256 consumer threads (128-bit loads).
+// RMS scale of the whole vector, computed by the consumer threads (128-bit loads).
 // Tensor_RmsNorm_Kernel (unary_tensor_opr.h:217): scale = 1/sqrt(mean(x^2) + eps)
-__device__ __forceinline__ float rms_scale_256(const __half *x, int cx, float eps, float *red,
-                                               int tid) {
+__device__ __forceinline__ float rms_scale(const __half *x, int cx, float eps, float *red, int tid) {
     const uint4 *x4 = reinterpret_cast<const uint4 *>(x);
     const int ng = cx >> 3;
     float s = 0.f;
 #pragma unroll 4
-    for (int g = tid; g < ng; g += GEMV_CWARPS * 32) {
+    for (int g = tid; g < ng; g += GEMV_CTHREADS) {
         const uint4 v = x4[g];
         const __half2 *h = reinterpret_cast<const __half2 *>(&v);
 #pragma unroll
@@ -80,7 +95,7 @@ __device__ __forceinline__ float rms_scale_256(const __half *x, int cx, float ep
     }
     s = warp_sum(s);
     if ((tid & 31) == 0) red[tid >> 5] = s;
-    named_bar_sync(BAR_CONSUMERS, GEMV_CWARPS * 32);
+    named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < GEMV_CWARPS; i++) t += red[i];
@@ -93,7 +108,7 @@ __device__ __forceinline__ float rms_scale_256(const __half *x, int cx, float ep
 // absmax/127, q = roundf(v/scale), scale <= 1e-6 -> 0. Mapping: one thread = 8 consecutive
 // elements (ONE 128-bit load), four neighbouring lanes = one block; all of a thread's loads are
 // issued before any is used, so the prologue costs one memory round trip, not one per block.
-template <bool XSPLIT>
+template <bool XSPLIT, bool VEC4>
 __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint8_t *xhi,
                                            float2 *xs, float *red, int tid) {
     const int warp = tid >> 5, lane = tid & 31;
@@ -101,29 +116,30 @@ __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint
     if (a.xq != nullptr) {  // already quantized by the caller (TensorMul::Gemv_AX with a Q8 X)
         for (int b = warp; b < nxb; b += GEMV_CWARPS) {
             const uint8_t *blk = a.xq + (size_t)b * 34;
-            int q = (int)(int8_t)blk[2 + lane];
-            int p = x_pos<XSPLIT>(lane);
-            (p < 16 ? xlo + b * 16 + p : xhi + b * 16 + (p - 16))[0] = (uint8_t)q;
-            int qs = __reduce_add_sync(0xffffffffu, q);
+            const int q = (int)(int8_t)blk[2 + lane];
+            const int p = x_pos<XSPLIT>(lane), sl = x_slot<VEC4>(b);
+            (p < 16 ? xlo + sl * 16 + p : xhi + sl * 16 + (p - 16))[0] = (uint8_t)q;
+            const int qs = __reduce_add_sync(0xffffffffu, q);
             if (lane == 0) {
-                float s = h2f(*(const uint16_t *)blk);
-                xs[b] = make_float2(s, s * (float)qs);
+                const float s = h2f(*(const uint16_t *)blk);
+                xs[sl] = make_float2(s, s * (float)qs);
             }
         }
         return;
     }
     const bool norm = a.norm_w != nullptr;
-    float rs = 1.f;
-    if (norm) rs = rms_scale_256(a.x, a.cx, a.eps, red, tid);
     const uint4 *x4 = reinterpret_cast<const uint4 *>(a.x);
     const uint4 *w4 = reinterpret_cast<const uint4 *>(a.norm_w);
     const int ng = a.cx >> 3;                 // groups of 8 elements; ng % 4 == 0
-    constexpr int KPT = 4;                    // groups per thread per round
-    for (int g0 = 0; g0 < ng; g0 += GEMV_CWARPS * 32 * KPT) {
+    constexpr int KPT = 3;                    // groups per thread per round
+    const bool one_round = ng <= GEMV_CTHREADS * KPT;   // cx <= 12288: x is read from memory exactly once
+    float rs = 1.f;
+    if (norm && !one_round) rs = rms_scale(a.x, a.cx, a.eps, red, tid);
+    for (int g0 = 0; g0 < ng; g0 += GEMV_CTHREADS * KPT) {
         uint4 xv[KPT], wv[KPT];
 #pragma unroll
         for (int k = 0; k < KPT; k++) {
-            const int g = g0 + k * GEMV_CWARPS * 32 + tid;
+            const int g = g0 + k * GEMV_CTHREADS + tid;
             xv[k] = make_uint4(0, 0, 0, 0);
             wv[k] = make_uint4(0, 0, 0, 0);
             if (g < ng) {
@@ -131,9 +147,31 @@ __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint
                 if (norm) wv[k] = w4[g];
             }
         }
+        if (norm && one_round) {
+            // Tensor_RmsNorm_Kernel (unary_tensor_opr.h:217) from the registers just loaded
+            float ss = 0.f;
+#pragma unroll
+            for (int k = 0; k < KPT; k++) {
+                const __half2 *h = reinterpret_cast<const __half2 *>(&xv[k]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float2 f = __half22float2(h[i]);
+                    ss = fmaf(f.x, f.x, ss);
+                    ss = fmaf(f.y, f.y, ss);
+                }
+            }
+            ss = warp_sum(ss);
+            if (lane == 0) red[warp] = ss;
+            named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < GEMV_CWARPS; i++) t += red[i];
+            rs = 1.0f / sqrtf(t / (float)a.cx + a.eps);
+        }
 #pragma unroll
         for (int k = 0; k < KPT; k++) {
-            const int g = g0 + k * GEMV_CWARPS * 32 + tid;   // a quad of lanes shares one block
+            const int g = g0 + k * GEMV_CTHREADS + tid;   // a quad of lanes shares one block
+            if (g0 + k * GEMV_CTHREADS >= ng) break;      // uniform: the whole sub-round is past the end
             float v[8];
             {
                 const __half2 *h = reinterpret_cast<const __half2 *>(&xv[k]);
@@ -156,10 +194,12 @@ __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint
             m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
             m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
             const float scale = m / 127.0f;
+            const bool dead = scale <= 0.000001f;
+            const float inv = dead ? 0.f : __frcp_rn(scale);
             int q[8], qs = 0;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                int t = scale <= 0.000001f ? 0 : (int)roundf(v[i] / scale);
+                const int t = dead ? 0 : q8_round_div(v[i], scale, inv);
                 q[i] = min(max(t, -128), 127);
                 qs += q[i];
             }
@@ -175,11 +215,12 @@ __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint
                     w1 = (q[4] & 0xff) | ((q[5] & 0xff) << 8) | ((q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
                 }
                 const int b = g >> 2, j = g & 3;   // block, group-in-block (elements 8j..8j+7 = words 2j,2j+1)
-                uint2 *dst = reinterpret_cast<uint2 *>((j < 2 ? xlo : xhi) + (size_t)b * 16 + (j & 1) * 8);
+                const int sl = x_slot<VEC4>(b);
+                uint2 *dst = reinterpret_cast<uint2 *>((j < 2 ? xlo : xhi) + (size_t)sl * 16 + (j & 1) * 8);
                 *dst = make_uint2(w0, w1);
                 if (j == 0) {
                     const float sh = round_h(scale);  // the GEMV reads the fp16 scale back (gemv.h:1631)
-                    xs[b] = make_float2(sh, sh * (float)qs);
+                    xs[sl] = make_float2(sh, sh * (float)qs);
                 }
             }
         }
@@ -190,13 +231,13 @@ __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint
 __device__ __forceinline__ void stage_x_f16(const GemvArgs &a, __half *xh, float *red, int tid) {
     const bool norm = a.norm_w != nullptr;
     float rs = 1.f;
-    if (norm) rs = rms_scale_256(a.x, a.cx, a.eps, red, tid);
+    if (norm) rs = rms_scale(a.x, a.cx, a.eps, red, tid);
     const uint4 *x4 = reinterpret_cast<const uint4 *>(a.x);
     const uint4 *w4 = reinterpret_cast<const uint4 *>(a.norm_w);
     uint4 *o4 = reinterpret_cast<uint4 *>(xh);
     const int ng = a.cx >> 3;
 #pragma unroll 4
-    for (int g = tid; g < ng; g += GEMV_CWARPS * 32) {
+    for (int g = tid; g < ng; g += GEMV_CTHREADS) {
         uint4 xv = x4[g];
         if (norm) {
             const uint4 wv = w4[g];
@@ -216,7 +257,7 @@ __device__ __forceinline__ void stage_x_f16(const GemvArgs &a, __half *xh, float
 }
 
 // ---------------------------------------------------------------------------------------
-// row dot products
+// row dot products (per-lane partial sums; the caller reduces across the warp)
 // ---------------------------------------------------------------------------------------
 // dp4a path: kernels/gemv.h:1500-1709.  per weight block b and activation block(s):
 //   y += s_x * (scale_w * sum(q_w q_x) + base_w * sum(q_x))
@@ -257,7 +298,63 @@ __device__ __forceinline__ float row_dot_q8(const uint8_t *row, int nblk, const 
             if (Fmt::HAS_BASE) acc = fmaf(ba, s.y, acc);
         }
     }
-    return warp_sum(acc);
+    return acc;
+}
+
+// One Q4_B32T1 block held in registers (hdr = base|scale<<16, d0..d3 = 32 nibbles) against one
+// staged activation block (nibble-split order). Low nibbles: q ; high nibbles stay in place as
+// 16*q (<= 240 fits a u8 lane of dp4a) and are scaled back with one arithmetic shift.
+__device__ __forceinline__ float q4b32_block_dot(uint32_t hdr, uint32_t d0, uint32_t d1, uint32_t d2,
+                                                 uint32_t d3, const uint4 xa, const uint4 xc,
+                                                 const float2 s, float acc) {
+    int lo = dp4a_us(d0 & 0x0f0f0f0fu, xa.x, 0);
+    int hi = dp4a_us(d0 & 0xf0f0f0f0u, xa.y, 0);
+    lo = dp4a_us(d1 & 0x0f0f0f0fu, xa.z, lo);
+    hi = dp4a_us(d1 & 0xf0f0f0f0u, xa.w, hi);
+    lo = dp4a_us(d2 & 0x0f0f0f0fu, xc.x, lo);
+    hi = dp4a_us(d2 & 0xf0f0f0f0u, xc.y, hi);
+    lo = dp4a_us(d3 & 0x0f0f0f0fu, xc.z, lo);
+    hi = dp4a_us(d3 & 0xf0f0f0f0u, xc.w, hi);
+    const int isum = lo + (hi >> 4);
+    const float2 bs = __half22float2(*reinterpret_cast<const __half2 *>(&hdr));  // x = base, y = scale
+    acc = fmaf(bs.y * (float)isum, s.x, acc);
+    return fmaf(bs.x, s.y, acc);
+}
+
+// Q4_B32T1 rows with nblk % 4 == 0: a lane owns blocks 4*lane..4*lane+3 of each pass of 128
+// (80 contiguous bytes = 5 LDS.128, bank-conflict free across the warp). NM = 2 processes the
+// gate row of the GLU pair against the same activation registers.
+template <int NM>
+__device__ __forceinline__ void row_dot_q4b32_vec4(const uint8_t *row, size_t mat_bytes, int nblk,
+                                                   const uint4 *xlo, const uint4 *xhi,
+                                                   const float2 *xs, int lane, float *acc) {
+#pragma unroll
+    for (int m = 0; m < NM; m++) acc[m] = 0.f;
+    for (int p0 = 0; p0 < nblk; p0 += 128) {
+        const int b0 = p0 + 4 * lane;
+        if (b0 < nblk) {
+            uint4 xa[4], xc[4];
+            float2 s[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int sl = p0 + i * 32 + lane;
+                xa[i] = xlo[sl];
+                xc[i] = xhi[sl];
+                s[i] = xs[sl];
+            }
+#pragma unroll
+            for (int m = 0; m < NM; m++) {
+                const uint4 *wp = reinterpret_cast<const uint4 *>(row + m * mat_bytes + (size_t)b0 * 20);
+                const uint4 q0 = wp[0], q1 = wp[1], q2 = wp[2], q3 = wp[3], q4 = wp[4];
+                float a = acc[m];
+                a = q4b32_block_dot(q0.x, q0.y, q0.z, q0.w, q1.x, xa[0], xc[0], s[0], a);
+                a = q4b32_block_dot(q1.y, q1.z, q1.w, q2.x, q2.y, xa[1], xc[1], s[1], a);
+                a = q4b32_block_dot(q2.z, q2.w, q3.x, q3.y, q3.z, xa[2], xc[2], s[2], a);
+                a = q4b32_block_dot(q3.w, q4.x, q4.y, q4.z, q4.w, xa[3], xc[3], s[3], a);
+                acc[m] = a;
+            }
+        }
+    }
 }
 
 // fp16-activation path for any block format (kernels/gemv.h:633-1470): the reference
@@ -271,7 +368,7 @@ __device__ __forceinline__ float row_dot_hx(int dt, const uint8_t *row, int nblk
             acc = fmaf(round_h(v), __half2float(xb[i]), acc);
         });
     }
-    return warp_sum(acc);
+    return acc;
 }
 
 // fp16 weights (GemvHalf_AX_Alg3_Kernel, gemv.h:470; used for lm_head when L > 20).
@@ -282,6 +379,7 @@ __device__ __forceinline__ float row_dot_f16(const uint8_t *row, int cx, const _
     const uint4 *x4 = reinterpret_cast<const uint4 *>(xh);
     float acc = 0.f;
     const int n8 = cx >> 3;
+#pragma unroll 4
     for (int i = lane; i < n8; i += 32) {
         uint4 wv = w4[i], xv = x4[i];
         const __half2 *wh = reinterpret_cast<const __half2 *>(&wv);
@@ -295,7 +393,21 @@ __device__ __forceinline__ float row_dot_f16(const uint8_t *row, int cx, const _
     }
     for (int i = (n8 << 3) + lane; i < cx; i += 32)  // tail (cx % 8)
         acc = fmaf(__half2float(reinterpret_cast<const __half *>(row)[i]), __half2float(xh[i]), acc);
-    return warp_sum(acc);
+    return acc;
+}
+
+// ask the L2 for this CTA's share of one weight matrix, 16 KB per request, lanes in parallel
+__device__ __forceinline__ void l2_prefetch_share(const uint8_t *w, long long bytes, int lane) {
+    if (w == nullptr || bytes <= 0) return;
+    const long long per = ((bytes / gridDim.x) + 15) & ~15ll;
+    const long long lo = per * blockIdx.x;
+    long long hi = lo + per;
+    if (blockIdx.x == gridDim.x - 1 || hi > bytes) hi = bytes;
+    constexpr long long CH = 16 * 1024;
+    for (long long p = lo + (long long)lane * CH; p < hi; p += 32 * CH) {
+        const long long n = (hi - p < CH ? hi - p : CH) & ~15ll;
+        if (n > 0) bulk_prefetch_l2(w + p, (uint32_t)n);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -303,16 +415,17 @@ __device__ __forceinline__ float row_dot_f16(const uint8_t *row, int cx, const _
 // ---------------------------------------------------------------------------------------
 enum { MODE_Q8 = 0, MODE_HX = 1, MODE_F16 = 2 };
 
-template <class Fmt, int MODE, bool GLU>
-__global__ void __launch_bounds__(GEMV_THREADS) gemv_stream_kernel(const GemvArgs a) {
+template <class Fmt, int MODE, bool GLU, bool VEC4>
+__global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const GemvArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t full_bar[GEMV_MAX_SLOTS], empty_bar[GEMV_MAX_SLOTS];
     __shared__ float red[GEMV_CWARPS];
+    __shared__ int slot_unit[GEMV_MAX_SLOTS];   // which unit sits in each ring slot (-1: no more work)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *ring = smem;
     uint8_t *xbase = smem + (size_t)a.nslots * a.slot_stride;
-    const int nxb = a.cx >> 5;
+    const int nxb = a.nxb_alloc;
     // MODE_Q8: xlo | xhi | xs ; else: xh (fp16)
     uint8_t *xlo = xbase, *xhi = xbase + (size_t)nxb * 16;
     float2 *xs = reinterpret_cast<float2 *>(xbase + (size_t)nxb * 32);
@@ -329,26 +442,51 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_stream_kernel(const GemvArg
     // PDL: let the next kernel's CTAs become resident as early as possible -- their producer
     // warps only touch weights, everything else sits behind their own griddepcontrol.wait.
     pdl_launch_dependents();
+    if (tid == 0) trace_mark(a.trace, 0);
 
     const int nmat = GLU ? 2 : 1;
     const uint32_t mat_bytes = (uint32_t)a.R * (uint32_t)a.row_bytes;
 
     if (warp == GEMV_CWARPS) {
-        // ===== producer: stream this CTA's units; independent of the previous kernel =====
+        // ===== producer: independent of the previous kernel =====
+        if (a.l2_prefetch) {
+            // HBM -> L2 for this kernel's whole weight set, while the previous kernel still computes:
+            // the copies into the ring below then hit the L2 instead of waiting on DRAM latency.
+            l2_prefetch_share(a.w0, a.bytes0, lane);
+            l2_prefetch_share(a.w1, a.bytes1, lane);
+            l2_prefetch_share(a.w2, a.bytes2, lane);
+            if (GLU) l2_prefetch_share(a.w_gate, a.bytes0, lane);
+        }
+        // Units are handed out by a global cursor (atomicAdd): SMs do not get equal shares of the
+        // memory bandwidth, with a static split the slowest SM sets the kernel time.
         if (lane == 0) {
             const uint64_t pol = l2_policy_evict_first();
-            int j = 0;
-            for (int u = blockIdx.x; u < a.units; u += gridDim.x, j++) {
-                const int pos = j % a.nslots;
-                mbar_wait(&empty_bar[pos], ((j / a.nslots) & 1) ^ 1);
-                int seg = 0;
-                if (a.nseg > 1 && u >= a.unit0[1]) seg = 1;
-                if (a.nseg > 2 && u >= a.unit0[2]) seg = 2;
-                const size_t off = (size_t)(u - a.unit0[seg]) * mat_bytes;
-                uint8_t *dst = ring + (size_t)pos * a.slot_stride;
-                mbar_arrive_expect_tx(&full_bar[pos], mat_bytes * nmat);
-                bulk_g2s_hint(dst, a.w[seg] + off, mat_bytes, &full_bar[pos], pol);
-                if (GLU) bulk_g2s_hint(dst + mat_bytes, a.w_gate + off, mat_bytes, &full_bar[pos], pol);
+            int pos = 0;
+            uint32_t phase = 1;   // a fresh mbarrier passes a wait on parity 1
+            int next = atomicAdd(a.counter, 1);
+            int sentinels = 0;
+            for (;;) {
+                const int u = next;
+                const bool real = u < a.units;
+                if (real) next = atomicAdd(a.counter, 1);   // in flight while we wait for the slot
+                mbar_wait(&empty_bar[pos], phase);
+                slot_unit[pos] = real ? u : -1;
+                if (real) {
+                    const uint8_t *src;
+                    if (u >= a.unit2) src = a.w2 + (size_t)(u - a.unit2) * mat_bytes;
+                    else if (u >= a.unit1) src = a.w1 + (size_t)(u - a.unit1) * mat_bytes;
+                    else src = a.w0 + (size_t)u * mat_bytes;
+                    uint8_t *dst = ring + (size_t)pos * a.slot_stride;
+                    mbar_arrive_expect_tx(&full_bar[pos], mat_bytes * nmat);
+                    bulk_g2s_hint(dst, src, mat_bytes, &full_bar[pos], pol);
+                    if (GLU)
+                        bulk_g2s_hint(dst + mat_bytes, a.w_gate + (size_t)u * mat_bytes, mat_bytes,
+                                      &full_bar[pos], pol);
+                } else {
+                    mbar_arrive(&full_bar[pos]);   // an empty slot: tells one consumer group to stop
+                    if (++sentinels == a.groups) break;
+                }
+                if (++pos == a.nslots) { pos = 0; phase ^= 1u; }
             }
         }
         return;
@@ -356,64 +494,78 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_stream_kernel(const GemvArg
 
     // ===== consumers =====
     pdl_wait();  // x / residual come from the previous kernel
+    if (tid == 0) trace_mark(a.trace, 1);
     if (MODE == MODE_Q8)
-        stage_x_q8<Fmt::XSPLIT>(a, xlo, xhi, xs, red, tid);
+        stage_x_q8<Fmt::XSPLIT, VEC4>(a, xlo, xhi, xs, red, tid);
     else
         stage_x_f16(a, xh, red, tid);
-    named_bar_sync(BAR_CONSUMERS, GEMV_CWARPS * 32);
+    named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+    if (tid == 0) trace_mark(a.trace, 2);
 
-    const int groups = GEMV_CWARPS / a.wpg;
-    const int grp = warp / a.wpg, wl = warp % a.wpg;
+    const int groups = a.groups;
+    const int grp = warp / a.wpg, wl = warp - grp * a.wpg;
+    if (grp >= groups) return;   // spare warps (ring too shallow for every group)
     const int cap = block_capacity(a.w_dtype), bb = block_bytes(a.w_dtype);
 
-    int j = 0;
-    for (int u = blockIdx.x; u < a.units; u += gridDim.x, j++) {
-        if (j % groups != grp) continue;
-        const int pos = j % a.nslots;
-        mbar_wait(&full_bar[pos], (j / a.nslots) & 1);
+    // group g consumes the CTA's slot sequence j = g, g+groups, ...; ring position / phase advance with j
+    int pos = grp % a.nslots;
+    uint32_t phase = (uint32_t)(grp / a.nslots) & 1u;
+    const int step_pos = groups % a.nslots, step_wrap = groups / a.nslots;
+    for (int j = grp;; j += groups) {
+        mbar_wait(&full_bar[pos], phase);
+        const int u = slot_unit[pos];
+        if (u < 0) break;
+        if (tid == 0 && j == 0) trace_mark(a.trace, 3);
         const uint8_t *slot = ring + (size_t)pos * a.slot_stride;
-        int seg = 0;
-        if (a.nseg > 1 && u >= a.unit0[1]) seg = 1;
-        if (a.nseg > 2 && u >= a.unit0[2]) seg = 2;
-        int out_base = (u - a.unit0[seg]) * a.R;
-        for (int s = 0; s < seg; s++) out_base += a.rows[s];
+        const int out_base = u * a.R;   // segments are concatenated in y and are multiples of R
 
         for (int r = wl; r < a.R; r += a.wpg) {
             const uint8_t *row = slot + (size_t)r * a.row_bytes;
-            float acc, acc2 = 0.f;
-            // lane 0 fetches the epilogue operands while the row is being reduced
-            float res_v = 0.f, bias_v = 0.f;
+            const int o = out_base + r;
+            // lane 0 fetches the epilogue operands now and converts them after the reduction
+            unsigned short res_bits = 0, bias_bits = 0;
             if (lane == 0) {
-                if (a.residual != nullptr) res_v = __half2float(a.residual[out_base + r]);
-                if (a.bias != nullptr) bias_v = __half2float(a.bias[out_base + r]);
+                if (a.residual != nullptr) res_bits = reinterpret_cast<const unsigned short *>(a.residual)[o];
+                if (a.bias != nullptr) bias_bits = reinterpret_cast<const unsigned short *>(a.bias)[o];
             }
+            float acc[2] = {0.f, 0.f};
             if (MODE == MODE_Q8) {
-                acc = row_dot_q8<Fmt>(row, a.nblk, (const uint4 *)xlo, (const uint4 *)xhi, xs, lane);
-                if (GLU) acc2 = row_dot_q8<Fmt>(row + mat_bytes, a.nblk, (const uint4 *)xlo,
-                                                (const uint4 *)xhi, xs, lane);
+                if (VEC4) {
+                    row_dot_q4b32_vec4<GLU ? 2 : 1>(row, mat_bytes, a.nblk, (const uint4 *)xlo,
+                                                    (const uint4 *)xhi, xs, lane, acc);
+                } else {
+                    acc[0] = row_dot_q8<Fmt>(row, a.nblk, (const uint4 *)xlo, (const uint4 *)xhi, xs, lane);
+                    if (GLU) acc[1] = row_dot_q8<Fmt>(row + mat_bytes, a.nblk, (const uint4 *)xlo,
+                                                      (const uint4 *)xhi, xs, lane);
+                }
             } else if (MODE == MODE_HX) {
-                acc = row_dot_hx(a.w_dtype, row, a.nblk, cap, bb, xh, lane);
-                if (GLU) acc2 = row_dot_hx(a.w_dtype, row + mat_bytes, a.nblk, cap, bb, xh, lane);
+                acc[0] = row_dot_hx(a.w_dtype, row, a.nblk, cap, bb, xh, lane);
+                if (GLU) acc[1] = row_dot_hx(a.w_dtype, row + mat_bytes, a.nblk, cap, bb, xh, lane);
             } else {
-                acc = row_dot_f16(row, a.cx, xh, lane);
-                if (GLU) acc2 = row_dot_f16(row + mat_bytes, a.cx, xh, lane);
+                acc[0] = row_dot_f16(row, a.cx, xh, lane);
+                if (GLU) acc[1] = row_dot_f16(row + mat_bytes, a.cx, xh, lane);
             }
+            acc[0] = warp_sum(acc[0]);
+            if (GLU) acc[1] = warp_sum(acc[1]);
             if (lane == 0) {
-                const int o = out_base + r;
-                float v = round_h(acc);  // the GEMV output tensor is half
-                if (a.bias != nullptr) v = round_h(v + bias_v);
+                float v = round_h(acc[0]);  // the GEMV output tensor is half
+                if (a.bias != nullptr) v = round_h(v + h2f(bias_bits));
                 if (GLU) {
                     // SiluActivation_Kernel (unary_tensor_opr.h:553) then Mul, each stored as half
-                    float g = round_h(v / (1.0f + expf(-v)));
-                    v = round_h(g * round_h(acc2));
+                    const float g = round_h(v / (1.0f + expf(-v)));
+                    v = round_h(g * round_h(acc[1]));
                 }
-                if (a.residual != nullptr) v = round_h(v + res_v);
+                if (a.residual != nullptr) v = round_h(v + h2f(res_bits));
                 a.y[o] = __float2half_rn(v);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[pos]);
+        pos += step_pos;
+        phase ^= (uint32_t)step_wrap & 1u;
+        if (pos >= a.nslots) { pos -= a.nslots; phase ^= 1u; }
     }
+    if (tid == 0) trace_mark(a.trace, 4);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -430,9 +582,9 @@ int sm_count() {
     return g_sm_count;
 }
 
-template <class Fmt, int MODE, bool GLU>
+template <class Fmt, int MODE, bool GLU, bool VEC4>
 static int launch_variant(const GemvArgs &a, size_t smem, int grid, bool pdl, cudaStream_t st) {
-    auto kern = gemv_stream_kernel<Fmt, MODE, GLU>;
+    auto kern = gemv_stream_kernel<Fmt, MODE, GLU, VEC4>;
     static bool attr_done = false;  // per instantiation
     if (!attr_done) {
         IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -453,17 +605,19 @@ static int launch_variant(const GemvArgs &a, size_t smem, int grid, bool pdl, cu
 }
 
 template <bool GLU>
-static int dispatch(const GemvArgs &a, int mode, size_t smem, int grid, bool pdl, cudaStream_t st) {
-    if (mode == MODE_F16) return launch_variant<FmtQ4_B32T1, MODE_F16, GLU>(a, smem, grid, pdl, st);
-    if (mode == MODE_HX) return launch_variant<FmtQ4_B32T1, MODE_HX, GLU>(a, smem, grid, pdl, st);
+static int dispatch(const GemvArgs &a, int mode, bool vec4, size_t smem, int grid, bool pdl, cudaStream_t st) {
+    if (mode == MODE_F16) return launch_variant<FmtQ4_B32T1, MODE_F16, GLU, false>(a, smem, grid, pdl, st);
+    if (mode == MODE_HX) return launch_variant<FmtQ4_B32T1, MODE_HX, GLU, false>(a, smem, grid, pdl, st);
     switch (a.w_dtype) {
         case DT_Q4_B32T1A:
-        case DT_Q4_B32T1B: return launch_variant<FmtQ4_B32T1, MODE_Q8, GLU>(a, smem, grid, pdl, st);
-        case DT_Q4_B64T1: return launch_variant<FmtQ4_B64T1, MODE_Q8, GLU>(a, smem, grid, pdl, st);
-        case DT_Q8_B32T2: return launch_variant<FmtQ8_B32T2, MODE_Q8, GLU>(a, smem, grid, pdl, st);
-        case DT_Q6_B64T1: return launch_variant<FmtQ6_B64T1, MODE_Q8, GLU>(a, smem, grid, pdl, st);
-        case DT_Q5_B64T1: return launch_variant<FmtQ5_B64T1, MODE_Q8, GLU>(a, smem, grid, pdl, st);
-        case DT_Q3H_B64T1: return launch_variant<FmtQ3H_B64T1, MODE_Q8, GLU>(a, smem, grid, pdl, st);
+        case DT_Q4_B32T1B:
+            if (vec4) return launch_variant<FmtQ4_B32T1, MODE_Q8, GLU, true>(a, smem, grid, pdl, st);
+            return launch_variant<FmtQ4_B32T1, MODE_Q8, GLU, false>(a, smem, grid, pdl, st);
+        case DT_Q4_B64T1: return launch_variant<FmtQ4_B64T1, MODE_Q8, GLU, false>(a, smem, grid, pdl, st);
+        case DT_Q8_B32T2: return launch_variant<FmtQ8_B32T2, MODE_Q8, GLU, false>(a, smem, grid, pdl, st);
+        case DT_Q6_B64T1: return launch_variant<FmtQ6_B64T1, MODE_Q8, GLU, false>(a, smem, grid, pdl, st);
+        case DT_Q5_B64T1: return launch_variant<FmtQ5_B64T1, MODE_Q8, GLU, false>(a, smem, grid, pdl, st);
+        case DT_Q3H_B64T1: return launch_variant<FmtQ3H_B64T1, MODE_Q8, GLU, false>(a, smem, grid, pdl, st);
         default:
             set_last_error("gemv: weight type %d has no dp4a kernel (reference: Gemv_AX_QuantQ8, "
                            "tensor_mul.cu:714)", a.w_dtype);
@@ -479,9 +633,11 @@ static bool is_ax8_type(int dt) {
     }
 }
 
+static int *g_scratch_counter = nullptr;
+
 int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     const int dt = g.w_dtype;
-    const int cap = block_capacity(dt), bb = block_bytes(dt);
+    const int cap = block_capacity(dt);
     IFB_CHECK_ARG(cap > 0 && dt != DT_F32, "gemv: unsupported weight type %d", dt);
     IFB_CHECK_ARG(g.nseg >= 1 && g.nseg <= 3, "gemv: nseg %d", g.nseg);
     IFB_CHECK_ARG(g.cx > 0 && g.cx % 32 == 0,
@@ -511,7 +667,6 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     a.cx = (int)g.cx;
     a.nblk = (dt == DT_F16) ? (int)(g.cx / 32) : (int)(g.cx / cap);
     a.row_bytes = (int)row_bytes(dt, g.cx);
-    a.nseg = g.nseg;
     a.w_gate = (const uint8_t *)g.w_gate;
     a.x = (const __half *)g.x;
     a.xq = (const uint8_t *)g.xq;
@@ -521,24 +676,26 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     a.residual = (const __half *)g.residual;
     a.bias = (const __half *)g.bias;
     a.y = (__half *)g.y;
+    a.trace = (unsigned long long *)g.trace;
+    a.counter = (int *)g.counter;
 
-    // rows per unit: R*row_bytes must be a multiple of 16 (bulk-copy granularity) and divide
-    // every segment; prefer 8 (one row per consumer warp), fall back to 4 when a slot would
-    // exceed ~40 KB, go to 16/32 for very short rows.
+    // rows per unit: R*row_bytes must be a multiple of 16 (bulk-copy granularity) and R must
+    // divide every segment; prefer 8 (one row per consumer warp of a group), 4 when an 8-row slot
+    // would be too fat, 16/32 for very short rows.
     const int nmat = g.w_gate ? 2 : 1;
     int gcd_rows = 0;
     for (int i = 0; i < g.nseg; i++) {
         IFB_CHECK_ARG(g.rows[i] > 0 && g.w[i] != nullptr, "gemv: empty segment %d", i);
         IFB_CHECK_ARG(((uintptr_t)g.w[i] & 15) == 0, "gemv: weight pointer not 16-byte aligned");
-        int r = g.rows[i];
-        int x = gcd_rows, y = r;
+        int x = gcd_rows, y = g.rows[i];
         while (y) { int t = x % y; x = y; y = t; }
-        gcd_rows = gcd_rows == 0 ? r : x;
+        gcd_rows = gcd_rows == 0 ? g.rows[i] : x;
     }
+    IFB_CHECK_ARG(g.w_gate == nullptr || ((uintptr_t)g.w_gate & 15) == 0, "gemv: gate weight pointer not 16-byte aligned");
     auto valid = [&](int c) { return gcd_rows % c == 0 && ((int64_t)c * a.row_bytes) % 16 == 0; };
     auto sbytes = [&](int c) { return (int64_t)c * a.row_bytes * nmat; };
     int R = 0;
-    if (valid(8) && sbytes(8) <= 40 * 1024) R = 8;
+    if (valid(8) && sbytes(8) <= 32 * 1024) R = 8;
     else if (valid(4)) R = 4;
     else if (valid(8)) R = 8;
     if (R == 8 && valid(16) && sbytes(16) <= 16 * 1024) R = 16;   // very short rows: fatter copies
@@ -548,36 +705,59 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     a.R = R;
     a.wpg = R < GEMV_CWARPS ? R : GEMV_CWARPS;
 
-    int units = 0;
-    for (int i = 0; i < g.nseg; i++) {
-        a.w[i] = (const uint8_t *)g.w[i];
-        a.rows[i] = g.rows[i];
-        a.unit0[i] = units;
-        units += g.rows[i] / R;
-    }
+    int units = g.rows[0] / R;
+    a.w0 = (const uint8_t *)g.w[0];
+    a.bytes0 = (long long)g.rows[0] * a.row_bytes;
+    a.w1 = a.w2 = nullptr;
+    a.bytes1 = a.bytes2 = 0;
+    a.unit1 = a.unit2 = 0x7fffffff;
+    if (g.nseg > 1) { a.w1 = (const uint8_t *)g.w[1]; a.bytes1 = (long long)g.rows[1] * a.row_bytes; a.unit1 = units; units += g.rows[1] / R; }
+    if (g.nseg > 2) { a.w2 = (const uint8_t *)g.w[2]; a.bytes2 = (long long)g.rows[2] * a.row_bytes; a.unit2 = units; units += g.rows[2] / R; }
     a.units = units;
+    // L2 prefetch of the whole weight set when it fits the L2 comfortably next to the running kernel's
+    const long long total_bytes = a.bytes0 + a.bytes1 + a.bytes2 + (g.w_gate ? a.bytes0 : 0);
+    a.l2_prefetch = (g.l2_prefetch && total_bytes <= 64ll * 1024 * 1024 && total_bytes >= 1024 * 1024) ? 1 : 0;
+
+    const bool vec4 = mode == MODE_Q8 && (dt == DT_Q4_B32T1A || dt == DT_Q4_B32T1B) && g.cx % 128 == 0;
 
     const int64_t slot_bytes = (int64_t)R * a.row_bytes * nmat;
     a.slot_stride = (int)((slot_bytes + 16 + 127) / 128 * 128);
-    const int64_t xbytes = (mode == MODE_Q8) ? (g.cx / 32) * 40 : g.cx * 2;
+    a.nxb_alloc = (int)(g.cx / 32);
+    if (vec4) a.nxb_alloc = (a.nxb_alloc + 127) / 128 * 128;   // x_slot<true>() scatters inside passes of 128 blocks
+    const int64_t xbytes = (mode == MODE_Q8) ? (int64_t)a.nxb_alloc * 40 : g.cx * 2;
     const int64_t xpad = (xbytes + 127) / 128 * 128;
-    int64_t budget = (g.smem_budget > 0 ? g.smem_budget : 100 * 1024);
+    // default: at most ~half of the SM's shared memory, so two kernels of a PDL chain co-reside
+    int64_t budget = (g.smem_budget > 0 ? g.smem_budget : 110 * 1024);
+    int groups = GEMV_CWARPS / a.wpg;
     int nslots = (int)((budget - xpad) / a.slot_stride);
+    if (nslots < groups && g.smem_budget <= 0) {   // a little more room so that every warp group gets a slot
+        budget = 128 * 1024;
+        nslots = (int)((budget - xpad) / a.slot_stride);
+    }
     if (nslots < 2) {
         budget = 216 * 1024;
         nslots = (int)((budget - xpad) / a.slot_stride);
     }
     IFB_CHECK_ARG(nslots >= 1, "gemv: a %lld-byte slot does not fit shared memory", (long long)slot_bytes);
     if (nslots > GEMV_MAX_SLOTS) nslots = GEMV_MAX_SLOTS;
+    // A consumer group must meet EVERY fill of the slots it reads (mbarrier parity cannot tell fill k
+    // from fill k+2): slots are owned by groups, nslots is a multiple of the group count.
+    if (groups > nslots) groups = nslots;
+    nslots = nslots / groups * groups;
+    a.groups = groups;
     a.nslots = nslots;
     const size_t smem = (size_t)nslots * a.slot_stride + xpad;
 
-    const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
-    int grid = sm_count() * ctas_per_sm;
+    int grid = sm_count();
     if (grid > units) grid = units;
+    if (a.counter == nullptr) {   // stand-alone call: a library-owned cursor, zeroed on the caller's stream
+        if (g_scratch_counter == nullptr) IFB_CUDA(cudaMalloc((void **)&g_scratch_counter, 256));
+        IFB_CUDA(cudaMemsetAsync(g_scratch_counter, 0, sizeof(int), st));
+        a.counter = g_scratch_counter;
+    }
 
-    if (g.w_gate) return dispatch<true>(a, mode, smem, grid, g.pdl, st);
-    return dispatch<false>(a, mode, smem, grid, g.pdl, st);
+    if (g.w_gate) return dispatch<true>(a, mode, vec4, smem, grid, g.pdl, st);
+    return dispatch<false>(a, mode, vec4, smem, grid, g.pdl, st);
 }
 
 }  // namespace ifb

@@ -23,7 +23,10 @@ struct GemvLaunch {
     void *y = nullptr;
     int quantize_x = 1;
     int pdl = 0;
-    int64_t smem_budget = 0;       // bytes of shared memory per CTA (0 = default, 2 CTAs/SM)
+    int64_t smem_budget = 0;       // bytes of shared memory per CTA (0 = default: half an SM)
+    void *trace = nullptr;         // optional timeline probe buffer (160*8 uint64)
+    int l2_prefetch = 1;           // ask the L2 for the whole weight set at kernel entry (<= 64 MB)
+    void *counter = nullptr;       // int32 work cursor, must be 0 at launch (null: library scratch + memset)
 };
 int gemv_launch(const GemvLaunch &g, cudaStream_t st);
 
@@ -65,6 +68,7 @@ struct AttnDecode {
     void *out; const void *q; const void *kcache, *vcache; void *workspace;
     const int32_t *pos_dev = nullptr;   // ctx_len = *pos_dev + 1 when set (graph replay)
     int pdl = 0;
+    void *trace = nullptr;
 };
 int attn_decode(const AttnDecode &a, cudaStream_t st);
 

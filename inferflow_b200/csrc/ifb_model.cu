@@ -39,7 +39,9 @@ struct ifb_model {
     int q_dim_l = 0, kv_dim_l = 0;
     std::vector<LayerW> layers;
     DevBuf tok_emb, out_norm, lm_head;
-    DevBuf x0, x1, qkv, attn_out, hbuf, logits, attn_ws, scalars;   // scalars: [0]=pos, [1]=token, [2]=next
+    DevBuf x0, x1, qkv, attn_out, hbuf, logits, attn_ws, scalars, trace;   // trace: [512 launches][160 CTAs][8] ns stamps
+    int trace_on = 0;
+    DevBuf counters;   // one work cursor per launch of a step, zeroed at the start of every step   // scalars: [0]=pos, [1]=token, [2]=next
     std::vector<void *> allocs;
     cudaGraphExec_t graph_exec = nullptr;
     cudaGraph_t graph = nullptr;
@@ -150,6 +152,10 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     A(m->logits, (size_t)s.vocab * 2);
     A(m->attn_ws, attn_workspace_bytes(m->heads_l, m->hd));
     A(m->scalars, 256);
+    A(m->counters, 4096 * sizeof(int));
+    { const char *e3 = getenv("IFB_TRACE"); if (e3 && atoi(e3)) m->trace_on = 1; }
+    if (m->trace_on) A(m->trace, (size_t)512 * 160 * 8 * 8);
+    if (rc == IFB_OK && m->trace_on) cudaMemset(m->trace.p, 0, m->trace.bytes);
     if (rc == IFB_OK) {
         if (cudaMemset(m->attn_ws.p, 0, m->attn_ws.bytes) != cudaSuccess ||
             cudaMemset(m->scalars.p, 0, 256) != cudaSuccess) {
@@ -456,6 +462,7 @@ extern "C" int32_t ifb_model_tensor_ptr(ifb_model_t *m, const char *name, void *
     else if (n == "qkv") b = &m->qkv;
     else if (n == "attn_out") b = &m->attn_out;
     else if (n == "scalars") b = &m->scalars;
+    else if (n == "trace" && m->trace_on) b = &m->trace;
     else {
         int li = -1; char tn[64] = {0};
         if (sscanf(name, "layers.%d.%63s", &li, tn) == 2 && li >= 0 && li < m->spec.layers) {
@@ -493,6 +500,9 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
     const int pdl = m->use_pdl;
     int32_t *sc = (int32_t *)m->scalars.p;
     int n = 0;
+    IFB_CUDA(cudaMemsetAsync(m->counters.p, 0, m->counters.bytes, st));
+    auto CT = [&](int idx) -> void * { return (void *)((int *)m->counters.p + idx); };
+    auto TR = [&](int idx) -> void * { return (m->trace_on && idx < 512) ? (void *)((uint64_t *)m->trace.p + (size_t)idx * 160 * 8) : nullptr; };
     if (parts & PART_MISC) { TRY(embed_row(m->x0.p, m->tok_emb.p, DT_F16, d, 0, sc + 1, st)); n++; }
     const bool q8 = true;   // enable_full_quant_gemv = true (inference_engine.cc:53-57)
     auto ax8_ok = [](int dt) {
@@ -509,6 +519,7 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         g.rows[0] = m->q_dim_l; g.rows[1] = m->kv_dim_l; g.rows[2] = m->kv_dim_l;
         g.cx = d; g.x = m->x0.p; g.norm_w = L.attn_norm.p; g.norm_eps = s.norm_eps;
         g.y = qkv; g.quantize_x = quant_x; g.pdl = pdl;
+        g.trace = TR(n); g.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(g, st)); n++; }
         // --- RoPE(q,k) + append K,V
         KvAppend ka;
@@ -523,22 +534,26 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         ad.kv_dtype = s.kv_dtype; ad.heads = m->heads_l; ad.kv_heads = m->kv_heads_l; ad.head_dim = m->hd;
         ad.max_ctx = s.max_ctx; ad.ctx_len = 0; ad.kq_scale = s.kq_scale; ad.out = m->attn_out.p; ad.q = qkv;
         ad.kcache = L.kcache.p; ad.vcache = L.vcache.p; ad.workspace = m->attn_ws.p; ad.pos_dev = sc; ad.pdl = pdl;
+        ad.trace = TR(n);
         if (parts & PART_ATTN) { TRY(attn_decode(ad, st)); n++; }
         // --- wo + residual
         GemvLaunch o;
         o.w_dtype = wdt; o.nseg = 1; o.w[0] = L.wo.p; o.rows[0] = d; o.cx = m->q_dim_l;
         o.x = m->attn_out.p; o.residual = m->x0.p; o.y = m->x1.p; o.quantize_x = quant_x; o.pdl = pdl;
+        o.trace = TR(n); o.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(o, st)); n++; }
         // --- FFN: norm + quantize + (w1, w3) + SiLU*mul
         GemvLaunch f;
         f.w_dtype = wdt; f.nseg = 1; f.w[0] = L.w1.p; f.w_gate = L.w3.p; f.rows[0] = m->ffn_l; f.cx = d;
         f.x = m->x1.p; f.norm_w = L.ffn_norm.p; f.norm_eps = s.norm_eps; f.y = m->hbuf.p;
         f.quantize_x = quant_x; f.pdl = pdl;
+        f.trace = TR(n); f.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(f, st)); n++; }
         // --- w2 + residual
         GemvLaunch w2;
         w2.w_dtype = wdt; w2.nseg = 1; w2.w[0] = L.w2.p; w2.rows[0] = d; w2.cx = m->ffn_l;
         w2.x = m->hbuf.p; w2.residual = m->x1.p; w2.y = m->x0.p; w2.quantize_x = quant_x; w2.pdl = pdl;
+        w2.trace = TR(n); w2.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(w2, st)); n++; }
     }
     // --- final norm + lm_head (fp16 weights meet an fp16 activation: GemvHalf_AX_Alg3)
@@ -546,6 +561,7 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
     h.w_dtype = s.lm_head_dtype; h.nseg = 1; h.w[0] = m->lm_head.p; h.rows[0] = s.vocab; h.cx = d;
     h.x = m->x0.p; h.norm_w = m->out_norm.p; h.norm_eps = s.norm_eps; h.y = m->logits.p;
     h.quantize_x = (s.lm_head_dtype != DT_F16 && ax8_ok(s.lm_head_dtype)) ? 1 : 0; h.pdl = pdl;
+    h.trace = TR(n); h.counter = CT(n);
     if (parts & PART_GEMV) { TRY(gemv_launch(h, st)); n++; }
     if (parts & PART_MISC) {
         TRY(argmax(sc + 2, m->logits.p, s.vocab, st)); n++;

@@ -74,6 +74,11 @@ def weights(dt, cy, cx, seed):
 def test_quantize_bit_exact(ib, dt):
     rng = np.random.default_rng(10 + dt)
     for sigma, rows, cx in ((0.02, 64, 1024), (1.0, 33, 256), (1e-4, 8, 128)):
+        if dt == orc.Q4_B16 and sigma < 1e-3:
+            # Q4_B16 rounds its base to 1/100: values BELOW the rounded base make the reference convert a
+            # negative float to unsigned (undefined behaviour: the x86 build wraps to code 15, the CUDA
+            # build saturates to 0, as we do). Outside the format's domain; see DESIGN.md.
+            continue
         src = orc.f16(rng.normal(0, sigma, (rows, cx)))
         src[0, :64] = 0.25                      # constant blocks -> scale < 1e-5
         if dt == orc.Q4_B16:
@@ -160,6 +165,34 @@ def test_gemv_f16_weights(ib, shape):
     wt, xt = dev(w), dev(x.astype(np.float16))
     ib.check(ib.lib.ifb_gemv(orc.F16, ptr(y), ptr(wt), orc.F16, ptr(xt), cy, cx, None, None), "gemv")
     close(y.cpu().numpy(), want)
+
+
+def test_gemv_ring_wraps_many_times(ib):
+    """tall matrices: every CTA's shared-memory ring wraps several times, for every warp-group shape
+    (R = 4 and 8 rows per slot, GLU pairs, fp16 rows)"""
+    o = orc.oracle()
+    rng = np.random.default_rng(55)
+    for dt, cy, cx in ((orc.Q4_B32T1A, 148 * 8 * 9, 4096), (orc.Q4_B32T1A, 148 * 4 * 7, 11008), (orc.Q6_B64T1, 148 * 8 * 5, 2048)):
+        w = rng.integers(0, 256, size=(cy, orc.row_bytes(dt, cx)), dtype=np.uint8)
+        bb = orc.BYTES[dt]
+        w[:, 0::bb] = 0x00; w[:, 1::bb] = 0xa4; w[:, 2::bb] = 0x00; w[:, 3::bb] = 0x1c   # base -0.0156, scale 0.0039
+        x = orc.f16(rng.normal(0, 1, cx))
+        xq = o.quantize(orc.Q8_B32T2, x[None, :])
+        want = o.gemv_ax8(dt, w, xq, cy, cx)
+        got = _gemv(ib, dt, w, orc.Q8_B32T2, dev(xq), cy, cx)
+        close(got, want)
+    # GLU pair (R = 4, two matrices per slot)
+    dt, f, cx = orc.Q4_B32T1A, 11008, 4096
+    w1 = rng.integers(0, 256, size=(f, orc.row_bytes(dt, cx)), dtype=np.uint8)
+    w3 = rng.integers(0, 256, size=(f, orc.row_bytes(dt, cx)), dtype=np.uint8)
+    for w in (w1, w3):
+        w[:, 0::20] = 0x00; w[:, 1::20] = 0xa4; w[:, 2::20] = 0x00; w[:, 3::20] = 0x1c
+    x = orc.f16(rng.normal(0, 1, cx))
+    xq = o.quantize(orc.Q8_B32T2, x[None, :])
+    a = orc.f16(o.gemv_ax8(dt, w1, xq, f, cx)); b = orc.f16(o.gemv_ax8(dt, w3, xq, f, cx))
+    want = orc.f16(orc.f16(a / (1.0 + np.exp(-a.astype(np.float64)))) * b)
+    got = _fused(ib, dt, [(w1, f)], cx, x, gate=w3)
+    close(got, want, rel=2 ** -9)
 
 
 def test_gemv_bias_and_errors(ib):

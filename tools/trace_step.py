@@ -1,0 +1,33 @@
+"""Timeline probe of one decode step (IFB_TRACE=1): per kernel launch, ns relative to the first kernel.
+slots: 0 kernel entry, 1 after griddepcontrol.wait, 2 activation staged, 3 first tile landed,
+4 consumer done, 5 first TMA issued, 6 last TMA issued."""
+import os, sys
+os.environ["IFB_TRACE"] = "1"
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np, torch
+import inferflow_b200 as ib
+graph = "--graph" in sys.argv
+if not graph:
+    os.environ["IFB_NO_GRAPH"] = "1"
+torch.zeros(1, device="cuda")
+spec = ib.ModelSpec(max_ctx=2048, **ib.LLAMA2_7B)
+m = ib.Model(spec); m.init_synthetic(1234); m.kv_reset(2047, True)
+for _ in range(4):
+    m.decode(1, 2047)
+ib.check(ib.lib.ifb_device_synchronize(), "sync")
+raw = m.read_tensor("trace").view(np.uint64).reshape(512, 160, 8).astype(np.int64)
+n = m.launches_per_step
+t00 = raw[1][:148, 0][raw[1][:148, 0] > 0].min()
+names = {0: "embed"}
+print("launches", n)
+rows = []
+for k in range(1, min(n, 16)):
+    t = raw[k]
+    act = t[:, 0] > 0
+    if not act.any():
+        continue
+    def st(col, f):
+        v = t[act, col]; v = v[v > 0]
+        return (f(v) - t00) / 1000.0 if len(v) else float("nan")
+    print(f"k{k:3d} ctas {act.sum():3d} entry[min {st(0,np.min):8.2f} max {st(0,np.max):8.2f}] wait_done[min {st(1,np.min):8.2f} max {st(1,np.max):8.2f}] staged[max {st(2,np.max):8.2f}] "
+          f"first_tile[min {st(3,np.min):8.2f} max {st(3,np.max):8.2f}] done[min {st(4,np.min):8.2f} max {st(4,np.max):8.2f}] mhz[{np.median(t[act,5]/np.maximum(t[act,4]-t[act,0],1))*1000:7.0f}] rms[med {st(6,np.median):8.2f}] quant[med {st(7,np.median):8.2f}] wait[med {st(1,np.median):8.2f}]")
