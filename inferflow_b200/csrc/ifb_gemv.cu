@@ -25,6 +25,7 @@
 //    from the fp16 vector with one memory round trip.
 #include "ifb_formats.cuh"
 #include "ifb_kernels.h"
+#include <cstdlib>
 
 namespace ifb {
 
@@ -46,7 +47,8 @@ struct GemvArgs {
     int groups;      // consumer groups in use; nslots % groups == 0 so a group meets every fill of its slots in order
     int nslots, slot_stride;
     int units;
-    int l2_prefetch; // 1: ask the L2 for this kernel's weights at kernel entry
+    int l2_prefetch; // >0: software prefetch distance in UNITS: unit u+dist is requested into the L2 when unit u is copied
+    int debug_nocompute;  // measurement aid (IFB_GEMV_NOCOMPUTE=1): consumers release slots without doing the math
     const __half *x;
     const uint8_t *xq;  // pre-quantized activation (Q8_B32T2 blocks) or null
     const __half *norm_w;
@@ -396,20 +398,6 @@ __device__ __forceinline__ float row_dot_f16(const uint8_t *row, int cx, const _
     return acc;
 }
 
-// ask the L2 for this CTA's share of one weight matrix, 16 KB per request, lanes in parallel
-__device__ __forceinline__ void l2_prefetch_share(const uint8_t *w, long long bytes, int lane) {
-    if (w == nullptr || bytes <= 0) return;
-    const long long per = ((bytes / gridDim.x) + 15) & ~15ll;
-    const long long lo = per * blockIdx.x;
-    long long hi = lo + per;
-    if (blockIdx.x == gridDim.x - 1 || hi > bytes) hi = bytes;
-    constexpr long long CH = 16 * 1024;
-    for (long long p = lo + (long long)lane * CH; p < hi; p += 32 * CH) {
-        const long long n = (hi - p < CH ? hi - p : CH) & ~15ll;
-        if (n > 0) bulk_prefetch_l2(w + p, (uint32_t)n);
-    }
-}
-
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
@@ -449,13 +437,20 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
 
     if (warp == GEMV_CWARPS) {
         // ===== producer: independent of the previous kernel =====
-        if (a.l2_prefetch) {
-            // HBM -> L2 for this kernel's whole weight set, while the previous kernel still computes:
-            // the copies into the ring below then hit the L2 instead of waiting on DRAM latency.
-            l2_prefetch_share(a.w0, a.bytes0, lane);
-            l2_prefetch_share(a.w1, a.bytes1, lane);
-            l2_prefetch_share(a.w2, a.bytes2, lane);
-            if (GLU) l2_prefetch_share(a.w_gate, a.bytes0, lane);
+        // Software prefetch HBM -> L2, a fixed distance ahead of the copies into the ring: the bulk
+        // copies then hit the L2 (short latency: the shallow ring is enough to keep the stream full)
+        // and the DRAM traffic stays in consumption order instead of racing the running kernel.
+        auto unit_src = [&](int u) -> const uint8_t * {
+            if (u >= a.unit2) return a.w2 + (size_t)(u - a.unit2) * mat_bytes;
+            if (u >= a.unit1) return a.w1 + (size_t)(u - a.unit1) * mat_bytes;
+            return a.w0 + (size_t)u * mat_bytes;
+        };
+        if (a.l2_prefetch > 0) {
+            // the first `dist` units: shared out across CTAs and lanes, issued at kernel entry
+            for (int u = blockIdx.x * 32 + lane; u < a.l2_prefetch && u < a.units; u += gridDim.x * 32) {
+                bulk_prefetch_l2(unit_src(u), mat_bytes);
+                if (GLU) bulk_prefetch_l2(a.w_gate + (size_t)u * mat_bytes, mat_bytes);
+            }
         }
         // Units are handed out by a global cursor (atomicAdd): SMs do not get equal shares of the
         // memory bandwidth, with a static split the slowest SM sets the kernel time.
@@ -472,11 +467,12 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
                 mbar_wait(&empty_bar[pos], phase);
                 slot_unit[pos] = real ? u : -1;
                 if (real) {
-                    const uint8_t *src;
-                    if (u >= a.unit2) src = a.w2 + (size_t)(u - a.unit2) * mat_bytes;
-                    else if (u >= a.unit1) src = a.w1 + (size_t)(u - a.unit1) * mat_bytes;
-                    else src = a.w0 + (size_t)u * mat_bytes;
+                    const uint8_t *src = unit_src(u);
                     uint8_t *dst = ring + (size_t)pos * a.slot_stride;
+                    if (a.l2_prefetch > 0 && u + a.l2_prefetch < a.units) {
+                        bulk_prefetch_l2(unit_src(u + a.l2_prefetch), mat_bytes);
+                        if (GLU) bulk_prefetch_l2(a.w_gate + (size_t)(u + a.l2_prefetch) * mat_bytes, mat_bytes);
+                    }
                     mbar_arrive_expect_tx(&full_bar[pos], mat_bytes * nmat);
                     bulk_g2s_hint(dst, src, mat_bytes, &full_bar[pos], pol);
                     if (GLU)
@@ -519,7 +515,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
         const uint8_t *slot = ring + (size_t)pos * a.slot_stride;
         const int out_base = u * a.R;   // segments are concatenated in y and are multiples of R
 
-        for (int r = wl; r < a.R; r += a.wpg) {
+        for (int r = wl; r < a.R && !a.debug_nocompute; r += a.wpg) {
             const uint8_t *row = slot + (size_t)r * a.row_bytes;
             const int o = out_base + r;
             // lane 0 fetches the epilogue operands now and converts them after the reduction
@@ -678,6 +674,14 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     a.y = (__half *)g.y;
     a.trace = (unsigned long long *)g.trace;
     a.counter = (int *)g.counter;
+    {
+        static int nocompute = -1;
+        if (nocompute < 0) { const char *e = getenv("IFB_GEMV_NOCOMPUTE"); nocompute = (e && atoi(e)) ? 1 : 0; }
+        a.debug_nocompute = nocompute;
+        static int nol2 = -1;
+        if (nol2 < 0) { const char *e = getenv("IFB_NO_L2_PREFETCH"); nol2 = (e && atoi(e)) ? 1 : 0; }
+        if (nol2) const_cast<GemvLaunch &>(g).l2_prefetch = 0;
+    }
 
     // rows per unit: R*row_bytes must be a multiple of 16 (bulk-copy granularity) and R must
     // divide every segment; prefer 8 (one row per consumer warp of a group), 4 when an 8-row slot
@@ -714,9 +718,15 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     if (g.nseg > 1) { a.w1 = (const uint8_t *)g.w[1]; a.bytes1 = (long long)g.rows[1] * a.row_bytes; a.unit1 = units; units += g.rows[1] / R; }
     if (g.nseg > 2) { a.w2 = (const uint8_t *)g.w[2]; a.bytes2 = (long long)g.rows[2] * a.row_bytes; a.unit2 = units; units += g.rows[2] / R; }
     a.units = units;
-    // L2 prefetch of the whole weight set when it fits the L2 comfortably next to the running kernel's
-    const long long total_bytes = a.bytes0 + a.bytes1 + a.bytes2 + (g.w_gate ? a.bytes0 : 0);
-    a.l2_prefetch = (g.l2_prefetch && total_bytes <= 64ll * 1024 * 1024 && total_bytes >= 1024 * 1024) ? 1 : 0;
+    {   // software prefetch distance (bytes -> units); 0 disables
+        static long long dist_bytes = -1;
+        if (dist_bytes < 0) {
+            const char *e = getenv("IFB_L2_DIST_MB");
+            dist_bytes = (e ? atoll(e) : 12) * 1024 * 1024;
+        }
+        const long long unit_bytes = (long long)R * a.row_bytes * nmat;
+        a.l2_prefetch = g.l2_prefetch ? (int)(dist_bytes / unit_bytes) : 0;
+    }
 
     const bool vec4 = mode == MODE_Q8 && (dt == DT_Q4_B32T1A || dt == DT_Q4_B32T1B) && g.cx % 128 == 0;
 
