@@ -722,7 +722,7 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
         static long long dist_bytes = -1;
         if (dist_bytes < 0) {
             const char *e = getenv("IFB_L2_DIST_MB");
-            dist_bytes = (e ? atoll(e) : 12) * 1024 * 1024;
+            dist_bytes = (e ? atoll(e) : 0) * 1024 * 1024;   // measured on B200: no gain (profiles/README.md), off by default
         }
         const long long unit_bytes = (long long)R * a.row_bytes * nmat;
         a.l2_prefetch = g.l2_prefetch ? (int)(dist_bytes / unit_bytes) : 0;

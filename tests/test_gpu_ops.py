@@ -208,8 +208,9 @@ def test_gemv_bias_and_errors(ib):
     y = torch.zeros(cy, dtype=torch.float16, device="cuda")
     rc = ib.lib.ifb_gemv(orc.Q2_B32T1B, ptr(y), ptr(dev(w)), orc.Q8_B32T2, ptr(dev(xq)), cy, cx, None, None)
     assert rc == -2
-    rc = ib.lib.ifb_gemv(orc.Q4_B32T1A, ptr(y), ptr(dev(w)), orc.F16, ptr(dev(x.astype(np.float16))), 6, cx, None, None)
-    assert rc == -1   # rows not tileable
+    # 34-byte blocks, one block per row: 6 rows cannot be cut into 16-byte-aligned units (needs 8)
+    rc = ib.lib.ifb_gemv(orc.Q8_B32T2, ptr(y), ptr(dev(w)), orc.F16, ptr(dev(x.astype(np.float16))), 6, 32, None, None)
+    assert rc == -1 and b"cannot be tiled" in ib.lib.ifb_last_error()
 
 
 def _fused(ib, dt, segs, cx, x, norm_w=None, gate=None, residual=None, quantize_x=1, pdl=0):
