@@ -178,6 +178,16 @@ __device__ __forceinline__ uint16_t f2h_bits(float v) {
 // round-trip through fp16 (the reference stores every intermediate tensor as half)
 __device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
 
+// system-scope flag traffic between GPUs (peer memory over NVLink)
+__device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // q = (int)roundf(v / scale) exactly as the reference's alg-2 quantizer computes it
 // (kernels/tensor_quant.h:64), but cheaply: r = v * (1/scale) is within ~3e-5 of the correctly rounded
 // quotient for |q| <= 127; round it to nearest with the 1.5*2^23 trick and take the IEEE division +

@@ -58,6 +58,7 @@ struct GemvArgs {
     int w_dtype;
     unsigned long long *trace;
     int *counter;    // work-stealing cursor over the units (zero before the launch)
+    TpExchange tp;   // tensor-parallel push / gather (size 1: unused)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -105,6 +106,49 @@ __device__ __forceinline__ float rms_scale(const __half *x, int cx, float eps, f
     return 1.0f / sqrtf(mean + eps);
 }
 
+// Tensor-parallel gather of one group of 8 activations: residual + partial sums of all ranks, added in
+// rank order with fp16 rounding after every add (MergeTensors adds worker 1..n-1 onto worker 0 with
+// TensorOpr::Add, then the layer adds the residual: inference_worker.cc:2264-2289, :849).
+__device__ __forceinline__ uint4 tp_gather8(const GemvArgs &a, int g, int parity) {
+    const uint8_t *base = reinterpret_cast<const uint8_t *>(a.tp.peer[a.tp.rank]) + a.tp.src_off +
+                          (size_t)parity * a.tp.src_parity_stride;
+    uint4 part[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++)
+        if (p < a.tp.size) part[p] = reinterpret_cast<const uint4 *>(base + (size_t)p * a.tp.src_rank_stride)[g];
+    const uint4 rv = reinterpret_cast<const uint4 *>(a.tp.resid)[g];
+    uint4 out;
+    __half2 *o = reinterpret_cast<__half2 *>(&out);
+    const __half2 *r = reinterpret_cast<const __half2 *>(&rv);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float2 acc = __half22float2(reinterpret_cast<const __half2 *>(&part[0])[i]);
+#pragma unroll
+        for (int p = 1; p < 8; p++)
+            if (p < a.tp.size) {
+                const float2 f = __half22float2(reinterpret_cast<const __half2 *>(&part[p])[i]);
+                acc.x = round_h(acc.x + f.x);
+                acc.y = round_h(acc.y + f.y);
+            }
+        const float2 rf = __half22float2(r[i]);
+        o[i] = __floats2half2_rn(acc.x + rf.x, acc.y + rf.y);
+    }
+    if (blockIdx.x == 0) reinterpret_cast<uint4 *>(a.tp.xout)[g] = out;
+    return out;
+}
+
+// wait until every rank has published the epoch this rank is at (its own push kernel ran just before)
+__device__ __forceinline__ int tp_wait_peers(const GemvArgs &a, int tid) {
+    const uint8_t *loc = reinterpret_cast<const uint8_t *>(a.tp.peer[a.tp.rank]);
+    const uint32_t e = *reinterpret_cast<const volatile uint32_t *>(loc + a.tp.gepoch_off);
+    if (tid < a.tp.size) {
+        const uint32_t *f = reinterpret_cast<const uint32_t *>(loc + a.tp.gflags_off) + tid;
+        while ((int32_t)(ld_acquire_sys_u32(f) - e) < 0) {}
+    }
+    named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+    return (int)(e & 1u);
+}
+
 // Stage x as Q8_B32T2 (codes + fp16-rounded scale + scale*sum(q)) into shared memory.
 // The arithmetic per block of 32 is the reference's alg 2 (tensor_quant.h:45-82): scale =
 // absmax/127, q = roundf(v/scale), scale <= 1e-6 -> 0. Mapping: one thread = 8 consecutive
@@ -134,7 +178,9 @@ __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint
     const uint4 *w4 = reinterpret_cast<const uint4 *>(a.norm_w);
     const int ng = a.cx >> 3;                 // groups of 8 elements; ng % 4 == 0
     constexpr int KPT = 3;                    // groups per thread per round
-    const bool one_round = ng <= GEMV_CTHREADS * KPT;   // cx <= 12288: x is read from memory exactly once
+    const bool gather = a.tp.gather != 0;
+    const bool one_round = ng <= GEMV_CTHREADS * KPT || gather;   // cx <= 12288: x is read from memory exactly once
+    const int parity = gather ? tp_wait_peers(a, tid) : 0;
     float rs = 1.f;
     if (norm && !one_round) rs = rms_scale(a.x, a.cx, a.eps, red, tid);
     for (int g0 = 0; g0 < ng; g0 += GEMV_CTHREADS * KPT) {
@@ -145,7 +191,7 @@ __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint
             xv[k] = make_uint4(0, 0, 0, 0);
             wv[k] = make_uint4(0, 0, 0, 0);
             if (g < ng) {
-                xv[k] = x4[g];
+                xv[k] = gather ? tp_gather8(a, g, parity) : x4[g];
                 if (norm) wv[k] = w4[g];
             }
         }
@@ -233,14 +279,49 @@ __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint
 __device__ __forceinline__ void stage_x_f16(const GemvArgs &a, __half *xh, float *red, int tid) {
     const bool norm = a.norm_w != nullptr;
     float rs = 1.f;
-    if (norm) rs = rms_scale(a.x, a.cx, a.eps, red, tid);
+    if (norm && !a.tp.gather) rs = rms_scale(a.x, a.cx, a.eps, red, tid);
     const uint4 *x4 = reinterpret_cast<const uint4 *>(a.x);
     const uint4 *w4 = reinterpret_cast<const uint4 *>(a.norm_w);
     uint4 *o4 = reinterpret_cast<uint4 *>(xh);
     const int ng = a.cx >> 3;
 #pragma unroll 4
+    const int parity = a.tp.gather ? tp_wait_peers(a, tid) : 0;
+    if (a.tp.gather) {
+        // gathered vector: stage it raw first, then normalise from shared memory (two passes over smem)
+        float ss = 0.f;
+        for (int g = tid; g < ng; g += GEMV_CTHREADS) {
+            const uint4 xv = tp_gather8(a, g, parity);
+            o4[g] = xv;
+            const __half2 *h = reinterpret_cast<const __half2 *>(&xv);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const float2 f = __half22float2(h[i]); ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss); }
+        }
+        if (norm) {
+            ss = warp_sum(ss);
+            if ((tid & 31) == 0) red[tid >> 5] = ss;
+            named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < GEMV_CWARPS; i++) t += red[i];
+            rs = 1.0f / sqrtf(t / (float)a.cx + a.eps);
+            for (int g = tid; g < ng; g += GEMV_CTHREADS) {
+                uint4 xv = o4[g];
+                const uint4 wv = w4[g];
+                __half2 *h = reinterpret_cast<__half2 *>(&xv);
+                const __half2 *hw = reinterpret_cast<const __half2 *>(&wv);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    float2 f = __half22float2(h[i]);
+                    const float2 fw = __half22float2(hw[i]);
+                    h[i] = __floats2half2_rn(f.x * rs * (a.norm_base + fw.x), f.y * rs * (a.norm_base + fw.y));
+                }
+                o4[g] = xv;
+            }
+        }
+        return;
+    }
     for (int g = tid; g < ng; g += GEMV_CTHREADS) {
-        uint4 xv = x4[g];
+        uint4 xv = a.tp.gather ? tp_gather8(a, g, parity) : x4[g];
         if (norm) {
             const uint4 wv = w4[g];
             __half2 *h = reinterpret_cast<__half2 *>(&xv);
@@ -409,6 +490,8 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
     __shared__ uint64_t full_bar[GEMV_MAX_SLOTS], empty_bar[GEMV_MAX_SLOTS];
     __shared__ float red[GEMV_CWARPS];
     __shared__ int slot_unit[GEMV_MAX_SLOTS];   // which unit sits in each ring slot (-1: no more work)
+    __shared__ __align__(16) __half push_y[GEMV_MAX_SLOTS][32];   // tensor-parallel push: a unit's R outputs, per ring slot
+    __shared__ unsigned int push_cnt[GEMV_MAX_SLOTS];             // ... and how many of the group's warps have delivered theirs
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *ring = smem;
@@ -423,6 +506,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
         for (int i = 0; i < a.nslots; i++) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], a.wpg);
+            push_cnt[i] = 0;
         }
         mbar_fence_init();
     }
@@ -491,6 +575,11 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
     // ===== consumers =====
     pdl_wait();  // x / residual come from the previous kernel
     if (tid == 0) trace_mark(a.trace, 1);
+    // epoch of the last completed push on this rank (only this kernel's last CTA will bump it, at the very end)
+    uint32_t tp_epoch = 0;
+    if (a.tp.push)
+        tp_epoch = *reinterpret_cast<const volatile uint32_t *>(
+            reinterpret_cast<const uint8_t *>(a.tp.peer[a.tp.rank]) + a.tp.epoch_off);
     if (MODE == MODE_Q8)
         stage_x_q8<Fmt::XSPLIT, VEC4>(a, xlo, xhi, xs, red, tid);
     else
@@ -552,16 +641,66 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
                     v = round_h(g * round_h(acc[1]));
                 }
                 if (a.residual != nullptr) v = round_h(v + h2f(res_bits));
-                a.y[o] = __float2half_rn(v);
+                if (a.tp.push) {
+                    push_y[pos][r] = __float2half_rn(v);   // sent below, R outputs at a time
+                } else {
+                    a.y[o] = __float2half_rn(v);
+                }
             }
         }
         __syncwarp();
+        if (a.tp.push && !a.debug_nocompute) {
+            // Tensor-parallel partial sums go straight into every rank's exchange region over NVLink. The
+            // group's last warp to finish its rows sends the unit's R outputs as 8-byte stores (a 2-byte
+            // store per row would cost one NVLink packet each). push_y/push_cnt are per ring slot: the slot
+            // is not refilled before this warp has arrived on its empty barrier below.
+            unsigned int old = 0;
+            if (lane == 0) {
+                __threadfence_block();
+                old = atomicAdd(&push_cnt[pos], 1u);
+                if (old == (unsigned)a.wpg - 1u) push_cnt[pos] = 0;
+                __threadfence_block();
+            }
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old == (unsigned)a.wpg - 1u) {
+                const size_t off = a.tp.dst_off + (size_t)((tp_epoch + 1u) & 1u) * a.tp.dst_parity_stride +
+                                   (size_t)(a.tp.dst_index0 + out_base) * 2;
+                const int chunks = a.R >> 2;   // 8-byte pieces of the unit's outputs
+                for (int i = lane; i < a.tp.size * chunks; i += 32) {
+                    const int p = i / chunks, c = i - p * chunks;
+                    const uint2 v = reinterpret_cast<const uint2 *>(push_y[pos])[c];
+                    reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(a.tp.peer[p]) + off)[c] = v;
+                }
+                __syncwarp();
+            }
+        }
         if (lane == 0) mbar_arrive(&empty_bar[pos]);
         pos += step_pos;
         phase ^= (uint32_t)step_wrap & 1u;
         if (pos >= a.nslots) { pos -= a.nslots; phase ^= 1u; }
     }
     if (tid == 0) trace_mark(a.trace, 4);
+    if (a.tp.push) {
+        // every consumer warp of this CTA is done with its rows: make the peer stores visible system-wide,
+        // count the CTA in, and let the LAST CTA of the grid publish the new epoch to every rank
+        __threadfence_system();
+        __syncwarp();
+        uint8_t *loc = reinterpret_cast<uint8_t *>(a.tp.peer[a.tp.rank]);
+        unsigned int *done = reinterpret_cast<unsigned int *>(loc + a.tp.epoch_off + 4);
+        if (lane == 0) {
+            const unsigned int total = gridDim.x * (unsigned)(groups * a.wpg);   // consumer warps that reach this point
+            if (atomicAdd(done, 1u) == total - 1u) {
+                __threadfence_system();
+                uint32_t *ep = reinterpret_cast<uint32_t *>(loc + a.tp.epoch_off);
+                const uint32_t e = *ep + 1u;
+                *ep = e;
+                *done = 0u;
+                __threadfence_system();
+                for (int p = 0; p < a.tp.size; p++)
+                    st_release_sys_u32(reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(a.tp.peer[p]) + a.tp.flags_off) + a.tp.rank, e);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -674,6 +813,10 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     a.y = (__half *)g.y;
     a.trace = (unsigned long long *)g.trace;
     a.counter = (int *)g.counter;
+    if (g.tp != nullptr) a.tp = *g.tp;
+    IFB_CHECK_ARG(!(a.tp.gather && g.xq != nullptr), "gemv: tensor-parallel gather needs an fp16 activation");
+    IFB_CHECK_ARG(!(a.tp.gather && g.cx > 12288), "gemv: tensor-parallel gather supports d_model <= 12288");
+    IFB_CHECK_ARG(a.tp.size >= 1 && a.tp.size <= 8, "gemv: tensor-parallel size %d", a.tp.size);
     {
         static int nocompute = -1;
         if (nocompute < 0) { const char *e = getenv("IFB_GEMV_NOCOMPUTE"); nocompute = (e && atoi(e)) ? 1 : 0; }

@@ -8,6 +8,31 @@ namespace ifb {
 
 int sm_count();
 
+// Tensor-parallel exchange through peer memory (NVLink): every rank owns one exchange region
+// (same layout on all ranks) and holds the mapped base pointers of all peers.
+//   push  : the GEMV epilogue writes its fp16 partial output into EVERY peer's region
+//           (slot = this rank), then the last CTA publishes an epoch number to every peer;
+//   gather: the next GEMV's prologue waits for all peers' epochs and reads
+//           x = residual + sum over ranks (in rank order, fp16 adds like the reference's MergeTensors,
+//           inference_worker.cc:2264-2289), CTA 0 stores x as the new residual stream.
+struct TpExchange {
+    int size = 1, rank = 0;
+    void *peer[8] = {nullptr};     // exchange region of every rank as mapped in THIS process
+    // push (epilogue)
+    int push = 0;
+    int64_t dst_off = 0;           // byte offset of the destination array inside a region
+    int64_t dst_parity_stride = 0; // bytes between the two parities (0: single buffer)
+    int64_t dst_index0 = 0;        // element offset of this rank's slice
+    int64_t flags_off = 0;         // uint32[8] epochs written by peers
+    int64_t epoch_off = 0;         // uint32 local epoch counter (+4: done-CTA counter)
+    // gather (prologue)
+    int gather = 0;
+    int64_t src_off = 0, src_parity_stride = 0, src_rank_stride = 0;   // partial of rank p at src_off + parity*.. + p*..
+    int64_t gflags_off = 0, gepoch_off = 0;
+    const void *resid = nullptr;   // fp16 [cx]
+    void *xout = nullptr;          // fp16 [cx] (written by CTA 0)
+};
+
 struct GemvLaunch {
     int w_dtype = 0;
     int nseg = 1;
@@ -27,6 +52,7 @@ struct GemvLaunch {
     void *trace = nullptr;         // optional timeline probe buffer (160*8 uint64)
     int l2_prefetch = 1;           // ask the L2 for the whole weight set at kernel entry (<= 64 MB)
     void *counter = nullptr;       // int32 work cursor, must be 0 at launch (null: library scratch + memset)
+    const TpExchange *tp = nullptr;
 };
 int gemv_launch(const GemvLaunch &g, cudaStream_t st);
 
@@ -40,6 +66,9 @@ int rope(void *x, int tokens, int heads, int head_dim, int rope_dims, int pos0, 
 int silu_mul(void *out, const void *a, const void *b, int64_t n, cudaStream_t st);
 int add(void *c, const void *a, const void *b, int64_t n, cudaStream_t st);
 int argmax(int32_t *out, const void *logits, int64_t n, cudaStream_t st);
+// argmax after waiting until every peer has published `*epoch` in flags[0..n_peers)
+int argmax_tp(int32_t *out, const void *logits, int64_t n, const uint32_t *flags, const uint32_t *epoch,
+              int n_peers, cudaStream_t st);
 int embed_row(void *dst_f16, const void *table, int table_dtype, int64_t cols, int token_id,
               const int32_t *token_dev, cudaStream_t st);
 

@@ -50,10 +50,13 @@ struct ifb_model {
     int use_pdl = 1;
     int use_graph = 1;
     int64_t weight_bytes = 0;
-    // tensor-parallel exchange (peer memory)
-    DevBuf xchg;                    // this rank's exchange buffer
-    std::vector<void *> peer_xchg;  // mapped peer buffers, [tp_size]
-    uint32_t xchg_epoch = 0;
+    // tensor-parallel exchange (peer memory): same layout on every rank
+    DevBuf xchg;                    // this rank's exchange region
+    std::vector<void *> peer_xchg;  // every rank's region as mapped here, [tp_size] (own entry = xchg.p)
+    int64_t x_recv = 0, x_recv_parity = 0, x_recv_rank = 0;   // partial sums: [2 parities][8 ranks][d_model] fp16
+    int64_t x_logits = 0;                                     // gathered logits [vocab] fp16
+    int64_t x_flags_ar = 0, x_flags_lg = 0, x_epoch_ar = 0, x_epoch_lg = 0;
+    int vocab_l = 0;                // lm_head rows held by this rank (vocabulary-sharded under TP)
 };
 
 static int dev_alloc(ifb_model *m, DevBuf &b, size_t bytes) {
@@ -90,6 +93,7 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
                   "tensor parallelism %d does not divide heads %d / kv_heads %d / d_ffn %d", tp,
                   s.heads, s.kv_heads, s.d_ffn);
     IFB_CHECK_ARG(s.experts == 0, "MoE layers are not built in this runtime yet");
+    IFB_CHECK_ARG(tp <= 8 && s.vocab % tp == 0 && (s.vocab / tp) % 8 == 0, "vocab %d cannot be sharded %d ways", s.vocab, tp);
     const int wdt = s.weight_dtype;
     const int wcap = block_capacity(wdt);
     IFB_CHECK_ARG(wcap > 0 && wdt != DT_F32, "unsupported device_weight_data_type %d", wdt);
@@ -107,6 +111,8 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     m->ffn_l = s.d_ffn / tp;
     m->q_dim_l = m->heads_l * m->hd;
     m->kv_dim_l = m->kv_heads_l * m->hd;
+    m->vocab_l = s.vocab / tp;      // ours: lm_head rows sharded (the reference keeps it whole on the last GPU,
+                                    // network_builder.cc:1271-1283); the slices meet in every rank's exchange region
     const char *e1 = getenv("IFB_NO_PDL");
     if (e1 && atoi(e1)) m->use_pdl = 0;
     const char *e2 = getenv("IFB_NO_GRAPH");
@@ -141,8 +147,21 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
         set_last_error("unsupported lm_head type %d", ldt);
         rc = IFB_ERR_TYPE;
     }
-    A(m->lm_head, wbytes(ldt, s.vocab, d));
-    wsum += wbytes(ldt, s.vocab, d);
+    A(m->lm_head, wbytes(ldt, m->vocab_l, d));
+    wsum += wbytes(ldt, m->vocab_l, d);
+    if (tp > 1) {
+        auto up = [](int64_t v) { return (v + 255) / 256 * 256; };
+        m->x_recv = 0;
+        m->x_recv_rank = (int64_t)d * 2;
+        m->x_recv_parity = 8 * m->x_recv_rank;
+        m->x_logits = up(2 * m->x_recv_parity);
+        m->x_flags_ar = up(m->x_logits + (int64_t)s.vocab * 2);
+        m->x_flags_lg = m->x_flags_ar + 64;
+        m->x_epoch_ar = m->x_flags_ar + 128;
+        m->x_epoch_lg = m->x_flags_ar + 160;
+        A(m->xchg, m->x_flags_ar + 256);
+        if (rc == IFB_OK && cudaMemset(m->xchg.p, 0, m->xchg.bytes) != cudaSuccess) { set_last_error("cudaMemset failed"); rc = IFB_ERR_CUDA; }
+    }
     m->weight_bytes = wsum;
     A(m->x0, d * 2);
     A(m->x1, d * 2);
@@ -317,7 +336,7 @@ extern "C" int32_t ifb_model_init_synthetic(ifb_model_t *m, uint64_t seed, ifb_s
     }
     TRY(synth_tensor(m->tok_emb.p, DT_F16, s.vocab, d, seed * 1000003ull + 11, 1.0f, st));   // same on all ranks
     TRY(const_f16(m->out_norm.p, d, 1.0f, st));
-    TRY(synth_tensor(m->lm_head.p, s.lm_head_dtype, s.vocab, d, seed * 1000003ull + 13, 0.02f, st));
+    TRY(synth_tensor(m->lm_head.p, s.lm_head_dtype, m->vocab_l, d, seed * 1000003ull + 13 + 17ull * s.tp_rank, 0.02f, st));
     return IFB_OK;
 }
 
@@ -422,7 +441,10 @@ extern "C" int32_t ifb_model_load_tensor(ifb_model_t *m, const char *name, const
     m->graph_ready = m->graph_ready;  // weights are read through fixed pointers: the graph stays valid
     if (n == "tok_embeddings") return load_shard(m->tok_emb, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
     if (n == "output_norm") return load_shard(m->out_norm, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
-    if (n == "output") return load_shard(m->lm_head, s.lm_head_dtype, host, host_dt, rows, cols, 0, rows, 0, cols, st);
+    if (n == "output") {
+        IFB_CHECK_ARG(rows == s.vocab && cols == d, "output shape");
+        return load_shard(m->lm_head, s.lm_head_dtype, host, host_dt, rows, cols, (int64_t)rk * m->vocab_l, m->vocab_l, 0, cols, st);
+    }
     int li = -1;
     char tn[64] = {0};
     if (sscanf(name, "layers.%d.%63s", &li, tn) != 2 || li < 0 || li >= s.layers) {
@@ -457,6 +479,7 @@ extern "C" int32_t ifb_model_tensor_ptr(ifb_model_t *m, const char *name, void *
     if (n == "tok_embeddings") b = &m->tok_emb;
     else if (n == "output_norm") b = &m->out_norm;
     else if (n == "output") b = &m->lm_head;
+    else if (n == "logits" && m->spec.tp_size > 1) { *ptr = (uint8_t *)m->xchg.p + m->x_logits; *bytes = (int64_t)m->spec.vocab * 2; return IFB_OK; }
     else if (n == "logits") b = &m->logits;
     else if (n == "x") b = &m->x0;
     else if (n == "qkv") b = &m->qkv;
@@ -511,6 +534,17 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
     };
     const int quant_x = (q8 && ax8_ok(wdt)) ? 1 : 0;
     __half *qkv = (__half *)m->qkv.p;
+    const int tp = s.tp_size;
+    TpExchange tpx;   // common fields
+    tpx.size = tp; tpx.rank = s.tp_rank;
+    if (tp > 1) for (int p = 0; p < tp; p++) tpx.peer[p] = m->peer_xchg[p];
+    auto tp_push_ar = [&]() { TpExchange t = tpx; t.push = 1; t.dst_off = m->x_recv; t.dst_parity_stride = m->x_recv_parity;
+                              t.dst_index0 = (int64_t)s.tp_rank * d; t.flags_off = m->x_flags_ar; t.epoch_off = m->x_epoch_ar; return t; };
+    auto tp_gather_ar = [&](const void *resid, void *xout) { TpExchange t = tpx; t.gather = 1; t.src_off = m->x_recv;
+                              t.src_parity_stride = m->x_recv_parity; t.src_rank_stride = m->x_recv_rank; t.gflags_off = m->x_flags_ar;
+                              t.gepoch_off = m->x_epoch_ar; t.resid = resid; t.xout = xout; return t; };
+    TpExchange t_qkv, t_wo, t_glu, t_w2, t_head;
+    int li = 0;
     for (auto &L : m->layers) {
         // --- attention: norm + quantize + wq|wk|wv
         GemvLaunch g;
@@ -519,6 +553,7 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         g.rows[0] = m->q_dim_l; g.rows[1] = m->kv_dim_l; g.rows[2] = m->kv_dim_l;
         g.cx = d; g.x = m->x0.p; g.norm_w = L.attn_norm.p; g.norm_eps = s.norm_eps;
         g.y = qkv; g.quantize_x = quant_x; g.pdl = pdl;
+        if (tp > 1 && li > 0) { t_qkv = tp_gather_ar(m->x1.p, m->x0.p); g.tp = &t_qkv; }   // x0 = x1 + sum(w2 partials) of the previous layer
         g.trace = TR(n); g.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(g, st)); n++; }
         // --- RoPE(q,k) + append K,V
@@ -540,6 +575,7 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         GemvLaunch o;
         o.w_dtype = wdt; o.nseg = 1; o.w[0] = L.wo.p; o.rows[0] = d; o.cx = m->q_dim_l;
         o.x = m->attn_out.p; o.residual = m->x0.p; o.y = m->x1.p; o.quantize_x = quant_x; o.pdl = pdl;
+        if (tp > 1) { o.residual = nullptr; t_wo = tp_push_ar(); o.tp = &t_wo; }             // row-parallel: partial sums go to the peers
         o.trace = TR(n); o.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(o, st)); n++; }
         // --- FFN: norm + quantize + (w1, w3) + SiLU*mul
@@ -547,24 +583,41 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         f.w_dtype = wdt; f.nseg = 1; f.w[0] = L.w1.p; f.w_gate = L.w3.p; f.rows[0] = m->ffn_l; f.cx = d;
         f.x = m->x1.p; f.norm_w = L.ffn_norm.p; f.norm_eps = s.norm_eps; f.y = m->hbuf.p;
         f.quantize_x = quant_x; f.pdl = pdl;
+        if (tp > 1) { t_glu = tp_gather_ar(m->x0.p, m->x1.p); f.tp = &t_glu; }               // x1 = x0 + sum(wo partials)
         f.trace = TR(n); f.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(f, st)); n++; }
         // --- w2 + residual
         GemvLaunch w2;
         w2.w_dtype = wdt; w2.nseg = 1; w2.w[0] = L.w2.p; w2.rows[0] = d; w2.cx = m->ffn_l;
         w2.x = m->hbuf.p; w2.residual = m->x1.p; w2.y = m->x0.p; w2.quantize_x = quant_x; w2.pdl = pdl;
+        if (tp > 1) { w2.residual = nullptr; t_w2 = tp_push_ar(); w2.tp = &t_w2; }
+        li++;
         w2.trace = TR(n); w2.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(w2, st)); n++; }
     }
     // --- final norm + lm_head (fp16 weights meet an fp16 activation: GemvHalf_AX_Alg3)
     GemvLaunch h;
-    h.w_dtype = s.lm_head_dtype; h.nseg = 1; h.w[0] = m->lm_head.p; h.rows[0] = s.vocab; h.cx = d;
+    h.w_dtype = s.lm_head_dtype; h.nseg = 1; h.w[0] = m->lm_head.p; h.rows[0] = m->vocab_l; h.cx = d;
     h.x = m->x0.p; h.norm_w = m->out_norm.p; h.norm_eps = s.norm_eps; h.y = m->logits.p;
     h.quantize_x = (s.lm_head_dtype != DT_F16 && ax8_ok(s.lm_head_dtype)) ? 1 : 0; h.pdl = pdl;
     h.trace = TR(n); h.counter = CT(n);
+    if (tp > 1) {
+        // input: x0 = x1 + sum(w2 partials of the last layer); output: this rank's logits slice to every rank
+        t_head = tp_gather_ar(m->x1.p, m->x0.p);
+        t_head.push = 1; t_head.dst_off = m->x_logits; t_head.dst_parity_stride = 0;
+        t_head.dst_index0 = (int64_t)s.tp_rank * m->vocab_l; t_head.flags_off = m->x_flags_lg; t_head.epoch_off = m->x_epoch_lg;
+        h.tp = &t_head;
+    }
     if (parts & PART_GEMV) { TRY(gemv_launch(h, st)); n++; }
     if (parts & PART_MISC) {
-        TRY(argmax(sc + 2, m->logits.p, s.vocab, st)); n++;
+        if (tp > 1) {
+            uint8_t *loc = (uint8_t *)m->xchg.p;
+            TRY(argmax_tp(sc + 2, loc + m->x_logits, s.vocab, (const uint32_t *)(loc + m->x_flags_lg),
+                          (const uint32_t *)(loc + m->x_epoch_lg), tp, st));
+        } else {
+            TRY(argmax(sc + 2, m->logits.p, s.vocab, st));
+        }
+        n++;
         advance_kernel<<<1, 1, 0, st>>>(sc); n++;
         IFB_LAUNCH_CHECK();
     }
@@ -624,17 +677,34 @@ extern "C" int32_t ifb_model_issue_parts(ifb_model_t *m, int32_t parts, ifb_stre
     return rc != IFB_OK ? rc : n;
 }
 
-extern "C" const void *ifb_model_logits(const ifb_model_t *m) { return m ? m->logits.p : nullptr; }
+extern "C" const void *ifb_model_logits(const ifb_model_t *m) {
+    if (!m) return nullptr;
+    return m->spec.tp_size > 1 ? (const void *)((const uint8_t *)m->xchg.p + m->x_logits) : m->logits.p;
+}
 extern "C" const int32_t *ifb_model_next_token(const ifb_model_t *m) { return m ? (const int32_t *)m->scalars.p + 2 : nullptr; }
 extern "C" int32_t ifb_model_kernel_launches_per_step(const ifb_model_t *m) { return m ? m->launches_per_step : 0; }
 
 extern "C" int32_t ifb_model_tp_export(ifb_model_t *m, void *host_handle) {
-    (void)m; (void)host_handle;
-    set_last_error("tensor-parallel exchange is not built yet");
-    return IFB_ERR_STATE;
+    IFB_CHECK_ARG(m != nullptr && host_handle != nullptr, "tp_export: null argument");
+    IFB_CHECK_ARG(m->spec.tp_size > 1 && m->xchg.p != nullptr, "tp_export: not a tensor-parallel model");
+    cudaIpcMemHandle_t h;
+    IFB_CUDA(cudaIpcGetMemHandle(&h, m->xchg.p));
+    static_assert(sizeof(h) == 64, "IPC handle is 64 bytes");
+    memcpy(host_handle, &h, sizeof(h));
+    return IFB_OK;
 }
 extern "C" int32_t ifb_model_tp_import(ifb_model_t *m, const void *handles, int32_t n) {
-    (void)m; (void)handles; (void)n;
-    set_last_error("tensor-parallel exchange is not built yet");
-    return IFB_ERR_STATE;
+    IFB_CHECK_ARG(m != nullptr && handles != nullptr, "tp_import: null argument");
+    IFB_CHECK_ARG(n == m->spec.tp_size && n > 1, "tp_import: %d handles for a tensor-parallel group of %d", n, m->spec.tp_size);
+    m->peer_xchg.assign(n, nullptr);
+    for (int p = 0; p < n; p++) {
+        if (p == m->spec.tp_rank) { m->peer_xchg[p] = m->xchg.p; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const uint8_t *)handles + (size_t)p * 64, 64);
+        void *ptr = nullptr;
+        IFB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        m->peer_xchg[p] = ptr;
+    }
+    m->graph_ready = false;
+    return IFB_OK;
 }

@@ -116,9 +116,16 @@ int add(void *c, const void *a, const void *b, int64_t n, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------- argmax (first max wins)
-__global__ void __launch_bounds__(1024) argmax_kernel(int32_t *out, const __half *x, int64_t n) {
+__global__ void __launch_bounds__(1024) argmax_kernel(int32_t *out, const __half *x, int64_t n,
+                                                      const uint32_t *flags, const uint32_t *epoch, int n_peers) {
     __shared__ float sv[32];
     __shared__ int si[32];
+    if (flags != nullptr) {   // vocabulary-sharded lm_head: wait until every rank's slice has landed
+        const uint32_t e = *reinterpret_cast<const volatile uint32_t *>(epoch);
+        if ((int)threadIdx.x < n_peers)
+            while ((int32_t)(ld_acquire_sys_u32(flags + threadIdx.x) - e) < 0) {}
+        __syncthreads();
+    }
     float best = -INFINITY;
     int bi = 0x7fffffff;
     for (int64_t i = threadIdx.x; i < n; i += 1024) {
@@ -147,7 +154,14 @@ __global__ void __launch_bounds__(1024) argmax_kernel(int32_t *out, const __half
 }
 int argmax(int32_t *out, const void *logits, int64_t n, cudaStream_t st) {
     IFB_CHECK_ARG(n > 0, "argmax: empty input");
-    argmax_kernel<<<1, 1024, 0, st>>>(out, (const __half *)logits, n);
+    argmax_kernel<<<1, 1024, 0, st>>>(out, (const __half *)logits, n, nullptr, nullptr, 0);
+    IFB_LAUNCH_CHECK();
+    return IFB_OK;
+}
+int argmax_tp(int32_t *out, const void *logits, int64_t n, const uint32_t *flags, const uint32_t *epoch,
+              int n_peers, cudaStream_t st) {
+    IFB_CHECK_ARG(n > 0 && n_peers >= 1 && n_peers <= 8, "argmax_tp: bad arguments");
+    argmax_kernel<<<1, 1024, 0, st>>>(out, (const __half *)logits, n, flags, epoch, n_peers);
     IFB_LAUNCH_CHECK();
     return IFB_OK;
 }

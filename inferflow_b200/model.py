@@ -99,6 +99,28 @@ class Model:
     def decode_next(self, stream=0):
         check(lib.ifb_model_decode_next(self._h, stream), "ifb_model_decode_next")
 
+    # -- tensor parallelism ------------------------------------------------------------------------------
+    def tp_export(self):
+        """64-byte IPC handle of this rank's exchange region (partial sums, logits, flags)."""
+        buf = (C.c_uint8 * 64)()
+        check(lib.ifb_model_tp_export(self._h, buf), "ifb_model_tp_export")
+        return bytes(buf)
+
+    def tp_import(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        check(lib.ifb_model_tp_import(self._h, blob, len(handles)), "ifb_model_tp_import")
+
+    def tp_connect(self, dist, group=None):
+        """Exchange the IPC handles over the process group (control plane only; the data path is the kernels'
+        own peer-memory stores) and map every peer's exchange region."""
+        if self.spec.tp_size == 1:
+            return
+        handles = exchange_handles(dist, self.tp_export(), group)
+        assert len(handles) == self.spec.tp_size
+        self.tp_import(handles)
+        dist.barrier(group)
+
     def issue_parts(self, parts, stream=0):
         n = lib.ifb_model_issue_parts(self._h, parts, stream)
         if n < 0:
@@ -116,3 +138,32 @@ class Model:
     @property
     def launches_per_step(self):
         return lib.ifb_model_kernel_launches_per_step(self._h)
+
+
+def exchange_handles(dist, handle: bytes, group=None):
+    """all_gather of fixed-size opaque handles; works over nccl (device tensors) and gloo (host tensors)."""
+    import torch
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
+    world = dist.get_world_size(group)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    return [bytes(t.cpu().numpy().tobytes()) for t in out]
+
+
+def shard_rows(rows, rank, size):
+    """[begin, end) of a tensor's rows held by `rank` when the rows are split `size` ways
+    (column-parallel weights wq/wk/wv/w1/w3 and the lm_head; reference: TensorPartitionType::BY_COL,
+    network_builder.cc:1138-1215 splits ne[1])."""
+    assert rows % size == 0, f"{rows} rows do not split {size} ways"
+    n = rows // size
+    return rank * n, (rank + 1) * n
+
+
+def shard_cols(cols, rank, size, block=64):
+    """[begin, end) of the input columns held by `rank` for row-parallel weights (wo, w2; reference BY_ROW);
+    shard edges stay on quantization-block boundaries so every shard quantizes to the same block bytes."""
+    assert cols % (size * block) == 0, f"{cols} columns do not split {size} ways on {block}-element blocks"
+    n = cols // size
+    return rank * n, (rank + 1) * n
