@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -62,7 +62,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def wait_first(self, timeout=5.0):
+        """nvidia-smi takes a few hundred ms to come up: do not start the timed region before it samples"""
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        """only samples taken after this point (the start of the timed regions) are reported"""
+        self.t_mark = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -73,7 +83,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if ts < getattr(self, "t_mark", 0.0):
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -187,15 +199,17 @@ def run_ours(args):
     pos = CTX - 1
     token = 1
     # ---- device-resident timing ("value")
+    sampler = ClockSampler(local)
+    sampler.start()
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             model.decode(token, pos, stream=sh)
         stream.synchronize()
+        sampler.wait_first()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local)
-        sampler.start()
+        sampler.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
@@ -206,7 +220,6 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop()
     if dist is not None:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -237,6 +250,7 @@ def run_ours(args):
         f1.record(stream)
         stream.synchronize()
         e2e_ms = f0.elapsed_time(f1)
+    clocks = sampler.stop()   # sampled across both timed regions (device-resident and end-to-end)
     if dist is not None:
         t = torch.tensor([e2e_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -284,7 +284,6 @@ __device__ __forceinline__ void stage_x_f16(const GemvArgs &a, __half *xh, float
     const uint4 *w4 = reinterpret_cast<const uint4 *>(a.norm_w);
     uint4 *o4 = reinterpret_cast<uint4 *>(xh);
     const int ng = a.cx >> 3;
-#pragma unroll 4
     const int parity = a.tp.gather ? tp_wait_peers(a, tid) : 0;
     if (a.tp.gather) {
         // gathered vector: stage it raw first, then normalise from shared memory (two passes over smem)

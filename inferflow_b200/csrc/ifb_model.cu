@@ -482,6 +482,9 @@ extern "C" int32_t ifb_model_tensor_ptr(ifb_model_t *m, const char *name, void *
     else if (n == "logits" && m->spec.tp_size > 1) { *ptr = (uint8_t *)m->xchg.p + m->x_logits; *bytes = (int64_t)m->spec.vocab * 2; return IFB_OK; }
     else if (n == "logits") b = &m->logits;
     else if (n == "x") b = &m->x0;
+    else if (n == "x1") b = &m->x1;
+    else if (n == "hbuf") b = &m->hbuf;
+    else if (n == "xchg" && m->spec.tp_size > 1) b = &m->xchg;
     else if (n == "qkv") b = &m->qkv;
     else if (n == "attn_out") b = &m->attn_out;
     else if (n == "scalars") b = &m->scalars;

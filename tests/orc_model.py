@@ -9,8 +9,12 @@ AX8 = set(orc.AX8_TYPES)
 
 
 class OracleModel:
-    def __init__(self, spec, tensors):
-        """tensors: name -> raw uint8 bytes as stored on the device (reference block layout)"""
+    def __init__(self, spec, tensors, tp=1):
+        """tensors: name -> raw uint8 bytes as stored on the device (reference block layout), UNSHARDED.
+        tp > 1: the row-parallel products (wo, w2) are computed as tp partial sums over column shards, each
+        stored as half and added in rank order, the residual last -- the order the reference's tensor-parallel
+        merge uses (MergeTensors: inference_worker.cc:2264-2289, then the layer's residual Add)."""
+        self.tp = tp
         self.s = spec
         self.t = tensors
         self.hd = spec.d_model // spec.heads
@@ -26,6 +30,28 @@ class OracleModel:
             xq = self.o.quantize(orc.Q8_B32T2, x[None, :])
             return self.o.gemv_ax8(dt, w, xq, rows, cols)
         return self.o.gemv_half(dt, w, x, rows, cols)
+
+    def _gemv_rowpar(self, name, dt, x, rows, cols, resid):
+        """round_h(W x) + resid, or its tensor-parallel restatement"""
+        if self.tp == 1:
+            return orc.f16(orc.f16(self._gemv(name, dt, x, rows, cols)) + resid)
+        rb = orc.row_bytes(dt, cols) if dt != orc.F16 else cols * 2
+        w = self.t[name][: rb * rows].reshape(rows, rb)
+        nc = cols // self.tp
+        sb = rb // self.tp
+        acc = None
+        for r in range(self.tp):
+            shard = np.ascontiguousarray(w[:, r * sb:(r + 1) * sb]).reshape(-1)
+            xs = np.ascontiguousarray(x[r * nc:(r + 1) * nc])
+            if dt == orc.F16:
+                part = self.o.gemv_f16(shard.view(np.float16).reshape(rows, nc), xs, rows, nc)
+            elif dt in AX8:
+                part = self.o.gemv_ax8(dt, shard, self.o.quantize(orc.Q8_B32T2, xs[None, :]), rows, nc)
+            else:
+                part = self.o.gemv_half(dt, shard, xs, rows, nc)
+            part = orc.f16(part)
+            acc = part if acc is None else orc.f16(acc + part)
+        return orc.f16(acc + resid)
 
     def _norm(self, name, x):
         w = self.t[name][: x.size * 2].view(np.float16).astype(np.float32)
@@ -51,11 +77,11 @@ class OracleModel:
             assert len(self.K[l]) == pos
             self.K[l].append(k); self.V[l].append(v)
             a = orc.f16(o.attn_decode(q, np.stack(self.K[l]), np.stack(self.V[l]), s.heads, s.kv_heads, hd, 1.0, True))
-            x1 = orc.f16(orc.f16(self._gemv(p + "wo", wdt, a, d, qd)) + x)
+            x1 = self._gemv_rowpar(p + "wo", wdt, a, d, qd, x)
             x1n = self._norm(p + "ffn_norm", x1)
             g = orc.f16(self._gemv(p + "w1", wdt, x1n, s.d_ffn, d))
             u = orc.f16(self._gemv(p + "w3", wdt, x1n, s.d_ffn, d))
             h = orc.f16(orc.f16(g / (1.0 + np.exp(-g.astype(np.float64)))) * u)
-            x = orc.f16(orc.f16(self._gemv(p + "w2", wdt, h, d, s.d_ffn)) + x1)
+            x = self._gemv_rowpar(p + "w2", wdt, h, d, s.d_ffn, x1)
         xn = self._norm("output_norm", x)
         return self._gemv("output", s.lm_head_dtype, xn, s.vocab, d)

@@ -9,12 +9,22 @@ import inferflow_b200 as ib
 graph = "--graph" in sys.argv
 if not graph:
     os.environ["IFB_NO_GRAPH"] = "1"
+rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+torch.cuda.set_device(rank)
 torch.zeros(1, device="cuda")
-spec = ib.ModelSpec(max_ctx=2048, **ib.LLAMA2_7B)
+spec = ib.ModelSpec(max_ctx=2048, tp_rank=rank, tp_size=world, **ib.LLAMA2_7B)
 m = ib.Model(spec); m.init_synthetic(1234); m.kv_reset(2047, True)
+if world > 1:   # torchrun: one process per GPU, the timeline printed is rank 0's
+    import torch.distributed as dist
+    dist.init_process_group("nccl")
+    m.tp_connect(dist)
 for _ in range(4):
     m.decode(1, 2047)
 ib.check(ib.lib.ifb_device_synchronize(), "sync")
+if world > 1:
+    dist.barrier()
+    if rank != 0:
+        dist.destroy_process_group(); sys.exit(0)
 raw = m.read_tensor("trace").view(np.uint64).reshape(512, 160, 8).astype(np.int64)
 n = m.launches_per_step
 t00 = raw[1][:148, 0][raw[1][:148, 0] > 0].min()
