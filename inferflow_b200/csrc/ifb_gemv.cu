@@ -115,7 +115,7 @@ __device__ __forceinline__ uint4 tp_gather8(const GemvArgs &a, int g, int parity
     uint4 part[8];
 #pragma unroll
     for (int p = 0; p < 8; p++)
-        if (p < a.tp.size) part[p] = reinterpret_cast<const uint4 *>(base + (size_t)p * a.tp.src_rank_stride)[g];
+        if (p < a.tp.size) part[p] = ld_relaxed_sys_v4(reinterpret_cast<const uint4 *>(base + (size_t)p * a.tp.src_rank_stride) + g);
     const uint4 rv = reinterpret_cast<const uint4 *>(a.tp.resid)[g];
     uint4 out;
     __half2 *o = reinterpret_cast<__half2 *>(&out);
@@ -143,9 +143,11 @@ __device__ __forceinline__ int tp_wait_peers(const GemvArgs &a, int tid) {
     const uint32_t e = *reinterpret_cast<const volatile uint32_t *>(loc + a.tp.gepoch_off);
     if (tid < a.tp.size) {
         const uint32_t *f = reinterpret_cast<const uint32_t *>(loc + a.tp.gflags_off) + tid;
-        while ((int32_t)(ld_acquire_sys_u32(f) - e) < 0) {}
+        // relaxed polling, then ONE acquire fence (an acquire load per poll pays a system fence every time)
+        while ((int32_t)(ld_relaxed_sys_u32(f) - e) < 0) {}
     }
     named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+    if (tid == 0) trace_mark(a.trace, 6);
     return (int)(e & 1u);
 }
 
@@ -490,6 +492,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
     __shared__ float red[GEMV_CWARPS];
     __shared__ int slot_unit[GEMV_MAX_SLOTS];   // which unit sits in each ring slot (-1: no more work)
     __shared__ __align__(16) __half push_y[GEMV_MAX_SLOTS][32];   // tensor-parallel push: a unit's R outputs, per ring slot
+    __shared__ unsigned int push_cta_done;                        // ... and how many consumer warps of the CTA have finished
     __shared__ unsigned int push_cnt[GEMV_MAX_SLOTS];             // ... and how many of the group's warps have delivered theirs
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -507,6 +510,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
             mbar_init(&empty_bar[i], a.wpg);
             push_cnt[i] = 0;
         }
+        push_cta_done = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -680,23 +684,31 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
     }
     if (tid == 0) trace_mark(a.trace, 4);
     if (a.tp.push) {
-        // every consumer warp of this CTA is done with its rows: make the peer stores visible system-wide,
-        // count the CTA in, and let the LAST CTA of the grid publish the new epoch to every rank
-        __threadfence_system();
+        // Publish: every warp makes its peer stores visible system-wide (ONE fence per warp -- it is cumulative
+        // over the lanes that synchronised with lane 0; a fence per thread costs ~15 us per launch), the last
+        // warp of the CTA counts the CTA in, and the LAST CTA of the grid hands the new epoch to every rank.
         __syncwarp();
-        uint8_t *loc = reinterpret_cast<uint8_t *>(a.tp.peer[a.tp.rank]);
-        unsigned int *done = reinterpret_cast<unsigned int *>(loc + a.tp.epoch_off + 4);
         if (lane == 0) {
-            const unsigned int total = gridDim.x * (unsigned)(groups * a.wpg);   // consumer warps that reach this point
-            if (atomicAdd(done, 1u) == total - 1u) {
+            __threadfence_block();
+            if (atomicAdd(&push_cta_done, 1u) == (unsigned)(groups * a.wpg) - 1u) {
+                // the CTA's last warp: one system fence for the whole CTA (cumulative over the warps that
+                // counted in before it), then the CTA counts in at GPU scope
                 __threadfence_system();
-                uint32_t *ep = reinterpret_cast<uint32_t *>(loc + a.tp.epoch_off);
-                const uint32_t e = *ep + 1u;
-                *ep = e;
-                *done = 0u;
-                __threadfence_system();
-                for (int p = 0; p < a.tp.size; p++)
-                    st_release_sys_u32(reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(a.tp.peer[p]) + a.tp.flags_off) + a.tp.rank, e);
+                trace_mark(a.trace, 5);
+                uint8_t *loc = reinterpret_cast<uint8_t *>(a.tp.peer[a.tp.rank]);
+                unsigned int *done = reinterpret_cast<unsigned int *>(loc + a.tp.epoch_off + 4);
+                if (atomicAdd(done, 1u) == gridDim.x - 1u) {
+                    // every warp fenced its stores before counting in; one more system fence orders the flags
+                    // behind all of them (each extra fence on this path is ~2 us of pure latency)
+                    __threadfence_system();
+                    uint32_t *ep = reinterpret_cast<uint32_t *>(loc + a.tp.epoch_off);
+                    const uint32_t e = *ep + 1u;
+                    for (int p = 0; p < a.tp.size; p++)
+                        st_relaxed_sys_u32(reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(a.tp.peer[p]) + a.tp.flags_off) + a.tp.rank, e);
+                    *ep = e;
+                    *done = 0u;
+                    trace_mark(a.trace, 7);
+                }
             }
         }
     }
