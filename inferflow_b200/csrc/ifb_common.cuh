@@ -196,6 +196,14 @@ __device__ __forceinline__ uint4 ld_relaxed_sys_v4(const uint4 *p) {
     asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_relaxed_sys_v4(void *p, uint4 v) {
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint2 ld_relaxed_sys_v2(const void *p) {
+    uint2 v;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

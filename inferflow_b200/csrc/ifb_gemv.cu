@@ -109,46 +109,51 @@ __device__ __forceinline__ float rms_scale(const __half *x, int cx, float eps, f
 // Tensor-parallel gather of one group of 8 activations: residual + partial sums of all ranks, added in
 // rank order with fp16 rounding after every add (MergeTensors adds worker 1..n-1 onto worker 0 with
 // TensorOpr::Add, then the layer adds the residual: inference_worker.cc:2264-2289, :849).
-__device__ __forceinline__ uint4 tp_gather8(const GemvArgs &a, int g, int parity) {
-    const uint8_t *base = reinterpret_cast<const uint8_t *>(a.tp.peer[a.tp.rank]) + a.tp.src_off +
-                          (size_t)parity * a.tp.src_parity_stride;
-    uint4 part[8];
+// The partials arrive as flag-in-data words {half2, flag} written by the peers' push epilogues: a thread polls
+// exactly the 4 words (32 bytes) per rank it needs -- no fence, no CTA-wide wait.
+__device__ __forceinline__ uint32_t tp_flag(const int32_t *seq, uint32_t idx) {
+    return ((uint32_t)*reinterpret_cast<const volatile int32_t *>(seq) << 8) | idx;
+}
+__device__ __forceinline__ uint4 tp_gather8(const GemvArgs &a, int g, uint32_t flag) {
+    const uint8_t *base = reinterpret_cast<const uint8_t *>(a.tp.peer[a.tp.rank]) + a.tp.src_off;
+    float acc[8];
 #pragma unroll
-    for (int p = 0; p < 8; p++)
-        if (p < a.tp.size) part[p] = ld_relaxed_sys_v4(reinterpret_cast<const uint4 *>(base + (size_t)p * a.tp.src_rank_stride) + g);
+    for (int p0 = 0; p0 < 8; p0 += 4) {
+        if (p0 >= a.tp.size) break;
+        uint4 w[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (p0 + i < a.tp.size) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(base + (size_t)(p0 + i) * a.tp.src_rank_stride) + 2 * g;
+                w[i][0] = ld_relaxed_sys_v4(src);
+                w[i][1] = ld_relaxed_sys_v4(src + 1);
+            }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (p0 + i < a.tp.size) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(base + (size_t)(p0 + i) * a.tp.src_rank_stride) + 2 * g;
+                while (w[i][0].y != flag || w[i][0].w != flag) w[i][0] = ld_relaxed_sys_v4(src);
+                while (w[i][1].y != flag || w[i][1].w != flag) w[i][1] = ld_relaxed_sys_v4(src + 1);
+                const uint32_t d[4] = {w[i][0].x, w[i][0].z, w[i][1].x, w[i][1].z};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&d[k]));
+                    if (p0 + i == 0) { acc[2 * k] = f.x; acc[2 * k + 1] = f.y; }
+                    else { acc[2 * k] = round_h(acc[2 * k] + f.x); acc[2 * k + 1] = round_h(acc[2 * k + 1] + f.y); }
+                }
+            }
+    }
     const uint4 rv = reinterpret_cast<const uint4 *>(a.tp.resid)[g];
     uint4 out;
     __half2 *o = reinterpret_cast<__half2 *>(&out);
     const __half2 *r = reinterpret_cast<const __half2 *>(&rv);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        float2 acc = __half22float2(reinterpret_cast<const __half2 *>(&part[0])[i]);
-#pragma unroll
-        for (int p = 1; p < 8; p++)
-            if (p < a.tp.size) {
-                const float2 f = __half22float2(reinterpret_cast<const __half2 *>(&part[p])[i]);
-                acc.x = round_h(acc.x + f.x);
-                acc.y = round_h(acc.y + f.y);
-            }
         const float2 rf = __half22float2(r[i]);
-        o[i] = __floats2half2_rn(acc.x + rf.x, acc.y + rf.y);
+        o[i] = __floats2half2_rn(acc[2 * i] + rf.x, acc[2 * i + 1] + rf.y);
     }
     if (blockIdx.x == 0) reinterpret_cast<uint4 *>(a.tp.xout)[g] = out;
     return out;
-}
-
-// wait until every rank has published the epoch this rank is at (its own push kernel ran just before)
-__device__ __forceinline__ int tp_wait_peers(const GemvArgs &a, int tid) {
-    const uint8_t *loc = reinterpret_cast<const uint8_t *>(a.tp.peer[a.tp.rank]);
-    const uint32_t e = *reinterpret_cast<const volatile uint32_t *>(loc + a.tp.gepoch_off);
-    if (tid < a.tp.size) {
-        const uint32_t *f = reinterpret_cast<const uint32_t *>(loc + a.tp.gflags_off) + tid;
-        // relaxed polling, then ONE acquire fence (an acquire load per poll pays a system fence every time)
-        while ((int32_t)(ld_relaxed_sys_u32(f) - e) < 0) {}
-    }
-    named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
-    if (tid == 0) trace_mark(a.trace, 6);
-    return (int)(e & 1u);
 }
 
 // Stage x as Q8_B32T2 (codes + fp16-rounded scale + scale*sum(q)) into shared memory.
@@ -182,7 +187,7 @@ __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint
     constexpr int KPT = 3;                    // groups per thread per round
     const bool gather = a.tp.gather != 0;
     const bool one_round = ng <= GEMV_CTHREADS * KPT || gather;   // cx <= 12288: x is read from memory exactly once
-    const int parity = gather ? tp_wait_peers(a, tid) : 0;
+    const uint32_t gflag = gather ? tp_flag(a.tp.seq, a.tp.gather_idx) : 0u;
     float rs = 1.f;
     if (norm && !one_round) rs = rms_scale(a.x, a.cx, a.eps, red, tid);
     for (int g0 = 0; g0 < ng; g0 += GEMV_CTHREADS * KPT) {
@@ -193,7 +198,7 @@ __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint
             xv[k] = make_uint4(0, 0, 0, 0);
             wv[k] = make_uint4(0, 0, 0, 0);
             if (g < ng) {
-                xv[k] = gather ? tp_gather8(a, g, parity) : x4[g];
+                xv[k] = gather ? tp_gather8(a, g, gflag) : x4[g];
                 if (norm) wv[k] = w4[g];
             }
         }
@@ -286,12 +291,12 @@ __device__ __forceinline__ void stage_x_f16(const GemvArgs &a, __half *xh, float
     const uint4 *w4 = reinterpret_cast<const uint4 *>(a.norm_w);
     uint4 *o4 = reinterpret_cast<uint4 *>(xh);
     const int ng = a.cx >> 3;
-    const int parity = a.tp.gather ? tp_wait_peers(a, tid) : 0;
+    const uint32_t gflag = a.tp.gather ? tp_flag(a.tp.seq, a.tp.gather_idx) : 0u;
     if (a.tp.gather) {
         // gathered vector: stage it raw first, then normalise from shared memory (two passes over smem)
         float ss = 0.f;
         for (int g = tid; g < ng; g += GEMV_CTHREADS) {
-            const uint4 xv = tp_gather8(a, g, parity);
+            const uint4 xv = tp_gather8(a, g, gflag);
             o4[g] = xv;
             const __half2 *h = reinterpret_cast<const __half2 *>(&xv);
 #pragma unroll
@@ -322,7 +327,7 @@ __device__ __forceinline__ void stage_x_f16(const GemvArgs &a, __half *xh, float
         return;
     }
     for (int g = tid; g < ng; g += GEMV_CTHREADS) {
-        uint4 xv = a.tp.gather ? tp_gather8(a, g, parity) : x4[g];
+        uint4 xv = a.tp.gather ? tp_gather8(a, g, gflag) : x4[g];
         if (norm) {
             const uint4 wv = w4[g];
             __half2 *h = reinterpret_cast<__half2 *>(&xv);
@@ -492,7 +497,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
     __shared__ float red[GEMV_CWARPS];
     __shared__ int slot_unit[GEMV_MAX_SLOTS];   // which unit sits in each ring slot (-1: no more work)
     __shared__ __align__(16) __half push_y[GEMV_MAX_SLOTS][32];   // tensor-parallel push: a unit's R outputs, per ring slot
-    __shared__ unsigned int push_cta_done;                        // ... and how many consumer warps of the CTA have finished
     __shared__ unsigned int push_cnt[GEMV_MAX_SLOTS];             // ... and how many of the group's warps have delivered theirs
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -510,7 +514,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
             mbar_init(&empty_bar[i], a.wpg);
             push_cnt[i] = 0;
         }
-        push_cta_done = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -578,11 +581,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
     // ===== consumers =====
     pdl_wait();  // x / residual come from the previous kernel
     if (tid == 0) trace_mark(a.trace, 1);
-    // epoch of the last completed push on this rank (only this kernel's last CTA will bump it, at the very end)
-    uint32_t tp_epoch = 0;
-    if (a.tp.push)
-        tp_epoch = *reinterpret_cast<const volatile uint32_t *>(
-            reinterpret_cast<const uint8_t *>(a.tp.peer[a.tp.rank]) + a.tp.epoch_off);
+    const uint32_t pflag = a.tp.push ? tp_flag(a.tp.seq, a.tp.push_idx) : 0u;
     if (MODE == MODE_Q8)
         stage_x_q8<Fmt::XSPLIT, VEC4>(a, xlo, xhi, xs, red, tid);
     else
@@ -655,7 +654,8 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
         if (a.tp.push && !a.debug_nocompute) {
             // Tensor-parallel partial sums go straight into every rank's exchange region over NVLink. The
             // group's last warp to finish its rows sends the unit's R outputs as 8-byte stores (a 2-byte
-            // store per row would cost one NVLink packet each). push_y/push_cnt are per ring slot: the slot
+            // store per row would cost one NVLink packet each; the words carry their own validity flag, so there is
+            // nothing to publish afterwards). push_y/push_cnt are per ring slot: the slot
             // is not refilled before this warp has arrived on its empty barrier below.
             unsigned int old = 0;
             if (lane == 0) {
@@ -666,13 +666,15 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
             }
             old = __shfl_sync(0xffffffffu, old, 0);
             if (old == (unsigned)a.wpg - 1u) {
-                const size_t off = a.tp.dst_off + (size_t)((tp_epoch + 1u) & 1u) * a.tp.dst_parity_stride +
-                                   (size_t)(a.tp.dst_index0 + out_base) * 2;
-                const int chunks = a.R >> 2;   // 8-byte pieces of the unit's outputs
+                // 16-byte stores of two words {half2, flag, half2, flag}: 4 outputs each, consecutive lanes write
+                // consecutive addresses of one peer, so a unit costs one coalesced NVLink write per peer
+                const size_t off = a.tp.dst_off + (size_t)out_base * 4;
+                const int chunks = a.R >> 2;
                 for (int i = lane; i < a.tp.size * chunks; i += 32) {
                     const int p = i / chunks, c = i - p * chunks;
-                    const uint2 v = reinterpret_cast<const uint2 *>(push_y[pos])[c];
-                    reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(a.tp.peer[p]) + off)[c] = v;
+                    const uint2 d = reinterpret_cast<const uint2 *>(push_y[pos])[c];
+                    st_relaxed_sys_v4(reinterpret_cast<uint8_t *>(a.tp.peer[p]) + off + (size_t)c * 16,
+                                      make_uint4(d.x, pflag, d.y, pflag));
                 }
                 __syncwarp();
             }
@@ -683,35 +685,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
         if (pos >= a.nslots) { pos -= a.nslots; phase ^= 1u; }
     }
     if (tid == 0) trace_mark(a.trace, 4);
-    if (a.tp.push) {
-        // Publish: every warp makes its peer stores visible system-wide (ONE fence per warp -- it is cumulative
-        // over the lanes that synchronised with lane 0; a fence per thread costs ~15 us per launch), the last
-        // warp of the CTA counts the CTA in, and the LAST CTA of the grid hands the new epoch to every rank.
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            if (atomicAdd(&push_cta_done, 1u) == (unsigned)(groups * a.wpg) - 1u) {
-                // the CTA's last warp: one system fence for the whole CTA (cumulative over the warps that
-                // counted in before it), then the CTA counts in at GPU scope
-                __threadfence_system();
-                trace_mark(a.trace, 5);
-                uint8_t *loc = reinterpret_cast<uint8_t *>(a.tp.peer[a.tp.rank]);
-                unsigned int *done = reinterpret_cast<unsigned int *>(loc + a.tp.epoch_off + 4);
-                if (atomicAdd(done, 1u) == gridDim.x - 1u) {
-                    // every warp fenced its stores before counting in; one more system fence orders the flags
-                    // behind all of them (each extra fence on this path is ~2 us of pure latency)
-                    __threadfence_system();
-                    uint32_t *ep = reinterpret_cast<uint32_t *>(loc + a.tp.epoch_off);
-                    const uint32_t e = *ep + 1u;
-                    for (int p = 0; p < a.tp.size; p++)
-                        st_relaxed_sys_u32(reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(a.tp.peer[p]) + a.tp.flags_off) + a.tp.rank, e);
-                    *ep = e;
-                    *done = 0u;
-                    trace_mark(a.trace, 7);
-                }
-            }
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -15,20 +15,22 @@ int sm_count();
 //   gather: the next GEMV's prologue waits for all peers' epochs and reads
 //           x = residual + sum over ranks (in rank order, fp16 adds like the reference's MergeTensors,
 //           inference_worker.cc:2264-2289), CTA 0 stores x as the new residual stream.
+// Tensor-parallel exchange through peer memory, flag-in-data ("LL") words: every 8-byte word of an exchange
+// buffer is {two fp16 values, 32-bit flag}; a word is valid for an exchange when its flag equals
+// (step sequence number << 8 | exchange index). 8-byte stores are atomic, so neither side needs a fence, a
+// counter or a separate flag: the sender stores, the receiver polls the data words themselves.
 struct TpExchange {
     int size = 1, rank = 0;
     void *peer[8] = {nullptr};     // exchange region of every rank as mapped in THIS process
-    // push (epilogue)
+    const int32_t *seq = nullptr;  // device: step sequence number (same value on every rank)
+    // push (epilogue): this rank's outputs -> every rank's region
     int push = 0;
-    int64_t dst_off = 0;           // byte offset of the destination array inside a region
-    int64_t dst_parity_stride = 0; // bytes between the two parities (0: single buffer)
-    int64_t dst_index0 = 0;        // element offset of this rank's slice
-    int64_t flags_off = 0;         // uint32[8] epochs written by peers
-    int64_t epoch_off = 0;         // uint32 local epoch counter (+4: done-CTA counter)
-    // gather (prologue)
+    int64_t dst_off = 0;           // byte offset (inside a region) of the word that receives output row 0
+    uint32_t push_idx = 0;         // exchange index 1..255
+    // gather (prologue): x = resid + sum over ranks of the partial vectors, in rank order
     int gather = 0;
-    int64_t src_off = 0, src_parity_stride = 0, src_rank_stride = 0;   // partial of rank p at src_off + parity*.. + p*..
-    int64_t gflags_off = 0, gepoch_off = 0;
+    int64_t src_off = 0, src_rank_stride = 0;   // words of rank p's partial start at src_off + p*src_rank_stride
+    uint32_t gather_idx = 0;
     const void *resid = nullptr;   // fp16 [cx]
     void *xout = nullptr;          // fp16 [cx] (written by CTA 0)
 };
@@ -67,8 +69,7 @@ int silu_mul(void *out, const void *a, const void *b, int64_t n, cudaStream_t st
 int add(void *c, const void *a, const void *b, int64_t n, cudaStream_t st);
 int argmax(int32_t *out, const void *logits, int64_t n, cudaStream_t st);
 // argmax after waiting until every peer has published `*epoch` in flags[0..n_peers)
-int argmax_tp(int32_t *out, const void *logits, int64_t n, const uint32_t *flags, const uint32_t *epoch,
-              int n_peers, cudaStream_t st);
+int argmax_tp(int32_t *out, void *logits_f16, const void *ll_words, int64_t n, const int32_t *seq, uint32_t idx, cudaStream_t st);
 int embed_row(void *dst_f16, const void *table, int table_dtype, int64_t cols, int token_id,
               const int32_t *token_dev, cudaStream_t st);
 

@@ -53,9 +53,8 @@ struct ifb_model {
     // tensor-parallel exchange (peer memory): same layout on every rank
     DevBuf xchg;                    // this rank's exchange region
     std::vector<void *> peer_xchg;  // every rank's region as mapped here, [tp_size] (own entry = xchg.p)
-    int64_t x_recv = 0, x_recv_parity = 0, x_recv_rank = 0;   // partial sums: [2 parities][8 ranks][d_model] fp16
-    int64_t x_logits = 0;                                     // gathered logits [vocab] fp16
-    int64_t x_flags_ar = 0, x_flags_lg = 0, x_epoch_ar = 0, x_epoch_lg = 0;
+    int64_t x_recv = 0, x_recv_parity = 0, x_recv_rank = 0;   // partial sums: [2 parities][8 ranks][d_model/2] words {half2, flag}
+    int64_t x_logits = 0;                                     // logits of all ranks: [vocab/2] words {half2, flag}
     int vocab_l = 0;                // lm_head rows held by this rank (vocabulary-sharded under TP)
 };
 
@@ -94,6 +93,7 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
                   s.heads, s.kv_heads, s.d_ffn);
     IFB_CHECK_ARG(s.experts == 0, "MoE layers are not built in this runtime yet");
     IFB_CHECK_ARG(tp <= 8 && s.vocab % tp == 0 && (s.vocab / tp) % 8 == 0, "vocab %d cannot be sharded %d ways", s.vocab, tp);
+    IFB_CHECK_ARG(tp == 1 || s.layers <= 127, "tensor parallel: at most 127 layers (exchange index is 8 bits)");
     const int wdt = s.weight_dtype;
     const int wcap = block_capacity(wdt);
     IFB_CHECK_ARG(wcap > 0 && wdt != DT_F32, "unsupported device_weight_data_type %d", wdt);
@@ -152,14 +152,10 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     if (tp > 1) {
         auto up = [](int64_t v) { return (v + 255) / 256 * 256; };
         m->x_recv = 0;
-        m->x_recv_rank = (int64_t)d * 2;
+        m->x_recv_rank = (int64_t)d * 4;             // d/2 words of 8 bytes
         m->x_recv_parity = 8 * m->x_recv_rank;
         m->x_logits = up(2 * m->x_recv_parity);
-        m->x_flags_ar = up(m->x_logits + (int64_t)s.vocab * 2);
-        m->x_flags_lg = m->x_flags_ar + 64;
-        m->x_epoch_ar = m->x_flags_ar + 128;
-        m->x_epoch_lg = m->x_flags_ar + 160;
-        A(m->xchg, m->x_flags_ar + 256);
+        A(m->xchg, up(m->x_logits + (int64_t)s.vocab * 4));
         if (rc == IFB_OK && cudaMemset(m->xchg.p, 0, m->xchg.bytes) != cudaSuccess) { set_last_error("cudaMemset failed"); rc = IFB_ERR_CUDA; }
     }
     m->weight_bytes = wsum;
@@ -479,7 +475,6 @@ extern "C" int32_t ifb_model_tensor_ptr(ifb_model_t *m, const char *name, void *
     if (n == "tok_embeddings") b = &m->tok_emb;
     else if (n == "output_norm") b = &m->out_norm;
     else if (n == "output") b = &m->lm_head;
-    else if (n == "logits" && m->spec.tp_size > 1) { *ptr = (uint8_t *)m->xchg.p + m->x_logits; *bytes = (int64_t)m->spec.vocab * 2; return IFB_OK; }
     else if (n == "logits") b = &m->logits;
     else if (n == "x") b = &m->x0;
     else if (n == "x1") b = &m->x1;
@@ -514,9 +509,13 @@ __global__ void set_scalars_kernel(int32_t *sc, int pos, int token, const int32_
     sc[1] = token_dev != nullptr ? *token_dev : token;
 }
 // next token + advance the position so the graph can be replayed back-to-back
-__global__ void advance_kernel(int32_t *sc) {
-    sc[0] = sc[0] + 1;
-    sc[1] = sc[2];
+// sc[3]: step sequence number, the flag base of the tensor-parallel exchange (every rank runs every step)
+__global__ void advance_kernel(int32_t *sc, int advance) {
+    if (advance) {
+        sc[0] = sc[0] + 1;
+        sc[1] = sc[2];
+    }
+    sc[3] = sc[3] + 1;
 }
 
 enum { PART_GEMV = 1, PART_ATTN = 2, PART_MISC = 4, PART_ALL = 7 };
@@ -541,11 +540,14 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
     TpExchange tpx;   // common fields
     tpx.size = tp; tpx.rank = s.tp_rank;
     if (tp > 1) for (int p = 0; p < tp; p++) tpx.peer[p] = m->peer_xchg[p];
-    auto tp_push_ar = [&]() { TpExchange t = tpx; t.push = 1; t.dst_off = m->x_recv; t.dst_parity_stride = m->x_recv_parity;
-                              t.dst_index0 = (int64_t)s.tp_rank * d; t.flags_off = m->x_flags_ar; t.epoch_off = m->x_epoch_ar; return t; };
-    auto tp_gather_ar = [&](const void *resid, void *xout) { TpExchange t = tpx; t.gather = 1; t.src_off = m->x_recv;
-                              t.src_parity_stride = m->x_recv_parity; t.src_rank_stride = m->x_recv_rank; t.gflags_off = m->x_flags_ar;
-                              t.gepoch_off = m->x_epoch_ar; t.resid = resid; t.xout = xout; return t; };
+    tpx.seq = sc + 3;
+    // exchange index: wo of layer l -> 2l+1, w2 of layer l -> 2l+2; buffers alternate with the index parity
+    // (a rank can run at most one exchange ahead of its slowest peer, so two buffers are enough)
+    auto tp_push_ar = [&](int idx) { TpExchange t = tpx; t.push = 1; t.push_idx = (uint32_t)idx;
+                              t.dst_off = m->x_recv + (idx & 1) * m->x_recv_parity + (int64_t)s.tp_rank * m->x_recv_rank; return t; };
+    auto tp_gather_ar = [&](int idx, const void *resid, void *xout) { TpExchange t = tpx; t.gather = 1; t.gather_idx = (uint32_t)idx;
+                              t.src_off = m->x_recv + (idx & 1) * m->x_recv_parity; t.src_rank_stride = m->x_recv_rank;
+                              t.resid = resid; t.xout = xout; return t; };
     TpExchange t_qkv, t_wo, t_glu, t_w2, t_head;
     int li = 0;
     for (auto &L : m->layers) {
@@ -556,7 +558,7 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         g.rows[0] = m->q_dim_l; g.rows[1] = m->kv_dim_l; g.rows[2] = m->kv_dim_l;
         g.cx = d; g.x = m->x0.p; g.norm_w = L.attn_norm.p; g.norm_eps = s.norm_eps;
         g.y = qkv; g.quantize_x = quant_x; g.pdl = pdl;
-        if (tp > 1 && li > 0) { t_qkv = tp_gather_ar(m->x1.p, m->x0.p); g.tp = &t_qkv; }   // x0 = x1 + sum(w2 partials) of the previous layer
+        if (tp > 1 && li > 0) { t_qkv = tp_gather_ar(2 * li, m->x1.p, m->x0.p); g.tp = &t_qkv; }   // x0 = x1 + sum(w2 partials) of the previous layer
         g.trace = TR(n); g.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(g, st)); n++; }
         // --- RoPE(q,k) + append K,V
@@ -578,7 +580,7 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         GemvLaunch o;
         o.w_dtype = wdt; o.nseg = 1; o.w[0] = L.wo.p; o.rows[0] = d; o.cx = m->q_dim_l;
         o.x = m->attn_out.p; o.residual = m->x0.p; o.y = m->x1.p; o.quantize_x = quant_x; o.pdl = pdl;
-        if (tp > 1) { o.residual = nullptr; t_wo = tp_push_ar(); o.tp = &t_wo; }             // row-parallel: partial sums go to the peers
+        if (tp > 1) { o.residual = nullptr; t_wo = tp_push_ar(2 * li + 1); o.tp = &t_wo; }             // row-parallel: partial sums go to the peers
         o.trace = TR(n); o.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(o, st)); n++; }
         // --- FFN: norm + quantize + (w1, w3) + SiLU*mul
@@ -586,14 +588,14 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         f.w_dtype = wdt; f.nseg = 1; f.w[0] = L.w1.p; f.w_gate = L.w3.p; f.rows[0] = m->ffn_l; f.cx = d;
         f.x = m->x1.p; f.norm_w = L.ffn_norm.p; f.norm_eps = s.norm_eps; f.y = m->hbuf.p;
         f.quantize_x = quant_x; f.pdl = pdl;
-        if (tp > 1) { t_glu = tp_gather_ar(m->x0.p, m->x1.p); f.tp = &t_glu; }               // x1 = x0 + sum(wo partials)
+        if (tp > 1) { t_glu = tp_gather_ar(2 * li + 1, m->x0.p, m->x1.p); f.tp = &t_glu; }               // x1 = x0 + sum(wo partials)
         f.trace = TR(n); f.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(f, st)); n++; }
         // --- w2 + residual
         GemvLaunch w2;
         w2.w_dtype = wdt; w2.nseg = 1; w2.w[0] = L.w2.p; w2.rows[0] = d; w2.cx = m->ffn_l;
         w2.x = m->hbuf.p; w2.residual = m->x1.p; w2.y = m->x0.p; w2.quantize_x = quant_x; w2.pdl = pdl;
-        if (tp > 1) { w2.residual = nullptr; t_w2 = tp_push_ar(); w2.tp = &t_w2; }
+        if (tp > 1) { w2.residual = nullptr; t_w2 = tp_push_ar(2 * li + 2); w2.tp = &t_w2; }
         li++;
         w2.trace = TR(n); w2.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(w2, st)); n++; }
@@ -606,22 +608,24 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
     h.trace = TR(n); h.counter = CT(n);
     if (tp > 1) {
         // input: x0 = x1 + sum(w2 partials of the last layer); output: this rank's logits slice to every rank
-        t_head = tp_gather_ar(m->x1.p, m->x0.p);
-        t_head.push = 1; t_head.dst_off = m->x_logits; t_head.dst_parity_stride = 0;
-        t_head.dst_index0 = (int64_t)s.tp_rank * m->vocab_l; t_head.flags_off = m->x_flags_lg; t_head.epoch_off = m->x_epoch_lg;
+        t_head = tp_gather_ar(2 * s.layers, m->x1.p, m->x0.p);
+        t_head.push = 1; t_head.push_idx = 255;
+        t_head.dst_off = m->x_logits + (int64_t)s.tp_rank * m->vocab_l * 4;
         h.tp = &t_head;
     }
     if (parts & PART_GEMV) { TRY(gemv_launch(h, st)); n++; }
     if (parts & PART_MISC) {
         if (tp > 1) {
-            uint8_t *loc = (uint8_t *)m->xchg.p;
-            TRY(argmax_tp(sc + 2, loc + m->x_logits, s.vocab, (const uint32_t *)(loc + m->x_flags_lg),
-                          (const uint32_t *)(loc + m->x_epoch_lg), tp, st));
+            TRY(argmax_tp(sc + 2, m->logits.p, (const uint8_t *)m->xchg.p + m->x_logits, s.vocab, sc + 3, 255, st));
         } else {
             TRY(argmax(sc + 2, m->logits.p, s.vocab, st));
         }
         n++;
-        advance_kernel<<<1, 1, 0, st>>>(sc); n++;
+        advance_kernel<<<1, 1, 0, st>>>(sc, 1); n++;
+        IFB_LAUNCH_CHECK();
+    } else if (tp > 1) {
+        // a partial issue (measurement aid) is still one exchange round for the peers: new flags next time
+        advance_kernel<<<1, 1, 0, st>>>(sc, 0);
         IFB_LAUNCH_CHECK();
     }
     if (launches) *launches = n;
@@ -641,7 +645,8 @@ extern "C" int32_t ifb_model_decode(ifb_model_t *m, int32_t token_id, const int3
     if (!m->use_graph) return issue_step(m, st, &m->launches_per_step);
     if (!m->graph_ready) {
         // warm every kernel once outside capture (cudaFuncSetAttribute etc. are not capturable)
-        int32_t saved[4];
+        int32_t saved[3];   // pos, token, next token -- NOT the step sequence number (sc[3]): the warm-up step was a
+                            // real exchange round for the peers
         IFB_CUDA(cudaStreamSynchronize(st));
         IFB_CUDA(cudaMemcpy(saved, m->scalars.p, sizeof(saved), cudaMemcpyDeviceToHost));
         TRY(issue_step(m, st, &m->launches_per_step));
@@ -680,10 +685,7 @@ extern "C" int32_t ifb_model_issue_parts(ifb_model_t *m, int32_t parts, ifb_stre
     return rc != IFB_OK ? rc : n;
 }
 
-extern "C" const void *ifb_model_logits(const ifb_model_t *m) {
-    if (!m) return nullptr;
-    return m->spec.tp_size > 1 ? (const void *)((const uint8_t *)m->xchg.p + m->x_logits) : m->logits.p;
-}
+extern "C" const void *ifb_model_logits(const ifb_model_t *m) { return m ? m->logits.p : nullptr; }
 extern "C" const int32_t *ifb_model_next_token(const ifb_model_t *m) { return m ? (const int32_t *)m->scalars.p + 2 : nullptr; }
 extern "C" int32_t ifb_model_kernel_launches_per_step(const ifb_model_t *m) { return m ? m->launches_per_step : 0; }
 

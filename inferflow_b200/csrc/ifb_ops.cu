@@ -116,21 +116,29 @@ int add(void *c, const void *a, const void *b, int64_t n, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------- argmax (first max wins)
-__global__ void __launch_bounds__(1024) argmax_kernel(int32_t *out, const __half *x, int64_t n,
-                                                      const uint32_t *flags, const uint32_t *epoch, int n_peers) {
+// ll != nullptr: the logits arrive as flag-in-data words {half2, flag} from the vocabulary-sharded lm_head of every
+// rank (ifb_gemv.cu, tensor-parallel push); wait for each word, store the compact fp16 logits, take the argmax.
+__global__ void __launch_bounds__(1024) argmax_kernel(int32_t *out, const __half *x, int64_t n, __half *compact,
+                                                      const uint2 *ll, const int32_t *seq, uint32_t idx) {
     __shared__ float sv[32];
     __shared__ int si[32];
-    if (flags != nullptr) {   // vocabulary-sharded lm_head: wait until every rank's slice has landed
-        const uint32_t e = *reinterpret_cast<const volatile uint32_t *>(epoch);
-        if ((int)threadIdx.x < n_peers)
-            while ((int32_t)(ld_acquire_sys_u32(flags + threadIdx.x) - e) < 0) {}
-        __syncthreads();
-    }
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    for (int64_t i = threadIdx.x; i < n; i += 1024) {
-        float v = __half2float(x[i]);
-        if (v > best || (v == best && (int)i < bi)) { best = v; bi = (int)i; }
+    if (ll != nullptr) {
+        const uint32_t flag = ((uint32_t)*reinterpret_cast<const volatile int32_t *>(seq) << 8) | idx;
+        for (int64_t w = threadIdx.x; w < n / 2; w += 1024) {
+            uint2 v = ld_relaxed_sys_v2(ll + w);
+            while (v.y != flag) v = ld_relaxed_sys_v2(ll + w);
+            reinterpret_cast<uint32_t *>(compact)[w] = v.x;
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&v.x));
+            if (f.x > best) { best = f.x; bi = (int)(2 * w); }       // ascending index per thread: first max wins
+            if (f.y > best) { best = f.y; bi = (int)(2 * w + 1); }
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < n; i += 1024) {
+            float v = __half2float(x[i]);
+            if (v > best || (v == best && (int)i < bi)) { best = v; bi = (int)i; }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -154,14 +162,14 @@ __global__ void __launch_bounds__(1024) argmax_kernel(int32_t *out, const __half
 }
 int argmax(int32_t *out, const void *logits, int64_t n, cudaStream_t st) {
     IFB_CHECK_ARG(n > 0, "argmax: empty input");
-    argmax_kernel<<<1, 1024, 0, st>>>(out, (const __half *)logits, n, nullptr, nullptr, 0);
+    argmax_kernel<<<1, 1024, 0, st>>>(out, (const __half *)logits, n, nullptr, nullptr, nullptr, 0);
     IFB_LAUNCH_CHECK();
     return IFB_OK;
 }
-int argmax_tp(int32_t *out, const void *logits, int64_t n, const uint32_t *flags, const uint32_t *epoch,
-              int n_peers, cudaStream_t st) {
-    IFB_CHECK_ARG(n > 0 && n_peers >= 1 && n_peers <= 8, "argmax_tp: bad arguments");
-    argmax_kernel<<<1, 1024, 0, st>>>(out, (const __half *)logits, n, flags, epoch, n_peers);
+int argmax_tp(int32_t *out, void *logits_f16, const void *ll_words, int64_t n, const int32_t *seq, uint32_t idx,
+              cudaStream_t st) {
+    IFB_CHECK_ARG(n > 0 && n % 2 == 0 && ll_words != nullptr && seq != nullptr, "argmax_tp: bad arguments");
+    argmax_kernel<<<1, 1024, 0, st>>>(out, nullptr, n, (__half *)logits_f16, (const uint2 *)ll_words, seq, idx);
     IFB_LAUNCH_CHECK();
     return IFB_OK;
 }
