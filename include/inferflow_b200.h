@@ -148,6 +148,17 @@ int32_t ifb_attn_decode(int32_t kv_dtype, void *out_f16, const void *q_f16, cons
                         int32_t max_ctx, int32_t ctx_len, float kq_scale, void *workspace,
                         ifb_stream_t stream);
 
+/* The same with the append fused in (what the layer runtime launches per layer and token): RoPE on q (kept in
+ * shared memory, q_f16 is NOT modified) and on the new K row (PositionEmbedding, tensor_opr.cu:693-760), store of
+ * the new K/V row at position ctx_len-1 (SetKRows/SetVRows, kv_cache.cc:104-183), then the attention above over
+ * positions 0..ctx_len-1. k_new/v_new fp16 [kv_heads][head_dim]. rope_order < 0: no rotation. Results are
+ * bit-identical to ifb_rope + ifb_kv_append + ifb_attn_decode. */
+int32_t ifb_attn_decode_append(int32_t kv_dtype, void *out_f16, const void *q_f16, const void *k_new_f16,
+                               const void *v_new_f16, void *kcache, void *vcache, int32_t heads,
+                               int32_t kv_heads, int32_t head_dim, int32_t max_ctx, int32_t ctx_len,
+                               float kq_scale, int32_t rope_order, int32_t rope_dims, float rope_theta,
+                               void *workspace, ifb_stream_t stream);
+
 /* ------------------------------------------------------------------ MoE router
  * HostTensorOpr::BuildRowsForMoE (src/tensor/host_tensor_opr.cc:190-244) on device:
  * scores fp16 [rows][experts] (softmax over all experts already applied, as in

@@ -202,6 +202,10 @@ struct AttnArgs {
     unsigned int *counters;  // [kv_heads]
     const int32_t *pos_dev;
     unsigned long long *trace;
+    // fused append
+    const __half *k_new, *v_new;
+    int fuse, rope, rope_order, rope_dims;
+    float rope_theta;
 };
 
 int64_t attn_workspace_bytes(int heads, int head_dim) {
@@ -237,6 +241,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
     __shared__ __align__(16) float s_q[G][HD / 16][20];   // 16 dims + 4 pad: conflict-free LDS.128
     __shared__ float s_ml[NW][G][2];
     __shared__ unsigned int s_last;
+    __shared__ float s_cos[HD / 2], s_sin[HD / 2];          // fused RoPE table of this position
+    __shared__ float s_new[2][HD];                          // the new K (after RoPE) and V rows, fp16-rounded
+    __shared__ __align__(16) uint8_t s_newrow[2][HD * 2];   // ... as stored in the cache (codes or halves)
+    __shared__ __half s_newsc[2][NB];                       // ... and their block scales (Q8)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kvh = blockIdx.y, split = blockIdx.x;
@@ -282,19 +290,108 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
     bool issued = false;
     // prefetch paced to one tile in flight per CTA (warp w goes after warp w-1's tile has landed):
     // a deep backlog on the SM's memory port would only delay the running kernels' small loads
-    if (lane == 0 && c < c1 && c != new_chunk) {
+    // (fused append: the tile with the new row can be fetched early too -- its stale row is patched in shared
+    //  memory from s_newrow once the tile has landed)
+    if (lane == 0 && c < c1 && (c != new_chunk || a.fuse)) {
         issue(c);
         issued = true;
+    }
+    const int rd = a.rope_dims > 0 ? a.rope_dims : HD;
+    const int pairs = rd / 2;
+    if (a.fuse && a.rope) {
+        // angle_i = pos * theta_scale^i, theta_scale = theta^(-2/dims) (unary_tensor_opr.h:666-679,706-719);
+        // the position is known before the QKV GEMV has finished
+        const float theta_scale = powf(a.rope_theta, -2.0f / (float)rd);
+        for (int i = tid; i < pairs; i += ATT_THREADS) {
+            float ang = (float)(ctx - 1);
+            if (i > 0) ang *= powf(theta_scale, (float)i);
+            s_cos[i] = cosf(ang);
+            s_sin[i] = sinf(ang);
+        }
     }
 
     pdl_wait();  // q and the new K/V row come from the previous kernels
     if (tid == 0) trace_mark(a.trace, 1);
     if (lane == 0 && c < c1 && !issued) issue(c);
+    if (a.fuse && a.rope) __syncthreads();   // rotation table complete
 
     // stage q (scaled) for the G heads of this group
-    for (int i = tid; i < G * HD; i += ATT_THREADS) {
-        int g = i / HD, d = i % HD;
-        s_q[g][d / 16][d % 16] = __half2float(a.q[(int64_t)(kvh * G + g) * HD + d]) * a.softmax_scale;
+    if (a.fuse && a.rope) {
+        // PositionEmbedding writes q back as half (tensor_opr.cu:693-760): rotate, round, then scale
+        for (int i = tid; i < G * HD; i += ATT_THREADS) {
+            const int g = i / HD, d = i % HD;
+            const __half *qh = a.q + (int64_t)(kvh * G + g) * HD;
+            float v = __half2float(qh[d]);
+            int pi = -1, other = 0;
+            bool first = false;
+            if (a.rope_order == 2) {
+                if (d < rd / 2) { pi = d; other = d + rd / 2; first = true; }
+                else if (d < rd) { pi = d - rd / 2; other = d - rd / 2; }
+            } else if (d < rd) {
+                pi = d >> 1; other = d ^ 1; first = (d & 1) == 0;
+            }
+            if (pi >= 0) {
+                const float o = __half2float(qh[other]), cs = s_cos[pi], sn = s_sin[pi];
+                v = first ? round_h(v * cs - o * sn) : round_h(o * sn + v * cs);
+            }
+            s_q[g][d / 16][d % 16] = v * a.softmax_scale;
+        }
+    } else {
+        for (int i = tid; i < G * HD; i += ATT_THREADS) {
+            int g = i / HD, d = i % HD;
+            s_q[g][d / 16][d % 16] = __half2float(a.q[(int64_t)(kvh * G + g) * HD + d]) * a.softmax_scale;
+        }
+    }
+    // the CTA whose range holds the new position builds the new K/V row: RoPE(k), quantize, store to the cache
+    // (SetKRows / SetVRows, kv_cache.cc:104-183) and keep it in shared memory for its own tile
+    const bool owns_new = a.fuse && new_chunk >= c0 && new_chunk < c1;
+    if (owns_new) {
+        const __half *kn = a.k_new + (int64_t)kvh * HD, *vn = a.v_new + (int64_t)kvh * HD;
+        for (int d = tid; d < HD; d += ATT_THREADS) {
+            float v = __half2float(kn[d]);
+            if (a.rope) {
+                int pi = -1, other = 0;
+                bool first = false;
+                if (a.rope_order == 2) {
+                    if (d < rd / 2) { pi = d; other = d + rd / 2; first = true; }
+                    else if (d < rd) { pi = d - rd / 2; other = d - rd / 2; }
+                } else if (d < rd) {
+                    pi = d >> 1; other = d ^ 1; first = (d & 1) == 0;
+                }
+                if (pi >= 0) {
+                    const float o = __half2float(kn[other]), cs = s_cos[pi], sn = s_sin[pi];
+                    v = first ? round_h(v * cs - o * sn) : round_h(o * sn + v * cs);
+                }
+            }
+            s_new[0][d] = v;
+            s_new[1][d] = __half2float(vn[d]);
+        }
+        __syncthreads();
+        const int pos = ctx - 1;
+        const int64_t base = head_rows + pos;
+        for (int b = warp; b < 2 * NB; b += NW) {
+            const int which = b / NB, blk = b % NB;
+            const float v = s_new[which][blk * 32 + lane];
+            uint8_t *cache = const_cast<uint8_t *>(which == 0 ? a.kcache : a.vcache);
+            if (Q8) {
+                // Tensor_QuantizeQ8_B32T2_Alg2_Kernel (tensor_quant.h:45-82)
+                const float m = warp_max(fabsf(v));
+                const float scale = __fdiv_rn(m, 127.0f);
+                int q = scale <= 0.000001f ? 0 : (int)roundf(__fdiv_rn(v, scale));
+                q = min(max(q, -128), 127);
+                s_newrow[which][blk * 32 + lane] = (uint8_t)(int8_t)q;
+                reinterpret_cast<int8_t *>(cache)[base * HD + blk * 32 + lane] = (int8_t)q;
+                if (lane == 0) {
+                    const __half hs = __float2half_rn(scale);
+                    s_newsc[which][blk] = hs;
+                    reinterpret_cast<__half *>(cache + (int64_t)a.kv_heads * a.max_ctx_pad * HD)[base * NB + blk] = hs;
+                }
+            } else {
+                const __half hv = __float2half_rn(v);
+                reinterpret_cast<__half *>(s_newrow[which])[blk * 32 + lane] = hv;
+                reinterpret_cast<__half *>(cache)[base * HD + blk * 32 + lane] = hv;
+            }
+        }
     }
     __syncthreads();
 
@@ -316,6 +413,21 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
         const uint8_t *tV = tK + KBYTES + SBYTES;
         const uint8_t *tVs = tV + KBYTES;
         const int pbase = c * ATT_CHUNK;
+        if (a.fuse && c == new_chunk) {
+            // the copy raced with (or preceded) the store of the new row: put the row in place here
+            const int r = (ctx - 1) - pbase;
+            constexpr int ROWB = Q8 ? HD : HD * 2;
+            uint8_t *wK = const_cast<uint8_t *>(tK), *wV = const_cast<uint8_t *>(tV);
+            for (int i = lane; i < ROWB / 4; i += 32) {
+                reinterpret_cast<uint32_t *>(wK + r * ROWB)[i] = reinterpret_cast<const uint32_t *>(s_newrow[0])[i];
+                reinterpret_cast<uint32_t *>(wV + r * ROWB)[i] = reinterpret_cast<const uint32_t *>(s_newrow[1])[i];
+            }
+            if (Q8 && lane < NB) {
+                reinterpret_cast<__half *>(const_cast<uint8_t *>(tKs))[r * NB + lane] = s_newsc[0][lane];
+                reinterpret_cast<__half *>(const_cast<uint8_t *>(tVs))[r * NB + lane] = s_newsc[1][lane];
+            }
+            __syncwarp();
+        }
 
         // ---- scores: LPP lanes per position, 16 dims per lane
         {
@@ -368,6 +480,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
             }
         }
         __syncwarp();
+        if (tid == 0 && c == c0) trace_mark(a.trace, 5);
 
         // ---- online softmax for the G heads (whole warp per head)
 #pragma unroll
@@ -386,6 +499,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
             acc[g][0] *= corr; acc[g][1] *= corr; acc[g][2] *= corr; acc[g][3] *= corr;
         }
         __syncwarp();
+        if (tid == 0 && c == c0) trace_mark(a.trace, 6);
 
         // ---- P.V: lane owns 4 dims (one code word), loop over the tile's positions
         if (lane < HD / 4) {
@@ -462,6 +576,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
     }
     __threadfence();
     __syncthreads();
+    if (tid == 0) trace_mark(a.trace, 7);
     if (tid == 0) {
         unsigned int prev = atomicAdd(&a.counters[kvh], 1u);
         s_last = (prev == (unsigned)a.nsplit - 1) ? 1u : 0u;
@@ -560,6 +675,12 @@ int attn_decode(const AttnDecode &p, cudaStream_t st) {
     a.ws = reinterpret_cast<float *>((uint8_t *)p.workspace + 4096);
     a.pos_dev = p.pos_dev;
     a.trace = (unsigned long long *)p.trace;
+    a.k_new = (const __half *)p.k_new; a.v_new = (const __half *)p.v_new;
+    a.fuse = p.k_new != nullptr ? 1 : 0;
+    IFB_CHECK_ARG((p.k_new == nullptr) == (p.v_new == nullptr), "attention: fused append needs both the new K and V rows");
+    a.rope = p.rope; a.rope_order = p.rope_order; a.rope_dims = p.rope_dims; a.rope_theta = p.rope_theta;
+    IFB_CHECK_ARG(!a.fuse || !a.rope || ((p.rope_order == 0 || p.rope_order == 2) && p.rope_dims % 2 == 0 && p.rope_dims <= p.head_dim),
+                  "attention: rope order %d / dims %d", p.rope_order, p.rope_dims);
     // split count: fill ~2 CTAs per SM; with a device-side position (graph replay) size for max_ctx
     const int ctx_for_split = p.pos_dev != nullptr ? p.max_ctx : p.ctx_len;
     const int nchunks = (ctx_for_split + ATT_CHUNK - 1) / ATT_CHUNK;

@@ -158,6 +158,20 @@ int32_t ifb_attn_decode(int32_t kv_dtype, void *out, const void *q, const void *
     return attn_decode(a, (cudaStream_t)st);
 }
 
+int32_t ifb_attn_decode_append(int32_t kv_dtype, void *out, const void *q, const void *k_new, const void *v_new,
+                               void *kc, void *vc, int32_t heads, int32_t kv_heads, int32_t hd, int32_t max_ctx,
+                               int32_t ctx_len, float kq_scale, int32_t rope_order, int32_t rope_dims,
+                               float rope_theta, void *ws, ifb_stream_t st) {
+    IFB_CHECK_ARG(out && q && k_new && v_new && kc && vc && ws, "attention: null tensor");
+    AttnDecode a;
+    a.kv_dtype = kv_dtype; a.heads = heads; a.kv_heads = kv_heads; a.head_dim = hd; a.max_ctx = max_ctx;
+    a.ctx_len = ctx_len; a.kq_scale = kq_scale; a.out = out; a.q = q; a.kcache = kc; a.vcache = vc; a.workspace = ws;
+    a.k_new = k_new; a.v_new = v_new;
+    a.rope = rope_order >= 0 ? 1 : 0; a.rope_order = rope_order >= 0 ? rope_order : 0; a.rope_dims = rope_dims;
+    a.rope_theta = rope_theta;
+    return attn_decode(a, (cudaStream_t)st);
+}
+
 int32_t ifb_moe_topk(int32_t *ids, float *w, int32_t *cnt, const void *scores, int32_t rows, int32_t experts,
                      int32_t top_k, int32_t norm, ifb_stream_t st) {
     IFB_CHECK_ARG(ids && w && cnt && scores, "BuildRowsForMoE: null tensor");

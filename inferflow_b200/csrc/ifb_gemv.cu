@@ -48,6 +48,8 @@ struct GemvArgs {
     int nslots, slot_stride;
     int units;
     int l2_prefetch; // >0: software prefetch distance in UNITS: unit u+dist is requested into the L2 when unit u is copied
+    int xg_off;      // byte offset (from the staged-x area) of the fp16 vector a tensor-parallel gather builds
+    int pdl_late;
     int debug_nocompute;  // measurement aid (IFB_GEMV_NOCOMPUTE=1): consumers release slots without doing the math
     const __half *x;
     const uint8_t *xq;  // pre-quantized activation (Q8_B32T2 blocks) or null
@@ -162,7 +164,7 @@ __device__ __forceinline__ uint4 tp_gather8(const GemvArgs &a, int g, uint32_t f
 // elements (ONE 128-bit load), four neighbouring lanes = one block; all of a thread's loads are
 // issued before any is used, so the prologue costs one memory round trip, not one per block.
 template <bool XSPLIT, bool VEC4>
-__device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint8_t *xhi,
+__device__ __forceinline__ void stage_x_q8(const GemvArgs &a, const void *xsrc, uint8_t *xlo, uint8_t *xhi,
                                            float2 *xs, float *red, int tid) {
     const int warp = tid >> 5, lane = tid & 31;
     const int nxb = a.cx >> 5;
@@ -181,15 +183,13 @@ __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint
         return;
     }
     const bool norm = a.norm_w != nullptr;
-    const uint4 *x4 = reinterpret_cast<const uint4 *>(a.x);
+    const uint4 *x4 = reinterpret_cast<const uint4 *>(xsrc);
     const uint4 *w4 = reinterpret_cast<const uint4 *>(a.norm_w);
     const int ng = a.cx >> 3;                 // groups of 8 elements; ng % 4 == 0
     constexpr int KPT = 3;                    // groups per thread per round
-    const bool gather = a.tp.gather != 0;
-    const bool one_round = ng <= GEMV_CTHREADS * KPT || gather;   // cx <= 12288: x is read from memory exactly once
-    const uint32_t gflag = gather ? tp_flag(a.tp.seq, a.tp.gather_idx) : 0u;
+    const bool one_round = ng <= GEMV_CTHREADS * KPT;   // cx <= 12288: x is read from memory exactly once
     float rs = 1.f;
-    if (norm && !one_round) rs = rms_scale(a.x, a.cx, a.eps, red, tid);
+    if (norm && !one_round) rs = rms_scale(reinterpret_cast<const __half *>(xsrc), a.cx, a.eps, red, tid);
     for (int g0 = 0; g0 < ng; g0 += GEMV_CTHREADS * KPT) {
         uint4 xv[KPT], wv[KPT];
 #pragma unroll
@@ -198,7 +198,7 @@ __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint
             xv[k] = make_uint4(0, 0, 0, 0);
             wv[k] = make_uint4(0, 0, 0, 0);
             if (g < ng) {
-                xv[k] = gather ? tp_gather8(a, g, gflag) : x4[g];
+                xv[k] = x4[g];
                 if (norm) wv[k] = w4[g];
             }
         }
@@ -283,51 +283,17 @@ __device__ __forceinline__ void stage_x_q8(const GemvArgs &a, uint8_t *xlo, uint
 }
 
 // Stage x as fp16 (optionally RMS-normalised) for the fp16-activation paths.
-__device__ __forceinline__ void stage_x_f16(const GemvArgs &a, __half *xh, float *red, int tid) {
+__device__ __forceinline__ void stage_x_f16(const GemvArgs &a, const void *xsrc, __half *xh, float *red, int tid) {
     const bool norm = a.norm_w != nullptr;
     float rs = 1.f;
-    if (norm && !a.tp.gather) rs = rms_scale(a.x, a.cx, a.eps, red, tid);
-    const uint4 *x4 = reinterpret_cast<const uint4 *>(a.x);
+    if (norm) rs = rms_scale(reinterpret_cast<const __half *>(xsrc), a.cx, a.eps, red, tid);
+    const uint4 *x4 = reinterpret_cast<const uint4 *>(xsrc);
     const uint4 *w4 = reinterpret_cast<const uint4 *>(a.norm_w);
     uint4 *o4 = reinterpret_cast<uint4 *>(xh);
     const int ng = a.cx >> 3;
-    const uint32_t gflag = a.tp.gather ? tp_flag(a.tp.seq, a.tp.gather_idx) : 0u;
-    if (a.tp.gather) {
-        // gathered vector: stage it raw first, then normalise from shared memory (two passes over smem)
-        float ss = 0.f;
-        for (int g = tid; g < ng; g += GEMV_CTHREADS) {
-            const uint4 xv = tp_gather8(a, g, gflag);
-            o4[g] = xv;
-            const __half2 *h = reinterpret_cast<const __half2 *>(&xv);
-#pragma unroll
-            for (int i = 0; i < 4; i++) { const float2 f = __half22float2(h[i]); ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss); }
-        }
-        if (norm) {
-            ss = warp_sum(ss);
-            if ((tid & 31) == 0) red[tid >> 5] = ss;
-            named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
-            float t = 0.f;
-#pragma unroll
-            for (int i = 0; i < GEMV_CWARPS; i++) t += red[i];
-            rs = 1.0f / sqrtf(t / (float)a.cx + a.eps);
-            for (int g = tid; g < ng; g += GEMV_CTHREADS) {
-                uint4 xv = o4[g];
-                const uint4 wv = w4[g];
-                __half2 *h = reinterpret_cast<__half2 *>(&xv);
-                const __half2 *hw = reinterpret_cast<const __half2 *>(&wv);
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    float2 f = __half22float2(h[i]);
-                    const float2 fw = __half22float2(hw[i]);
-                    h[i] = __floats2half2_rn(f.x * rs * (a.norm_base + fw.x), f.y * rs * (a.norm_base + fw.y));
-                }
-                o4[g] = xv;
-            }
-        }
-        return;
-    }
+#pragma unroll 4
     for (int g = tid; g < ng; g += GEMV_CTHREADS) {
-        uint4 xv = a.tp.gather ? tp_gather8(a, g, gflag) : x4[g];
+        uint4 xv = x4[g];
         if (norm) {
             const uint4 wv = w4[g];
             __half2 *h = reinterpret_cast<__half2 *>(&xv);
@@ -490,7 +456,7 @@ __device__ __forceinline__ float row_dot_f16(const uint8_t *row, int cx, const _
 // ---------------------------------------------------------------------------------------
 enum { MODE_Q8 = 0, MODE_HX = 1, MODE_F16 = 2 };
 
-template <class Fmt, int MODE, bool GLU, bool VEC4>
+template <class Fmt, int MODE, bool GLU, bool VEC4, bool TP>
 __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const GemvArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t full_bar[GEMV_MAX_SLOTS], empty_bar[GEMV_MAX_SLOTS];
@@ -519,7 +485,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
     __syncthreads();
     // PDL: let the next kernel's CTAs become resident as early as possible -- their producer
     // warps only touch weights, everything else sits behind their own griddepcontrol.wait.
-    pdl_launch_dependents();
+    if (!a.pdl_late) pdl_launch_dependents();
     if (tid == 0) trace_mark(a.trace, 0);
 
     const int nmat = GLU ? 2 : 1;
@@ -581,12 +547,26 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
     // ===== consumers =====
     pdl_wait();  // x / residual come from the previous kernel
     if (tid == 0) trace_mark(a.trace, 1);
-    const uint32_t pflag = a.tp.push ? tp_flag(a.tp.seq, a.tp.push_idx) : 0u;
+    uint32_t pflag = 0u;
+    const void *xsrc = a.x;
+    if constexpr (TP) {
+        if (a.tp.push) pflag = tp_flag(a.tp.seq, a.tp.push_idx);
+        if (a.tp.gather) {
+            // tensor-parallel input: x = residual + sum of the ranks' partial vectors, built once into shared
+            // memory (fp16); the staging below then reads it from there exactly as it reads a.x otherwise
+            uint4 *xg = reinterpret_cast<uint4 *>(xbase + a.xg_off);
+            const uint32_t gflag = tp_flag(a.tp.seq, a.tp.gather_idx);
+            for (int g = tid; g < (a.cx >> 3); g += GEMV_CTHREADS) xg[g] = tp_gather8(a, g, gflag);
+            named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+            xsrc = xg;
+        }
+    }
     if (MODE == MODE_Q8)
-        stage_x_q8<Fmt::XSPLIT, VEC4>(a, xlo, xhi, xs, red, tid);
+        stage_x_q8<Fmt::XSPLIT, VEC4>(a, xsrc, xlo, xhi, xs, red, tid);
     else
-        stage_x_f16(a, xh, red, tid);
+        stage_x_f16(a, xsrc, xh, red, tid);
     named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+    if (a.pdl_late) pdl_launch_dependents();   // experiment (IFB_PDL_LATE=1): dependents start after our staging
     if (tid == 0) trace_mark(a.trace, 2);
 
     const int groups = a.groups;
@@ -643,7 +623,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
                     v = round_h(g * round_h(acc[1]));
                 }
                 if (a.residual != nullptr) v = round_h(v + h2f(res_bits));
-                if (a.tp.push) {
+                if (TP && a.tp.push) {
                     push_y[pos][r] = __float2half_rn(v);   // sent below, R outputs at a time
                 } else {
                     a.y[o] = __float2half_rn(v);
@@ -651,7 +631,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const Gemv
             }
         }
         __syncwarp();
-        if (a.tp.push && !a.debug_nocompute) {
+        if (TP && a.tp.push && !a.debug_nocompute) {
             // Tensor-parallel partial sums go straight into every rank's exchange region over NVLink. The
             // group's last warp to finish its rows sends the unit's R outputs as 8-byte stores (a 2-byte
             // store per row would cost one NVLink packet each; the words carry their own validity flag, so there is
@@ -701,9 +681,9 @@ int sm_count() {
     return g_sm_count;
 }
 
-template <class Fmt, int MODE, bool GLU, bool VEC4>
-static int launch_variant(const GemvArgs &a, size_t smem, int grid, bool pdl, cudaStream_t st) {
-    auto kern = gemv_stream_kernel<Fmt, MODE, GLU, VEC4>;
+template <class Fmt, int MODE, bool GLU, bool VEC4, bool TP>
+static int launch_variant_tp(const GemvArgs &a, size_t smem, int grid, bool pdl, cudaStream_t st) {
+    auto kern = gemv_stream_kernel<Fmt, MODE, GLU, VEC4, TP>;
     static bool attr_done = false;  // per instantiation
     if (!attr_done) {
         IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -721,6 +701,14 @@ static int launch_variant(const GemvArgs &a, size_t smem, int grid, bool pdl, cu
     cfg.numAttrs = pdl ? 1 : 0;
     IFB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     return IFB_OK;
+}
+
+// the tensor-parallel code (peer stores in the epilogue, the gather pre-pass) lives in its own instantiations:
+// inlined into the single-GPU kernels it cost registers and made them spill
+template <class Fmt, int MODE, bool GLU, bool VEC4>
+static int launch_variant(const GemvArgs &a, size_t smem, int grid, bool pdl, cudaStream_t st) {
+    if (a.tp.push || a.tp.gather) return launch_variant_tp<Fmt, MODE, GLU, VEC4, true>(a, smem, grid, pdl, st);
+    return launch_variant_tp<Fmt, MODE, GLU, VEC4, false>(a, smem, grid, pdl, st);
 }
 
 template <bool GLU>
@@ -799,12 +787,14 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     a.counter = (int *)g.counter;
     if (g.tp != nullptr) a.tp = *g.tp;
     IFB_CHECK_ARG(!(a.tp.gather && g.xq != nullptr), "gemv: tensor-parallel gather needs an fp16 activation");
-    IFB_CHECK_ARG(!(a.tp.gather && g.cx > 12288), "gemv: tensor-parallel gather supports d_model <= 12288");
     IFB_CHECK_ARG(a.tp.size >= 1 && a.tp.size <= 8, "gemv: tensor-parallel size %d", a.tp.size);
     {
         static int nocompute = -1;
         if (nocompute < 0) { const char *e = getenv("IFB_GEMV_NOCOMPUTE"); nocompute = (e && atoi(e)) ? 1 : 0; }
         a.debug_nocompute = nocompute;
+        static int late = -1;
+        if (late < 0) { const char *e = getenv("IFB_PDL_LATE"); late = (e && atoi(e)) ? 1 : 0; }
+        a.pdl_late = late;
         static int nol2 = -1;
         if (nol2 < 0) { const char *e = getenv("IFB_NO_L2_PREFETCH"); nol2 = (e && atoi(e)) ? 1 : 0; }
         if (nol2) const_cast<GemvLaunch &>(g).l2_prefetch = 0;
@@ -861,7 +851,10 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     a.slot_stride = (int)((slot_bytes + 16 + 127) / 128 * 128);
     a.nxb_alloc = (int)(g.cx / 32);
     if (vec4) a.nxb_alloc = (a.nxb_alloc + 127) / 128 * 128;   // x_slot<true>() scatters inside passes of 128 blocks
-    const int64_t xbytes = (mode == MODE_Q8) ? (int64_t)a.nxb_alloc * 40 : g.cx * 2;
+    int64_t xbytes = (mode == MODE_Q8) ? (int64_t)a.nxb_alloc * 40 : g.cx * 2;
+    xbytes = (xbytes + 127) / 128 * 128;
+    a.xg_off = (int)xbytes;
+    if (a.tp.gather) xbytes += g.cx * 2;      // the gathered fp16 vector, consumed by the staging pass
     const int64_t xpad = (xbytes + 127) / 128 * 128;
     // default: at most ~half of the SM's shared memory, so two kernels of a PDL chain co-reside
     int64_t budget = (g.smem_budget > 0 ? g.smem_budget : 110 * 1024);

@@ -99,6 +99,12 @@ struct AttnDecode {
     const int32_t *pos_dev = nullptr;   // ctx_len = *pos_dev + 1 when set (graph replay)
     int pdl = 0;
     void *trace = nullptr;
+    // fused append (layer runtime): the kernel itself applies RoPE to q (in shared memory only) and to the new
+    // K row, quantizes and stores the new K/V row at position ctx_len-1, and attends over it -- replaces the
+    // separate kv_append launch. k_new/v_new: fp16 [kv_heads][head_dim] of the current token.
+    const void *k_new = nullptr, *v_new = nullptr;
+    int rope = 0, rope_order = 2, rope_dims = 0;
+    float rope_theta = 10000.0f;
 };
 int attn_decode(const AttnDecode &a, cudaStream_t st);
 

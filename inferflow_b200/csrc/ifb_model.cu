@@ -561,16 +561,10 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         if (tp > 1 && li > 0) { t_qkv = tp_gather_ar(2 * li, m->x1.p, m->x0.p); g.tp = &t_qkv; }   // x0 = x1 + sum(w2 partials) of the previous layer
         g.trace = TR(n); g.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(g, st)); n++; }
-        // --- RoPE(q,k) + append K,V
-        KvAppend ka;
-        ka.kv_dtype = s.kv_dtype; ka.kv_heads = m->kv_heads_l; ka.head_dim = m->hd; ka.max_ctx = s.max_ctx;
-        ka.pos0 = 0; ka.n_tokens = 1; ka.kcache = L.kcache.p; ka.vcache = L.vcache.p;
-        ka.k = qkv + m->q_dim_l; ka.v = qkv + m->q_dim_l + m->kv_dim_l;
-        ka.rope = 1; ka.rope_order = s.rope_order; ka.rope_dims = 0; ka.rope_theta = s.rope_theta;
-        ka.q = qkv; ka.q_heads = m->heads_l; ka.pos_dev = sc; ka.pdl = pdl;
-        if (parts & PART_ATTN) { TRY(kv_append(ka, st)); n++; }
-        // --- attention over the cache
+        // --- RoPE(q,k) + append K,V + attention over the cache: one kernel
         AttnDecode ad;
+        ad.k_new = qkv + m->q_dim_l; ad.v_new = qkv + m->q_dim_l + m->kv_dim_l;
+        ad.rope = 1; ad.rope_order = s.rope_order; ad.rope_dims = 0; ad.rope_theta = s.rope_theta;
         ad.kv_dtype = s.kv_dtype; ad.heads = m->heads_l; ad.kv_heads = m->kv_heads_l; ad.head_dim = m->hd;
         ad.max_ctx = s.max_ctx; ad.ctx_len = 0; ad.kq_scale = s.kq_scale; ad.out = m->attn_out.p; ad.q = qkv;
         ad.kcache = L.kcache.p; ad.vcache = L.vcache.p; ad.workspace = m->attn_ws.p; ad.pos_dev = sc; ad.pdl = pdl;

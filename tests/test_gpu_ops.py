@@ -411,3 +411,50 @@ def test_attn_decode(ib, kv_dt, case):
     err_ours = np.abs(got - want).max()
     err_ref = np.abs(ref_style - want).max()
     assert err_ours <= max(err_ref, 2 ** -10 * np.abs(want).max())
+
+
+FUSED = [(32, 32, 128, 1, 2), (32, 32, 128, 64, 2), (32, 32, 128, 65, 0), (32, 32, 128, 2048, 2), (8, 2, 128, 129, 2),
+         (12, 12, 64, 200, 0), (4, 4, 32, 90, 2), (8, 1, 128, 700, -1)]
+
+
+@pytest.mark.parametrize("kv_dt", [orc.F16, orc.Q8_B32T2], ids=["F16", "Q8"])
+@pytest.mark.parametrize("case", FUSED, ids=[f"h{h}g{g}d{d}c{c}o{o}" for h, g, d, c, o in FUSED])
+def test_attn_decode_append_equals_separate_ops(ib, kv_dt, case):
+    """the fused launch (RoPE + append + attention) is bit-identical to rope -> kv_append -> attn_decode:
+    same output, same cache bytes, q untouched"""
+    heads, kv_heads, hd, ctx, order = case
+    max_ctx = 2048
+    rng = np.random.default_rng(300 + ctx)
+    k = orc.f16(rng.normal(0, 1, (ctx - 1, kv_heads * hd))); v = orc.f16(rng.normal(0, 1, (ctx - 1, kv_heads * hd)))
+    q = rng.normal(0, 1, heads * hd).astype(np.float16)
+    kn = rng.normal(0, 1, kv_heads * hd).astype(np.float16); vn = rng.normal(0, 1, kv_heads * hd).astype(np.float16)
+    ws = torch.zeros(ib.lib.ifb_attn_workspace_bytes(heads, hd), dtype=torch.uint8, device="cuda")
+    nbytes = ib.lib.ifb_kv_cache_bytes(kv_dt, kv_heads, hd, max_ctx)
+    outs, caches = [], []
+    for fused in (False, True):
+        if ctx > 1:
+            kc, vc = _kv_setup(ib, kv_dt, kv_heads, hd, max_ctx, k, v)
+        else:
+            kc = torch.zeros(nbytes, dtype=torch.uint8, device="cuda"); vc = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        qd, knd, vnd = dev(q.copy()), dev(kn.copy()), dev(vn.copy())
+        out = torch.zeros(heads * hd, dtype=torch.float16, device="cuda")
+        if fused:
+            ib.check(ib.lib.ifb_attn_decode_append(kv_dt, ptr(out), ptr(qd), ptr(knd), ptr(vnd), ptr(kc), ptr(vc), heads,
+                                                   kv_heads, hd, max_ctx, ctx, 1.0, order, 0, 10000.0, ptr(ws), None), "fused")
+            assert np.array_equal(qd.cpu().numpy(), q), "the fused kernel must not write q back"
+        else:
+            if order >= 0:
+                ib.check(ib.lib.ifb_rope(ptr(qd), 1, heads, hd, 0, ctx - 1, 10000.0, order, None), "rope q")
+                ib.check(ib.lib.ifb_rope(ptr(knd), 1, kv_heads, hd, 0, ctx - 1, 10000.0, order, None), "rope k")
+            ib.check(ib.lib.ifb_kv_append(kv_dt, ptr(kc), ptr(vc), ptr(knd), ptr(vnd), kv_heads, hd, max_ctx, ctx - 1, 1, None), "append")
+            ib.check(ib.lib.ifb_attn_decode(kv_dt, ptr(out), ptr(qd), ptr(kc), ptr(vc), heads, kv_heads, hd, max_ctx, ctx,
+                                            1.0, ptr(ws), None), "attn")
+        outs.append(out.cpu().numpy())
+        rows = torch.zeros(ctx * kv_heads * hd, dtype=torch.float16, device="cuda")
+        both = []
+        for cache in (kc, vc):
+            ib.check(ib.lib.ifb_kv_get_rows(kv_dt, ptr(rows), ptr(cache), kv_heads, hd, max_ctx, 0, ctx, None), "get")
+            both.append(rows.cpu().numpy().copy())
+        caches.append(both)
+    assert np.array_equal(caches[0][0], caches[1][0]) and np.array_equal(caches[0][1], caches[1][1]), "cache rows differ"
+    assert np.array_equal(outs[0], outs[1]), f"fused output differs: max {np.abs(outs[0].astype(np.float32) - outs[1].astype(np.float32)).max()}"

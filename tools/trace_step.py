@@ -39,5 +39,8 @@ for k in range(1, min(n, 16)):
     def st(col, f):
         v = t[act, col]; v = v[v > 0]
         return (f(v) - t00) / 1000.0 if len(v) else float("nan")
+    if "--attn" in sys.argv and act.sum() < 148:
+        print(f"k{k:3d} attn: wait {st(1,np.median):7.2f} tile {st(3,np.median):7.2f} qk {st(5,np.median):7.2f} softmax {st(6,np.median):7.2f} pv_done[med {st(4,np.median):7.2f} max {st(4,np.max):7.2f}] partial_written[med {st(7,np.median):7.2f} max {st(7,np.max):7.2f}]")
+        continue
     print(f"k{k:3d} ctas {act.sum():3d} entry[min {st(0,np.min):8.2f} max {st(0,np.max):8.2f}] wait_done[min {st(1,np.min):8.2f} max {st(1,np.max):8.2f}] staged[max {st(2,np.max):8.2f}] "
           f"first_tile[min {st(3,np.min):8.2f} max {st(3,np.max):8.2f}] done[min {st(4,np.min):8.2f} max {st(4,np.max):8.2f}] staged[med {st(2,np.median):8.2f}] cta_done[med {st(5,np.median):8.2f} max {st(5,np.max):8.2f}] peers_seen[min {st(6,np.min):8.2f} med {st(6,np.median):8.2f} max {st(6,np.max):8.2f}] published[{st(7,np.max):8.2f}]")
