@@ -21,8 +21,9 @@
 
 namespace ifb {
 
-constexpr int ATT_CHUNK = 64;    // positions per staged tile
-constexpr int ATT_THREADS = 128;
+constexpr int ATT_CHUNK = 64;    // the cache's position padding (layout constant)
+constexpr int ATT_TILE = 32;     // positions per staged tile: one per lane in the score phase
+constexpr int ATT_THREADS = 256;
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -228,8 +229,8 @@ __device__ __forceinline__ uint32_t s8bias(uint32_t w) { return w ^ 0x80808080u;
 template <int HD, int G, bool Q8>
 __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs a) {
     constexpr int NB = HD / 32;                       // scale blocks per (pos, head)
-    constexpr int KBYTES = Q8 ? ATT_CHUNK * HD : ATT_CHUNK * HD * 2;
-    constexpr int SBYTES = Q8 ? ATT_CHUNK * NB * 2 : 0;
+    constexpr int KBYTES = Q8 ? ATT_TILE * HD : ATT_TILE * HD * 2;
+    constexpr int SBYTES = Q8 ? ATT_TILE * NB * 2 : 0;
     constexpr int TILE = 2 * (KBYTES + SBYTES);       // K codes, K scales, V codes, V scales
     constexpr int LPP = HD / 16;                      // lanes per position in the QK phase
     constexpr int PPW = 32 / LPP;                     // positions per warp iteration
@@ -237,8 +238,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
 
     extern __shared__ __align__(128) uint8_t smem[];  // [NW][TILE]
     __shared__ uint64_t full_bar[NW];
-    __shared__ float s_p[NW][G][ATT_CHUNK];           // scores / probabilities of the warp's tile
+    __shared__ float s_p[NW][G][ATT_TILE];           // scores / probabilities of the warp's tile
     __shared__ __align__(16) float s_q[G][HD / 16][20];   // 16 dims + 4 pad: conflict-free LDS.128
+    // Q8 cache: q as TWO int8 terms per 32-dim block, q ~= s1*qh + s2*ql (s2 <= s1/254: ~15 bits, finer than the
+    // fp16 q it is made from), so q.k over int8 K codes is two dp4a per 4 dims instead of 4 converts + 4 FMAs
+    __shared__ __align__(16) int8_t s_qh[G][HD], s_ql[G][HD];
+    __shared__ float s_qs[G][NB][2];
     __shared__ float s_ml[NW][G][2];
     __shared__ unsigned int s_last;
     __shared__ float s_cos[HD / 2], s_sin[HD / 2];          // fused RoPE table of this position
@@ -261,10 +266,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
     // ahead of us) is older than the previous token: those tiles are fetched BEFORE the grid
     // dependency resolves, i.e. while the QKV GEMV is still running.
     const int ctx = a.pos_dev != nullptr ? (*a.pos_dev + 1) : a.ctx_len;
-    const int nchunks_total = (ctx + ATT_CHUNK - 1) / ATT_CHUNK;
+    const int nchunks_total = (ctx + ATT_TILE - 1) / ATT_TILE;
     const int cps = (nchunks_total + a.nsplit - 1) / a.nsplit;   // chunks per CTA
     const int c0 = split * cps, c1 = min(c0 + cps, nchunks_total);
-    const int new_chunk = (ctx - 1) / ATT_CHUNK;                 // the tile holding the new row
+    const int new_chunk = (ctx - 1) / ATT_TILE;                 // the tile holding the new row
 
     const int64_t head_rows = (int64_t)kvh * a.max_ctx_pad;
     const uint8_t *kc = a.kcache + (Q8 ? head_rows * HD : head_rows * HD * 2);
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
     uint8_t *tile = smem + (size_t)warp * TILE;
 
     auto issue = [&](int c) {  // tile c of the sequence -> this warp's buffer
-        const int64_t p0 = (int64_t)c * ATT_CHUNK;
+        const int64_t p0 = (int64_t)c * ATT_TILE;
         mbar_arrive_expect_tx(&full_bar[warp], TILE);
         if (Q8) {
             bulk_g2s(tile, kc + p0 * HD, KBYTES, &full_bar[warp]);
@@ -394,6 +399,21 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
         }
     }
     __syncthreads();
+    if (Q8) {
+        for (int b = warp; b < G * NB; b += NW) {
+            const int g = b / NB, blk = b % NB, d = blk * 32 + lane;
+            const float v = s_q[g][d / 16][d % 16];
+            const float s1 = warp_max(fabsf(v)) * (1.0f / 127.0f);
+            const float qh = s1 > 0.f ? rintf(v / s1) : 0.f;
+            const float r = v - qh * s1;
+            const float s2 = warp_max(fabsf(r)) * (1.0f / 127.0f);
+            const float ql = s2 > 0.f ? rintf(r / s2) : 0.f;
+            s_qh[g][d] = (int8_t)(int)qh;
+            s_ql[g][d] = (int8_t)(int)ql;
+            if (lane == 0) { s_qs[g][blk][0] = s1; s_qs[g][blk][1] = s2; }
+        }
+        __syncthreads();
+    }
 
     float m_run[G], l_run[G], acc[G][4];
 #pragma unroll
@@ -412,7 +432,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
         const uint8_t *tKs = tK + KBYTES;
         const uint8_t *tV = tK + KBYTES + SBYTES;
         const uint8_t *tVs = tV + KBYTES;
-        const int pbase = c * ATT_CHUNK;
+        const int pbase = c * ATT_TILE;
         if (a.fuse && c == new_chunk) {
             // the copy raced with (or preceded) the store of the new row: put the row in place here
             const int r = (ctx - 1) - pbase;
@@ -429,32 +449,50 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
             __syncwarp();
         }
 
-        // ---- scores: LPP lanes per position, 16 dims per lane
-        {
+        // ---- scores
+        if (Q8) {
+            // lane = position. A row is HD code bytes; the 16-byte pieces are visited in a per-lane rotated order
+            // so that the 8 lanes of an LDS.128 phase hit 8 different bank groups (rows are 128 B or less apart).
+            constexpr int C = HD / 16;                 // 16-byte pieces per row
+            constexpr int RPL = (C >= 8) ? 1 : 8 / C;  // rows per 128 bytes
+            const int rot = lane / RPL;
+            float sc[G];
+#pragma unroll
+            for (int g = 0; g < G; g++) sc[g] = 0.f;
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                const int ci = (j + rot) & (C - 1);
+                const uint4 kw = *reinterpret_cast<const uint4 *>(tK + lane * HD + ci * 16);
+                const float ksc = __half2float(reinterpret_cast<const __half *>(tKs)[lane * NB + (ci >> 1)]);
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const uint4 qh = *reinterpret_cast<const uint4 *>(&s_qh[g][ci * 16]);
+                    const uint4 ql = *reinterpret_cast<const uint4 *>(&s_ql[g][ci * 16]);
+                    int dh = dp4a_ss(kw.x, qh.x, 0), dl = dp4a_ss(kw.x, ql.x, 0);
+                    dh = dp4a_ss(kw.y, qh.y, dh); dl = dp4a_ss(kw.y, ql.y, dl);
+                    dh = dp4a_ss(kw.z, qh.z, dh); dl = dp4a_ss(kw.z, ql.z, dl);
+                    dh = dp4a_ss(kw.w, qh.w, dh); dl = dp4a_ss(kw.w, ql.w, dl);
+                    const float t = fmaf(s_qs[g][ci >> 1][0], (float)dh, s_qs[g][ci >> 1][1] * (float)dl);
+                    sc[g] = fmaf(ksc, t, sc[g]);
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < G; g++) s_p[warp][g][lane] = (pbase + lane < ctx) ? sc[g] : -INFINITY;
+        } else {
+            // fp16 cache: LPP lanes per position, 16 dims per lane
             const int sub = lane % LPP, pl = lane / LPP;
 #pragma unroll 2
-            for (int pp = pl; pp < ATT_CHUNK; pp += PPW) {
+            for (int pp = pl; pp < ATT_TILE; pp += PPW) {
                 float kf[16];
-                float ksc = 1.f;
-                if (Q8) {
-                    const uint4 w = *reinterpret_cast<const uint4 *>(tK + pp * HD + sub * 16);
-                    const uint32_t ww[4] = {s8bias(w.x), s8bias(w.y), s8bias(w.z), s8bias(w.w)};
+                const uint4 w0 = *reinterpret_cast<const uint4 *>(tK + (pp * HD + sub * 16) * 2);
+                const uint4 w1 = *reinterpret_cast<const uint4 *>(tK + (pp * HD + sub * 16) * 2 + 16);
+                const __half2 *h0 = reinterpret_cast<const __half2 *>(&w0);
+                const __half2 *h1 = reinterpret_cast<const __half2 *>(&w1);
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-#pragma unroll
-                        for (int k = 0; k < 4; k++) kf[4 * j + k] = s8f(ww[j], k);
-                    ksc = __half2float(reinterpret_cast<const __half *>(tKs)[pp * NB + sub / 2]);
-                } else {
-                    const uint4 w0 = *reinterpret_cast<const uint4 *>(tK + (pp * HD + sub * 16) * 2);
-                    const uint4 w1 = *reinterpret_cast<const uint4 *>(tK + (pp * HD + sub * 16) * 2 + 16);
-                    const __half2 *h0 = reinterpret_cast<const __half2 *>(&w0);
-                    const __half2 *h1 = reinterpret_cast<const __half2 *>(&w1);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        float2 f0 = __half22float2(h0[j]), f1 = __half22float2(h1[j]);
-                        kf[2 * j] = f0.x; kf[2 * j + 1] = f0.y;
-                        kf[8 + 2 * j] = f1.x; kf[8 + 2 * j + 1] = f1.y;
-                    }
+                for (int j = 0; j < 4; j++) {
+                    float2 f0 = __half22float2(h0[j]), f1 = __half22float2(h1[j]);
+                    kf[2 * j] = f0.x; kf[2 * j + 1] = f0.y;
+                    kf[8 + 2 * j] = f1.x; kf[8 + 2 * j + 1] = f1.y;
                 }
 #pragma unroll
                 for (int g = 0; g < G; g++) {
@@ -472,7 +510,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
                         s0 = fmaf(kf[4 * j + 3], qa.w, s0);
                         s1 = fmaf(kf[4 * j + 7], qb.w, s1);
                     }
-                    float sc = (s0 + s1) * ksc;
+                    float sc = s0 + s1;
 #pragma unroll
                     for (int o = LPP / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
                     if (sub == 0) s_p[warp][g][pp] = (pbase + pp < ctx) ? sc : -INFINITY;
@@ -485,14 +523,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
         // ---- online softmax for the G heads (whole warp per head)
 #pragma unroll
         for (int g = 0; g < G; g++) {
-            const float v0 = s_p[warp][g][lane], v1 = s_p[warp][g][lane + 32];
-            const float cm = warp_max(fmaxf(v0, v1));
+            const float v0 = s_p[warp][g][lane];
+            const float cm = warp_max(v0);
             const float m_new = fmaxf(m_run[g], cm);
             const float e0 = (v0 == -INFINITY) ? 0.f : __expf(v0 - m_new);
-            const float e1 = (v1 == -INFINITY) ? 0.f : __expf(v1 - m_new);
-            const float cs = warp_sum(e0 + e1);
+            const float cs = warp_sum(e0);
             s_p[warp][g][lane] = e0;
-            s_p[warp][g][lane + 32] = e1;
             const float corr = (m_run[g] == -INFINITY) ? 0.f : __expf(m_run[g] - m_new);
             l_run[g] = l_run[g] * corr + cs;
             m_run[g] = m_new;
@@ -503,15 +539,15 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
 
         // ---- P.V: lane owns 4 dims (one code word), loop over the tile's positions
         if (lane < HD / 4) {
-            const int npos = min(ATT_CHUNK, ctx - pbase);
+            const int npos = min(ATT_TILE, ctx - pbase);
 #pragma unroll 4
             for (int pp = 0; pp < npos; pp++) {
-                float vf[4];
+                float vf[4], vsc = 1.f;
                 if (Q8) {
                     const uint32_t w = s8bias(reinterpret_cast<const uint32_t *>(tV + pp * HD)[lane]);
-                    const float vsc = __half2float(reinterpret_cast<const __half *>(tVs)[pp * NB + lane / 8]);
+                    vsc = __half2float(reinterpret_cast<const __half *>(tVs)[pp * NB + lane / 8]);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) vf[k] = s8f(w, k) * vsc;
+                    for (int k = 0; k < 4; k++) vf[k] = s8f(w, k);
                 } else {
                     const uint2 w = reinterpret_cast<const uint2 *>(tV + pp * HD * 2)[lane];
                     float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&w.x));
@@ -520,7 +556,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
                 }
 #pragma unroll
                 for (int g = 0; g < G; g++) {
-                    const float p = s_p[warp][g][pp];
+                    const float p = s_p[warp][g][pp] * vsc;   // the block scale rides on the probability
                     acc[g][0] = fmaf(p, vf[0], acc[g][0]);
                     acc[g][1] = fmaf(p, vf[1], acc[g][1]);
                     acc[g][2] = fmaf(p, vf[2], acc[g][2]);
@@ -618,7 +654,7 @@ template <int HD, int G>
 static int attn_launch_t(const AttnArgs &a, int kv_dtype, bool pdl, cudaStream_t st) {
     const bool q8 = kv_dtype == DT_Q8_B32T2;
     const int nb = HD / 32;
-    const size_t tile = q8 ? 2 * (ATT_CHUNK * HD + ATT_CHUNK * nb * 2) : 2 * (ATT_CHUNK * HD * 2);
+    const size_t tile = q8 ? 2 * (ATT_TILE * HD + ATT_TILE * nb * 2) : 2 * (ATT_TILE * HD * 2);
     size_t smem = (ATT_THREADS / 32) * tile;
     const size_t red = (size_t)(ATT_THREADS / 32) * G * HD * sizeof(float);
     const size_t wts = (size_t)G * a.nsplit * sizeof(float);
@@ -683,7 +719,7 @@ int attn_decode(const AttnDecode &p, cudaStream_t st) {
                   "attention: rope order %d / dims %d", p.rope_order, p.rope_dims);
     // split count: fill ~2 CTAs per SM; with a device-side position (graph replay) size for max_ctx
     const int ctx_for_split = p.pos_dev != nullptr ? p.max_ctx : p.ctx_len;
-    const int nchunks = (ctx_for_split + ATT_CHUNK - 1) / ATT_CHUNK;
+    const int nchunks = (ctx_for_split + ATT_TILE - 1) / ATT_TILE;
     // one tile per warp while that still fills the machine: CTAs per head = ceil(tiles / 4),
     // capped at ~4 CTAs per SM overall (longer contexts: several tiles per warp)
     int nsplit = (nchunks + (ATT_THREADS / 32) - 1) / (ATT_THREADS / 32);

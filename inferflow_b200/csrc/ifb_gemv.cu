@@ -821,6 +821,11 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     else if (valid(8)) R = 8;
     if (R == 8 && valid(16) && sbytes(16) <= 16 * 1024) R = 16;   // very short rows: fatter copies
     if (R == 16 && valid(32) && sbytes(32) <= 16 * 1024) R = 32;
+    {
+        static int env_r = -1;        // tuning aid: IFB_GEMV_R forces the rows per unit when it tiles the launch
+        if (env_r < 0) { const char *e = getenv("IFB_GEMV_R"); env_r = e ? atoi(e) : 0; }
+        if (env_r > 0 && valid(env_r)) R = env_r;
+    }
     IFB_CHECK_ARG(R != 0, "gemv: rows (gcd %d) x row_bytes %d cannot be tiled in 16-byte units "
                   "(rows must be a multiple of 4, or 8 for 34-byte blocks)", gcd_rows, a.row_bytes);
     a.R = R;
@@ -857,7 +862,9 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     if (a.tp.gather) xbytes += g.cx * 2;      // the gathered fp16 vector, consumed by the staging pass
     const int64_t xpad = (xbytes + 127) / 128 * 128;
     // default: at most ~half of the SM's shared memory, so two kernels of a PDL chain co-reside
-    int64_t budget = (g.smem_budget > 0 ? g.smem_budget : 110 * 1024);
+    static int64_t env_budget = -1;   // tuning aid: IFB_GEMV_SMEM_KB overrides the default per-CTA ring budget
+    if (env_budget < 0) { const char *e = getenv("IFB_GEMV_SMEM_KB"); env_budget = e ? atoll(e) * 1024 : 0; }
+    int64_t budget = (g.smem_budget > 0 ? g.smem_budget : (env_budget > 0 ? env_budget : 110 * 1024));
     int groups = GEMV_CWARPS / a.wpg;
     int nslots = (int)((budget - xpad) / a.slot_stride);
     if (nslots < groups && g.smem_budget <= 0) {   // a little more room so that every warp group gets a slot
