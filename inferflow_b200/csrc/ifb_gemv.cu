@@ -457,7 +457,7 @@ __device__ __forceinline__ float row_dot_f16(const uint8_t *row, int cx, const _
 enum { MODE_Q8 = 0, MODE_HX = 1, MODE_F16 = 2 };
 
 template <class Fmt, int MODE, bool GLU, bool VEC4, bool TP>
-__global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_stream_kernel(const GemvArgs a) {
+__global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_stream_kernel(const GemvArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t full_bar[GEMV_MAX_SLOTS], empty_bar[GEMV_MAX_SLOTS];
     __shared__ float red[GEMV_CWARPS];
@@ -864,13 +864,13 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     // default: at most ~half of the SM's shared memory, so two kernels of a PDL chain co-reside
     static int64_t env_budget = -1;   // tuning aid: IFB_GEMV_SMEM_KB overrides the default per-CTA ring budget
     if (env_budget < 0) { const char *e = getenv("IFB_GEMV_SMEM_KB"); env_budget = e ? atoll(e) * 1024 : 0; }
-    int64_t budget = (g.smem_budget > 0 ? g.smem_budget : (env_budget > 0 ? env_budget : 110 * 1024));
+    // Default ring: (almost) the whole SM. Measured on B200 (tools/sweep_smem.sh, Llama-2-7B Q4 decode): 110 KB
+    // (two kernels of a PDL chain co-resident) 512 tok/s, 150 KB 559, 200-216 KB 586 -- bytes in flight per SM
+    // matter more than the next kernel's early ring fill. Callers that want a co-resident successor (the QKV
+    // GEMV ahead of attention) pass a smaller budget.
+    int64_t budget = (g.smem_budget > 0 ? g.smem_budget : (env_budget > 0 ? env_budget : 216 * 1024));
     int groups = GEMV_CWARPS / a.wpg;
     int nslots = (int)((budget - xpad) / a.slot_stride);
-    if (nslots < groups && g.smem_budget <= 0) {   // a little more room so that every warp group gets a slot
-        budget = 128 * 1024;
-        nslots = (int)((budget - xpad) / a.slot_stride);
-    }
     if (nslots < 2) {
         budget = 216 * 1024;
         nslots = (int)((budget - xpad) / a.slot_stride);

@@ -56,6 +56,7 @@ struct ifb_model {
     int64_t x_recv = 0, x_recv_parity = 0, x_recv_rank = 0;   // partial sums: [2 parities][8 ranks][d_model/2] words {half2, flag}
     int64_t x_logits = 0;                                     // logits of all ranks: [vocab/2] words {half2, flag}
     int vocab_l = 0;                // lm_head rows held by this rank (vocabulary-sharded under TP)
+    int64_t smem_kb[5] = {0, 0, 0, 0, 0};   // per-CTA shared-memory budget of the QKV / wo / GLU / w2 / lm_head GEMVs (KB, 0 = kernel default)
 };
 
 static int dev_alloc(ifb_model *m, DevBuf &b, size_t bytes) {
@@ -115,6 +116,15 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
                                     // network_builder.cc:1271-1283); the slices meet in every rank's exchange region
     const char *e1 = getenv("IFB_NO_PDL");
     if (e1 && atoi(e1)) m->use_pdl = 0;
+    {
+        // ring depth per launch kind (tuning aid; the defaults are set below from measurements on B200)
+        const char *names[5] = {"IFB_SMEM_QKV", "IFB_SMEM_WO", "IFB_SMEM_GLU", "IFB_SMEM_W2", "IFB_SMEM_HEAD"};
+        const int64_t defaults[5] = {150, 0, 0, 0, 0};   // QKV: leave room for the attention kernel's CTAs (early KV prefetch)
+        for (int i = 0; i < 5; i++) {
+            const char *e = getenv(names[i]);
+            m->smem_kb[i] = e ? atoll(e) : defaults[i];
+        }
+    }
     const char *e2 = getenv("IFB_NO_GRAPH");
     if (e2 && atoi(e2)) m->use_graph = 0;
 
@@ -557,7 +567,7 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         g.w[0] = L.wq.p; g.w[1] = L.wk.p; g.w[2] = L.wv.p;
         g.rows[0] = m->q_dim_l; g.rows[1] = m->kv_dim_l; g.rows[2] = m->kv_dim_l;
         g.cx = d; g.x = m->x0.p; g.norm_w = L.attn_norm.p; g.norm_eps = s.norm_eps;
-        g.y = qkv; g.quantize_x = quant_x; g.pdl = pdl;
+        g.y = qkv; g.quantize_x = quant_x; g.pdl = pdl; g.smem_budget = m->smem_kb[0] * 1024;
         if (tp > 1 && li > 0) { t_qkv = tp_gather_ar(2 * li, m->x1.p, m->x0.p); g.tp = &t_qkv; }   // x0 = x1 + sum(w2 partials) of the previous layer
         g.trace = TR(n); g.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(g, st)); n++; }
@@ -573,7 +583,7 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         // --- wo + residual
         GemvLaunch o;
         o.w_dtype = wdt; o.nseg = 1; o.w[0] = L.wo.p; o.rows[0] = d; o.cx = m->q_dim_l;
-        o.x = m->attn_out.p; o.residual = m->x0.p; o.y = m->x1.p; o.quantize_x = quant_x; o.pdl = pdl;
+        o.x = m->attn_out.p; o.residual = m->x0.p; o.y = m->x1.p; o.quantize_x = quant_x; o.pdl = pdl; o.smem_budget = m->smem_kb[1] * 1024;
         if (tp > 1) { o.residual = nullptr; t_wo = tp_push_ar(2 * li + 1); o.tp = &t_wo; }             // row-parallel: partial sums go to the peers
         o.trace = TR(n); o.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(o, st)); n++; }
@@ -581,14 +591,14 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         GemvLaunch f;
         f.w_dtype = wdt; f.nseg = 1; f.w[0] = L.w1.p; f.w_gate = L.w3.p; f.rows[0] = m->ffn_l; f.cx = d;
         f.x = m->x1.p; f.norm_w = L.ffn_norm.p; f.norm_eps = s.norm_eps; f.y = m->hbuf.p;
-        f.quantize_x = quant_x; f.pdl = pdl;
+        f.quantize_x = quant_x; f.pdl = pdl; f.smem_budget = m->smem_kb[2] * 1024;
         if (tp > 1) { t_glu = tp_gather_ar(2 * li + 1, m->x0.p, m->x1.p); f.tp = &t_glu; }               // x1 = x0 + sum(wo partials)
         f.trace = TR(n); f.counter = CT(n);
         if (parts & PART_GEMV) { TRY(gemv_launch(f, st)); n++; }
         // --- w2 + residual
         GemvLaunch w2;
         w2.w_dtype = wdt; w2.nseg = 1; w2.w[0] = L.w2.p; w2.rows[0] = d; w2.cx = m->ffn_l;
-        w2.x = m->hbuf.p; w2.residual = m->x1.p; w2.y = m->x0.p; w2.quantize_x = quant_x; w2.pdl = pdl;
+        w2.x = m->hbuf.p; w2.residual = m->x1.p; w2.y = m->x0.p; w2.quantize_x = quant_x; w2.pdl = pdl; w2.smem_budget = m->smem_kb[3] * 1024;
         if (tp > 1) { w2.residual = nullptr; t_w2 = tp_push_ar(2 * li + 2); w2.tp = &t_w2; }
         li++;
         w2.trace = TR(n); w2.counter = CT(n);
@@ -599,6 +609,7 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
     h.w_dtype = s.lm_head_dtype; h.nseg = 1; h.w[0] = m->lm_head.p; h.rows[0] = m->vocab_l; h.cx = d;
     h.x = m->x0.p; h.norm_w = m->out_norm.p; h.norm_eps = s.norm_eps; h.y = m->logits.p;
     h.quantize_x = (s.lm_head_dtype != DT_F16 && ax8_ok(s.lm_head_dtype)) ? 1 : 0; h.pdl = pdl;
+    h.smem_budget = m->smem_kb[4] * 1024;
     h.trace = TR(n); h.counter = CT(n);
     if (tp > 1) {
         // input: x0 = x1 + sum(w2 partials of the last layer); output: this rank's logits slice to every rank
