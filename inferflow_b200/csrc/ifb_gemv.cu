@@ -50,6 +50,7 @@ struct GemvArgs {
     int l2_prefetch; // >0: software prefetch distance in UNITS: unit u+dist is requested into the L2 when unit u is copied
     int xg_off;      // byte offset (from the staged-x area) of the fp16 vector a tensor-parallel gather builds
     int pdl_late;
+    int batch_claim;
     int debug_nocompute;  // measurement aid (IFB_GEMV_NOCOMPUTE=1): consumers release slots without doing the math
     const __half *x;
     const uint8_t *xq;  // pre-quantized activation (Q8_B32T2 blocks) or null
@@ -514,12 +515,18 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_stream_kernel(const Gemv
             const uint64_t pol = l2_policy_evict_first();
             int pos = 0;
             uint32_t phase = 1;   // a fresh mbarrier passes a wait on parity 1
-            int next = atomicAdd(a.counter, 1);
+            // The cursor is a global atomic (~0.6 us round trip): claim a whole ring's worth of units at once so the
+            // empty ring fills without waiting for one atomic per slot, then one unit at a time, fetched while
+            // the producer waits for a free slot.
+            const int nb = a.batch_claim ? a.nslots : 1;
+            int batch = atomicAdd(a.counter, nb), left = nb, next = -1;
             int sentinels = 0;
             for (;;) {
-                const int u = next;
+                int u;
+                if (left > 0) { u = batch++; left--; }
+                else { if (next < 0) next = atomicAdd(a.counter, 1); u = next; next = -1; }
                 const bool real = u < a.units;
-                if (real) next = atomicAdd(a.counter, 1);   // in flight while we wait for the slot
+                if (real && left == 0) next = atomicAdd(a.counter, 1);   // in flight while we wait for the slot
                 mbar_wait(&empty_bar[pos], phase);
                 slot_unit[pos] = real ? u : -1;
                 if (real) {
@@ -742,6 +749,23 @@ static bool is_ax8_type(int dt) {
 
 static int *g_scratch_counter = nullptr;
 
+// Several GEMVs in one call. A fused "chain" kernel (one persistent launch walking all ops, grid-wide completion
+// counters between them) was built and measured in round 1 -- experiments/gemv_chain/ -- and lost to separate
+// launches of this kernel (507 vs 595 tok/s): here the ops simply go out one after the other.
+int gemv_chain_launch(const GemvLaunch *ops, int nops, cudaStream_t st) {
+    IFB_CHECK_ARG(ops != nullptr && nops >= 1 && nops <= 4, "gemv: a chain holds 1..4 ops");
+    for (int k = 0; k < nops; k++) {
+        GemvLaunch g = ops[k];
+        if (k > 0) {
+            g.trace = nullptr;
+            g.counter = ops[0].counter ? (void *)((int *)ops[0].counter + k) : nullptr;
+        }
+        int rc = gemv_launch(g, st);
+        if (rc != IFB_OK) return rc;
+    }
+    return IFB_OK;
+}
+
 int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     const int dt = g.w_dtype;
     const int cap = block_capacity(dt);
@@ -795,6 +819,9 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
         static int late = -1;
         if (late < 0) { const char *e = getenv("IFB_PDL_LATE"); late = (e && atoi(e)) ? 1 : 0; }
         a.pdl_late = late;
+        static int bc = -1;
+        if (bc < 0) { const char *e = getenv("IFB_GEMV_BATCH"); bc = e ? atoi(e) : 0; }
+        a.batch_claim = bc;
         static int nol2 = -1;
         if (nol2 < 0) { const char *e = getenv("IFB_NO_L2_PREFETCH"); nol2 = (e && atoi(e)) ? 1 : 0; }
         if (nol2) const_cast<GemvLaunch &>(g).l2_prefetch = 0;

@@ -53,10 +53,12 @@ struct GemvLaunch {
     int64_t smem_budget = 0;       // bytes of shared memory per CTA (0 = default: half an SM)
     void *trace = nullptr;         // optional timeline probe buffer (160*8 uint64)
     int l2_prefetch = 1;           // ask the L2 for the whole weight set at kernel entry (<= 64 MB)
-    void *counter = nullptr;       // int32 work cursor, must be 0 at launch (null: library scratch + memset)
+    void *counter = nullptr;       // int32[8]: work cursor + per-op completion counts, must be 0 at launch (null: library scratch + memset)
     const TpExchange *tp = nullptr;
 };
 int gemv_launch(const GemvLaunch &g, cudaStream_t st);
+// up to 4 GEMVs in ONE launch; op k+1 reads what op k wrote (counter: 8 ints, zero before the launch)
+int gemv_chain_launch(const GemvLaunch *ops, int nops, cudaStream_t st);
 
 int quantize_rows(int dt, void *dst, const void *src_f16, int64_t rows, int64_t cx, cudaStream_t st);
 int dequantize_rows(int dt, void *dst_f16, const void *src, int64_t rows, int64_t cx, cudaStream_t st);

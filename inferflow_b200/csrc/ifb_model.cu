@@ -56,6 +56,7 @@ struct ifb_model {
     int64_t x_recv = 0, x_recv_parity = 0, x_recv_rank = 0;   // partial sums: [2 parities][8 ranks][d_model/2] words {half2, flag}
     int64_t x_logits = 0;                                     // logits of all ranks: [vocab/2] words {half2, flag}
     int vocab_l = 0;                // lm_head rows held by this rank (vocabulary-sharded under TP)
+    int chain_mode = 0;             // 0: one launch per GEMV (the measured optimum, see gemv_chain_launch)
     int64_t smem_kb[5] = {0, 0, 0, 0, 0};   // per-CTA shared-memory budget of the QKV / wo / GLU / w2 / lm_head GEMVs (KB, 0 = kernel default)
 };
 
@@ -536,7 +537,7 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
     int32_t *sc = (int32_t *)m->scalars.p;
     int n = 0;
     IFB_CUDA(cudaMemsetAsync(m->counters.p, 0, m->counters.bytes, st));
-    auto CT = [&](int idx) -> void * { return (void *)((int *)m->counters.p + idx); };
+    auto CT = [&](int idx) -> void * { return (void *)((int *)m->counters.p + (size_t)idx * 8); };   // cursor + per-op completion counts
     auto TR = [&](int idx) -> void * { return (m->trace_on && idx < 512) ? (void *)((uint64_t *)m->trace.p + (size_t)idx * 160 * 8) : nullptr; };
     if (parts & PART_MISC) { TRY(embed_row(m->x0.p, m->tok_emb.p, DT_F16, d, 0, sc + 1, st)); n++; }
     const bool q8 = true;   // enable_full_quant_gemv = true (inference_engine.cc:53-57)
@@ -558,19 +559,48 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
     auto tp_gather_ar = [&](int idx, const void *resid, void *xout) { TpExchange t = tpx; t.gather = 1; t.gather_idx = (uint32_t)idx;
                               t.src_off = m->x_recv + (idx & 1) * m->x_recv_parity; t.src_rank_stride = m->x_recv_rank;
                               t.resid = resid; t.xout = xout; return t; };
-    TpExchange t_qkv, t_wo, t_glu, t_w2, t_head;
-    int li = 0;
-    for (auto &L : m->layers) {
+    TpExchange t_head;
+    // every GEMV of the step first (descriptors only), then the launches: consecutive GEMVs go out as ONE chained
+    // launch (ifb_gemv.cu): mode 2 = [wo, w1|w3, w2, next layer's wq|wk|wv], 1 = [wo, w1|w3, w2], 0 = one per GEMV
+    const int nl = s.layers;
+    std::vector<GemvLaunch> g_qkv(nl), g_wo(nl), g_glu(nl), g_w2(nl);
+    std::vector<TpExchange> t_qkv(nl), t_wo(nl), t_glu(nl), t_w2(nl);
+    for (int li = 0; li < nl; li++) {
+        LayerW &L = m->layers[li];
         // --- attention: norm + quantize + wq|wk|wv
-        GemvLaunch g;
+        GemvLaunch &g = g_qkv[li];
         g.w_dtype = wdt; g.nseg = 3;
         g.w[0] = L.wq.p; g.w[1] = L.wk.p; g.w[2] = L.wv.p;
         g.rows[0] = m->q_dim_l; g.rows[1] = m->kv_dim_l; g.rows[2] = m->kv_dim_l;
         g.cx = d; g.x = m->x0.p; g.norm_w = L.attn_norm.p; g.norm_eps = s.norm_eps;
         g.y = qkv; g.quantize_x = quant_x; g.pdl = pdl; g.smem_budget = m->smem_kb[0] * 1024;
-        if (tp > 1 && li > 0) { t_qkv = tp_gather_ar(2 * li, m->x1.p, m->x0.p); g.tp = &t_qkv; }   // x0 = x1 + sum(w2 partials) of the previous layer
-        g.trace = TR(n); g.counter = CT(n);
-        if (parts & PART_GEMV) { TRY(gemv_launch(g, st)); n++; }
+        if (tp > 1 && li > 0) { t_qkv[li] = tp_gather_ar(2 * li, m->x1.p, m->x0.p); g.tp = &t_qkv[li]; }   // x0 = x1 + sum(w2 partials) of the previous layer
+        // --- wo + residual
+        GemvLaunch &o = g_wo[li];
+        o.w_dtype = wdt; o.nseg = 1; o.w[0] = L.wo.p; o.rows[0] = d; o.cx = m->q_dim_l;
+        o.x = m->attn_out.p; o.residual = m->x0.p; o.y = m->x1.p; o.quantize_x = quant_x; o.pdl = pdl; o.smem_budget = m->smem_kb[1] * 1024;
+        if (tp > 1) { o.residual = nullptr; t_wo[li] = tp_push_ar(2 * li + 1); o.tp = &t_wo[li]; }             // row-parallel: partial sums go to the peers
+        // --- FFN: norm + quantize + (w1, w3) + SiLU*mul
+        GemvLaunch &f = g_glu[li];
+        f.w_dtype = wdt; f.nseg = 1; f.w[0] = L.w1.p; f.w_gate = L.w3.p; f.rows[0] = m->ffn_l; f.cx = d;
+        f.x = m->x1.p; f.norm_w = L.ffn_norm.p; f.norm_eps = s.norm_eps; f.y = m->hbuf.p;
+        f.quantize_x = quant_x; f.pdl = pdl; f.smem_budget = m->smem_kb[2] * 1024;
+        if (tp > 1) { t_glu[li] = tp_gather_ar(2 * li + 1, m->x0.p, m->x1.p); f.tp = &t_glu[li]; }               // x1 = x0 + sum(wo partials)
+        // --- w2 + residual
+        GemvLaunch &w2 = g_w2[li];
+        w2.w_dtype = wdt; w2.nseg = 1; w2.w[0] = L.w2.p; w2.rows[0] = d; w2.cx = m->ffn_l;
+        w2.x = m->hbuf.p; w2.residual = m->x1.p; w2.y = m->x0.p; w2.quantize_x = quant_x; w2.pdl = pdl; w2.smem_budget = m->smem_kb[3] * 1024;
+        if (tp > 1) { w2.residual = nullptr; t_w2[li] = tp_push_ar(2 * li + 2); w2.tp = &t_w2[li]; }
+    }
+    auto launch = [&](GemvLaunch *ops, int nops) -> int {
+        ops[0].trace = TR(n); ops[0].counter = CT(n);
+        if (parts & PART_GEMV) { TRY(gemv_chain_launch(ops, nops, st)); n++; }
+        return IFB_OK;
+    };
+    const int chain = m->chain_mode;
+    for (int li = 0; li < nl; li++) {
+        LayerW &L = m->layers[li];
+        if (chain < 2 || li == 0) TRY(launch(&g_qkv[li], 1));
         // --- RoPE(q,k) + append K,V + attention over the cache: one kernel
         AttnDecode ad;
         ad.k_new = qkv + m->q_dim_l; ad.v_new = qkv + m->q_dim_l + m->kv_dim_l;
@@ -580,29 +610,17 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         ad.kcache = L.kcache.p; ad.vcache = L.vcache.p; ad.workspace = m->attn_ws.p; ad.pos_dev = sc; ad.pdl = pdl;
         ad.trace = TR(n);
         if (parts & PART_ATTN) { TRY(attn_decode(ad, st)); n++; }
-        // --- wo + residual
-        GemvLaunch o;
-        o.w_dtype = wdt; o.nseg = 1; o.w[0] = L.wo.p; o.rows[0] = d; o.cx = m->q_dim_l;
-        o.x = m->attn_out.p; o.residual = m->x0.p; o.y = m->x1.p; o.quantize_x = quant_x; o.pdl = pdl; o.smem_budget = m->smem_kb[1] * 1024;
-        if (tp > 1) { o.residual = nullptr; t_wo = tp_push_ar(2 * li + 1); o.tp = &t_wo; }             // row-parallel: partial sums go to the peers
-        o.trace = TR(n); o.counter = CT(n);
-        if (parts & PART_GEMV) { TRY(gemv_launch(o, st)); n++; }
-        // --- FFN: norm + quantize + (w1, w3) + SiLU*mul
-        GemvLaunch f;
-        f.w_dtype = wdt; f.nseg = 1; f.w[0] = L.w1.p; f.w_gate = L.w3.p; f.rows[0] = m->ffn_l; f.cx = d;
-        f.x = m->x1.p; f.norm_w = L.ffn_norm.p; f.norm_eps = s.norm_eps; f.y = m->hbuf.p;
-        f.quantize_x = quant_x; f.pdl = pdl; f.smem_budget = m->smem_kb[2] * 1024;
-        if (tp > 1) { t_glu = tp_gather_ar(2 * li + 1, m->x0.p, m->x1.p); f.tp = &t_glu; }               // x1 = x0 + sum(wo partials)
-        f.trace = TR(n); f.counter = CT(n);
-        if (parts & PART_GEMV) { TRY(gemv_launch(f, st)); n++; }
-        // --- w2 + residual
-        GemvLaunch w2;
-        w2.w_dtype = wdt; w2.nseg = 1; w2.w[0] = L.w2.p; w2.rows[0] = d; w2.cx = m->ffn_l;
-        w2.x = m->hbuf.p; w2.residual = m->x1.p; w2.y = m->x0.p; w2.quantize_x = quant_x; w2.pdl = pdl; w2.smem_budget = m->smem_kb[3] * 1024;
-        if (tp > 1) { w2.residual = nullptr; t_w2 = tp_push_ar(2 * li + 2); w2.tp = &t_w2; }
-        li++;
-        w2.trace = TR(n); w2.counter = CT(n);
-        if (parts & PART_GEMV) { TRY(gemv_launch(w2, st)); n++; }
+        if (chain == 0) {
+            TRY(launch(&g_wo[li], 1));
+            TRY(launch(&g_glu[li], 1));
+            TRY(launch(&g_w2[li], 1));
+        } else {
+            GemvLaunch ops[4] = {g_wo[li], g_glu[li], g_w2[li], GemvLaunch()};
+            int nops = 3;
+            if (chain == 2 && li + 1 < nl) ops[nops++] = g_qkv[li + 1];
+            ops[0].smem_budget = m->smem_kb[1] * 1024;
+            TRY(launch(ops, nops));
+        }
     }
     // --- final norm + lm_head (fp16 weights meet an fp16 activation: GemvHalf_AX_Alg3)
     GemvLaunch h;
