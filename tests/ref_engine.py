@@ -88,6 +88,11 @@ def write_tree(root, hp, w, threads, name="synth", return_logits=True):
                                   "qk_column_order": 0, "tensor_name_prefix": "", "tensor_name_mapping": {}}}
     with open(os.path.join(mdir, "model_spec.json"), "w") as f:
         json.dump(spec, f, indent=1)
+    return write_ini(root, hp, threads, name, return_logits)
+
+
+def write_ini(root, hp, threads, name="synth", return_logits=True):
+    """(re)write <root>/bin/ref.ini only -- e.g. another cpu_threads value for the same model files"""
     ini = f"""[transformer_engine]
 models = {name}
 devices = 0

@@ -117,7 +117,9 @@ def test_quantize_golden_fixture(ib):
 
 
 # ------------------------------------------------------------------ GEMV
-SHAPES = [(64, 256), (40, 4096), (4096, 4096), (1000, 11008), (72, 288), (128, 768)]
+SHAPES = [(64, 256), (40, 4096), (4096, 4096), (1000, 11008), (72, 288), (128, 768),
+          # the per-rank shapes of Llama-2-7B at TP 8 / TP 4: w2 shards (cx = 11008/8, 11008/4), wo shards, w1 rows
+          (4096, 1376), (4096, 2752), (4096, 512), (1376, 4096)]
 
 
 def _gemv(ib, dt, w, x_dtype, x_t, cy, cx, bias=None):
@@ -154,7 +156,7 @@ def test_gemv_f16_activation(ib, dt):
     close(got, want)
 
 
-@pytest.mark.parametrize("shape", [(64, 256), (32000, 4096), (1000, 288)], ids=["64x256", "lm_head", "1000x288"])
+@pytest.mark.parametrize("shape", [(64, 256), (32000, 4096), (1000, 288), (4000, 4096)], ids=["64x256", "lm_head", "1000x288", "lm_head_tp8"])
 def test_gemv_f16_weights(ib, shape):
     cy, cx = shape
     rng = np.random.default_rng(50)

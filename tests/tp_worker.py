@@ -26,23 +26,23 @@ from orc_model import OracleModel  # noqa: E402
 LAYER_T = ["attention_norm", "ffn_norm", "wq", "wk", "wv", "wo", "w1", "w2", "w3"]
 
 
-def host_weights(spec, seed):
+def host_weights(spec, seed, std=0.02):
     rng = np.random.default_rng(seed)
     hd = spec.d_model // spec.heads
     w = {"tok_embeddings": rng.standard_normal((spec.vocab, spec.d_model)).astype(np.float32),
          "output_norm": (1 + 0.1 * rng.standard_normal((1, spec.d_model))).astype(np.float32),
-         "output": (0.05 * rng.standard_normal((spec.vocab, spec.d_model))).astype(np.float32)}
+         "output": (2.5 * std * rng.standard_normal((spec.vocab, spec.d_model))).astype(np.float32)}
     for l in range(spec.layers):
         p = f"layers.{l}."
         w[p + "attention_norm"] = (1 + 0.1 * rng.standard_normal((1, spec.d_model))).astype(np.float32)
         w[p + "ffn_norm"] = (1 + 0.1 * rng.standard_normal((1, spec.d_model))).astype(np.float32)
-        w[p + "wq"] = (0.06 * rng.standard_normal((spec.heads * hd, spec.d_model))).astype(np.float32)
-        w[p + "wk"] = (0.06 * rng.standard_normal((spec.kv_heads * hd, spec.d_model))).astype(np.float32)
-        w[p + "wv"] = (0.06 * rng.standard_normal((spec.kv_heads * hd, spec.d_model))).astype(np.float32)
-        w[p + "wo"] = (0.06 * rng.standard_normal((spec.d_model, spec.heads * hd))).astype(np.float32)
-        w[p + "w1"] = (0.06 * rng.standard_normal((spec.d_ffn, spec.d_model))).astype(np.float32)
-        w[p + "w3"] = (0.06 * rng.standard_normal((spec.d_ffn, spec.d_model))).astype(np.float32)
-        w[p + "w2"] = (0.06 * rng.standard_normal((spec.d_model, spec.d_ffn))).astype(np.float32)
+        w[p + "wq"] = (std * rng.standard_normal((spec.heads * hd, spec.d_model))).astype(np.float32)
+        w[p + "wk"] = (std * rng.standard_normal((spec.kv_heads * hd, spec.d_model))).astype(np.float32)
+        w[p + "wv"] = (std * rng.standard_normal((spec.kv_heads * hd, spec.d_model))).astype(np.float32)
+        w[p + "wo"] = (std * rng.standard_normal((spec.d_model, spec.heads * hd))).astype(np.float32)
+        w[p + "w1"] = (std * rng.standard_normal((spec.d_ffn, spec.d_model))).astype(np.float32)
+        w[p + "w3"] = (std * rng.standard_normal((spec.d_ffn, spec.d_model))).astype(np.float32)
+        w[p + "w2"] = (std * rng.standard_normal((spec.d_model, spec.d_ffn))).astype(np.float32)
     return w
 
 
