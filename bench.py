@@ -390,6 +390,9 @@ def run_ours(args):
 
     launches = model.launches_per_step
     model.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
     cpu = cpu_baseline_port() if world == 1 and not args.no_cpu_baseline else None
