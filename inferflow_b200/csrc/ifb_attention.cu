@@ -18,6 +18,8 @@
 // head-major so that a (head, position-range) tile is ONE contiguous byte range.
 #include "ifb_formats.cuh"
 #include "ifb_kernels.h"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace ifb {
 
@@ -203,6 +205,8 @@ struct AttnArgs {
     unsigned int *counters;  // [kv_heads]
     const int32_t *pos_dev;
     unsigned long long *trace;
+    int cluster;          // the nsplit CTAs of a kv head form one thread-block cluster: merge through DSMEM
+    int part_off;         // byte offset (dynamic shared memory) of the leader's [nsplit][G][HD+2] partials
     // fused append
     const __half *k_new, *v_new;
     int fuse, rope, rope_order, rope_dims;
@@ -596,9 +600,51 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
             num = fmaf(wt, red[((w * G) + g) * HD + d], num);
             den = fmaf(wt, s_ml[w][g][1], den);
         }
-        float *o = a.ws + ((int64_t)(kvh * G + g) * a.nsplit + split) * (HD + 2);
+        float *o;
+        if (a.cluster) {
+            // straight into the shared memory of the cluster's first CTA (distributed shared memory)
+            float *lead = cg::this_cluster().map_shared_rank(reinterpret_cast<float *>(smem + a.part_off), 0);
+            o = lead + ((int64_t)g * a.nsplit + split) * (HD + 2);
+        } else {
+            o = a.ws + ((int64_t)(kvh * G + g) * a.nsplit + split) * (HD + 2);
+        }
         o[2 + d] = num;
         if (d == 0) { o[0] = M; o[1] = den; }
+    }
+    if (a.cluster) {
+        // Every CTA of the head has delivered once the cluster barrier completes (release/acquire at cluster scope):
+        // no fence, no global round trip, no atomic. The first CTA finishes the log-sum-exp merge from its own
+        // shared memory.
+        cg::this_cluster().sync();
+        if (split != 0) return;
+        const float *pbase = reinterpret_cast<const float *>(smem + a.part_off);
+        float *wts = reinterpret_cast<float *>(smem);      // [G][nsplit] normalised weights (tile buffers are idle)
+        for (int g = warp; g < G; g += NW) {
+            const float *base = pbase + (int64_t)g * a.nsplit * (HD + 2);
+            float M = -INFINITY;
+            for (int sp = lane; sp < a.nsplit; sp += 32) M = fmaxf(M, base[sp * (HD + 2)]);
+            M = warp_max(M);
+            float den = 0.f;
+            for (int sp = lane; sp < a.nsplit; sp += 32) {
+                const float ms = base[sp * (HD + 2)];
+                const float wt = (ms == -INFINITY) ? 0.f : __expf(ms - M);
+                wts[g * a.nsplit + sp] = wt;
+                den = fmaf(wt, base[sp * (HD + 2) + 1], den);
+            }
+            den = warp_sum(den);
+            const float inv = 1.0f / den;
+            for (int sp = lane; sp < a.nsplit; sp += 32) wts[g * a.nsplit + sp] *= inv;
+        }
+        __syncthreads();
+        for (int i = tid; i < G * HD; i += ATT_THREADS) {
+            const int g = i / HD, d = i % HD;
+            const float *base = pbase + (int64_t)g * a.nsplit * (HD + 2) + 2 + d;
+            float num = 0.f;
+#pragma unroll 4
+            for (int sp = 0; sp < a.nsplit; sp++) num = fmaf(wts[g * a.nsplit + sp], base[(int64_t)sp * (HD + 2)], num);
+            a.out[(int64_t)(kvh * G + g) * HD + d] = __float2half_rn(num);
+        }
+        return;
     }
     if (a.nsplit == 1) {
         // single CTA per head: normalise right here
@@ -651,7 +697,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
 }
 
 template <int HD, int G>
-static int attn_launch_t(const AttnArgs &a, int kv_dtype, bool pdl, cudaStream_t st) {
+static int attn_launch_t(const AttnArgs &a_in, int kv_dtype, bool pdl, cudaStream_t st) {
+    AttnArgs a = a_in;
     const bool q8 = kv_dtype == DT_Q8_B32T2;
     const int nb = HD / 32;
     const size_t tile = q8 ? 2 * (ATT_TILE * HD + ATT_TILE * nb * 2) : 2 * (ATT_TILE * HD * 2);
@@ -660,16 +707,31 @@ static int attn_launch_t(const AttnArgs &a, int kv_dtype, bool pdl, cudaStream_t
     const size_t wts = (size_t)G * a.nsplit * sizeof(float);
     if (smem < red) smem = red;
     if (smem < wts) smem = wts;
+    a.part_off = 0;
+    if (a.cluster) {   // the leader's partials live behind the tile buffers: peers write them while it still scans
+        smem = (smem + 127) / 128 * 128;
+        a.part_off = (int)smem;
+        smem += (size_t)a.nsplit * G * (HD + 2) * sizeof(float);
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(a.nsplit, a.kv_heads);
     cfg.blockDim = dim3(ATT_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
+    if (a.cluster) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = a.nsplit; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        na++;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = na;
     static size_t attr_smem[2] = {0, 0};   // per <HD, G> instantiation
     if (q8) {
         auto kern = attn_decode_kernel<HD, G, true>;
@@ -727,6 +789,15 @@ int attn_decode(const AttnDecode &p, cudaStream_t st) {
     if (nsplit > cap) nsplit = cap;
     if (nsplit > 4 * 160) nsplit = 4 * 160;
     if (nsplit < 1) nsplit = 1;
+    // the splits of a head merge through distributed shared memory when they fit one portable cluster (<= 8 CTAs);
+    // longer contexts get more tiles per warp instead of more CTAs
+    static int no_cluster = -1;
+    if (no_cluster < 0) { const char *e = getenv("IFB_ATTN_NO_CLUSTER"); no_cluster = (e && atoi(e)) ? 1 : 0; }
+    a.cluster = 0;
+    if (!no_cluster && nsplit > 1) {
+        if (nsplit > 8) nsplit = 8;
+        a.cluster = 1;
+    }
     a.nsplit = nsplit;
     const int group = p.heads / p.kv_heads;
     switch (p.head_dim) {
