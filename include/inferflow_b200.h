@@ -183,7 +183,9 @@ typedef struct ifb_model_spec {
     float kq_scale;
     int32_t tp_rank, tp_size; /* tensor-parallel shard this instance holds (BY_COL/BY_ROW rules,
                                  network_builder.cc:1373-1406) */
-    int32_t experts, experts_top_k; /* 0 = dense FFN */
+    int32_t experts, experts_top_k; /* 0 = dense FFN; else every layer's FFN is a mixture of `experts` GLU FFNs,
+                                       `experts_top_k` active per token (ProcessGpuLayer_Moe, inference_worker.cc:1924-2146) */
+    int32_t moe_norm_top_k_prob;    /* hparams.moe_norm_top_k_prob (model.h:66): renormalise the selected weights */
 } ifb_model_spec_t;
 
 typedef struct ifb_model ifb_model_t;

@@ -37,7 +37,7 @@ class ModelSpecC(C.Structure):
         ("weight_dtype", C.c_int32), ("kv_dtype", C.c_int32), ("lm_head_dtype", C.c_int32),
         ("rope_order", C.c_int32), ("rope_theta", C.c_float), ("norm_eps", C.c_float),
         ("kq_scale", C.c_float), ("tp_rank", C.c_int32), ("tp_size", C.c_int32),
-        ("experts", C.c_int32), ("experts_top_k", C.c_int32),
+        ("experts", C.c_int32), ("experts_top_k", C.c_int32), ("moe_norm_top_k_prob", C.c_int32),
     ]
 
 

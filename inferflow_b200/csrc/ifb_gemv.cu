@@ -62,6 +62,9 @@ struct GemvArgs {
     unsigned long long *trace;
     int *counter;    // work-stealing cursor over the units (zero before the launch)
     TpExchange tp;   // tensor-parallel push / gather (size 1: unused)
+    // mixture of experts: the matrices of this launch are picked on the device (see GemvLaunch)
+    const uint8_t *const *w_table, *const *wg_table;
+    const int32_t *moe_id;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -497,16 +500,26 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_stream_kernel(const Gemv
         // Software prefetch HBM -> L2, a fixed distance ahead of the copies into the ring: the bulk
         // copies then hit the L2 (short latency: the shallow ring is enough to keep the stream full)
         // and the DRAM traffic stays in consumption order instead of racing the running kernel.
+        const uint8_t *w0p = a.w0, *wgp = a.w_gate;
+        if (a.w_table != nullptr) {
+            // expert weights: the id is written by the routing kernel earlier in this step, so this producer cannot
+            // run ahead of the grid dependency
+            pdl_wait();
+            const int e = *a.moe_id;
+            if (e < 0) return;
+            w0p = a.w_table[e];
+            if (a.wg_table != nullptr) wgp = a.wg_table[e];
+        }
         auto unit_src = [&](int u) -> const uint8_t * {
             if (u >= a.unit2) return a.w2 + (size_t)(u - a.unit2) * mat_bytes;
             if (u >= a.unit1) return a.w1 + (size_t)(u - a.unit1) * mat_bytes;
-            return a.w0 + (size_t)u * mat_bytes;
+            return w0p + (size_t)u * mat_bytes;
         };
         if (a.l2_prefetch > 0) {
             // the first `dist` units: shared out across CTAs and lanes, issued at kernel entry
             for (int u = blockIdx.x * 32 + lane; u < a.l2_prefetch && u < a.units; u += gridDim.x * 32) {
                 bulk_prefetch_l2(unit_src(u), mat_bytes);
-                if (GLU) bulk_prefetch_l2(a.w_gate + (size_t)u * mat_bytes, mat_bytes);
+                if (GLU) bulk_prefetch_l2(wgp + (size_t)u * mat_bytes, mat_bytes);
             }
         }
         // Units are handed out by a global cursor (atomicAdd): SMs do not get equal shares of the
@@ -534,12 +547,12 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_stream_kernel(const Gemv
                     uint8_t *dst = ring + (size_t)pos * a.slot_stride;
                     if (a.l2_prefetch > 0 && u + a.l2_prefetch < a.units) {
                         bulk_prefetch_l2(unit_src(u + a.l2_prefetch), mat_bytes);
-                        if (GLU) bulk_prefetch_l2(a.w_gate + (size_t)(u + a.l2_prefetch) * mat_bytes, mat_bytes);
+                        if (GLU) bulk_prefetch_l2(wgp + (size_t)(u + a.l2_prefetch) * mat_bytes, mat_bytes);
                     }
                     mbar_arrive_expect_tx(&full_bar[pos], mat_bytes * nmat);
                     bulk_g2s_hint(dst, src, mat_bytes, &full_bar[pos], pol);
                     if (GLU)
-                        bulk_g2s_hint(dst + mat_bytes, a.w_gate + (size_t)u * mat_bytes, mat_bytes,
+                        bulk_g2s_hint(dst + mat_bytes, wgp + (size_t)u * mat_bytes, mat_bytes,
                                       &full_bar[pos], pol);
                 } else {
                     mbar_arrive(&full_bar[pos]);   // an empty slot: tells one consumer group to stop
@@ -554,6 +567,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_stream_kernel(const Gemv
     // ===== consumers =====
     pdl_wait();  // x / residual come from the previous kernel
     if (tid == 0) trace_mark(a.trace, 1);
+    if (a.w_table != nullptr && *a.moe_id < 0) return;   // unused expert slot of this token
     uint32_t pflag = 0u;
     const void *xsrc = a.x;
     if constexpr (TP) {
@@ -810,6 +824,11 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     a.trace = (unsigned long long *)g.trace;
     a.counter = (int *)g.counter;
     if (g.tp != nullptr) a.tp = *g.tp;
+    a.w_table = (const uint8_t *const *)g.w_table;
+    a.wg_table = (const uint8_t *const *)g.wg_table;
+    a.moe_id = g.moe_id;
+    IFB_CHECK_ARG(g.w_table == nullptr || (g.moe_id != nullptr && g.nseg == 1), "gemv: an expert table needs the expert id and a single segment");
+    IFB_CHECK_ARG(g.w_table == nullptr || ((g.wg_table != nullptr) == (g.w_gate != nullptr)), "gemv: expert gate table and gate matrix go together");
     IFB_CHECK_ARG(!(a.tp.gather && g.xq != nullptr), "gemv: tensor-parallel gather needs an fp16 activation");
     IFB_CHECK_ARG(a.tp.size >= 1 && a.tp.size <= 8, "gemv: tensor-parallel size %d", a.tp.size);
     {

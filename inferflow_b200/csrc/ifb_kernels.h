@@ -55,6 +55,10 @@ struct GemvLaunch {
     int l2_prefetch = 1;           // ask the L2 for the whole weight set at kernel entry (<= 64 MB)
     void *counter = nullptr;       // int32[8]: work cursor + per-op completion counts, must be 0 at launch (null: library scratch + memset)
     const TpExchange *tp = nullptr;
+    // mixture of experts: the weights of THIS launch are w_table[*moe_id] (and wg_table[*moe_id] for the gate
+    // matrix), the expert id being read on the device after the grid dependency; *moe_id < 0: the launch does nothing
+    const void *const *w_table = nullptr, *const *wg_table = nullptr;
+    const int32_t *moe_id = nullptr;
 };
 int gemv_launch(const GemvLaunch &g, cudaStream_t st);
 // up to 4 GEMVs in ONE launch; op k+1 reads what op k wrote (counter: 8 ints, zero before the launch)
@@ -109,6 +113,13 @@ struct AttnDecode {
     float rope_theta = 10000.0f;
 };
 int attn_decode(const AttnDecode &a, cudaStream_t st);
+
+// router of one token: softmax over the experts' logits (SoftMax_Alg2 semantics), top-k (BuildRowsForMoE), slots in
+// ascending expert order as ProcessGpuLayer_Moe walks them; ids[top_k] (-1 = unused), weights as half
+int moe_route(int32_t *ids, void *weights_f16, const void *logits_f16, int experts, int top_k, int norm, cudaStream_t st);
+// x_out = x_res + sum_k w_k * y_k with the reference's fp16 FMA chain (AddByRowIdx_Kernel, binary_tensor_opr.h:81)
+int moe_combine(void *x_out, const void *x_res, const void *y, const int32_t *ids, const void *weights_f16, int top_k,
+                int64_t d, cudaStream_t st);
 
 int moe_topk(int32_t *ids, float *weights, int32_t *counts, const void *scores, int rows,
              int experts, int top_k, int norm, cudaStream_t st);

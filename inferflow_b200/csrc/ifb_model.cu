@@ -30,6 +30,11 @@ struct DevBuf {
 struct LayerW {
     DevBuf attn_norm, wq, wk, wv, wo, ffn_norm, w1, w2, w3;
     DevBuf kcache, vcache;
+    // mixture of experts (spec.experts > 0): router + one GLU FFN per expert; tbl_* = device arrays of the experts'
+    // weight pointers, read by the GEMV kernel with the expert id the routing kernel chose
+    DevBuf gate;
+    std::vector<DevBuf> ew1, ew3, ew2;
+    DevBuf tbl_w1, tbl_w3, tbl_w2;
 };
 
 struct ifb_model {
@@ -39,6 +44,7 @@ struct ifb_model {
     int q_dim_l = 0, kv_dim_l = 0;
     std::vector<LayerW> layers;
     DevBuf tok_emb, out_norm, lm_head;
+    DevBuf router, moe_ids, moe_wts, moe_y;   // MoE: router logits [experts] f16, slots' expert ids / weights, expert outputs [top_k][d]
     DevBuf x0, x1, qkv, attn_out, hbuf, logits, attn_ws, scalars, trace;   // trace: [512 launches][160 CTAs][8] ns stamps
     int trace_on = 0;
     DevBuf counters;   // one work cursor per launch of a step, zeroed at the start of every step   // scalars: [0]=pos, [1]=token, [2]=next
@@ -93,7 +99,10 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     IFB_CHECK_ARG(s.heads % tp == 0 && s.kv_heads % tp == 0 && s.d_ffn % tp == 0,
                   "tensor parallelism %d does not divide heads %d / kv_heads %d / d_ffn %d", tp,
                   s.heads, s.kv_heads, s.d_ffn);
-    IFB_CHECK_ARG(s.experts == 0, "MoE layers are not built in this runtime yet");
+    IFB_CHECK_ARG(s.experts >= 0 && s.experts <= 32, "experts %d (the routing kernel handles up to 32)", s.experts);
+    IFB_CHECK_ARG(s.experts == 0 || (s.experts_top_k >= 1 && s.experts_top_k <= 8 && s.experts_top_k <= s.experts),
+                  "experts_top_k %d (RowItemForMoe::MAX_SIZE is 8)", s.experts_top_k);
+    IFB_CHECK_ARG(s.experts == 0 || s.tp_size <= 1, "MoE layers are single-GPU in this runtime (the reference cannot run MoE on several GPUs either)");
     IFB_CHECK_ARG(tp <= 8 && s.vocab % tp == 0 && (s.vocab / tp) % 8 == 0, "vocab %d cannot be sharded %d ways", s.vocab, tp);
     IFB_CHECK_ARG(tp == 1 || s.layers <= 127, "tensor parallel: at most 127 layers (exchange index is 8 bits)");
     const int wdt = s.weight_dtype;
@@ -141,11 +150,33 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
         A(L.wk, wbytes(wdt, m->kv_dim_l, d));
         A(L.wv, wbytes(wdt, m->kv_dim_l, d));
         A(L.wo, wbytes(wdt, d, m->q_dim_l));
-        A(L.w1, wbytes(wdt, m->ffn_l, d));
-        A(L.w3, wbytes(wdt, m->ffn_l, d));
-        A(L.w2, wbytes(wdt, d, m->ffn_l));
-        wsum += wbytes(wdt, m->q_dim_l, d) + 2 * wbytes(wdt, m->kv_dim_l, d) + wbytes(wdt, d, m->q_dim_l) +
-                2 * wbytes(wdt, m->ffn_l, d) + wbytes(wdt, d, m->ffn_l);
+        const int64_t ffn_bytes = 2 * wbytes(wdt, m->ffn_l, d) + wbytes(wdt, d, m->ffn_l);
+        if (s.experts == 0) {
+            A(L.w1, wbytes(wdt, m->ffn_l, d));
+            A(L.w3, wbytes(wdt, m->ffn_l, d));
+            A(L.w2, wbytes(wdt, d, m->ffn_l));
+            wsum += ffn_bytes;
+        } else {
+            A(L.gate, (size_t)s.experts * d * 2);     // < tensor_quant_threshold: stays fp16 (network_builder.cc:1558)
+            L.ew1.resize(s.experts); L.ew3.resize(s.experts); L.ew2.resize(s.experts);
+            std::vector<void *> p1(s.experts), p3(s.experts), p2(s.experts);
+            for (int e = 0; e < s.experts; e++) {
+                A(L.ew1[e], wbytes(wdt, m->ffn_l, d));
+                A(L.ew3[e], wbytes(wdt, m->ffn_l, d));
+                A(L.ew2[e], wbytes(wdt, d, m->ffn_l));
+                p1[e] = L.ew1[e].p; p3[e] = L.ew3[e].p; p2[e] = L.ew2[e].p;
+            }
+            A(L.tbl_w1, s.experts * sizeof(void *));
+            A(L.tbl_w3, s.experts * sizeof(void *));
+            A(L.tbl_w2, s.experts * sizeof(void *));
+            if (rc == IFB_OK) {
+                cudaMemcpy(L.tbl_w1.p, p1.data(), s.experts * sizeof(void *), cudaMemcpyHostToDevice);
+                cudaMemcpy(L.tbl_w3.p, p3.data(), s.experts * sizeof(void *), cudaMemcpyHostToDevice);
+                cudaMemcpy(L.tbl_w2.p, p2.data(), s.experts * sizeof(void *), cudaMemcpyHostToDevice);
+            }
+            wsum += (int64_t)s.experts * d * 2 + (int64_t)s.experts_top_k * ffn_bytes;   // bytes READ per token
+        }
+        wsum += wbytes(wdt, m->q_dim_l, d) + 2 * wbytes(wdt, m->kv_dim_l, d) + wbytes(wdt, d, m->q_dim_l);
         int64_t kvb = kv_cache_bytes(s.kv_dtype, m->kv_heads_l, m->hd, s.max_ctx);
         if (kvb < 0 && rc == IFB_OK) { set_last_error("unsupported kv cache type %d", s.kv_dtype); rc = IFB_ERR_TYPE; }
         A(L.kcache, kvb);
@@ -175,6 +206,12 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     A(m->qkv, (size_t)(m->q_dim_l + 2 * m->kv_dim_l) * 2);
     A(m->attn_out, (size_t)m->q_dim_l * 2);
     A(m->hbuf, (size_t)m->ffn_l * 2);
+    if (s.experts > 0) {
+        A(m->router, 256);
+        A(m->moe_ids, 64);
+        A(m->moe_wts, 64);
+        A(m->moe_y, (size_t)s.experts_top_k * d * 2);
+    }
     A(m->logits, (size_t)s.vocab * 2);
     A(m->attn_ws, attn_workspace_bytes(m->heads_l, m->hd));
     A(m->scalars, 256);
@@ -336,9 +373,18 @@ extern "C" int32_t ifb_model_init_synthetic(ifb_model_t *m, uint64_t seed, ifb_s
         TRY(synth_tensor(L.wk.p, wdt, m->kv_dim_l, d, ls + 2, 0.02f, st));
         TRY(synth_tensor(L.wv.p, wdt, m->kv_dim_l, d, ls + 3, 0.02f, st));
         TRY(synth_tensor(L.wo.p, wdt, d, m->q_dim_l, ls + 4, 0.02f, st));
-        TRY(synth_tensor(L.w1.p, wdt, m->ffn_l, d, ls + 5, 0.02f, st));
-        TRY(synth_tensor(L.w3.p, wdt, m->ffn_l, d, ls + 6, 0.02f, st));
-        TRY(synth_tensor(L.w2.p, wdt, d, m->ffn_l, ls + 7, 0.02f, st));
+        if (s.experts == 0) {
+            TRY(synth_tensor(L.w1.p, wdt, m->ffn_l, d, ls + 5, 0.02f, st));
+            TRY(synth_tensor(L.w3.p, wdt, m->ffn_l, d, ls + 6, 0.02f, st));
+            TRY(synth_tensor(L.w2.p, wdt, d, m->ffn_l, ls + 7, 0.02f, st));
+        } else {
+            TRY(synth_tensor(L.gate.p, DT_F16, s.experts, d, ls + 8, 0.05f, st));   // router: non-degenerate expert choice
+            for (int e = 0; e < s.experts; e++) {
+                TRY(synth_tensor(L.ew1[e].p, wdt, m->ffn_l, d, ls + 20 + 3 * e, 0.02f, st));
+                TRY(synth_tensor(L.ew3[e].p, wdt, m->ffn_l, d, ls + 21 + 3 * e, 0.02f, st));
+                TRY(synth_tensor(L.ew2[e].p, wdt, d, m->ffn_l, ls + 22 + 3 * e, 0.02f, st));
+            }
+        }
         li++;
     }
     TRY(synth_tensor(m->tok_emb.p, DT_F16, s.vocab, d, seed * 1000003ull + 11, 1.0f, st));   // same on all ranks
@@ -473,6 +519,17 @@ extern "C" int32_t ifb_model_load_tensor(ifb_model_t *m, const char *name, const
     // BY_ROW (split the contraction dimension)
     if (t == "wo") { IFB_CHECK_ARG(rows == d && cols == (int64_t)s.heads * hd, "wo shape"); return load_shard(L.wo, wdt, host, host_dt, rows, cols, 0, rows, (int64_t)rk * m->q_dim_l, m->q_dim_l, st); }
     if (t == "w2") { IFB_CHECK_ARG(rows == d && cols == s.d_ffn, "w2 shape"); return load_shard(L.w2, wdt, host, host_dt, rows, cols, 0, rows, (int64_t)rk * m->ffn_l, m->ffn_l, st); }
+    // mixture of experts: "gate" [experts][d] (router, kept fp16), "experts.E.w1|w2|w3"
+    if (s.experts > 0) {
+        if (t == "gate") { IFB_CHECK_ARG(rows == s.experts && cols == d, "gate shape"); return load_shard(L.gate, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
+        int e = -1; char wn[16] = {0};
+        if (sscanf(tn, "experts.%d.%15s", &e, wn) == 2 && e >= 0 && e < s.experts) {
+            std::string w(wn);
+            if (w == "w1") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "expert w1 shape"); return load_shard(L.ew1[e], wdt, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
+            if (w == "w3") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "expert w3 shape"); return load_shard(L.ew3[e], wdt, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
+            if (w == "w2") { IFB_CHECK_ARG(rows == d && cols == s.d_ffn, "expert w2 shape"); return load_shard(L.ew2[e], wdt, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
+        }
+    }
     set_last_error("load_tensor: unknown tensor '%s'", name);
     (void)tp;
     return IFB_ERR_ARG;
@@ -489,6 +546,9 @@ extern "C" int32_t ifb_model_tensor_ptr(ifb_model_t *m, const char *name, void *
     else if (n == "logits") b = &m->logits;
     else if (n == "x") b = &m->x0;
     else if (n == "x1") b = &m->x1;
+    else if (n == "router" && m->spec.experts > 0) b = &m->router;
+    else if (n == "moe_ids" && m->spec.experts > 0) b = &m->moe_ids;
+    else if (n == "moe_wts" && m->spec.experts > 0) b = &m->moe_wts;
     else if (n == "hbuf") b = &m->hbuf;
     else if (n == "xchg" && m->spec.tp_size > 1) b = &m->xchg;
     else if (n == "qkv") b = &m->qkv;
@@ -504,6 +564,15 @@ extern "C" int32_t ifb_model_tensor_ptr(ifb_model_t *m, const char *name, void *
             else if (t == "wq") b = &L.wq; else if (t == "wk") b = &L.wk; else if (t == "wv") b = &L.wv;
             else if (t == "wo") b = &L.wo; else if (t == "w1") b = &L.w1; else if (t == "w2") b = &L.w2;
             else if (t == "w3") b = &L.w3; else if (t == "kcache") b = &L.kcache; else if (t == "vcache") b = &L.vcache;
+            else if (t == "gate") b = &L.gate;
+            else {
+                int e = -1; char wn[16] = {0};
+                if (sscanf(tn, "experts.%d.%15s", &e, wn) == 2 && e >= 0 && e < (int)L.ew1.size()) {
+                    std::string w(wn);
+                    if (w == "w1") b = &L.ew1[e]; else if (w == "w3") b = &L.ew3[e]; else if (w == "w2") b = &L.ew2[e];
+                }
+            }
+            if (b != nullptr && b->p == nullptr) b = nullptr;   // e.g. "w1" of a MoE model
         }
     }
     if (!b) { set_last_error("tensor_ptr: unknown tensor '%s'", name); return IFB_ERR_ARG; }
@@ -580,15 +649,17 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         o.w_dtype = wdt; o.nseg = 1; o.w[0] = L.wo.p; o.rows[0] = d; o.cx = m->q_dim_l;
         o.x = m->attn_out.p; o.residual = m->x0.p; o.y = m->x1.p; o.quantize_x = quant_x; o.pdl = pdl; o.smem_budget = m->smem_kb[1] * 1024;
         if (tp > 1) { o.residual = nullptr; t_wo[li] = tp_push_ar(2 * li + 1); o.tp = &t_wo[li]; }             // row-parallel: partial sums go to the peers
-        // --- FFN: norm + quantize + (w1, w3) + SiLU*mul
+        // --- FFN: norm + quantize + (w1, w3) + SiLU*mul  (MoE: the same two launches per active expert slot,
+        //     weights picked on the device: w[0] / w_gate below are only the alignment stand-ins)
+        const bool moe = s.experts > 0;
         GemvLaunch &f = g_glu[li];
-        f.w_dtype = wdt; f.nseg = 1; f.w[0] = L.w1.p; f.w_gate = L.w3.p; f.rows[0] = m->ffn_l; f.cx = d;
+        f.w_dtype = wdt; f.nseg = 1; f.w[0] = moe ? L.ew1[0].p : L.w1.p; f.w_gate = moe ? L.ew3[0].p : L.w3.p; f.rows[0] = m->ffn_l; f.cx = d;
         f.x = m->x1.p; f.norm_w = L.ffn_norm.p; f.norm_eps = s.norm_eps; f.y = m->hbuf.p;
         f.quantize_x = quant_x; f.pdl = pdl; f.smem_budget = m->smem_kb[2] * 1024;
         if (tp > 1) { t_glu[li] = tp_gather_ar(2 * li + 1, m->x0.p, m->x1.p); f.tp = &t_glu[li]; }               // x1 = x0 + sum(wo partials)
         // --- w2 + residual
         GemvLaunch &w2 = g_w2[li];
-        w2.w_dtype = wdt; w2.nseg = 1; w2.w[0] = L.w2.p; w2.rows[0] = d; w2.cx = m->ffn_l;
+        w2.w_dtype = wdt; w2.nseg = 1; w2.w[0] = moe ? L.ew2[0].p : L.w2.p; w2.rows[0] = d; w2.cx = m->ffn_l;
         w2.x = m->hbuf.p; w2.residual = m->x1.p; w2.y = m->x0.p; w2.quantize_x = quant_x; w2.pdl = pdl; w2.smem_budget = m->smem_kb[3] * 1024;
         if (tp > 1) { w2.residual = nullptr; t_w2[li] = tp_push_ar(2 * li + 2); w2.tp = &t_w2[li]; }
     }
@@ -610,7 +681,35 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         ad.kcache = L.kcache.p; ad.vcache = L.vcache.p; ad.workspace = m->attn_ws.p; ad.pos_dev = sc; ad.pdl = pdl;
         ad.trace = TR(n);
         if (parts & PART_ATTN) { TRY(attn_decode(ad, st)); n++; }
-        if (chain == 0) {
+        if (s.experts > 0) {
+            // ProcessGpuLayer_Moe (inference_worker.cc:1924-2146) without the host round trip: router GEMV on the
+            // normalised x1 -> softmax + top-k on the device -> per active slot (ascending expert id) GLU + w2 with
+            // device-selected weights -> out = sum_k w_k * y_k in half, + residual
+            TRY(launch(&g_wo[li], 1));
+            GemvLaunch r;
+            r.w_dtype = DT_F16; r.nseg = 1; r.w[0] = L.gate.p; r.rows[0] = s.experts; r.cx = d;
+            r.x = m->x1.p; r.norm_w = L.ffn_norm.p; r.norm_eps = s.norm_eps; r.y = m->router.p; r.quantize_x = 0; r.pdl = pdl;
+            TRY(launch(&r, 1));
+            if (parts & PART_GEMV) {
+                TRY(moe_route((int32_t *)m->moe_ids.p, m->moe_wts.p, m->router.p, s.experts, s.experts_top_k,
+                              s.moe_norm_top_k_prob, st));
+                n++;
+            }
+            for (int k = 0; k < s.experts_top_k; k++) {
+                GemvLaunch f = g_glu[li], w2 = g_w2[li];
+                f.w_table = (const void *const *)L.tbl_w1.p; f.wg_table = (const void *const *)L.tbl_w3.p;
+                f.moe_id = (const int32_t *)m->moe_ids.p + k;
+                w2.w_table = (const void *const *)L.tbl_w2.p; w2.moe_id = (const int32_t *)m->moe_ids.p + k;
+                w2.residual = nullptr; w2.y = (__half *)m->moe_y.p + (size_t)k * d;
+                TRY(launch(&f, 1));
+                TRY(launch(&w2, 1));
+            }
+            if (parts & PART_GEMV) {
+                TRY(moe_combine(m->x0.p, m->x1.p, m->moe_y.p, (const int32_t *)m->moe_ids.p, m->moe_wts.p,
+                                s.experts_top_k, d, st));
+                n++;
+            }
+        } else if (chain == 0) {
             TRY(launch(&g_wo[li], 1));
             TRY(launch(&g_glu[li], 1));
             TRY(launch(&g_w2[li], 1));

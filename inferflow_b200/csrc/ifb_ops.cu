@@ -248,4 +248,95 @@ int moe_topk(int32_t *ids, float *weights, int32_t *counts, const void *scores, 
     return IFB_OK;
 }
 
+// ---------------------------------------------------------------- MoE routing of one token, all on the device
+// ProcessGpuLayer_Moe (inference_worker.cc:1965-2010): SoftMax over ALL experts (Tensor_SoftMax_Alg2_Kernel,
+// unary_tensor_opr.h:481: fp32 max / exp / sum over a warp, the exponentials stored as half, then multiplied by
+// half(1/sum) in half), D2H, BuildRowsForMoE on the host, experts visited in ascending id. Here: one warp, no D2H.
+__global__ void moe_route_kernel(int32_t *ids, __half *wts, const __half *logits, int experts, int top_k, int norm) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x;
+    __shared__ float s_p[32];
+    float v = lane < experts ? __half2float(logits[lane]) : -INFINITY;
+    float mx = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float ex = lane < experts ? expf(v - mx) : 0.f;
+    float sum = ex;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const __half ph = __hmul(__float2half_rn(ex), __float2half_rn(1.0f / sum));
+    s_p[lane] = lane < experts ? __half2float(ph) : 0.f;
+    __syncwarp();
+    if (lane != 0) return;
+    int id[8];
+    float wt[8];
+    int n = 0;
+    for (int e = 0; e < experts; e++) {       // HostTensorOpr::BuildRowsForMoE (host_tensor_opr.cc:190-244)
+        const float sc = s_p[e];
+        if ((n >= top_k && wt[n - 1] >= sc) || sc < 0.00001f) continue;
+        if (n < top_k) { id[n] = -1; wt[n] = 0.f; n++; }
+        for (int j = n - 1; j >= 0; j--) {
+            if (wt[j] >= sc) break;
+            if (j + 1 < n) { id[j + 1] = id[j]; wt[j + 1] = wt[j]; }
+            id[j] = e;
+            wt[j] = sc;
+        }
+    }
+    if (norm) {
+        float t = 0.f;
+        for (int j = 0; j < n; j++) t += wt[j];
+        for (int j = 0; j < n; j++) wt[j] = __fdiv_rn(wt[j], t);
+    }
+    for (int i = 1; i < n; i++) {             // ascending expert id: the order the reference runs the experts in
+        const int ci = id[i];
+        const float cw = wt[i];
+        int j = i - 1;
+        while (j >= 0 && id[j] > ci) { id[j + 1] = id[j]; wt[j + 1] = wt[j]; j--; }
+        id[j + 1] = ci;
+        wt[j + 1] = cw;
+    }
+    for (int j = 0; j < top_k; j++) {
+        ids[j] = j < n ? id[j] : -1;
+        wts[j] = __float2half_rn(j < n ? wt[j] : 0.f);   // aux_buffer_ holds the weights as half
+    }
+}
+int moe_route(int32_t *ids, void *weights_f16, const void *logits_f16, int experts, int top_k, int norm, cudaStream_t st) {
+    IFB_CHECK_ARG(experts >= 1 && experts <= 32, "moe_route: %d experts (1..32)", experts);
+    IFB_CHECK_ARG(top_k >= 1 && top_k <= 8 && top_k <= experts, "moe_route: top_k %d", top_k);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(32); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    IFB_CUDA(cudaLaunchKernelEx(&cfg, moe_route_kernel, ids, (__half *)weights_f16, (const __half *)logits_f16, experts, top_k, norm));
+    return IFB_OK;
+}
+
+__global__ void moe_combine_kernel(__half *x_out, const __half *x_res, const __half *y, const int32_t *ids,
+                                   const __half *wts, int top_k, int64_t d) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d; i += (int64_t)gridDim.x * blockDim.x) {
+        __half out = __float2half_rn(0.f);                       // out_tensor->AssignZero()
+        for (int k = 0; k < top_k; k++)
+            if (ids[k] >= 0) out = __hfma(y[(int64_t)k * d + i], wts[k], out);   // AddByRowIdx_Kernel: B = fma(A, w, B) in half
+        x_out[i] = __hadd(x_res[i], out);                        // the layer's residual Add
+    }
+}
+int moe_combine(void *x_out, const void *x_res, const void *y, const int32_t *ids, const void *weights_f16, int top_k,
+                int64_t d, cudaStream_t st) {
+    IFB_CHECK_ARG(top_k >= 1 && top_k <= 8 && d > 0, "moe_combine: bad sizes");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((d + 255) / 256)); cfg.blockDim = dim3(256); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    IFB_CUDA(cudaLaunchKernelEx(&cfg, moe_combine_kernel, (__half *)x_out, (const __half *)x_res, (const __half *)y, ids,
+                                (const __half *)weights_f16, top_k, d));
+    return IFB_OK;
+}
+
 }  // namespace ifb

@@ -25,12 +25,13 @@ class ModelSpec:
     tp_size: int = 1
     experts: int = 0
     experts_top_k: int = 0
+    moe_norm_top_k_prob: int = 1
 
     def to_c(self):
         return ModelSpecC(self.layers, self.d_model, self.d_ffn, self.heads, self.kv_heads, self.vocab,
                           self.max_ctx, self.weight_dtype, self.kv_dtype, self.lm_head_dtype,
                           self.rope_order, self.rope_theta, self.norm_eps, self.kq_scale, self.tp_rank,
-                          self.tp_size, self.experts, self.experts_top_k)
+                          self.tp_size, self.experts, self.experts_top_k, self.moe_norm_top_k_prob)
 
 
 # shapes of SURVEY.md section 8

@@ -53,6 +53,46 @@ class OracleModel:
             acc = part if acc is None else orc.f16(acc + part)
         return orc.f16(acc + resid)
 
+    def _ffn(self, prefix, wdt, xn, d, f):
+        """GLU FFN on an already normalised input: silu(w1 x) * (w3 x) -> w2, every tensor stored as half"""
+        g = orc.f16(self._gemv(prefix + "w1", wdt, xn, f, d))
+        u = orc.f16(self._gemv(prefix + "w3", wdt, xn, f, d))
+        h = orc.f16(orc.f16(g / (1.0 + np.exp(-g.astype(np.float64)))) * u)
+        return orc.f16(self._gemv(prefix + "w2", wdt, h, d, f))
+
+    @staticmethod
+    def router_softmax(logits_f16):
+        """Tensor_SoftMax_Alg2_Kernel (unary_tensor_opr.h:481) on one row of <= 32 router logits: fp32 max / exp /
+        butterfly sum over a warp, exponentials stored as half, then multiplied by half(1/sum) in half"""
+        v = np.zeros(32, dtype=np.float32)
+        n = len(logits_f16)
+        v[:n] = logits_f16.astype(np.float32)
+        mx = np.float32(v[:n].max())
+        ex = np.zeros(32, dtype=np.float32)
+        ex[:n] = np.exp((v[:n] - mx).astype(np.float32)).astype(np.float32)
+        ssum = ex.copy()
+        idx = np.arange(32)
+        for o in (16, 8, 4, 2, 1):
+            ssum = (ssum + ssum[idx ^ o]).astype(np.float32)
+        scale = np.float16(np.float32(1.0) / ssum[0])
+        return (ex[:n].astype(np.float16).astype(np.float32) * np.float32(scale)).astype(np.float16)
+
+    def _moe(self, p, wdt, x1n, x1, d, f):
+        """ProcessGpuLayer_Moe (inference_worker.cc:1924-2146) for one token"""
+        s, o = self.s, self.o
+        gate = self.t[p + "gate"][: s.experts * d * 2].view(np.float16).reshape(s.experts, d)
+        logits = orc.f16(o.gemv_f16(gate, x1n, s.experts, d)).astype(np.float16)
+        probs = self.router_softmax(logits)
+        ids, wts, cnt = o.moe_topk(probs.astype(np.float32)[None, :], s.experts_top_k, bool(s.moe_norm_top_k_prob))
+        sel = sorted((int(ids[0, j]), float(wts[0, j])) for j in range(int(cnt[0])))     # ascending expert id
+        self.last_route = sel
+        out = np.zeros(d, dtype=np.float16)
+        for e, w in sel:
+            y = self._ffn(f"{p}experts.{e}.", wdt, x1n, d, f)
+            # AddByRowIdx_Kernel: B = __hfma(A, w, B) -- one rounding
+            out = (y.astype(np.float64) * np.float64(np.float16(w)) + out.astype(np.float64)).astype(np.float16)
+        return orc.f16(x1 + out.astype(np.float32))
+
     def _norm(self, name, x):
         w = self.t[name][: x.size * 2].view(np.float16).astype(np.float32)
         return orc.f16(self.o.rmsnorm(x, w, self.s.norm_eps))
@@ -79,6 +119,9 @@ class OracleModel:
             a = orc.f16(o.attn_decode(q, np.stack(self.K[l]), np.stack(self.V[l]), s.heads, s.kv_heads, hd, 1.0, True))
             x1 = self._gemv_rowpar(p + "wo", wdt, a, d, qd, x)
             x1n = self._norm(p + "ffn_norm", x1)
+            if getattr(s, "experts", 0):
+                x = self._moe(p, wdt, x1n, x1, d, s.d_ffn)
+                continue
             g = orc.f16(self._gemv(p + "w1", wdt, x1n, s.d_ffn, d))
             u = orc.f16(self._gemv(p + "w3", wdt, x1n, s.d_ffn, d))
             h = orc.f16(orc.f16(g / (1.0 + np.exp(-g.astype(np.float64)))) * u)

@@ -92,3 +92,52 @@ def test_graph_replay_matches_eager_and_decode_next():
         outs.append(toks)
         m.close()
     assert outs[0] == outs[1]
+
+
+MOE = [dict(weight_dtype=orc.Q4_B32T1A, experts=8, experts_top_k=2), dict(weight_dtype=orc.Q8_B32T2, experts=4, experts_top_k=2),
+       dict(weight_dtype=orc.Q4_B32T1A, experts=4, experts_top_k=1, moe_norm_top_k_prob=0)]
+
+
+@pytest.mark.parametrize("cfg", MOE, ids=[f"{orc.NAMES[c['weight_dtype']]}-e{c['experts']}k{c['experts_top_k']}" for c in MOE])
+def test_moe_decode_matches_oracle(cfg):
+    """mixture-of-experts FFN (ProcessGpuLayer_Moe): router GEMV, softmax + top-k ON THE DEVICE (expert ids bit-exact
+    with the host rule), expert FFNs with device-selected weights, half-precision FMA combine"""
+    import inferflow_b200 as ib
+    torch.zeros(1, device="cuda")
+    spec = ib.ModelSpec(layers=2, d_model=256, d_ffn=512, heads=4, kv_heads=4, vocab=512, max_ctx=64,
+                        kv_dtype=orc.Q8_B32T2, **cfg)
+    m = ib.Model(spec)
+    m.init_synthetic(seed=11)
+    t = {n: m.read_tensor(n) for n in ("tok_embeddings", "output_norm", "output")}
+    for l in range(spec.layers):
+        for n in ("attention_norm", "ffn_norm", "wq", "wk", "wv", "wo", "gate"):
+            t[f"layers.{l}.{n}"] = m.read_tensor(f"layers.{l}.{n}")
+        for e in range(spec.experts):
+            for n in ("w1", "w2", "w3"):
+                t[f"layers.{l}.experts.{e}.{n}"] = m.read_tensor(f"layers.{l}.experts.{e}.{n}")
+    orcm = OracleModel(spec, t)
+    tok = 9
+    seen = set()
+    for pos in range(6):
+        m.decode(tok, pos)
+        ib.check(ib.lib.ifb_device_synchronize(), "sync")
+        logits = np.empty(spec.vocab, dtype=np.float16)
+        ib.check(ib.lib.ifb_memcpy_d2h(logits.ctypes.data, m.logits_ptr, spec.vocab * 2), "d2h")
+        nxt = np.empty(1, dtype=np.int32)
+        ib.check(ib.lib.ifb_memcpy_d2h(nxt.ctypes.data, m.next_token_ptr, 4), "d2h")
+        want = orcm.step(tok, pos)
+        # the routing of the LAST layer is still in the device buffers: expert ids bit-exact, weights to the half
+        ids = m.read_tensor("moe_ids", 4 * spec.experts_top_k).view(np.int32)
+        wts = m.read_tensor("moe_wts", 2 * spec.experts_top_k).view(np.float16)
+        route = orcm.last_route
+        assert [int(i) for i in ids if i >= 0] == [e for e, _ in route], f"pos {pos}: expert ids {ids} vs oracle {route}"
+        for (e, w), got in zip(route, wts):
+            assert abs(float(got) - w) <= 2 ** -10 * max(w, 2 ** -4), f"pos {pos}: weight of expert {e}: {got} vs {w}"
+        seen.update(e for e, _ in route)
+        scale = np.abs(want).max()
+        err = np.abs(logits.astype(np.float64) - want).max()
+        assert err <= 2 ** -7 * scale, f"pos {pos}: logits differ by {err:.3e} (range {scale:.3e})"
+        tok = int(nxt[0])
+    assert len(seen) >= 2, "degenerate routing: the test never switched experts"
+    assert m.launches_per_step == 1 + (6 + 2 * spec.experts_top_k) * spec.layers + 3
+    m.close()
