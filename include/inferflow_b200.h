@@ -167,6 +167,19 @@ int32_t ifb_moe_topk(int32_t *ids, float *weights, int32_t *counts, const void *
                      int32_t rows, int32_t experts, int32_t top_k, int32_t norm_top_k_prob,
                      ifb_stream_t stream);
 
+/* The whole routing of ONE token on the device (no D2H): Tensor_SoftMax_Alg2_Kernel over the experts' logits
+ * (unary_tensor_opr.h:481: fp32 max/exp/sum, exponentials stored as half, scaled by half(1/sum) in half), then
+ * BuildRowsForMoE, slots in ascending expert id -- the order ProcessGpuLayer_Moe runs the experts in
+ * (inference_worker.cc:2027-2040). logits fp16 [experts <= 32] -> ids int32 [top_k] (-1 = unused slot),
+ * weights fp16 [top_k]. */
+int32_t ifb_moe_route(int32_t *ids, void *weights_f16, const void *logits_f16, int32_t experts, int32_t top_k,
+                      int32_t norm_top_k_prob, ifb_stream_t stream);
+/* x_out[d] = x_res + sum over the used slots of w_k * y_k[d], accumulated as AddByRowIdx_Kernel does
+ * (binary_tensor_opr.h:81: B = __hfma(A, w, B) in half, slots in order), then the layer's residual Add.
+ * y fp16 [top_k][d]. */
+int32_t ifb_moe_combine(void *x_out_f16, const void *x_res_f16, const void *y_f16, const int32_t *ids,
+                        const void *weights_f16, int32_t top_k, int64_t d, ifb_stream_t stream);
+
 /* ------------------------------------------------------------------ model runtime
  * The per-GPU decode runtime behind GpuInferenceWorker::Run / ProcessGpuLayer
  * (inference_worker.cc:234-977) for pre-norm llama-family decoders, one instance per GPU

@@ -75,6 +75,8 @@ def _load():
     L.ifb_attn_workspace_bytes.restype = i64
     L.ifb_attn_workspace_bytes.argtypes = [i32, i32]
     L.ifb_attn_decode.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp]
+    L.ifb_moe_route.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    L.ifb_moe_combine.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp]
     L.ifb_attn_decode_append.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, i32, f32, vp, vp]
     L.ifb_moe_topk.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.ifb_model_create.argtypes = [C.POINTER(vp), C.POINTER(ModelSpecC)]
@@ -108,7 +110,7 @@ DECLARED = [
     "ifb_version", "ifb_last_error", "ifb_block_capacity", "ifb_block_bytes", "ifb_row_bytes",
     "ifb_dtype_from_name", "ifb_quantize_rows", "ifb_dequantize_rows", "ifb_gemv", "ifb_gemv_fused",
     "ifb_rmsnorm", "ifb_rope", "ifb_silu_mul", "ifb_add", "ifb_argmax", "ifb_kv_cache_bytes",
-    "ifb_kv_append", "ifb_kv_get_rows", "ifb_attn_workspace_bytes", "ifb_attn_decode", "ifb_attn_decode_append", "ifb_moe_topk",
+    "ifb_kv_append", "ifb_kv_get_rows", "ifb_attn_workspace_bytes", "ifb_attn_decode", "ifb_attn_decode_append", "ifb_moe_topk", "ifb_moe_route", "ifb_moe_combine",
     "ifb_model_create", "ifb_model_destroy", "ifb_model_weight_bytes", "ifb_model_kv_bytes_per_token",
     "ifb_model_init_synthetic", "ifb_model_load_tensor", "ifb_model_kv_reset", "ifb_model_decode",
     "ifb_model_logits", "ifb_model_next_token", "ifb_model_kernel_launches_per_step",

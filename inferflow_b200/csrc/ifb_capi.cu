@@ -178,4 +178,15 @@ int32_t ifb_moe_topk(int32_t *ids, float *w, int32_t *cnt, const void *scores, i
     return moe_topk(ids, w, cnt, scores, rows, experts, top_k, norm, (cudaStream_t)st);
 }
 
+int32_t ifb_moe_route(int32_t *ids, void *w, const void *logits, int32_t experts, int32_t top_k, int32_t norm,
+                      ifb_stream_t st) {
+    IFB_CHECK_ARG(ids && w && logits, "moe_route: null tensor");
+    return moe_route(ids, w, logits, experts, top_k, norm, (cudaStream_t)st);
+}
+int32_t ifb_moe_combine(void *x_out, const void *x_res, const void *y, const int32_t *ids, const void *w,
+                        int32_t top_k, int64_t d, ifb_stream_t st) {
+    IFB_CHECK_ARG(x_out && x_res && y && ids && w, "moe_combine: null tensor");
+    return moe_combine(x_out, x_res, y, ids, w, top_k, d, (cudaStream_t)st);
+}
+
 }  // extern "C"

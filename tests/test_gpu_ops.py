@@ -350,6 +350,44 @@ def test_moe_topk_bit_exact(ib):
             assert np.array_equal(wts.cpu().numpy().reshape(rows, k), g[f"w_k{k}_n{norm}"])
 
 
+def test_moe_route_and_combine(ib):
+    """device routing of one token = router softmax (reference kernel arithmetic) + BuildRowsForMoE + ascending
+    expert order; combine = the reference's half-precision FMA chain + residual"""
+    from orc_model import OracleModel
+    o = orc.oracle()
+    rng = np.random.default_rng(77)
+    for trial in range(40):
+        experts = int(rng.choice([2, 4, 8, 16, 32]))
+        top_k = int(rng.integers(1, min(experts, 8) + 1))
+        norm = int(rng.integers(0, 2))
+        logits = (rng.normal(0, 2.0, experts)).astype(np.float16)
+        if trial % 5 == 0:
+            logits[: experts // 2] = logits[0]          # ties: the first expert wins
+        probs = OracleModel.router_softmax(logits)
+        ids_w, wts_w, cnt = o.moe_topk(probs.astype(np.float32)[None, :], top_k, bool(norm))
+        want = sorted((int(ids_w[0, j]), float(wts_w[0, j])) for j in range(int(cnt[0])))
+        ids = torch.full((top_k,), 7, dtype=torch.int32, device="cuda")
+        wts = torch.zeros(top_k, dtype=torch.float16, device="cuda")
+        ib.check(ib.lib.ifb_moe_route(ptr(ids), ptr(wts), ptr(dev(logits)), experts, top_k, norm, None), "moe_route")
+        gi, gw = ids.cpu().numpy(), wts.cpu().numpy()
+        assert [int(i) for i in gi if i >= 0] == [e for e, _ in want], (trial, gi, want)
+        assert all(int(i) == -1 for i in gi[len(want):])
+        for (e, w), g in zip(want, gw):
+            assert abs(float(g) - w) <= 2 ** -10 * max(w, 2 ** -4), (trial, e, float(g), w)
+        # combine with THE DEVICE's ids / weights: bit-exact half arithmetic
+        d = 512
+        y = rng.normal(0, 1, (top_k, d)).astype(np.float16)
+        xr = rng.normal(0, 1, d).astype(np.float16)
+        out = torch.zeros(d, dtype=torch.float16, device="cuda")
+        ib.check(ib.lib.ifb_moe_combine(ptr(out), ptr(dev(xr)), ptr(dev(y)), ptr(ids), ptr(wts), top_k, d, None), "moe_combine")
+        acc = np.zeros(d, dtype=np.float16)
+        for k in range(top_k):
+            if gi[k] >= 0:
+                acc = (y[k].astype(np.float64) * np.float64(gw[k]) + acc.astype(np.float64)).astype(np.float16)
+        wantx = (xr.astype(np.float32) + acc.astype(np.float32)).astype(np.float16)
+        assert np.array_equal(out.cpu().numpy(), wantx)
+
+
 # ------------------------------------------------------------------ KV cache + attention
 def _kv_setup(ib, kv_dt, kv_heads, hd, max_ctx, k_rows, v_rows):
     nb = ib.lib.ifb_kv_cache_bytes(kv_dt, kv_heads, hd, max_ctx)
