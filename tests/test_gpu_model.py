@@ -141,3 +141,4 @@ def test_moe_decode_matches_oracle(cfg):
     assert len(seen) >= 2, "degenerate routing: the test never switched experts"
     assert m.launches_per_step == 1 + (6 + 2 * spec.experts_top_k) * spec.layers + 3
     m.close()
+

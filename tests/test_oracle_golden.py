@@ -98,3 +98,22 @@ def test_round_trip_error_bounds():
 def test_q3h_fast_div11_exhaustive():
     """the device decoder's P/11 shortcut (ifb_formats.cuh) is exact on the 7-bit pair range"""
     assert all((P * 187) >> 11 == P // 11 for P in range(128))
+
+
+def test_router_softmax_restatement_is_a_softmax():
+    """tests/orc_model.py restates the reference softmax kernel's fp16 arithmetic for the MoE router: it must stay
+    within half-precision distance of the exact softmax, sum to ~1 and keep the order of the logits"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from orc_model import OracleModel
+    rng = np.random.default_rng(9)
+    for n in (2, 4, 8, 16, 32):
+        for _ in range(20):
+            z = rng.normal(0, 3, n).astype(np.float16)
+            p = OracleModel.router_softmax(z).astype(np.float64)
+            e = np.exp(z.astype(np.float64) - z.astype(np.float64).max())
+            want = e / e.sum()
+            assert np.abs(p - want).max() <= 2 ** -9
+            assert abs(p.sum() - 1.0) <= n * 2 ** -10
+            order = np.argsort(-z.astype(np.float64), kind="stable")
+            assert np.all(np.diff(p[order]) <= 1e-12)
