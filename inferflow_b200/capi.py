@@ -44,7 +44,7 @@ class ModelSpecC(C.Structure):
 def _load():
     if not os.path.exists(_SO):
         raise IfbError(
-            f"{_SO} is missing: build it with `python -m inferflow_b200.build` "
+            f"{_SO} is missing: build it with `python inferflow_b200/build.py` "
             "(or __graft_entry__.build()). There is no fallback path.")
     L = C.CDLL(_SO)
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
