@@ -242,6 +242,8 @@ extern "C" void ifb_model_destroy(ifb_model_t *m) {
     if (!m) return;
     if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
     if (m->graph) cudaGraphDestroy(m->graph);
+    for (size_t p = 0; p < m->peer_xchg.size(); p++)       // unmap the peers' exchange regions (ours is in allocs)
+        if ((int)p != m->spec.tp_rank && m->peer_xchg[p] != nullptr) cudaIpcCloseMemHandle(m->peer_xchg[p]);
     for (void *p : m->allocs) cudaFree(p);
     delete m;
 }
