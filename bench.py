@@ -389,6 +389,9 @@ def run_ours(args):
                         "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
 
     launches = model.launches_per_step
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()          # no rank frees its exchange region while a peer's last kernels still store into it
     model.close()
     if dist is not None:
         dist.barrier()
