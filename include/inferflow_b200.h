@@ -217,6 +217,17 @@ int32_t ifb_model_init_synthetic(ifb_model_t *m, uint64_t seed, ifb_stream_t str
  * ffn_norm,w1,w2,w3}" ; data is the FULL (unsharded) [rows][cols] matrix */
 int32_t ifb_model_load_tensor(ifb_model_t *m, const char *name, const void *host_data,
                               int32_t host_dtype, int64_t rows, int64_t cols, ifb_stream_t stream);
+/* Read a model file in the llama2.c format the reference reads (ModelReader::LoadModel_Llama2DotC,
+ * model_reader.cc:3245-3427: optional "ak42" v1 header or 7 x int32 {dim, hidden, layers, heads, kv_heads, +-vocab,
+ * seq_len}, then fp32 tensors: tok_embeddings, all layers' attention_norm, wq, wk, wv, wo, ffn_norm, w1, w2, w3,
+ * output_norm, seq_len*head_dim BYTES of rope tables (as the reference skips them), and the classifier when vocab < 0),
+ * create the runtime for it (llama2.c RoPE order, fp16 lm_head, shared classifier when the file has none) and load
+ * every tensor through ifb_model_load_tensor -- the same file drives the reference engine and this runtime.
+ * header_out (optional): the 7 header ints as read (vocab made positive). */
+int32_t ifb_llama2c_probe(const char *path, int32_t header_out[7], int32_t *shared_classifier);
+int32_t ifb_model_load_llama2c(ifb_model_t **out, const char *path, int32_t weight_dtype, int32_t kv_dtype,
+                               int32_t max_ctx, ifb_stream_t stream);
+
 /* reset the KV length (and optionally fill `ctx_len` synthetic rows for benchmarking) */
 int32_t ifb_model_kv_reset(ifb_model_t *m, int32_t ctx_len, int32_t fill_synthetic, uint64_t seed,
                            ifb_stream_t stream);

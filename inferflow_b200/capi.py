@@ -98,6 +98,8 @@ def _load():
     L.ifb_model_next_token.restype = vp
     L.ifb_model_next_token.argtypes = [vp]
     L.ifb_model_kernel_launches_per_step.argtypes = [vp]
+    L.ifb_llama2c_probe.argtypes = [C.c_char_p, vp, vp]
+    L.ifb_model_load_llama2c.argtypes = [vp, C.c_char_p, i32, i32, i32, vp]
     L.ifb_model_tp_export.argtypes = [vp, vp]
     L.ifb_model_tp_import.argtypes = [vp, vp, i32]
     return L
@@ -111,7 +113,7 @@ DECLARED = [
     "ifb_dtype_from_name", "ifb_quantize_rows", "ifb_dequantize_rows", "ifb_gemv", "ifb_gemv_fused",
     "ifb_rmsnorm", "ifb_rope", "ifb_silu_mul", "ifb_add", "ifb_argmax", "ifb_kv_cache_bytes",
     "ifb_kv_append", "ifb_kv_get_rows", "ifb_attn_workspace_bytes", "ifb_attn_decode", "ifb_attn_decode_append", "ifb_moe_topk", "ifb_moe_route", "ifb_moe_combine",
-    "ifb_model_create", "ifb_model_destroy", "ifb_model_weight_bytes", "ifb_model_kv_bytes_per_token",
+    "ifb_llama2c_probe", "ifb_model_load_llama2c", "ifb_model_create", "ifb_model_destroy", "ifb_model_weight_bytes", "ifb_model_kv_bytes_per_token",
     "ifb_model_init_synthetic", "ifb_model_load_tensor", "ifb_model_kv_reset", "ifb_model_decode",
     "ifb_model_logits", "ifb_model_next_token", "ifb_model_kernel_launches_per_step",
     "ifb_model_tp_export", "ifb_model_tp_import", "ifb_model_decode_next", "ifb_model_tensor_ptr",

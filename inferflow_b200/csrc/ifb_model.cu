@@ -11,6 +11,7 @@
 // creates/joins a thread per token, this runtime issues 6 fused kernels per layer, chained
 // with programmatic dependent launch, and replays the whole token as ONE CUDA graph whose
 // position / token inputs live in device memory.
+#include <cstdio>
 #include <string>
 #include <vector>
 #include <cstring>
@@ -535,6 +536,118 @@ extern "C" int32_t ifb_model_load_tensor(ifb_model_t *m, const char *name, const
     set_last_error("load_tensor: unknown tensor '%s'", name);
     (void)tp;
     return IFB_ERR_ARG;
+}
+
+// ---------------------------------------------------------------------------------------
+// llama2.c model files (the format of the reference's tiny models, model_reader.cc:3245-3427)
+// ---------------------------------------------------------------------------------------
+struct L2cHeader { int32_t dim, hidden, layers, heads, kv_heads, vocab, seq; bool shared; long data_off; };
+
+static int l2c_read_header(FILE *f, L2cHeader &h) {
+    uint32_t magic = 0;
+    if (fread(&magic, 4, 1, f) != 1) { set_last_error("llama2.c: cannot read the file header"); return IFB_ERR_IO; }
+    int version = 0;
+    if (magic == 0x616b3432u) {   // "ak42"
+        if (fread(&version, 4, 1, f) != 1 || version != 1) { set_last_error("llama2.c: version %d is not supported", version); return IFB_ERR_IO; }
+    } else {
+        fseek(f, 0, SEEK_SET);
+    }
+    int32_t v[7];
+    if (fread(v, 4, 7, f) != 7) { set_last_error("llama2.c: truncated header"); return IFB_ERR_IO; }
+    h.dim = v[0]; h.hidden = v[1]; h.layers = v[2]; h.heads = v[3]; h.kv_heads = v[4]; h.vocab = v[5]; h.seq = v[6];
+    h.shared = h.vocab >= 0;
+    if (h.vocab < 0) h.vocab = -h.vocab;
+    if (version == 1) {           // v1: shared_classifier byte, then padding up to 256 bytes
+        uint8_t sc = 0;
+        if (fread(&sc, 1, 1, f) != 1) { set_last_error("llama2.c: truncated v1 header"); return IFB_ERR_IO; }
+        h.shared = sc != 0;
+        fseek(f, 256, SEEK_SET);
+    }
+    h.data_off = ftell(f);
+    if (h.dim <= 0 || h.hidden <= 0 || h.layers <= 0 || h.heads <= 0 || h.kv_heads <= 0 || h.vocab <= 0 || h.seq <= 0 ||
+        h.dim % h.heads != 0 || h.heads % h.kv_heads != 0 || h.dim > (1 << 20) || h.layers > 4096 || h.vocab > (1 << 24)) {
+        set_last_error("llama2.c: implausible header (dim %d hidden %d layers %d heads %d kv_heads %d vocab %d seq %d)",
+                       h.dim, h.hidden, h.layers, h.heads, h.kv_heads, h.vocab, h.seq);
+        return IFB_ERR_IO;
+    }
+    return IFB_OK;
+}
+
+extern "C" int32_t ifb_llama2c_probe(const char *path, int32_t header_out[7], int32_t *shared_classifier) {
+    IFB_CHECK_ARG(path != nullptr, "llama2c_probe: null path");
+    FILE *f = fopen(path, "rb");
+    if (!f) { set_last_error("llama2.c: cannot open %s", path); return IFB_ERR_IO; }
+    L2cHeader h;
+    int rc = l2c_read_header(f, h);
+    if (rc == IFB_OK) {
+        // the file must hold every tensor the header promises
+        const int64_t hd = h.dim / h.heads, kvd = (int64_t)h.kv_heads * hd;
+        int64_t floats = (int64_t)h.vocab * h.dim + (int64_t)h.layers * (2 * h.dim + 2 * (int64_t)h.dim * h.dim + 2 * kvd * h.dim +
+                                                                         3 * (int64_t)h.hidden * h.dim) + h.dim;
+        int64_t need = h.data_off + floats * 4 + (int64_t)h.seq * hd + (h.shared ? 0 : (int64_t)h.vocab * h.dim * 4);
+        fseek(f, 0, SEEK_END);
+        const int64_t have = ftell(f);
+        if (have < need) { set_last_error("llama2.c: %s holds %lld bytes, the header needs %lld", path, (long long)have, (long long)need); rc = IFB_ERR_IO; }
+    }
+    fclose(f);
+    if (rc != IFB_OK) return rc;
+    if (header_out) { header_out[0] = h.dim; header_out[1] = h.hidden; header_out[2] = h.layers; header_out[3] = h.heads;
+                      header_out[4] = h.kv_heads; header_out[5] = h.vocab; header_out[6] = h.seq; }
+    if (shared_classifier) *shared_classifier = h.shared ? 1 : 0;
+    return IFB_OK;
+}
+
+extern "C" int32_t ifb_model_load_llama2c(ifb_model_t **out, const char *path, int32_t weight_dtype, int32_t kv_dtype,
+                                          int32_t max_ctx, ifb_stream_t stream) {
+    IFB_CHECK_ARG(out != nullptr && path != nullptr, "load_llama2c: null argument");
+    int32_t hv[7];
+    int32_t shared = 1;
+    TRY(ifb_llama2c_probe(path, hv, &shared));
+    ifb_model_spec_t s = {};
+    s.d_model = hv[0]; s.d_ffn = hv[1]; s.layers = hv[2]; s.heads = hv[3]; s.kv_heads = hv[4]; s.vocab = hv[5];
+    s.max_ctx = max_ctx > 0 ? max_ctx : hv[6];
+    s.weight_dtype = weight_dtype; s.kv_dtype = kv_dtype; s.lm_head_dtype = DT_F16;
+    s.rope_order = 0;              // llama2.c stores q/k for interleaved rotation (model_spec qk_column_order 0)
+    s.rope_theta = 10000.0f; s.norm_eps = 1e-5f; s.kq_scale = 1.0f; s.tp_rank = 0; s.tp_size = 1;
+    ifb_model_t *m = nullptr;
+    TRY(ifb_model_create(&m, &s));
+    FILE *f = fopen(path, "rb");
+    if (!f) { ifb_model_destroy(m); set_last_error("llama2.c: cannot open %s", path); return IFB_ERR_IO; }
+    L2cHeader h;
+    int rc = l2c_read_header(f, h);
+    const int64_t d = s.d_model, hd = d / s.heads, kvd = (int64_t)s.kv_heads * hd, ff = s.d_ffn;
+    std::vector<float> buf;
+    auto load = [&](const char *name, int64_t rows, int64_t cols) -> int {
+        buf.resize((size_t)rows * cols);
+        if (fread(buf.data(), 4, buf.size(), f) != buf.size()) { set_last_error("llama2.c: %s is truncated at %s", path, name); return IFB_ERR_IO; }
+        return ifb_model_load_tensor(m, name, buf.data(), DT_F32, rows, cols, stream);
+    };
+    if (rc == IFB_OK) rc = load("tok_embeddings", s.vocab, d);
+    const bool keep_emb = rc == IFB_OK && shared;
+    std::vector<float> emb;
+    if (keep_emb) emb = buf;       // shared classifier: the embedding table is the lm_head too
+    struct { const char *n; int64_t rows, cols; } per_layer[] = {
+        {"attention_norm", 1, d}, {"wq", d, d}, {"wk", kvd, d}, {"wv", kvd, d}, {"wo", d, d},
+        {"ffn_norm", 1, d}, {"w1", ff, d}, {"w2", d, ff}, {"w3", ff, d}};
+    for (auto &t : per_layer)
+        for (int l = 0; l < s.layers && rc == IFB_OK; l++) {
+            char name[64];
+            snprintf(name, sizeof(name), "layers.%d.%s", l, t.n);
+            rc = load(name, t.rows, t.cols);
+        }
+    if (rc == IFB_OK) rc = load("output_norm", 1, d);
+    if (rc == IFB_OK) {
+        if (shared) {
+            rc = ifb_model_load_tensor(m, "output", emb.data(), DT_F32, s.vocab, d, stream);
+        } else {
+            fseek(f, (long)((int64_t)h.seq * hd), SEEK_CUR);   // the reference skips exactly this many BYTES (model_reader.cc:3420)
+            rc = load("output", s.vocab, d);
+        }
+    }
+    fclose(f);
+    if (rc != IFB_OK) { ifb_model_destroy(m); return rc; }
+    *out = m;
+    return IFB_OK;
 }
 
 // raw access for tests (read back weights / activations / cache)

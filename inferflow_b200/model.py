@@ -40,12 +40,35 @@ LLAMA2_70B = dict(layers=80, d_model=8192, d_ffn=28672, heads=64, kv_heads=8, vo
 STORIES_110M = dict(layers=12, d_model=768, d_ffn=2048, heads=12, kv_heads=12, vocab=32000)
 
 
+def probe_llama2c(path):
+    """(dim, hidden, layers, heads, kv_heads, vocab, seq), shared_classifier of a llama2.c model file"""
+    hv = (C.c_int32 * 7)()
+    shared = C.c_int32(0)
+    check(lib.ifb_llama2c_probe(path.encode(), hv, C.byref(shared)), "ifb_llama2c_probe")
+    return tuple(hv), bool(shared.value)
+
+
 class Model:
-    def __init__(self, spec: ModelSpec):
+    def __init__(self, spec: ModelSpec, _handle=None):
         self.spec = spec
         self._h = C.c_void_p()
+        if _handle is not None:
+            self._h = _handle
+            return
         c = spec.to_c()
         check(lib.ifb_model_create(C.byref(self._h), C.byref(c)), "ifb_model_create")
+
+    @classmethod
+    def from_llama2c(cls, path, weight_dtype=DT.F16, kv_dtype=DT.F16, max_ctx=0, stream=0):
+        """the reference's llama2.c file format (model_reader.cc:3245-3427) -> a loaded runtime"""
+        (dim, hidden, layers, heads, kv_heads, vocab, seq), _ = probe_llama2c(path)
+        h = C.c_void_p()
+        check(lib.ifb_model_load_llama2c(C.byref(h), path.encode(), weight_dtype, kv_dtype, max_ctx, stream),
+              "ifb_model_load_llama2c")
+        spec = ModelSpec(layers=layers, d_model=dim, d_ffn=hidden, heads=heads, kv_heads=kv_heads, vocab=vocab,
+                         max_ctx=max_ctx if max_ctx > 0 else seq, weight_dtype=weight_dtype, kv_dtype=kv_dtype,
+                         lm_head_dtype=DT.F16, rope_order=0)
+        return cls(spec, _handle=h)
 
     def close(self):
         if self._h:
