@@ -226,7 +226,8 @@ int32_t ifb_model_load_tensor(ifb_model_t *m, const char *name, const void *host
  * header_out (optional): the 7 header ints as read (vocab made positive). */
 int32_t ifb_llama2c_probe(const char *path, int32_t header_out[7], int32_t *shared_classifier);
 int32_t ifb_model_load_llama2c(ifb_model_t **out, const char *path, int32_t weight_dtype, int32_t kv_dtype,
-                               int32_t max_ctx, ifb_stream_t stream);
+                               int32_t max_ctx, int32_t rope_order /* qk_column_order; < 0: the format's 0 */,
+                               ifb_stream_t stream);
 
 /* reset the KV length (and optionally fill `ctx_len` synthetic rows for benchmarking) */
 int32_t ifb_model_kv_reset(ifb_model_t *m, int32_t ctx_len, int32_t fill_synthetic, uint64_t seed,
@@ -252,6 +253,31 @@ int32_t ifb_model_kernel_launches_per_step(const ifb_model_t *m);
  * the host side (torch.distributed all_gather / MPI / fork) hands all handles to every rank */
 int32_t ifb_model_tp_export(ifb_model_t *m, void *host_handle_64B);
 int32_t ifb_model_tp_import(ifb_model_t *m, const void *host_handles_64B_each, int32_t n);
+
+/* ------------------------------------------------------------------ engine-shaped host layer
+ * The outermost seam of the reference for this path, for ONE live query and greedy decoding
+ * (InferenceEngine, src/transformer/inference_engine.h:39-66,118): it reads the same .ini (layout of
+ * bin/llm_inference*.ini: [transformer_engine] models / return_output_tensors, [model.<id>] model_dir,
+ * model_specification_file, device_weight_data_type, device_kv_cache_data_type, max_context_len,
+ * tensor_quant_threshold, [app_env.base] data_root_dir; ${config_dir} ${data_root_dir} ${model_name} macros) and the
+ * model specification json, for model_file_format "llama2.c". Token ids in, token ids out (tokenizer and samplers
+ * other than greedy are out of scope). */
+typedef struct ifb_engine ifb_engine_t;
+/* LoadConfig, resolved without touching the GPU. info_out = {weight_dtype, kv_dtype, max_context_len,
+ * qk_column_order, return_output_tensors} */
+int32_t ifb_engine_resolve(const char *ini_path, const char *section, const char *data_root_dir,
+                           char *model_path_out, int32_t path_capacity, int32_t info_out[5]);
+/* LoadConfig + Init */
+int32_t ifb_engine_create(ifb_engine_t **out, const char *ini_path, const char *section, const char *data_root_dir);
+void ifb_engine_destroy(ifb_engine_t *e);
+int32_t ifb_engine_vocab_size(const ifb_engine_t *e);
+/* AddQuery: > 0 query id, 0 busy, < 0 error */
+int32_t ifb_engine_add_query(ifb_engine_t *e, const int32_t *tokens, int32_t n);
+/* Infer: the whole prompt on the first call, the committed token afterwards; logits_f32 optional [vocab] */
+int32_t ifb_engine_infer(ifb_engine_t *e, int32_t *next_token, float *logits_f32);
+/* CommitInferenceResult / RemoveQuery */
+int32_t ifb_engine_commit(ifb_engine_t *e, int32_t token, int32_t is_end);
+int32_t ifb_engine_remove_query(ifb_engine_t *e, int32_t query_id);
 
 #ifdef __cplusplus
 }

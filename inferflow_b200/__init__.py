@@ -6,4 +6,4 @@ it plus small helpers for tests and bench.py; there is NO Python / CPU fallback:
 library is missing or there is no CUDA device, calls raise.
 """
 from .capi import lib, check, IfbError, DT, dtype_from_name, row_bytes  # noqa: F401
-from .model import Model, ModelSpec, probe_llama2c, LLAMA2_7B, LLAMA2_70B, STORIES_110M  # noqa: F401
+from .model import Model, ModelSpec, Engine, resolve_config, probe_llama2c, LLAMA2_7B, LLAMA2_70B, STORIES_110M  # noqa: F401

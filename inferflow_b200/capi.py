@@ -98,8 +98,17 @@ def _load():
     L.ifb_model_next_token.restype = vp
     L.ifb_model_next_token.argtypes = [vp]
     L.ifb_model_kernel_launches_per_step.argtypes = [vp]
+    L.ifb_engine_resolve.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, vp, i32, vp]
+    L.ifb_engine_create.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
+    L.ifb_engine_destroy.argtypes = [vp]
+    L.ifb_engine_destroy.restype = None
+    L.ifb_engine_vocab_size.argtypes = [vp]
+    L.ifb_engine_add_query.argtypes = [vp, vp, i32]
+    L.ifb_engine_infer.argtypes = [vp, vp, vp]
+    L.ifb_engine_commit.argtypes = [vp, i32, i32]
+    L.ifb_engine_remove_query.argtypes = [vp, i32]
     L.ifb_llama2c_probe.argtypes = [C.c_char_p, vp, vp]
-    L.ifb_model_load_llama2c.argtypes = [vp, C.c_char_p, i32, i32, i32, vp]
+    L.ifb_model_load_llama2c.argtypes = [vp, C.c_char_p, i32, i32, i32, i32, vp]
     L.ifb_model_tp_export.argtypes = [vp, vp]
     L.ifb_model_tp_import.argtypes = [vp, vp, i32]
     return L
@@ -113,7 +122,8 @@ DECLARED = [
     "ifb_dtype_from_name", "ifb_quantize_rows", "ifb_dequantize_rows", "ifb_gemv", "ifb_gemv_fused",
     "ifb_rmsnorm", "ifb_rope", "ifb_silu_mul", "ifb_add", "ifb_argmax", "ifb_kv_cache_bytes",
     "ifb_kv_append", "ifb_kv_get_rows", "ifb_attn_workspace_bytes", "ifb_attn_decode", "ifb_attn_decode_append", "ifb_moe_topk", "ifb_moe_route", "ifb_moe_combine",
-    "ifb_llama2c_probe", "ifb_model_load_llama2c", "ifb_model_create", "ifb_model_destroy", "ifb_model_weight_bytes", "ifb_model_kv_bytes_per_token",
+    "ifb_engine_resolve", "ifb_engine_create", "ifb_engine_destroy", "ifb_engine_vocab_size", "ifb_engine_add_query",
+    "ifb_engine_infer", "ifb_engine_commit", "ifb_engine_remove_query", "ifb_llama2c_probe", "ifb_model_load_llama2c", "ifb_model_create", "ifb_model_destroy", "ifb_model_weight_bytes", "ifb_model_kv_bytes_per_token",
     "ifb_model_init_synthetic", "ifb_model_load_tensor", "ifb_model_kv_reset", "ifb_model_decode",
     "ifb_model_logits", "ifb_model_next_token", "ifb_model_kernel_launches_per_step",
     "ifb_model_tp_export", "ifb_model_tp_import", "ifb_model_decode_next", "ifb_model_tensor_ptr",

@@ -598,7 +598,7 @@ extern "C" int32_t ifb_llama2c_probe(const char *path, int32_t header_out[7], in
 }
 
 extern "C" int32_t ifb_model_load_llama2c(ifb_model_t **out, const char *path, int32_t weight_dtype, int32_t kv_dtype,
-                                          int32_t max_ctx, ifb_stream_t stream) {
+                                          int32_t max_ctx, int32_t rope_order, ifb_stream_t stream) {
     IFB_CHECK_ARG(out != nullptr && path != nullptr, "load_llama2c: null argument");
     int32_t hv[7];
     int32_t shared = 1;
@@ -607,7 +607,7 @@ extern "C" int32_t ifb_model_load_llama2c(ifb_model_t **out, const char *path, i
     s.d_model = hv[0]; s.d_ffn = hv[1]; s.layers = hv[2]; s.heads = hv[3]; s.kv_heads = hv[4]; s.vocab = hv[5];
     s.max_ctx = max_ctx > 0 ? max_ctx : hv[6];
     s.weight_dtype = weight_dtype; s.kv_dtype = kv_dtype; s.lm_head_dtype = DT_F16;
-    s.rope_order = 0;              // llama2.c stores q/k for interleaved rotation (model_spec qk_column_order 0)
+    s.rope_order = rope_order >= 0 ? rope_order : 0;   // llama2.c stores q/k for interleaved rotation (qk_column_order 0)
     s.rope_theta = 10000.0f; s.norm_eps = 1e-5f; s.kq_scale = 1.0f; s.tp_rank = 0; s.tp_size = 1;
     ifb_model_t *m = nullptr;
     TRY(ifb_model_create(&m, &s));

@@ -63,7 +63,7 @@ class Model:
         """the reference's llama2.c file format (model_reader.cc:3245-3427) -> a loaded runtime"""
         (dim, hidden, layers, heads, kv_heads, vocab, seq), _ = probe_llama2c(path)
         h = C.c_void_p()
-        check(lib.ifb_model_load_llama2c(C.byref(h), path.encode(), weight_dtype, kv_dtype, max_ctx, stream),
+        check(lib.ifb_model_load_llama2c(C.byref(h), path.encode(), weight_dtype, kv_dtype, max_ctx, -1, stream),
               "ifb_model_load_llama2c")
         spec = ModelSpec(layers=layers, d_model=dim, d_ffn=hidden, heads=heads, kv_heads=kv_heads, vocab=vocab,
                          max_ctx=max_ctx if max_ctx > 0 else seq, weight_dtype=weight_dtype, kv_dtype=kv_dtype,
@@ -191,3 +191,69 @@ def shard_cols(cols, rank, size, block=64):
     assert cols % (size * block) == 0, f"{cols} columns do not split {size} ways on {block}-element blocks"
     n = cols // size
     return rank * n, (rank + 1) * n
+
+
+def resolve_config(ini_path, section="transformer_engine", data_root_dir=""):
+    """what Engine(ini_path) would load, without a GPU: (model file, weight dtype, kv dtype, max_context_len,
+    qk_column_order, return_output_tensors)"""
+    path = C.create_string_buffer(4096)
+    info = (C.c_int32 * 5)()
+    check(lib.ifb_engine_resolve(ini_path.encode(), section.encode(), data_root_dir.encode(), path, 4096, info),
+          "ifb_engine_resolve")
+    return (path.value.decode(),) + tuple(info)
+
+
+class Engine:
+    """InferenceEngine-shaped door (LoadConfig/Init, AddQuery, Infer, CommitInferenceResult, RemoveQuery) for one
+    greedy query; reads the reference's .ini + model-spec json (see ifb_engine.cu)."""
+
+    def __init__(self, ini_path, section="transformer_engine", data_root_dir=""):
+        self._h = C.c_void_p()
+        check(lib.ifb_engine_create(C.byref(self._h), ini_path.encode(), section.encode(), data_root_dir.encode()),
+              "ifb_engine_create")
+        self.vocab = lib.ifb_engine_vocab_size(self._h)
+
+    def add_query(self, tokens):
+        import numpy as np
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        qid = lib.ifb_engine_add_query(self._h, t.ctypes.data, len(t))
+        if qid < 0:
+            check(qid, "ifb_engine_add_query")
+        return qid
+
+    def infer(self, want_logits=False):
+        import numpy as np
+        nxt = C.c_int32(0)
+        logits = np.zeros(self.vocab, dtype=np.float32) if want_logits else None
+        check(lib.ifb_engine_infer(self._h, C.byref(nxt), logits.ctypes.data if want_logits else None), "ifb_engine_infer")
+        return nxt.value, logits
+
+    def commit(self, token, is_end=False):
+        check(lib.ifb_engine_commit(self._h, int(token), 1 if is_end else 0), "ifb_engine_commit")
+
+    def remove_query(self, qid):
+        check(lib.ifb_engine_remove_query(self._h, int(qid)), "ifb_engine_remove_query")
+
+    def generate(self, prompt, max_new, want_logits=False):
+        """the loop of oracle/ref_cpu_shim.cc ifref_engine_generate, on this engine"""
+        qid = self.add_query(prompt)
+        assert qid > 0
+        toks, logs = [], []
+        for step in range(max_new):
+            t, lg = self.infer(want_logits)
+            toks.append(t)
+            if want_logits:
+                logs.append(lg)
+            self.commit(t, is_end=(step + 1 >= max_new))
+        return toks, logs
+
+    def close(self):
+        if self._h:
+            lib.ifb_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
