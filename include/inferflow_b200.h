@@ -249,6 +249,12 @@ int32_t ifb_model_issue_parts(ifb_model_t *m, int32_t parts, ifb_stream_t stream
 const void *ifb_model_logits(const ifb_model_t *m);      /* device fp16 [vocab] */
 const int32_t *ifb_model_next_token(const ifb_model_t *m); /* device int32 */
 int32_t ifb_model_kernel_launches_per_step(const ifb_model_t *m);
+/* 1 when the model decodes with the persistent step kernel (one launch per token; replaces GpuInferenceWorker::Run,
+ * inference_worker.cc:234-977, and under tensor parallelism DistributeAndMergeTensors, :2148-2335), 0 when it keeps the
+ * multi-launch path (mixture of experts, weight types without a dp4a kernel). rec (optional, 4 ints) receives the
+ * record {code, op, detail, cta} a step kernel left in pinned host memory before it trapped on a missed deadline --
+ * e.g. a tensor-parallel peer that never delivered its partial sums (code 0: none). Readable after a failed sync. */
+int32_t ifb_model_step_status(ifb_model_t *m, int32_t rec[4]);
 /* tensor-parallel plumbing: every rank exports the IPC handle of its exchange buffer,
  * the host side (torch.distributed all_gather / MPI / fork) hands all handles to every rank */
 int32_t ifb_model_tp_export(ifb_model_t *m, void *host_handle_64B);

@@ -98,6 +98,7 @@ def _load():
     L.ifb_model_next_token.restype = vp
     L.ifb_model_next_token.argtypes = [vp]
     L.ifb_model_kernel_launches_per_step.argtypes = [vp]
+    L.ifb_model_step_status.argtypes = [vp, vp]
     L.ifb_engine_resolve.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, vp, i32, vp]
     L.ifb_engine_create.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
     L.ifb_engine_destroy.argtypes = [vp]
@@ -127,7 +128,7 @@ DECLARED = [
     "ifb_model_init_synthetic", "ifb_model_load_tensor", "ifb_model_kv_reset", "ifb_model_decode",
     "ifb_model_logits", "ifb_model_next_token", "ifb_model_kernel_launches_per_step",
     "ifb_model_tp_export", "ifb_model_tp_import", "ifb_model_decode_next", "ifb_model_tensor_ptr",
-    "ifb_memcpy_d2h", "ifb_memcpy_h2d", "ifb_device_synchronize", "ifb_model_issue_parts", "ifb_memcpy_d2h_async", "ifb_memcpy_h2d_async",
+    "ifb_memcpy_d2h", "ifb_memcpy_h2d", "ifb_device_synchronize", "ifb_model_issue_parts", "ifb_memcpy_d2h_async", "ifb_memcpy_h2d_async", "ifb_model_step_status",
 ]
 
 

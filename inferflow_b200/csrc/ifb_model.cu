@@ -19,6 +19,7 @@
 
 #include "ifb_formats.cuh"
 #include "ifb_kernels.h"
+#include "ifb_step.h"
 #include "../../include/inferflow_b200.h"
 
 using namespace ifb;
@@ -63,7 +64,13 @@ struct ifb_model {
     int64_t x_recv = 0, x_recv_parity = 0, x_recv_rank = 0;   // partial sums: [2 parities][8 ranks][d_model/2] words {half2, flag}
     int64_t x_logits = 0;                                     // logits of all ranks: [vocab/2] words {half2, flag}
     int vocab_l = 0;                // lm_head rows held by this rank (vocabulary-sharded under TP)
-    int chain_mode = 0;             // 0: one launch per GEMV (the measured optimum, see gemv_chain_launch)
+    // persistent step kernel (ifb_step.cu): ONE launch per token for dense models it supports
+    int use_step = 1;               // IFB_STEP=0 keeps the multi-launch path
+    bool step_built = false, step_ok = false;
+    StepParams step;
+    DevBuf step_layers, step_ctr, partials, ybuf;
+    int *step_err = nullptr;        // pinned host memory: error record of a step kernel that hit its deadline
+    int host_pos = -1;              // host mirror of the device-side position (decode_next must not run past max_ctx)
     int64_t smem_kb[5] = {0, 0, 0, 0, 0};   // per-CTA shared-memory budget of the QKV / wo / GLU / w2 / lm_head GEMVs (KB, 0 = kernel default)
 };
 
@@ -138,6 +145,8 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     }
     const char *e2 = getenv("IFB_NO_GRAPH");
     if (e2 && atoi(e2)) m->use_graph = 0;
+    const char *e4 = getenv("IFB_STEP");
+    if (e4) m->use_step = atoi(e4) ? 1 : 0;
 
     int rc = IFB_OK;
     auto A = [&](DevBuf &b, size_t bytes) { if (rc == IFB_OK) rc = dev_alloc(m, b, bytes); };
@@ -216,7 +225,12 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     A(m->logits, (size_t)s.vocab * 2);
     A(m->attn_ws, attn_workspace_bytes(m->heads_l, m->hd));
     A(m->scalars, 256);
-    A(m->counters, 4096 * sizeof(int));
+    {   // one 8-int cursor block per launch of a step: dense 5 per layer, MoE 6 + 2*top_k per layer, + embedding, lm_head, argmax, advance
+        const size_t per_layer = s.experts > 0 ? 6 + 2 * (size_t)s.experts_top_k : 5;
+        A(m->counters, (per_layer * s.layers + 8) * 8 * sizeof(int));
+    }
+    A(m->ybuf, d * 2);
+    A(m->partials, (size_t)m->heads_l * ((s.max_ctx + 31) / 32) * (m->hd + 4) * sizeof(float));
     { const char *e3 = getenv("IFB_TRACE"); if (e3 && atoi(e3)) m->trace_on = 1; }
     if (m->trace_on) A(m->trace, (size_t)512 * 160 * 8 * 8);
     if (rc == IFB_OK && m->trace_on) cudaMemset(m->trace.p, 0, m->trace.bytes);
@@ -246,6 +260,7 @@ extern "C" void ifb_model_destroy(ifb_model_t *m) {
     for (size_t p = 0; p < m->peer_xchg.size(); p++)       // unmap the peers' exchange regions (ours is in allocs)
         if ((int)p != m->spec.tp_rank && m->peer_xchg[p] != nullptr) cudaIpcCloseMemHandle(m->peer_xchg[p]);
     for (void *p : m->allocs) cudaFree(p);
+    if (m->step_err) cudaFreeHost(m->step_err);
     delete m;
 }
 
@@ -494,7 +509,7 @@ extern "C" int32_t ifb_model_load_tensor(ifb_model_t *m, const char *name, const
     const auto &s = m->spec;
     const int tp = s.tp_size, rk = s.tp_rank, d = s.d_model, wdt = s.weight_dtype;
     std::string n(name);
-    m->graph_ready = m->graph_ready;  // weights are read through fixed pointers: the graph stays valid
+    // weights are read through fixed pointers: a captured graph stays valid
     if (n == "tok_embeddings") return load_shard(m->tok_emb, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
     if (n == "output_norm") return load_shard(m->out_norm, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
     if (n == "output") {
@@ -714,7 +729,91 @@ __global__ void advance_kernel(int32_t *sc, int advance) {
 }
 
 enum { PART_GEMV = 1, PART_ATTN = 2, PART_MISC = 4, PART_ALL = 7 };
+
+// Build the plan of the persistent step kernel (ifb_step.cu) once the weights' addresses and, under tensor
+// parallelism, the peers' exchange regions are known. Models it does not cover (mixture of experts, weight types
+// without a dp4a path, head_dim other than 64/128) keep the multi-launch path: step_ok stays false.
+static int step_prepare(ifb_model *m) {
+    if (m->step_built) return IFB_OK;
+    m->step_built = true;
+    m->step_ok = false;
+    const auto &s = m->spec;
+    if (!m->use_step || s.experts > 0) return IFB_OK;
+    StepParams &P = m->step;
+    P = StepParams();
+    P.n_layers = s.layers;
+    P.d = s.d_model; P.q_dim = m->q_dim_l; P.kv_dim = m->kv_dim_l; P.ffn = m->ffn_l;
+    P.heads = m->heads_l; P.kv_heads = m->kv_heads_l; P.hd = m->hd; P.group = m->heads_l / m->kv_heads_l;
+    P.vocab = s.vocab; P.vocab_l = m->vocab_l;
+    P.max_ctx = s.max_ctx; P.max_ctx_pad = (s.max_ctx + 63) / 64 * 64;
+    P.rope_order = s.rope_order; P.rope_theta = s.rope_theta;
+    P.w_dtype = s.weight_dtype;
+    P.eps = s.norm_eps;
+    P.softmax_scale = 1.0f / sqrtf((float)m->hd);     // alpha * kq_scale (inference_worker.cc:1666), as attn_decode
+    if (step_build(P, s.kv_dtype, s.lm_head_dtype, sm_count()) != IFB_OK) return IFB_OK;   // not covered: reason in ifb_last_error
+    if (s.rope_order != 0 && s.rope_order != 2) return IFB_OK;
+    std::vector<StepLayer> hl(s.layers);
+    for (int l = 0; l < s.layers; l++) {
+        const LayerW &L = m->layers[l];
+        hl[l].wq = (const uint8_t *)L.wq.p; hl[l].wk = (const uint8_t *)L.wk.p; hl[l].wv = (const uint8_t *)L.wv.p;
+        hl[l].wo = (const uint8_t *)L.wo.p; hl[l].w1 = (const uint8_t *)L.w1.p; hl[l].w3 = (const uint8_t *)L.w3.p;
+        hl[l].w2 = (const uint8_t *)L.w2.p;
+        hl[l].attn_norm = (const __half *)L.attn_norm.p; hl[l].ffn_norm = (const __half *)L.ffn_norm.p;
+        hl[l].kcache = (uint8_t *)L.kcache.p; hl[l].vcache = (uint8_t *)L.vcache.p;
+    }
+    if (m->step_layers.p == nullptr) TRY(dev_alloc(m, m->step_layers, s.layers * sizeof(StepLayer)));
+    IFB_CUDA(cudaMemcpy(m->step_layers.p, hl.data(), s.layers * sizeof(StepLayer), cudaMemcpyHostToDevice));
+    if (m->step_ctr.p == nullptr) TRY(dev_alloc(m, m->step_ctr, (size_t)step_counter_bytes(P)));
+    if (m->step_err == nullptr) {
+        IFB_CUDA(cudaHostAlloc((void **)&m->step_err, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(m->step_err, 0, 64);
+    }
+    P.layers = (const StepLayer *)m->step_layers.p;
+    P.tok_emb = (const __half *)m->tok_emb.p; P.out_norm = (const __half *)m->out_norm.p;
+    P.lm_head = (const uint8_t *)m->lm_head.p;
+    P.qkv = (__half *)m->qkv.p; P.attn_out = (__half *)m->attn_out.p; P.hbuf = (__half *)m->hbuf.p;
+    P.ybuf = (__half *)m->ybuf.p; P.logits = (__half *)m->logits.p; P.x_out = (__half *)m->x0.p;
+    P.partials = (float *)m->partials.p;
+    P.scalars = (int32_t *)m->scalars.p;
+    P.cursors = (int *)m->step_ctr.p;
+    P.done = (unsigned int *)((int *)m->step_ctr.p + P.n_ops);
+    P.amax = (unsigned long long *)((uint8_t *)m->step_ctr.p + ((size_t)(2 * P.n_ops + s.layers + 1) * 4 + 7) / 8 * 8);
+    P.parts = STEP_PART_ALL; P.advance = 1;
+    P.tp_size = s.tp_size; P.tp_rank = s.tp_rank;
+    if (s.tp_size > 1) {
+        if (m->peer_xchg.empty()) { m->step_built = false; return IFB_OK; }   // not connected yet: decide at the first decode
+        for (int p = 0; p < s.tp_size; p++) P.peer[p] = m->peer_xchg[p];
+        P.x_recv = m->x_recv; P.x_recv_parity = m->x_recv_parity; P.x_recv_rank = m->x_recv_rank; P.x_logits = m->x_logits;
+    }
+    void *dev_err = nullptr;
+    IFB_CUDA(cudaHostGetDevicePointer(&dev_err, m->step_err, 0));
+    P.err = (int *)dev_err;
+    {
+        const char *e = getenv("IFB_STEP_TIMEOUT_MS");
+        const long long ms = e ? atoll(e) : 2000;
+        P.timeout_ns = (unsigned long long)(ms > 0 ? ms : 2000) * 1000000ull;
+    }
+    if (m->trace_on) {
+        // [n_ops][grid][4] stamps; the multi-launch trace buffer is large enough for models up to ~800 ops
+        if ((size_t)P.n_ops * sm_count() * 4 * 8 <= m->trace.bytes) P.trace = (unsigned long long *)m->trace.p;
+    }
+    m->step_ok = true;
+    return IFB_OK;
+}
+
+static int issue_step_kernel(ifb_model *m, cudaStream_t st, int *launches, int parts) {
+    StepParams P = m->step;
+    P.parts = ((parts & PART_GEMV) ? STEP_PART_GEMV : 0) | ((parts & PART_ATTN) ? STEP_PART_ATT : 0);
+    P.advance = parts == PART_ALL ? 1 : 0;
+    IFB_CUDA(cudaMemsetAsync(m->step_ctr.p, 0, m->step_ctr.bytes, st));
+    TRY(step_launch(P, sm_count(), st));
+    if (launches) *launches = 1;
+    return IFB_OK;
+}
+
 static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = PART_ALL) {
+    TRY(step_prepare(m));
+    if (m->step_ok) return issue_step_kernel(m, st, launches, parts);
     const auto &s = m->spec;
     const int d = s.d_model, wdt = s.weight_dtype;
     const int pdl = m->use_pdl;
@@ -744,8 +843,7 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
                               t.src_off = m->x_recv + (idx & 1) * m->x_recv_parity; t.src_rank_stride = m->x_recv_rank;
                               t.resid = resid; t.xout = xout; return t; };
     TpExchange t_head;
-    // every GEMV of the step first (descriptors only), then the launches: consecutive GEMVs go out as ONE chained
-    // launch (ifb_gemv.cu): mode 2 = [wo, w1|w3, w2, next layer's wq|wk|wv], 1 = [wo, w1|w3, w2], 0 = one per GEMV
+    // every GEMV of the step first (descriptors only), then the launches
     const int nl = s.layers;
     std::vector<GemvLaunch> g_qkv(nl), g_wo(nl), g_glu(nl), g_w2(nl);
     std::vector<TpExchange> t_qkv(nl), t_wo(nl), t_glu(nl), t_w2(nl);
@@ -778,15 +876,14 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
         w2.x = m->hbuf.p; w2.residual = m->x1.p; w2.y = m->x0.p; w2.quantize_x = quant_x; w2.pdl = pdl; w2.smem_budget = m->smem_kb[3] * 1024;
         if (tp > 1) { w2.residual = nullptr; t_w2[li] = tp_push_ar(2 * li + 2); w2.tp = &t_w2[li]; }
     }
-    auto launch = [&](GemvLaunch *ops, int nops) -> int {
-        ops[0].trace = TR(n); ops[0].counter = CT(n);
-        if (parts & PART_GEMV) { TRY(gemv_chain_launch(ops, nops, st)); n++; }
+    auto launch = [&](GemvLaunch *op) -> int {
+        op->trace = TR(n); op->counter = CT(n);
+        if (parts & PART_GEMV) { TRY(gemv_launch(*op, st)); n++; }
         return IFB_OK;
     };
-    const int chain = m->chain_mode;
     for (int li = 0; li < nl; li++) {
         LayerW &L = m->layers[li];
-        if (chain < 2 || li == 0) TRY(launch(&g_qkv[li], 1));
+        TRY(launch(&g_qkv[li]));
         // --- RoPE(q,k) + append K,V + attention over the cache: one kernel
         AttnDecode ad;
         ad.k_new = qkv + m->q_dim_l; ad.v_new = qkv + m->q_dim_l + m->kv_dim_l;
@@ -800,11 +897,11 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
             // ProcessGpuLayer_Moe (inference_worker.cc:1924-2146) without the host round trip: router GEMV on the
             // normalised x1 -> softmax + top-k on the device -> per active slot (ascending expert id) GLU + w2 with
             // device-selected weights -> out = sum_k w_k * y_k in half, + residual
-            TRY(launch(&g_wo[li], 1));
+            TRY(launch(&g_wo[li]));
             GemvLaunch r;
             r.w_dtype = DT_F16; r.nseg = 1; r.w[0] = L.gate.p; r.rows[0] = s.experts; r.cx = d;
             r.x = m->x1.p; r.norm_w = L.ffn_norm.p; r.norm_eps = s.norm_eps; r.y = m->router.p; r.quantize_x = 0; r.pdl = pdl;
-            TRY(launch(&r, 1));
+            TRY(launch(&r));
             if (parts & PART_GEMV) {
                 TRY(moe_route((int32_t *)m->moe_ids.p, m->moe_wts.p, m->router.p, s.experts, s.experts_top_k,
                               s.moe_norm_top_k_prob, st));
@@ -816,24 +913,18 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
                 f.moe_id = (const int32_t *)m->moe_ids.p + k;
                 w2.w_table = (const void *const *)L.tbl_w2.p; w2.moe_id = (const int32_t *)m->moe_ids.p + k;
                 w2.residual = nullptr; w2.y = (__half *)m->moe_y.p + (size_t)k * d;
-                TRY(launch(&f, 1));
-                TRY(launch(&w2, 1));
+                TRY(launch(&f));
+                TRY(launch(&w2));
             }
             if (parts & PART_GEMV) {
                 TRY(moe_combine(m->x0.p, m->x1.p, m->moe_y.p, (const int32_t *)m->moe_ids.p, m->moe_wts.p,
                                 s.experts_top_k, d, st));
                 n++;
             }
-        } else if (chain == 0) {
-            TRY(launch(&g_wo[li], 1));
-            TRY(launch(&g_glu[li], 1));
-            TRY(launch(&g_w2[li], 1));
         } else {
-            GemvLaunch ops[4] = {g_wo[li], g_glu[li], g_w2[li], GemvLaunch()};
-            int nops = 3;
-            if (chain == 2 && li + 1 < nl) ops[nops++] = g_qkv[li + 1];
-            ops[0].smem_budget = m->smem_kb[1] * 1024;
-            TRY(launch(ops, nops));
+            TRY(launch(&g_wo[li]));
+            TRY(launch(&g_glu[li]));
+            TRY(launch(&g_w2[li]));
         }
     }
     // --- final norm + lm_head (fp16 weights meet an fp16 activation: GemvHalf_AX_Alg3)
@@ -874,11 +965,13 @@ extern "C" int32_t ifb_model_decode(ifb_model_t *m, int32_t token_id, const int3
     IFB_CHECK_ARG(m != nullptr, "null model");
     IFB_CHECK_ARG(pos >= 0 && pos < m->spec.max_ctx, "decode: position %d outside max_context_len %d", pos, m->spec.max_ctx);
     IFB_CHECK_ARG(m->spec.tp_size == 1 || !m->peer_xchg.empty(), "decode: tensor-parallel model without imported peer buffers");
+    IFB_CHECK_ARG(token_id < m->spec.vocab, "decode: token %d outside the vocabulary (%d)", token_id, m->spec.vocab);
     cudaStream_t st = (cudaStream_t)stream;
     if (pos >= 0 && (token_id >= 0 || token_dev != nullptr)) {
         set_scalars_kernel<<<1, 1, 0, st>>>((int32_t *)m->scalars.p, pos, token_id, token_id < 0 ? token_dev : nullptr);
         IFB_LAUNCH_CHECK();
     }
+    m->host_pos = pos;
     if (!m->use_graph) return issue_step(m, st, &m->launches_per_step);
     if (!m->graph_ready) {
         // warm every kernel once outside capture (cudaFuncSetAttribute etc. are not capturable)
@@ -894,10 +987,21 @@ extern "C" int32_t ifb_model_decode(ifb_model_t *m, int32_t token_id, const int3
         IFB_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
         int rc = issue_step(m, cs, &m->launches_per_step);
         cudaError_t e = cudaStreamEndCapture(cs, &m->graph);
-        if (rc != IFB_OK) { cudaStreamDestroy(cs); return rc; }
-        if (e != cudaSuccess) { cudaStreamDestroy(cs); set_last_error("graph capture failed: %s", cudaGetErrorString(e)); return IFB_ERR_CUDA; }
-        IFB_CUDA(cudaGraphInstantiate(&m->graph_exec, m->graph, 0));
+        if (rc == IFB_OK && e == cudaSuccess) e = cudaGraphInstantiate(&m->graph_exec, m->graph, 0);
         cudaStreamDestroy(cs);
+        if (rc != IFB_OK || e != cudaSuccess) {
+            if (m->step_ok) {
+                // a cooperative launch that this driver cannot capture: the step is one launch anyway, issue it directly
+                cudaGetLastError();
+                if (m->graph) { cudaGraphDestroy(m->graph); m->graph = nullptr; }
+                m->graph_exec = nullptr;
+                m->use_graph = 0;
+                return issue_step(m, st, &m->launches_per_step);
+            }
+            if (rc != IFB_OK) return rc;
+            set_last_error("graph capture failed: %s", cudaGetErrorString(e));
+            return IFB_ERR_CUDA;
+        }
         m->graph_ready = true;
     }
     IFB_CUDA(cudaGraphLaunch(m->graph_exec, st));
@@ -906,7 +1010,12 @@ extern "C" int32_t ifb_model_decode(ifb_model_t *m, int32_t token_id, const int3
 
 // replay without touching the scalars: continues from the position/token the previous step left
 extern "C" int32_t ifb_model_decode_next(ifb_model_t *m, ifb_stream_t stream) {
-    IFB_CHECK_ARG(m != nullptr && (m->graph_ready || !m->use_graph), "decode_next: call ifb_model_decode first");
+    IFB_CHECK_ARG(m != nullptr && m->host_pos >= 0 && (m->graph_ready || !m->use_graph), "decode_next: call ifb_model_decode first");
+    if (m->host_pos + 1 >= m->spec.max_ctx) {
+        set_last_error("decode_next: position %d is outside max_context_len %d", m->host_pos + 1, m->spec.max_ctx);
+        return IFB_ERR_STATE;
+    }
+    m->host_pos++;
     cudaStream_t st = (cudaStream_t)stream;
     if (!m->use_graph) return issue_step(m, st, &m->launches_per_step);
     IFB_CUDA(cudaGraphLaunch(m->graph_exec, st));
@@ -948,5 +1057,16 @@ extern "C" int32_t ifb_model_tp_import(ifb_model_t *m, const void *handles, int3
         m->peer_xchg[p] = ptr;
     }
     m->graph_ready = false;
+    m->step_built = false;          // the step kernel's plan holds the peers' addresses
+    if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+    if (m->graph) { cudaGraphDestroy(m->graph); m->graph = nullptr; }
     return IFB_OK;
+}
+
+// 1 when the model decodes with the persistent step kernel, 0 for the multi-launch path; rec[4] (optional) receives
+// the error record {code, op, detail, cta} a step kernel left before it trapped on a missed deadline (code 0: none)
+extern "C" int32_t ifb_model_step_status(ifb_model_t *m, int32_t rec[4]) {
+    if (m == nullptr) return 0;
+    if (rec != nullptr) for (int i = 0; i < 4; i++) rec[i] = m->step_err ? ((volatile int *)m->step_err)[i] : 0;
+    return m->step_ok ? 1 : 0;
 }

@@ -1,0 +1,1104 @@
+// One decoded token = ONE persistent kernel launch, sm_100a.
+//
+// Replaces, for batch-1 decode, the whole of GpuInferenceWorker::Run -> ProcessGpuLayer ->
+// {ProcessGpuLayer_Attention, ProcessGpuLayer_FeedForward} -> ProcessPostLayer (reference
+// src/transformer/inference_worker.cc:234-977, 983-1724, 1726-1900, 552-640) and, under tensor parallelism,
+// DistributeAndMergeTensors (:2148-2335). The reference issues ~60 synchronous launches per layer; round 1 of this
+// runtime issued 5 fused kernels per layer and measured that what was left was FIXED COST PER LAUNCH (activation
+// staging behind a cold ring, ring refill after the grid dependency, tail): 4-5 us on launches whose weight stream
+// takes 1.6-8.6 us. Here the launch boundaries are gone:
+//
+//  * grid = one CTA per SM, resident for the whole token: 16 consumer warps + 1 producer warp;
+//  * the PRODUCER (one elected thread) walks every op of the token in order -- per layer wq|wk|wv, the KV cache,
+//    wo, w1|w3, w2, then the lm_head -- claiming units from per-op global cursors and streaming them with 1-D TMA
+//    bulk copies into a shared-memory ring. It never waits for an activation: while the consumers of all SMs
+//    synchronise at an op boundary, the HBM pipe keeps filling the rings with the NEXT op's weights (the rings of
+//    148 SMs hold ~27 MB = 4 us of HBM time; a boundary costs ~1 us);
+//  * the CONSUMERS take ring slots in order; a slot's tasks (2 adjacent rows / one w1,w3 row pair / 32 cache
+//    positions) are dealt round-robin to the 16 warps. When the next slot belongs to a new op, the CTA signals
+//    "my part of op k is stored" (one release add on a global counter), waits until all CTAs have, and stages the
+//    new op's input into shared memory: residual add (fp16, the reference's order), RMSNorm, Q8_B32T2
+//    quantization (the reference's alg-2 arithmetic), or RoPE + two-term int8 q + the new K/V cache row for
+//    attention;
+//  * attention is flash-decoding over the cache as stored: a task is one 32-position tile of one kv head, its
+//    (m, l, acc) partial goes to an L2-resident workspace, one CTA per head merges them (log-sum-exp) before wo;
+//  * tensor parallelism: the row-parallel GEMVs (wo, w2) store their partial sums straight into every peer's
+//    exchange region over NVLink as flag-in-data words {half2, flag}; the next op's staging polls exactly those
+//    words (bounded: a deadline, then an error word in pinned host memory and a trap -- never an endless spin)
+//    and adds them in rank order with fp16 rounding (MergeTensors, inference_worker.cc:2264-2289).
+//
+// The arithmetic of every GEMV row and of the staging is the code of ifb_gemv_dev.cuh, shared with the stand-alone
+// kernels: the step kernel and the operator entries produce the same bits.
+#include <cstdlib>
+
+#include "ifb_gemv_dev.cuh"
+#include "ifb_kernels.h"
+#include "ifb_step.h"
+
+namespace ifb {
+
+constexpr int STEP_THREADS = GEMV_CTHREADS + 32;
+constexpr int STEP_MAX_SLOTS = 16;
+constexpr int STEP_TARGET_UNIT = 20480;   // bytes per ring slot the unit sizes aim for
+
+struct FmtF16 {   // tag: fp16 weights (tensors below tensor_quant_threshold, network_builder.cc:1558)
+    static constexpr bool XSPLIT = false;
+};
+template <class Fmt> struct is_f16_fmt { static constexpr bool value = false; };
+template <> struct is_f16_fmt<FmtF16> { static constexpr bool value = true; };
+template <class Fmt> struct is_q4b32_fmt { static constexpr bool value = false; };
+template <> struct is_q4b32_fmt<FmtQ4_B32T1> { static constexpr bool value = true; };
+
+// ---------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_cg128(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_cg_f32(const float *p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_cg_f32x4(const float *p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_v2(void *p, uint2 v) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __noinline__ void step_abort(const StepParams &P, int code, int op, int detail) {
+    if (P.err != nullptr) {
+        P.err[1] = op; P.err[2] = detail; P.err[3] = (int)blockIdx.x;
+        P.err[0] = code;
+        __threadfence_system();
+    }
+    __trap();
+}
+
+// every wait of this kernel is bounded: past the deadline the kernel leaves an error record and traps
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity, const StepParams &P, int op) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = globaltimer_ns();
+    for (unsigned it = 0;; it++) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((it & 63u) == 63u && globaltimer_ns() - t0 > P.timeout_ns) step_abort(P, STEP_ERR_RING, op, (int)parity);
+    }
+}
+
+// grid-wide dependency: thread 0 of the consumers waits until `target` CTAs have released the counter, then the
+// consumer warps meet at their named barrier. Data published before the release is read with ld.global.cg.
+__device__ __forceinline__ void dep_wait(const unsigned int *ctr, unsigned int target, const StepParams &P, int op, int tid) {
+    if (tid == 0) {
+        if (ld_acquire_gpu_u32(ctr) < target) {
+            const unsigned long long t0 = globaltimer_ns();
+            unsigned it = 0;
+            while (ld_acquire_gpu_u32(ctr) < target) {
+                if ((++it & 255u) == 0u && globaltimer_ns() - t0 > P.timeout_ns) step_abort(P, STEP_ERR_DEP, op, (int)ld_acquire_gpu_u32(ctr));
+            }
+        }
+    }
+    named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+}
+__device__ __forceinline__ void dep_signal(unsigned int *ctr, int tid) {
+    named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);     // every consumer thread's stores are ordered before thread 0's fence
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+    }
+}
+
+__device__ __forceinline__ void trace_op(const StepParams &P, int op, int k, int tid) {
+    if (P.trace != nullptr && tid == 0) P.trace[((size_t)op * gridDim.x + blockIdx.x) * 4 + k] = globaltimer_ns();
+}
+
+// monotone key of (logit, index): larger logit wins, ties go to the smaller index (argmax: first max wins)
+__device__ __forceinline__ unsigned long long amax_key(float v, int idx) {
+    uint32_t u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)idx);
+}
+
+// ---------------------------------------------------------------------------------------
+// residual stream: resid (shared memory, fp16 [d]) += the row-parallel GEMV's output
+// ---------------------------------------------------------------------------------------
+// single GPU: y = round_h(W x) was stored by the consumers of all CTAs (half tensor, as the reference's GEMV
+// output), x_new = round_h(y + resid) (TensorOpr::Add, inference_worker.cc:849)
+__device__ __noinline__ void resid_add_local(const StepParams &P, uint4 *resid, int tid) {
+    const int ng = P.d >> 3;
+    for (int g = tid; g < ng; g += GEMV_CTHREADS) {
+        const uint4 yv = ld_cg128(reinterpret_cast<const uint4 *>(P.ybuf) + g);
+        const uint4 rv = resid[g];
+        uint4 out;
+        const __half2 *y = reinterpret_cast<const __half2 *>(&yv), *r = reinterpret_cast<const __half2 *>(&rv);
+        __half2 *o = reinterpret_cast<__half2 *>(&out);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float2 yf = __half22float2(y[i]), rf = __half22float2(r[i]);
+            o[i] = __floats2half2_rn(yf.x + rf.x, yf.y + rf.y);
+        }
+        resid[g] = out;
+    }
+}
+
+// tensor parallel: the partial sums of all ranks arrive in this rank's exchange region as flag-in-data words
+// {half2, flag}; they are added in rank order with fp16 rounding after every add, the residual last
+// (MergeTensors adds worker 1..n-1 onto worker 0 with TensorOpr::Add, inference_worker.cc:2264-2289, then :849)
+__device__ __noinline__ void resid_add_gather(const StepParams &P, uint4 *resid, uint32_t idx, uint32_t seq, int op, int tid) {
+    const uint32_t flag = (seq << 8) | idx;
+    const uint8_t *base = reinterpret_cast<const uint8_t *>(P.peer[P.tp_rank]) + P.x_recv + (long long)(idx & 1u) * P.x_recv_parity;
+    const int ng = P.d >> 3;
+    for (int g = tid; g < ng; g += GEMV_CTHREADS) {
+        float acc[8];
+        for (int p = 0; p < P.tp_size; p++) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(base + (size_t)p * P.x_recv_rank) + 2 * g;
+            uint4 w0 = ld_relaxed_sys_v4(src), w1 = ld_relaxed_sys_v4(src + 1);
+            if (w0.y != flag || w0.w != flag || w1.y != flag || w1.w != flag) {
+                const unsigned long long t0 = globaltimer_ns();
+                unsigned it = 0;
+                while (w0.y != flag || w0.w != flag || w1.y != flag || w1.w != flag) {
+                    w0 = ld_relaxed_sys_v4(src);
+                    w1 = ld_relaxed_sys_v4(src + 1);
+                    if ((++it & 255u) == 0u && globaltimer_ns() - t0 > P.timeout_ns) step_abort(P, STEP_ERR_PEER, op, p);
+                }
+            }
+            const uint32_t dw[4] = {w0.x, w0.z, w1.x, w1.z};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&dw[k]));
+                if (p == 0) { acc[2 * k] = f.x; acc[2 * k + 1] = f.y; }
+                else { acc[2 * k] = round_h(acc[2 * k] + f.x); acc[2 * k + 1] = round_h(acc[2 * k + 1] + f.y); }
+            }
+        }
+        const uint4 rv = resid[g];
+        uint4 out;
+        __half2 *o = reinterpret_cast<__half2 *>(&out);
+        const __half2 *r = reinterpret_cast<const __half2 *>(&rv);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float2 rf = __half22float2(r[i]);
+            o[i] = __floats2half2_rn(acc[2 * i] + rf.x, acc[2 * i + 1] + rf.y);
+        }
+        resid[g] = out;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// attention: staging of q and the new K/V row, the 32-position task, the merge
+// ---------------------------------------------------------------------------------------
+// staged layout inside the x area (HD = head_dim, NB = HD/32):
+//   Q8 cache : int8 qh[heads][HD] | int8 ql[heads][HD] | float qs[heads][NB][2] | int8 newk[kvh][HD] | int8 newv[kvh][HD]
+//              | half newks[kvh][NB] | half newvs[kvh][NB]
+//   F16 cache: float q[heads][HD/16][20] | half newk[kvh][HD] | half newv[kvh][HD]
+struct AttLayout {
+    int qh, ql, qs, newk, newv, newks, newvs, total;
+};
+__host__ __device__ inline AttLayout att_layout(int heads, int kvh, int hd, bool q8) {
+    AttLayout a;
+    const int nb = hd / 32;
+    if (q8) {
+        a.qh = 0; a.ql = heads * hd; a.qs = 2 * heads * hd;
+        a.newk = a.qs + heads * nb * 8; a.newv = a.newk + kvh * hd;
+        a.newks = a.newv + kvh * hd; a.newvs = a.newks + kvh * nb * 2;
+        a.total = a.newvs + kvh * nb * 2;
+    } else {
+        a.qh = 0; a.ql = 0; a.qs = 0;
+        a.newk = heads * (hd / 16) * 20 * 4; a.newv = a.newk + kvh * hd * 2;
+        a.newks = a.newvs = 0;
+        a.total = a.newv + kvh * hd * 2;
+    }
+    a.total = (a.total + 127) / 128 * 128;
+    return a;
+}
+
+// RoPE of 8 consecutive dims d0..d0+7 of one head row (values v, partner group o for the half-split order), each
+// result rounded to half as PositionEmbedding stores it (tensor_opr.cu:693-760, unary_tensor_opr.h:662-740)
+__device__ __forceinline__ void rope8(float *v, const float *o, int d0, int hd, int order, const float *s_cos, const float *s_sin) {
+    if (order == 2) {
+        const bool first = d0 < hd / 2;
+        const int p0 = first ? d0 : d0 - hd / 2;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float cs = s_cos[p0 + i], sn = s_sin[p0 + i];
+            v[i] = first ? round_h(v[i] * cs - o[i] * sn) : round_h(o[i] * sn + v[i] * cs);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            const float cs = s_cos[(d0 + i) >> 1], sn = s_sin[(d0 + i) >> 1];
+            const float a = v[i], b = v[i + 1];
+            v[i] = round_h(a * cs - b * sn);
+            v[i + 1] = round_h(a * sn + b * cs);
+        }
+    }
+}
+__device__ __forceinline__ void unpack8(const uint4 w, float *v) {
+    const __half2 *h = reinterpret_cast<const __half2 *>(&w);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ float quad_max(float m) {
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    return fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+}
+__device__ __forceinline__ uint2 pack8_s8(const int *q) {
+    return make_uint2((q[0] & 0xff) | ((q[1] & 0xff) << 8) | ((q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24),
+                      (q[4] & 0xff) | ((q[5] & 0xff) << 8) | ((q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24));
+}
+
+// One thread = 8 consecutive dims, four neighbouring lanes = one 32-dim block (its max by two shuffles).
+template <bool Q8>
+__device__ __noinline__ void stage_att(const StepParams &P, int layer, int ctx, uint8_t *xst, const float *s_cos,
+                                       const float *s_sin, int tid) {
+    const int hd = P.hd, nb = hd / 32;
+    const AttLayout L = att_layout(P.heads, P.kv_heads, hd, Q8);
+    const __half *q = P.qkv, *k = P.qkv + P.q_dim, *v = P.qkv + P.q_dim + P.kv_dim;
+    // ---- q: RoPE, round to half, scale; Q8 cache: two int8 terms per block, q ~= s1*qh + s2*ql (s2 <= s1/254)
+    const int nq = P.q_dim >> 3;
+    for (int base = 0; base < nq; base += GEMV_CTHREADS) {
+        const int g8 = base + tid;
+        const bool act = g8 < nq;
+        const int e0 = act ? g8 * 8 : 0, hq = e0 / hd, d0 = e0 - hq * hd;
+        float x[8], o[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { x[i] = 0.f; o[i] = 0.f; }
+        if (act) {
+            unpack8(ld_cg128(q + e0), x);
+            if (P.rope_order == 2) unpack8(ld_cg128(q + hq * hd + (d0 < hd / 2 ? d0 + hd / 2 : d0 - hd / 2)), o);
+            rope8(x, o, d0, hd, P.rope_order, s_cos, s_sin);
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] *= P.softmax_scale;
+        }
+        if (Q8) {
+            float m = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) m = fmaxf(m, fabsf(x[i]));
+            const float s1 = quad_max(m) * (1.0f / 127.0f);
+            int qh[8], ql[8];
+            float r[8], m2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float t = s1 > 0.f ? rintf(x[i] / s1) : 0.f;
+                qh[i] = (int)t;
+                r[i] = x[i] - t * s1;
+                m2 = fmaxf(m2, fabsf(r[i]));
+            }
+            const float s2 = quad_max(m2) * (1.0f / 127.0f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) ql[i] = (int)(s2 > 0.f ? rintf(r[i] / s2) : 0.f);
+            if (act) {
+                *reinterpret_cast<uint2 *>(xst + L.qh + e0) = pack8_s8(qh);
+                *reinterpret_cast<uint2 *>(xst + L.ql + e0) = pack8_s8(ql);
+                if ((d0 & 31) == 0) reinterpret_cast<float2 *>(xst + L.qs)[hq * nb + (d0 >> 5)] = make_float2(s1, s2);
+            }
+        } else if (act) {
+            float *dst = reinterpret_cast<float *>(xst) + ((size_t)hq * (hd / 16) + (d0 >> 4)) * 20 + (d0 & 15);
+            *reinterpret_cast<float4 *>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+            *reinterpret_cast<float4 *>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
+        }
+    }
+    // ---- the new K row (RoPE) and V row of every kv head, as the cache stores them (SetKRows / SetVRows,
+    // kv_cache.cc:104-183; Q8: Tensor_QuantizeQ8_B32T2_Alg2_Kernel, tensor_quant.h:45-82). Every CTA keeps them in
+    // shared memory (a tile that holds position ctx-1 is patched there: its bulk copy may have been issued before
+    // this row existed); the CTA h % grid writes head h's row to the cache itself.
+    const int pos = ctx - 1;
+    const int nkv = P.kv_dim >> 3;
+    const StepLayer &lw = P.layers[layer];
+    for (int which = 0; which < 2; which++) {
+        const __half *src = which == 0 ? k : v;
+        uint8_t *cache = which == 0 ? lw.kcache : lw.vcache;
+        for (int base = 0; base < nkv; base += GEMV_CTHREADS) {
+            const int g8 = base + tid;
+            const bool act = g8 < nkv;
+            const int e0 = act ? g8 * 8 : 0, h = e0 / hd, d0 = e0 - h * hd;
+            float x[8], o[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) { x[i] = 0.f; o[i] = 0.f; }
+            if (act) {
+                unpack8(ld_cg128(src + e0), x);
+                if (which == 0) {
+                    if (P.rope_order == 2) unpack8(ld_cg128(src + h * hd + (d0 < hd / 2 ? d0 + hd / 2 : d0 - hd / 2)), o);
+                    rope8(x, o, d0, hd, P.rope_order, s_cos, s_sin);
+                }
+            }
+            const bool mine = act && (h % (int)gridDim.x) == (int)blockIdx.x;
+            const int64_t row = (int64_t)h * P.max_ctx_pad + pos;
+            if (Q8) {
+                float m = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; i++) m = fmaxf(m, fabsf(x[i]));
+                const float scale = __fdiv_rn(quad_max(m), 127.0f);
+                int qv[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    int t = scale <= 0.000001f ? 0 : (int)roundf(__fdiv_rn(x[i], scale));
+                    qv[i] = min(max(t, -128), 127);
+                }
+                if (act) {
+                    const uint2 pk = pack8_s8(qv);
+                    *reinterpret_cast<uint2 *>(xst + (which == 0 ? L.newk : L.newv) + e0) = pk;
+                    const __half hs = __float2half_rn(scale);
+                    if ((d0 & 31) == 0) reinterpret_cast<__half *>(xst + (which == 0 ? L.newks : L.newvs))[h * nb + (d0 >> 5)] = hs;
+                    if (mine) {
+                        *reinterpret_cast<uint2 *>(cache + row * hd + d0) = pk;
+                        if ((d0 & 31) == 0)
+                            reinterpret_cast<__half *>(cache + (int64_t)P.kv_heads * P.max_ctx_pad * hd)[row * nb + (d0 >> 5)] = hs;
+                    }
+                }
+            } else if (act) {
+                uint4 pk;
+                __half2 *ph = reinterpret_cast<__half2 *>(&pk);
+#pragma unroll
+                for (int i = 0; i < 4; i++) ph[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+                *reinterpret_cast<uint4 *>(xst + (which == 0 ? L.newk : L.newv) + (size_t)e0 * 2) = pk;
+                if (mine) *reinterpret_cast<uint4 *>(cache + (row * hd + d0) * 2) = pk;
+            }
+        }
+    }
+}
+
+// signed byte k of w -> float without I2F (see ifb_attention.cu)
+__device__ __forceinline__ float s8f_(uint32_t w_biased, int k) {
+    const uint32_t bits = __byte_perm(w_biased, 0x4b000000u, 0x7650u + (uint32_t)k);
+    return __uint_as_float(bits) - 8388736.0f;
+}
+
+// One task = the 32 positions [pbase, pbase+32) of kv head kvh against the G q heads of its group; the warp writes
+// the tile's (m, l, acc[HD]) partial of each q head. The arithmetic is the scan body of attn_decode_kernel
+// (ifb_attention.cu): dp4a scores with the two-term int8 q for a Q8 cache, fp32 softmax, lane-owns-4-dims P.V.
+template <int HD, int G, bool Q8>
+__device__ __noinline__ void att_task(const StepParams &P, uint8_t *slot, int tt, int kvh, int p0, int ctx,
+                                      const uint8_t *xst, float *sp, int lane) {
+    constexpr int NB = HD / 32;
+    const int pbase = p0 + tt * 32;
+    if (pbase >= ctx) return;
+    const AttLayout L = att_layout(P.heads, P.kv_heads, HD, Q8);
+    const int UP = P.att_pos;
+    uint8_t *tK, *tKs = nullptr, *tV, *tVs = nullptr;
+    if (Q8) {
+        tK = slot + tt * 32 * HD;
+        tKs = slot + UP * HD + tt * 32 * NB * 2;
+        tV = slot + UP * HD + UP * NB * 2 + tt * 32 * HD;
+        tVs = slot + 2 * UP * HD + UP * NB * 2 + tt * 32 * NB * 2;
+    } else {
+        tK = slot;
+        tV = slot + 32 * HD * 2;
+    }
+    if (ctx - 1 >= pbase && ctx - 1 < pbase + 32) {
+        // the copy raced with (or preceded) the store of this token's K/V row: put the row in place here
+        const int r = (ctx - 1) - pbase;
+        constexpr int ROWB = Q8 ? HD : HD * 2;
+        const uint32_t *nk = reinterpret_cast<const uint32_t *>(xst + L.newk + (size_t)kvh * ROWB);
+        const uint32_t *nv = reinterpret_cast<const uint32_t *>(xst + L.newv + (size_t)kvh * ROWB);
+        for (int i = lane; i < ROWB / 4; i += 32) {
+            reinterpret_cast<uint32_t *>(tK + r * ROWB)[i] = nk[i];
+            reinterpret_cast<uint32_t *>(tV + r * ROWB)[i] = nv[i];
+        }
+        if (Q8 && lane < NB) {
+            reinterpret_cast<__half *>(tKs)[r * NB + lane] = reinterpret_cast<const __half *>(xst + L.newks)[kvh * NB + lane];
+            reinterpret_cast<__half *>(tVs)[r * NB + lane] = reinterpret_cast<const __half *>(xst + L.newvs)[kvh * NB + lane];
+        }
+        fence_proxy_async_smem();   // generic-proxy writes into a buffer the next bulk copy (async proxy) will overwrite
+        __syncwarp();
+    }
+
+    // ---- scores
+    if (Q8) {
+        constexpr int C = HD / 16;
+        constexpr int RPL = (C >= 8) ? 1 : 8 / C;
+        const int rot = lane / RPL;
+        float sc[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) sc[g] = 0.f;
+        const float2 *qs = reinterpret_cast<const float2 *>(xst + L.qs);
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            const int ci = (j + rot) & (C - 1);
+            const uint4 kw = *reinterpret_cast<const uint4 *>(tK + lane * HD + ci * 16);
+            const float ksc = __half2float(reinterpret_cast<const __half *>(tKs)[lane * NB + (ci >> 1)]);
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int hq = kvh * G + g;
+                const uint4 qh = *reinterpret_cast<const uint4 *>(xst + L.qh + (size_t)hq * HD + ci * 16);
+                const uint4 ql = *reinterpret_cast<const uint4 *>(xst + L.ql + (size_t)hq * HD + ci * 16);
+                int dh = dp4a_ss(kw.x, qh.x, 0), dl = dp4a_ss(kw.x, ql.x, 0);
+                dh = dp4a_ss(kw.y, qh.y, dh); dl = dp4a_ss(kw.y, ql.y, dl);
+                dh = dp4a_ss(kw.z, qh.z, dh); dl = dp4a_ss(kw.z, ql.z, dl);
+                dh = dp4a_ss(kw.w, qh.w, dh); dl = dp4a_ss(kw.w, ql.w, dl);
+                const float2 s12 = qs[hq * NB + (ci >> 1)];
+                const float t = fmaf(s12.x, (float)dh, s12.y * (float)dl);
+                sc[g] = fmaf(ksc, t, sc[g]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) sp[g * 32 + lane] = (pbase + lane < ctx) ? sc[g] : -INFINITY;
+    } else {
+        constexpr int LPP = HD / 16, PPW = 32 / LPP;
+        const int sub = lane % LPP, pl = lane / LPP;
+        const float *sq = reinterpret_cast<const float *>(xst);
+#pragma unroll 2
+        for (int pp = pl; pp < 32; pp += PPW) {
+            float kf[16];
+            const uint4 w0 = *reinterpret_cast<const uint4 *>(tK + (pp * HD + sub * 16) * 2);
+            const uint4 w1 = *reinterpret_cast<const uint4 *>(tK + (pp * HD + sub * 16) * 2 + 16);
+            unpack8(w0, kf);
+            unpack8(w1, kf + 8);
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const float4 *qv = reinterpret_cast<const float4 *>(sq + ((size_t)(kvh * G + g) * (HD / 16) + sub) * 20);
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; j += 2) {
+                    const float4 qa = qv[j], qb = qv[j + 1];
+                    s0 = fmaf(kf[4 * j], qa.x, s0);
+                    s1 = fmaf(kf[4 * j + 4], qb.x, s1);
+                    s0 = fmaf(kf[4 * j + 1], qa.y, s0);
+                    s1 = fmaf(kf[4 * j + 5], qb.y, s1);
+                    s0 = fmaf(kf[4 * j + 2], qa.z, s0);
+                    s1 = fmaf(kf[4 * j + 6], qb.z, s1);
+                    s0 = fmaf(kf[4 * j + 3], qa.w, s0);
+                    s1 = fmaf(kf[4 * j + 7], qb.w, s1);
+                }
+                float s = s0 + s1;
+#pragma unroll
+                for (int of = LPP / 2; of > 0; of >>= 1) s += __shfl_xor_sync(0xffffffffu, s, of);
+                if (sub == 0) sp[g * 32 + pp] = (pbase + pp < ctx) ? s : -INFINITY;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- softmax of the tile (fp32), then P.V: lane owns 4 dims
+    float mrun[G], lrun[G], acc[G][4];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const float v0 = sp[g * 32 + lane];
+        const float cm = warp_max(v0);
+        const float e0 = (v0 == -INFINITY) ? 0.f : __expf(v0 - cm);
+        lrun[g] = warp_sum(e0);
+        mrun[g] = cm;
+        sp[g * 32 + lane] = e0;
+        acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f;
+    }
+    __syncwarp();
+    if (lane < HD / 4) {
+        const int npos = min(32, ctx - pbase);
+#pragma unroll 4
+        for (int pp = 0; pp < npos; pp++) {
+            float vf[4], vsc = 1.f;
+            if (Q8) {
+                const uint32_t w = reinterpret_cast<const uint32_t *>(tV + pp * HD)[lane] ^ 0x80808080u;
+                vsc = __half2float(reinterpret_cast<const __half *>(tVs)[pp * NB + lane / 8]);
+#pragma unroll
+                for (int k = 0; k < 4; k++) vf[k] = s8f_(w, k);
+            } else {
+                const uint2 w = reinterpret_cast<const uint2 *>(tV + pp * HD * 2)[lane];
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&w.x));
+                const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w.y));
+                vf[0] = f0.x; vf[1] = f0.y; vf[2] = f1.x; vf[3] = f1.y;
+            }
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const float p = sp[g * 32 + pp] * vsc;
+                acc[g][0] = fmaf(p, vf[0], acc[g][0]);
+                acc[g][1] = fmaf(p, vf[1], acc[g][1]);
+                acc[g][2] = fmaf(p, vf[2], acc[g][2]);
+                acc[g][3] = fmaf(p, vf[3], acc[g][3]);
+            }
+        }
+    }
+    const int tile = pbase >> 5;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        float *o = P.partials + ((size_t)(kvh * G + g) * P.max_tiles + tile) * (HD + 4);
+        if (lane == 0) *reinterpret_cast<float2 *>(o) = make_float2(mrun[g], lrun[g]);
+        if (lane < HD / 4) *reinterpret_cast<float4 *>(o + 4 + lane * 4) = make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
+    }
+    __syncwarp();
+}
+
+template <int HD, bool Q8>
+__device__ __forceinline__ void att_task_g(const StepParams &P, uint8_t *slot, int tt, int kvh, int p0, int ctx,
+                                           const uint8_t *xst, float *sp, int lane) {
+    switch (P.group) {
+        case 1: att_task<HD, 1, Q8>(P, slot, tt, kvh, p0, ctx, xst, sp, lane); break;
+        case 2: att_task<HD, 2, Q8>(P, slot, tt, kvh, p0, ctx, xst, sp, lane); break;
+        case 4: att_task<HD, 4, Q8>(P, slot, tt, kvh, p0, ctx, xst, sp, lane); break;
+        default: att_task<HD, 8, Q8>(P, slot, tt, kvh, p0, ctx, xst, sp, lane); break;
+    }
+}
+__device__ __forceinline__ void att_task_any(const StepParams &P, uint8_t *slot, int tt, int kvh, int p0, int ctx,
+                                             const uint8_t *xst, float *sp, int lane) {
+    if (P.hd == 128) {
+        if (P.kv_q8) att_task_g<128, true>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        else att_task_g<128, false>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
+    } else {
+        if (P.kv_q8) att_task_g<64, true>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        else att_task_g<64, false>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
+    }
+}
+
+// log-sum-exp merge of the tiles' partials: q head hq -> attn_out[hq][hd] (half, as the reference's attention output
+// tensor). 512 threads = (512/hd) tile groups x hd dims; scratch = the (idle) staging area.
+__device__ __noinline__ void att_merge(const StepParams &P, int ctx, float *scratch, int tid) {
+    const int hd = P.hd, ngrp = GEMV_CTHREADS / hd, grp = tid / hd, dd = tid - grp * hd;
+    const int ntile = (ctx + 31) >> 5;
+    for (int hq = (int)blockIdx.x; hq < P.heads; hq += (int)gridDim.x) {
+        const float *pb = P.partials + (size_t)hq * P.max_tiles * (hd + 4);
+        float M = -INFINITY;
+        for (int t = grp; t < ntile; t += ngrp) M = fmaxf(M, ld_cg_f32(pb + (size_t)t * (hd + 4)));
+        float num = 0.f, den = 0.f;
+        for (int t = grp; t < ntile; t += ngrp) {
+            const float *pt = pb + (size_t)t * (hd + 4);
+            const float w = __expf(ld_cg_f32(pt) - M);
+            num = fmaf(w, ld_cg_f32(pt + 4 + dd), num);
+            den = fmaf(w, ld_cg_f32(pt + 1), den);
+        }
+        scratch[(grp * hd + dd) * 3 + 0] = M;
+        scratch[(grp * hd + dd) * 3 + 1] = num;
+        scratch[(grp * hd + dd) * 3 + 2] = den;
+        named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+        if (tid < hd) {
+            float MM = -INFINITY;
+            for (int g = 0; g < ngrp; g++) MM = fmaxf(MM, scratch[(g * hd + tid) * 3]);
+            float n2 = 0.f, d2 = 0.f;
+            for (int g = 0; g < ngrp; g++) {
+                const float mg = scratch[(g * hd + tid) * 3];
+                const float w = (mg == -INFINITY) ? 0.f : __expf(mg - MM);
+                n2 = fmaf(w, scratch[(g * hd + tid) * 3 + 1], n2);
+                d2 = fmaf(w, scratch[(g * hd + tid) * 3 + 2], d2);
+            }
+            P.attn_out[(size_t)hq * hd + tid] = __float2half_rn(n2 / d2);
+        }
+        named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------
+template <class Fmt, int LD>
+__device__ __forceinline__ void stage_gemv_x(const StepParams &P, const StepOpShape &s, const void *src, const __half *norm_w,
+                                             uint8_t *xst, float *red, int tid) {
+    const XStage a = {s.cx, nullptr, norm_w, P.eps, 0.f};
+    if constexpr (is_f16_fmt<Fmt>::value) {
+        stage_x_f16<LD>(a, src, reinterpret_cast<__half *>(xst), red, tid);
+    } else {
+        uint8_t *xlo = xst, *xhi = xst + (size_t)s.nxb * 16;
+        float2 *xs = reinterpret_cast<float2 *>(xst + (size_t)s.nxb * 32);
+        if constexpr (is_q4b32_fmt<Fmt>::value) {
+            if (s.vec4) { stage_x_q8<true, true, LD>(a, src, xlo, xhi, xs, red, tid); return; }
+        }
+        stage_x_q8<Fmt::XSPLIT, false, LD>(a, src, xlo, xhi, xs, red, tid);
+    }
+}
+
+// two rows (row, row + stride) against the staged activation
+template <class Fmt>
+__device__ __forceinline__ void dot2(const StepOpShape &s, const uint8_t *row, size_t stride, const uint8_t *xst, int lane, float *acc) {
+    if constexpr (is_f16_fmt<Fmt>::value) {
+        acc[0] = row_dot_f16(row, s.cx, reinterpret_cast<const __half *>(xst), lane);
+        acc[1] = row_dot_f16(row + stride, s.cx, reinterpret_cast<const __half *>(xst), lane);
+    } else {
+        const uint4 *xlo = reinterpret_cast<const uint4 *>(xst), *xhi = reinterpret_cast<const uint4 *>(xst + (size_t)s.nxb * 16);
+        const float2 *xs = reinterpret_cast<const float2 *>(xst + (size_t)s.nxb * 32);
+        if constexpr (is_q4b32_fmt<Fmt>::value) {
+            if (s.vec4) { row_dot_q4b32_vec4<2>(row, stride, s.nblk, xlo, xhi, xs, lane, acc); return; }
+        }
+        acc[0] = row_dot_q8<Fmt>(row, s.nblk, xlo, xhi, xs, lane);
+        acc[1] = row_dot_q8<Fmt>(row + stride, s.nblk, xlo, xhi, xs, lane);
+    }
+}
+
+template <class Fmt>
+__global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __grid_constant__ StepParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full_bar[STEP_MAX_SLOTS], empty_bar[STEP_MAX_SLOTS];
+    __shared__ int2 slot_meta[STEP_MAX_SLOTS];   // (op, unit) of what sits in each ring slot
+    __shared__ float red[GEMV_CWARPS];
+    __shared__ unsigned long long s_key[GEMV_CWARPS];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *ring = smem;
+    uint8_t *xst = smem + P.x_off;
+    uint4 *resid = reinterpret_cast<uint4 *>(smem + P.resid_off);
+    float *s_cos = reinterpret_cast<float *>(smem + P.rope_off), *s_sin = s_cos + P.hd / 2;
+    const int n_ops = P.n_ops, head_op = n_ops - 1;
+
+    if (tid == 0) {
+        for (int i = 0; i < P.nslots; i++) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], GEMV_CWARPS);
+        }
+        mbar_fence_init();
+    }
+    // position / token / sequence number were written before this launch and only change in its last instruction
+    int pos_now = P.scalars[0];
+    if (pos_now < 0 || pos_now >= P.max_ctx) {      // the host checks this too (ifb_model_decode): never index past the cache
+        if (tid == 0 && blockIdx.x == 0 && P.err != nullptr) { P.err[1] = pos_now; P.err[0] = STEP_ERR_CTX; }
+        pos_now = max(0, min(pos_now, P.max_ctx - 1));
+    }
+    const int ctx = pos_now + 1;
+    const uint32_t seq = (uint32_t)P.scalars[3];
+    if (tid < P.hd / 2) {
+        // angle_i = pos * theta_scale^i, theta_scale = theta^(-2/dims) (unary_tensor_opr.h:666-679,706-719)
+        const float theta_scale = powf(P.rope_theta, -2.0f / (float)P.hd);
+        float ang = (float)pos_now;
+        if (tid > 0) ang *= powf(theta_scale, (float)tid);
+        s_cos[tid] = cosf(ang);
+        s_sin[tid] = sinf(ang);
+    }
+    __syncthreads();
+
+    const int att_units = (P.parts & STEP_PART_ATT) ? P.kv_heads * ((ctx + P.att_pos - 1) / P.att_pos) : 0;
+    const int tiles_per_head = (ctx + P.att_pos - 1) / P.att_pos;
+
+    if (warp == GEMV_CWARPS) {
+        // ===== producer: depends on nothing but free ring slots =====
+        if (lane != 0) return;
+        const uint64_t pol = l2_policy_evict_first();   // weights and cache tiles are read once per token
+        int op = 0, pos = 0;
+        uint32_t phase = 1;                              // a fresh mbarrier passes a wait on parity 1
+        int next = atomicAdd(&P.cursors[0], 1);
+        while (op < n_ops) {
+            const int kind = op == head_op ? OPK_HEAD : op % 5, layer = op / 5;
+            const StepOpShape &s = P.op[kind];
+            const int units = kind == OPK_ATT ? att_units : ((P.parts & STEP_PART_GEMV) ? s.units : 0);
+            const int u = next;
+            if (u >= units) {
+                if (++op < n_ops) next = atomicAdd(&P.cursors[op], 1);
+                continue;
+            }
+            next = atomicAdd(&P.cursors[op], 1);         // in flight while we wait for the slot
+            mbar_wait_bounded(&empty_bar[pos], phase, P, op);
+            slot_meta[pos] = make_int2(op, u);
+            uint8_t *dst = ring + (size_t)pos * P.slot_bytes;
+            const uint32_t ub = (uint32_t)s.unit_bytes;
+            if (kind == OPK_ATT) {
+                const StepLayer &lw = P.layers[layer];
+                const int h = u / tiles_per_head, t = u - h * tiles_per_head;
+                const int64_t row0 = (int64_t)h * P.max_ctx_pad + (int64_t)t * P.att_pos;
+                const int hd = P.hd, nb = hd / 32, UP = P.att_pos;
+                if (P.kv_q8) {
+                    const uint32_t kb = (uint32_t)(UP * hd), sb = (uint32_t)(UP * nb * 2);
+                    const int64_t soff = (int64_t)P.kv_heads * P.max_ctx_pad * hd;
+                    mbar_arrive_expect_tx(&full_bar[pos], 2 * (kb + sb));
+                    bulk_g2s_hint(dst, lw.kcache + row0 * hd, kb, &full_bar[pos], pol);
+                    bulk_g2s_hint(dst + kb, lw.kcache + soff + row0 * nb * 2, sb, &full_bar[pos], pol);
+                    bulk_g2s_hint(dst + kb + sb, lw.vcache + row0 * hd, kb, &full_bar[pos], pol);
+                    bulk_g2s_hint(dst + 2 * kb + sb, lw.vcache + soff + row0 * nb * 2, sb, &full_bar[pos], pol);
+                } else {
+                    const uint32_t kb = (uint32_t)(UP * hd * 2);
+                    mbar_arrive_expect_tx(&full_bar[pos], 2 * kb);
+                    bulk_g2s_hint(dst, lw.kcache + row0 * hd * 2, kb, &full_bar[pos], pol);
+                    bulk_g2s_hint(dst + kb, lw.vcache + row0 * hd * 2, kb, &full_bar[pos], pol);
+                }
+            } else if (kind == OPK_GLU) {
+                const StepLayer &lw = P.layers[layer];
+                mbar_arrive_expect_tx(&full_bar[pos], 2 * ub);
+                bulk_g2s_hint(dst, lw.w1 + (size_t)u * ub, ub, &full_bar[pos], pol);
+                bulk_g2s_hint(dst + ub, lw.w3 + (size_t)u * ub, ub, &full_bar[pos], pol);
+            } else {
+                const uint8_t *src;
+                if (kind == OPK_HEAD) src = P.lm_head + (size_t)u * ub;
+                else {
+                    const StepLayer &lw = P.layers[layer];
+                    if (kind == OPK_QKV) src = u >= s.seg2 ? lw.wv + (size_t)(u - s.seg2) * ub : (u >= s.seg1 ? lw.wk + (size_t)(u - s.seg1) * ub : lw.wq + (size_t)u * ub);
+                    else src = (kind == OPK_WO ? lw.wo : lw.w2) + (size_t)u * ub;
+                }
+                mbar_arrive_expect_tx(&full_bar[pos], ub);
+                bulk_g2s_hint(dst, src, ub, &full_bar[pos], pol);
+            }
+            if (++pos == P.nslots) { pos = 0; phase ^= 1u; }
+        }
+        mbar_wait_bounded(&empty_bar[pos], phase, P, n_ops);
+        slot_meta[pos] = make_int2(n_ops, 0);            // end of the token
+        mbar_arrive(&full_bar[pos]);
+        return;
+    }
+
+    // ===== consumers =====
+    float *sp = reinterpret_cast<float *>(smem + P.sp_off) + (size_t)warp * P.group * 32;
+    const int tp = P.tp_size;
+
+    // staging of op `op`'s input (every CTA runs it for every op, in order: the residual stream lives in each CTA's
+    // shared memory, and "this CTA has staged op k" is part of what its completion count of op k tells the peers)
+    auto stage_for = [&](int op) {
+        const int kind = op == head_op ? OPK_HEAD : op % 5, layer = op / 5;
+        trace_op(P, op, 0, tid);
+        if (kind == OPK_QKV || kind == OPK_GLU || kind == OPK_HEAD) {
+            if (op == 0) {
+                // GetEmbdTensor (inference_engine.cc:1324-1350): the token's embedding row starts the residual stream
+                int tok = P.scalars[1];
+                tok = max(0, min(tok, P.vocab - 1));
+                const uint4 *row = reinterpret_cast<const uint4 *>(P.tok_emb + (size_t)tok * P.d);
+                for (int g = tid; g < (P.d >> 3); g += GEMV_CTHREADS) resid[g] = row[g];
+            } else if (tp > 1) {
+                // exchange index: wo of layer l -> 2l+1, w2 of layer l -> 2l+2 (two buffers, alternating)
+                const uint32_t idx = kind == OPK_GLU ? (uint32_t)(2 * layer + 1) : (uint32_t)(2 * (kind == OPK_HEAD ? P.n_layers : layer));
+                resid_add_gather(P, resid, idx, seq, op, tid);
+            } else {
+                dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
+                resid_add_local(P, resid, tid);
+            }
+            trace_op(P, op, 1, tid);
+            named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+            const __half *nw = kind == OPK_HEAD ? P.out_norm : (kind == OPK_QKV ? P.layers[layer].attn_norm : P.layers[layer].ffn_norm);
+            if (kind == OPK_HEAD && P.head_f16) {
+                const XStage a = {P.d, nullptr, nw, P.eps, 0.f};
+                stage_x_f16<0>(a, resid, reinterpret_cast<__half *>(xst), red, tid);
+            } else {
+                stage_gemv_x<Fmt, 0>(P, P.op[kind], resid, nw, xst, red, tid);
+            }
+        } else if (kind == OPK_ATT) {
+            dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
+            trace_op(P, op, 1, tid);
+            if (P.kv_q8) stage_att<true>(P, layer, ctx, xst, s_cos, s_sin, tid);
+            else stage_att<false>(P, layer, ctx, xst, s_cos, s_sin, tid);
+        } else if (kind == OPK_WO) {
+            dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
+            att_merge(P, ctx, reinterpret_cast<float *>(xst), tid);
+            dep_signal(&P.done[n_ops + layer], tid);
+            dep_wait(&P.done[n_ops + layer], gridDim.x, P, op, tid);
+            trace_op(P, op, 1, tid);
+            stage_gemv_x<Fmt, 1>(P, P.op[kind], P.attn_out, nullptr, xst, red, tid);
+        } else {   // OPK_W2
+            dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
+            trace_op(P, op, 1, tid);
+            stage_gemv_x<Fmt, 1>(P, P.op[kind], P.hbuf, nullptr, xst, red, tid);
+        }
+        named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+        trace_op(P, op, 2, tid);
+    };
+
+    float best_v = -INFINITY;
+    int best_i = 0x7fffffff;
+    int traced_op = -1;
+    int cur_op = -1;            // nothing staged yet: the first pass stages op 0 while the first units are in flight
+    int pos = 0, tbase = 0;
+    uint32_t phase = 0;
+    for (;;) {
+        int2 meta = make_int2(0, -1);
+        if (cur_op >= 0) {
+            mbar_wait_bounded(&full_bar[pos], phase, P, cur_op);
+            meta = slot_meta[pos];
+        }
+        if (meta.x != cur_op) {
+            for (int k = cur_op; k < meta.x; k++) {
+                if (k >= 0) {
+                    if (k == head_op && tp == 1 && lane == 0 && best_i != 0x7fffffff) atomicMax(P.amax, amax_key(best_v, best_i));
+                    dep_signal(&P.done[k], tid);     // this CTA's rows of op k are stored (and its staging of op k is long done)
+                }
+                if (k + 1 < n_ops) stage_for(k + 1);
+            }
+            cur_op = meta.x;
+            if (cur_op >= n_ops) break;
+        }
+        if (meta.y < 0) continue;   // first pass: no slot in hand yet
+        const int kind = cur_op == head_op ? OPK_HEAD : cur_op % 5, layer = cur_op / 5;
+        const StepOpShape &s = P.op[kind];
+        uint8_t *slot = ring + (size_t)pos * P.slot_bytes;
+        const int u = meta.y;
+        const int ntask = s.tasks;
+        if (P.trace != nullptr && traced_op != cur_op) { trace_op(P, cur_op, 3, tid); traced_op = cur_op; }   // first unit of the op in hand
+        for (int t = (warp - tbase) & 15; t < ntask; t += GEMV_CWARPS) {
+            if (kind == OPK_ATT) {
+                const int h = u / tiles_per_head, tl = u - h * tiles_per_head;
+                att_task_any(P, slot, t, h, tl * P.att_pos, ctx, xst, sp, lane);
+                continue;
+            }
+            float acc[2];
+            int o;
+            if (kind == OPK_GLU) {
+                o = u * s.R + t;
+                dot2<Fmt>(s, slot + (size_t)t * s.row_bytes, (size_t)s.unit_bytes, xst, lane, acc);
+            } else {
+                o = u * s.R + 2 * t;
+                const uint8_t *row = slot + (size_t)(2 * t) * s.row_bytes;
+                if (kind == OPK_HEAD && P.head_f16) {
+                    acc[0] = row_dot_f16(row, s.cx, reinterpret_cast<const __half *>(xst), lane);
+                    acc[1] = row_dot_f16(row + s.row_bytes, s.cx, reinterpret_cast<const __half *>(xst), lane);
+                } else {
+                    dot2<Fmt>(s, row, (size_t)s.row_bytes, xst, lane, acc);
+                }
+            }
+            acc[0] = warp_sum(acc[0]);
+            acc[1] = warp_sum(acc[1]);
+            if (lane == 0) {
+                const float v0 = round_h(acc[0]), v1 = round_h(acc[1]);   // GEMV output tensors are half
+                if (kind == OPK_GLU) {
+                    // SiluActivation_Kernel (unary_tensor_opr.h:553) then Mul, each stored as half
+                    const float g = round_h(v0 / (1.0f + expf(-v0)));
+                    P.hbuf[o] = __float2half_rn(g * v1);
+                } else {
+                    const __half2 hv = __floats2half2_rn(v0, v1);
+                    const uint32_t bits = *reinterpret_cast<const uint32_t *>(&hv);
+                    if (kind == OPK_QKV) {
+                        reinterpret_cast<uint32_t *>(P.qkv)[o >> 1] = bits;
+                    } else if (kind == OPK_HEAD) {
+                        if (tp == 1) {
+                            reinterpret_cast<uint32_t *>(P.logits)[o >> 1] = bits;
+                            if (v0 == v0 && (v0 > best_v || (v0 == best_v && o < best_i))) { best_v = v0; best_i = o; }
+                            if (v1 == v1 && (v1 > best_v || (v1 == best_v && o + 1 < best_i))) { best_v = v1; best_i = o + 1; }
+                        } else {
+                            const uint2 wd = make_uint2(bits, (seq << 8) | 255u);
+                            const size_t off = (size_t)P.x_logits + ((size_t)(P.tp_rank * P.vocab_l + o) >> 1) * 8;
+                            for (int p = 0; p < tp; p++) st_relaxed_sys_v2(reinterpret_cast<uint8_t *>(P.peer[p]) + off, wd);
+                        }
+                    } else if (tp == 1) {
+                        reinterpret_cast<uint32_t *>(P.ybuf)[o >> 1] = bits;
+                    } else {
+                        // row-parallel partial sums go straight into every rank's exchange region over NVLink
+                        const uint32_t idx = kind == OPK_WO ? (uint32_t)(2 * layer + 1) : (uint32_t)(2 * layer + 2);
+                        const uint2 wd = make_uint2(bits, (seq << 8) | idx);
+                        const size_t off = (size_t)P.x_recv + (size_t)(idx & 1u) * P.x_recv_parity + (size_t)P.tp_rank * P.x_recv_rank + (size_t)(o >> 1) * 8;
+                        for (int p = 0; p < tp; p++) st_relaxed_sys_v2(reinterpret_cast<uint8_t *>(P.peer[p]) + off, wd);
+                    }
+                }
+            }
+        }
+        tbase = (tbase + ntask) & 15;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[pos]);
+        if (++pos == P.nslots) { pos = 0; phase ^= 1u; }
+    }
+
+    // ===== end of the token: next token id, position += 1 =====
+    if (tp > 1) {
+        // the vocabulary-sharded lm_head of every rank pushed its logits here as flag-in-data words: each CTA
+        // compacts a slice to fp16 and folds it into the argmax key
+        const uint2 *ll = reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(P.peer[P.tp_rank]) + P.x_logits);
+        const uint32_t flag = (seq << 8) | 255u;
+        const int nw = P.vocab >> 1;
+        const int per = (nw + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int w0 = (int)blockIdx.x * per, w1 = min(nw, w0 + per);
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int w = w0 + tid; w < w1; w += GEMV_CTHREADS) {
+            uint2 v = ld_relaxed_sys_v2(ll + w);
+            if (v.y != flag) {
+                const unsigned long long t0 = globaltimer_ns();
+                unsigned it = 0;
+                while (v.y != flag) {
+                    v = ld_relaxed_sys_v2(ll + w);
+                    if ((++it & 255u) == 0u && globaltimer_ns() - t0 > P.timeout_ns) step_abort(P, STEP_ERR_LOGITS, head_op, w);
+                }
+            }
+            reinterpret_cast<uint32_t *>(P.logits)[w] = v.x;
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&v.x));
+            if (f.x == f.x && f.x > bv) { bv = f.x; bi = 2 * w; }
+            if (f.y == f.y && f.y > bv) { bv = f.y; bi = 2 * w + 1; }
+        }
+        unsigned long long key = bi != 0x7fffffff ? amax_key(bv, bi) : 0ull;
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) {
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, of);
+            key = ok > key ? ok : key;
+        }
+        if (lane == 0) s_key[warp] = key;
+        named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+        if (tid == 0) {
+            for (int i = 1; i < GEMV_CWARPS; i++) key = s_key[i] > key ? s_key[i] : key;
+            if (key != 0ull) atomicMax(P.amax, key);
+        }
+        dep_signal(&P.done[n_ops + P.n_layers], tid);
+    }
+    if (blockIdx.x == 0) {
+        dep_wait(&P.done[tp > 1 ? n_ops + P.n_layers : head_op], gridDim.x, P, n_ops, tid);
+        for (int g = tid; g < (P.d >> 3); g += GEMV_CTHREADS) reinterpret_cast<uint4 *>(P.x_out)[g] = resid[g];
+        if (tid == 0) {
+            const unsigned long long key = ld_cg_u64(P.amax);
+            const int tok = key == 0ull ? 0 : (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+            P.scalars[2] = tok;
+            if (P.advance) { P.scalars[0] = pos_now + 1; P.scalars[1] = tok; }
+            P.scalars[3] = (int32_t)(seq + 1u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static bool ax8_fmt(int dt) {
+    switch (dt) {
+        case DT_Q8_B32T2: case DT_Q6_B64T1: case DT_Q5_B64T1: case DT_Q4_B32T1A:
+        case DT_Q4_B32T1B: case DT_Q4_B64T1: case DT_Q3H_B64T1: return true;
+        default: return false;
+    }
+}
+
+int64_t step_counter_bytes(const StepParams &P) {
+    return ((int64_t)P.n_ops * 4 + ((int64_t)P.n_ops + P.n_layers + 1) * 4 + 16 + 255) / 256 * 256;
+}
+
+// rows per unit: R * row_bytes * nmat <= target, R divides every segment, R*row_bytes % 16 == 0 (bulk-copy
+// granularity), R even for ops whose task is two adjacent rows; not larger than rows/grid when that leaves >= 2
+static int pick_rows(const int *seg_rows, int nseg, int row_bytes_, int nmat, bool even, int grid, int target) {
+    int total = 0;
+    for (int i = 0; i < nseg; i++) total += seg_rows[i];
+    const int byte_cap = target / (row_bytes_ * nmat);
+    const int fair = total / grid;
+    for (int pass = 0; pass < 2; pass++) {
+        int cap = byte_cap;
+        if (pass == 0) {                       // first choice: at least one unit per CTA
+            if (fair < 2 || cap <= fair) continue;
+            cap = fair;
+        }
+        for (int r = cap; r >= 1; r--) {
+            if (even && (r & 1)) continue;
+            if (((int64_t)r * row_bytes_) % 16 != 0) continue;
+            bool ok = true;
+            for (int i = 0; i < nseg; i++) ok = ok && seg_rows[i] % r == 0;
+            if (ok) return r;
+        }
+    }
+    return 0;
+}
+
+int step_build(StepParams &P, int kv_dtype, int head_dtype, int sms) {
+    const int wdt = P.w_dtype;
+    IFB_CHECK_ARG(wdt == DT_F16 || ax8_fmt(wdt), "step kernel: weight type %d has no dp4a path", wdt);
+    IFB_CHECK_ARG(head_dtype == DT_F16 || head_dtype == wdt, "step kernel: lm_head type %d differs from the weight type %d", head_dtype, wdt);
+    IFB_CHECK_ARG(P.hd == 64 || P.hd == 128, "step kernel: head_dim %d (64 / 128)", P.hd);
+    IFB_CHECK_ARG(P.group == 1 || P.group == 2 || P.group == 4 || P.group == 8, "step kernel: heads/kv_heads = %d", P.group);
+    IFB_CHECK_ARG(kv_dtype == DT_F16 || kv_dtype == DT_Q8_B32T2, "step kernel: kv cache type %d", kv_dtype);
+    IFB_CHECK_ARG(P.d % 8 == 0 && P.q_dim % 8 == 0 && P.ffn % 8 == 0 && P.vocab_l % 2 == 0 && P.vocab % 2 == 0, "step kernel: dims must be multiples of 8");
+    P.kv_q8 = kv_dtype == DT_Q8_B32T2 ? 1 : 0;
+    P.head_f16 = head_dtype == DT_F16 ? 1 : 0;
+    P.att_pos = P.kv_q8 ? 64 : 32;
+    P.n_ops = 5 * P.n_layers + 1;
+    P.max_tiles = (P.max_ctx + 31) / 32;
+    const int cap = wdt == DT_F16 ? 32 : block_capacity(wdt);
+
+    auto gemv_shape = [&](int kind, const int *segs, int nseg, int cx, int dt, int nmat) -> int {
+        StepOpShape &s = P.op[kind];
+        s = StepOpShape();
+        s.cx = cx;
+        s.row_bytes = (int)(dt == DT_F16 ? (int64_t)cx * 2 : row_bytes(dt, cx));
+        s.nblk = dt == DT_F16 ? cx / 32 : cx / block_capacity(dt);
+        int target = STEP_TARGET_UNIT;
+        int R = pick_rows(segs, nseg, s.row_bytes, nmat, nmat == 1, sms, target);
+        if (R == 0) { target = 2 * STEP_TARGET_UNIT; R = pick_rows(segs, nseg, s.row_bytes, nmat, nmat == 1, sms, target); }
+        IFB_CHECK_ARG(R > 0, "step kernel: rows of op %d (row_bytes %d) cannot be tiled into ring units", kind, s.row_bytes);
+        s.R = R;
+        s.tasks = nmat == 2 ? R : R / 2;
+        s.unit_bytes = R * s.row_bytes;
+        int units = 0;
+        s.seg1 = s.seg2 = 0x7fffffff;
+        for (int i = 0; i < nseg; i++) {
+            if (i == 1) s.seg1 = units;
+            if (i == 2) s.seg2 = units;
+            units += segs[i] / R;
+        }
+        s.units = units;
+        s.vec4 = (dt == DT_Q4_B32T1A || dt == DT_Q4_B32T1B) && cx % 128 == 0;
+        s.nxb = cx / 32;
+        if (s.vec4) s.nxb = (s.nxb + 127) / 128 * 128;
+        IFB_CHECK_ARG(cx % 32 == 0 && (dt == DT_F16 || cx % cap == 0), "step kernel: cx %d of op %d is not a multiple of the block capacity", cx, kind);
+        return IFB_OK;
+    };
+    int rc;
+    { const int segs[3] = {P.q_dim, P.kv_dim, P.kv_dim}; if ((rc = gemv_shape(OPK_QKV, segs, 3, P.d, wdt, 1)) != IFB_OK) return rc; }
+    { const int segs[1] = {P.d}; if ((rc = gemv_shape(OPK_WO, segs, 1, P.q_dim, wdt, 1)) != IFB_OK) return rc; }
+    { const int segs[1] = {P.ffn}; if ((rc = gemv_shape(OPK_GLU, segs, 1, P.d, wdt, 2)) != IFB_OK) return rc; }
+    { const int segs[1] = {P.d}; if ((rc = gemv_shape(OPK_W2, segs, 1, P.ffn, wdt, 1)) != IFB_OK) return rc; }
+    { const int segs[1] = {P.vocab_l}; if ((rc = gemv_shape(OPK_HEAD, segs, 1, P.d, head_dtype, 1)) != IFB_OK) return rc; }
+    StepOpShape &a = P.op[OPK_ATT];
+    a = StepOpShape();
+    a.tasks = P.att_pos / 32;
+    a.unit_bytes = P.kv_q8 ? P.att_pos * (2 * P.hd + 2 * (P.hd / 32) * 2) : P.att_pos * P.hd * 4;
+
+    // shared memory: ring | staged x | residual stream | per-warp score scratch | RoPE table
+    int64_t slot = a.unit_bytes;
+    for (int k = 0; k < OPK_COUNT; k++) {
+        if (k == OPK_ATT) continue;
+        const int64_t ub = (int64_t)P.op[k].unit_bytes * (k == OPK_GLU ? 2 : 1);
+        if (ub > slot) slot = ub;
+    }
+    slot = (slot + 16 + 127) / 128 * 128;        // + 16: Q8_B32T2 block decode reads one word past its block
+    int64_t xb = att_layout(P.heads, P.kv_heads, P.hd, P.kv_q8 != 0).total;
+    for (int k = 0; k < OPK_COUNT; k++) {
+        if (k == OPK_ATT) continue;
+        const bool f16x = (k == OPK_HEAD ? head_dtype : wdt) == DT_F16;
+        const int64_t b = f16x ? (int64_t)P.op[k].cx * 2 : (int64_t)P.op[k].nxb * 40;
+        if (b > xb) xb = b;
+    }
+    const int64_t merge_b = (int64_t)GEMV_CTHREADS * 3 * 4;
+    if (merge_b > xb) xb = merge_b;
+    xb = (xb + 127) / 128 * 128;
+    const int64_t resid_b = ((int64_t)P.d * 2 + 127) / 128 * 128;
+    const int64_t sp_b = ((int64_t)GEMV_CWARPS * P.group * 32 * 4 + 127) / 128 * 128;
+    const int64_t rope_b = ((int64_t)P.hd * 4 + 127) / 128 * 128;
+    const int64_t smem_max = 232448 - 1536;     // opt-in maximum per CTA minus this kernel's static shared memory
+    int64_t nslots = (smem_max - xb - resid_b - sp_b - rope_b) / slot;
+    if (nslots > STEP_MAX_SLOTS) nslots = STEP_MAX_SLOTS;
+    IFB_CHECK_ARG(nslots >= 3, "step kernel: only %lld ring slots of %lld bytes fit beside %lld bytes of staging", (long long)nslots, (long long)slot, (long long)(xb + resid_b));
+    P.nslots = (int)nslots;
+    P.slot_bytes = (int)slot;
+    P.x_off = (int)(nslots * slot);
+    P.resid_off = P.x_off + (int)xb;
+    P.sp_off = P.resid_off + (int)resid_b;
+    P.rope_off = P.sp_off + (int)sp_b;
+    P.smem_bytes = P.rope_off + (int)rope_b;
+    return IFB_OK;
+}
+
+template <class Fmt>
+static int launch_fmt(const StepParams &P, int grid, cudaStream_t st) {
+    auto kern = decode_step_kernel<Fmt>;
+    static int attr_dev = -1;   // per instantiation: the opt-in is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+        IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1536));
+        attr_dev = dev;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(STEP_THREADS);
+    cfg.dynamicSmemBytes = (size_t)P.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;   // every CTA must be resident: they wait for each other
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    IFB_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+    return IFB_OK;
+}
+
+int step_launch(const StepParams &P, int grid, cudaStream_t st) {
+    switch (P.w_dtype) {
+        case DT_F16: return launch_fmt<FmtF16>(P, grid, st);
+        case DT_Q4_B32T1A:
+        case DT_Q4_B32T1B: return launch_fmt<FmtQ4_B32T1>(P, grid, st);
+        case DT_Q4_B64T1: return launch_fmt<FmtQ4_B64T1>(P, grid, st);
+        case DT_Q8_B32T2: return launch_fmt<FmtQ8_B32T2>(P, grid, st);
+        case DT_Q6_B64T1: return launch_fmt<FmtQ6_B64T1>(P, grid, st);
+        case DT_Q5_B64T1: return launch_fmt<FmtQ5_B64T1>(P, grid, st);
+        case DT_Q3H_B64T1: return launch_fmt<FmtQ3H_B64T1>(P, grid, st);
+        default:
+            set_last_error("step kernel: weight type %d", P.w_dtype);
+            return IFB_ERR_TYPE;
+    }
+}
+
+}  // namespace ifb

@@ -1,0 +1,72 @@
+// Persistent decode-step kernel: ONE launch per token (ifb_step.cu). Internal interface between the kernel and the
+// model runtime (ifb_model.cu); the public surface stays include/inferflow_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace ifb {
+
+// op kinds of one pre-norm llama layer, in execution order, + the lm_head
+enum { OPK_QKV = 0, OPK_ATT = 1, OPK_WO = 2, OPK_GLU = 3, OPK_W2 = 4, OPK_HEAD = 5, OPK_COUNT = 6 };
+enum { STEP_PART_GEMV = 1, STEP_PART_ATT = 2, STEP_PART_ALL = 3 };
+
+// error codes the kernel leaves in StepParams::err[0] before it traps
+enum { STEP_ERR_NONE = 0, STEP_ERR_RING = 1, STEP_ERR_DEP = 2, STEP_ERR_PEER = 3, STEP_ERR_LOGITS = 4, STEP_ERR_CTX = 5 };
+
+// shape of one op kind (the same for every layer)
+struct StepOpShape {
+    int units;        // work units per instance (ATT: derived on the device from the context length)
+    int tasks;        // tasks per unit: a task is what ONE warp does (2 adjacent rows / one w1,w3 row pair / 32 positions)
+    int R;            // rows (row pairs for GLU) per unit
+    int cx, nblk, row_bytes;
+    int unit_bytes;   // bytes of ONE matrix per unit (R * row_bytes); GLU units carry two matrices
+    int seg1, seg2;   // QKV: first unit of the wk / wv segment
+    int vec4;         // Q4_B32T1 "lane owns 4 blocks" path (cx % 128 == 0)
+    int nxb;          // staged activation blocks (cx/32; padded to a multiple of 128 for vec4)
+};
+
+struct StepLayer {
+    const uint8_t *wq, *wk, *wv, *wo, *w1, *w3, *w2;
+    const __half *attn_norm, *ffn_norm;
+    uint8_t *kcache, *vcache;
+};
+
+struct StepParams {
+    StepOpShape op[OPK_COUNT];
+    const StepLayer *layers;     // device array [n_layers]
+    int n_layers, n_ops;         // n_ops = 5 * n_layers + 1
+    int d, q_dim, kv_dim, ffn, heads, kv_heads, hd, group, vocab, vocab_l;   // this rank's shard sizes
+    int max_ctx, max_ctx_pad, kv_q8, rope_order;
+    int w_dtype, head_f16;
+    float eps, softmax_scale, rope_theta;
+    const __half *tok_emb, *out_norm;
+    const uint8_t *lm_head;
+    __half *qkv, *attn_out, *hbuf, *ybuf, *logits, *x_out;
+    float *partials;             // attention partials [heads][max_tiles][hd + 4]: m, l, -, -, acc[hd]
+    int max_tiles;
+    int32_t *scalars;            // [0] position [1] token [2] next token [3] step sequence number
+    int *cursors;                // [n_ops] unit cursors               } one allocation, zeroed before every launch
+    unsigned int *done;          // [n_ops] + merge_done[n_layers] + 1 }
+    unsigned long long *amax;    // argmax key                         }
+    // shared-memory layout (bytes from the start of dynamic shared memory)
+    int nslots, slot_bytes, x_off, resid_off, sp_off, rope_off, smem_bytes;
+    int att_pos;                 // positions per ATT unit (64 for a Q8_B32T2 cache, 32 for fp16)
+    int parts, advance;
+    // tensor parallelism (size 1: unused) -- exchange regions as in ifb_model.cu
+    int tp_size, tp_rank;
+    void *peer[8];
+    long long x_recv, x_recv_parity, x_recv_rank, x_logits;
+    unsigned long long *trace;   // optional [n_ops][grid][4] globaltimer stamps
+    int *err;                    // pinned host memory: [0] code [1] op [2] detail [3] cta
+    unsigned long long timeout_ns;
+};
+
+// Fills op[], the shared-memory layout, att_pos, max_tiles from the dims / dtypes already set in P.
+// Returns IFB_OK, or IFB_ERR_ARG (message in ifb_last_error) when this model cannot run as one persistent kernel
+// (the caller then keeps the multi-launch path).
+int step_build(StepParams &P, int kv_dtype, int head_dtype, int sm_count_);
+int step_launch(const StepParams &P, int grid, cudaStream_t st);
+int64_t step_counter_bytes(const StepParams &P);   // cursors + done + amax
+
+}  // namespace ifb

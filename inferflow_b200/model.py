@@ -163,6 +163,12 @@ class Model:
     def launches_per_step(self):
         return lib.ifb_model_kernel_launches_per_step(self._h)
 
+    def step_status(self):
+        """(uses the persistent step kernel?, error record {code, op, detail, cta} of a step that missed a deadline)"""
+        rec = (C.c_int32 * 4)()
+        on = lib.ifb_model_step_status(self._h, rec)
+        return bool(on), tuple(rec)
+
 
 def exchange_handles(dist, handle: bytes, group=None):
     """all_gather of fixed-size opaque handles; works over nccl (device tensors) and gloo (host tensors)."""

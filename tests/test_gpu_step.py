@@ -1,0 +1,149 @@
+"""The persistent decode-step kernel (csrc/ifb_step.cu: one launch per token) against
+  * the host oracle of the layer schedule (tests/orc_model.py, pinned to the reference engine), and
+  * the multi-launch path of the same runtime (IFB_STEP=0: the operator kernels the other GPU tests pin to the
+    reference's CUDA operators) on the same weights and cache.
+Tolerances as everywhere: logits within 2^-7 of their range of the oracle, token ids equal whenever the
+oracle's top-2 margin exceeds 4x the error; step vs multi-launch: the GEMV arithmetic is the same code (bit-equal
+activations up to the attention merge order), logits within 2^-9 of the range."""
+import os
+
+import numpy as np
+import pytest
+
+import orc
+from orc_model import OracleModel
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+NAMES = ["attention_norm", "ffn_norm", "wq", "wk", "wv", "wo", "w1", "w2", "w3"]
+
+
+def _tensors(m, spec):
+    t = {n: m.read_tensor(n) for n in ("tok_embeddings", "output_norm", "output")}
+    for l in range(spec.layers):
+        for n in NAMES:
+            t[f"layers.{l}.{n}"] = m.read_tensor(f"layers.{l}.{n}")
+    return t
+
+
+def _read(ib, m, spec):
+    ib.check(ib.lib.ifb_device_synchronize(), "sync")
+    logits = np.empty(spec.vocab, dtype=np.float16)
+    ib.check(ib.lib.ifb_memcpy_d2h(logits.ctypes.data, m.logits_ptr, spec.vocab * 2), "d2h")
+    nxt = np.empty(1, dtype=np.int32)
+    ib.check(ib.lib.ifb_memcpy_d2h(nxt.ctypes.data, m.next_token_ptr, 4), "d2h")
+    return logits, int(nxt[0])
+
+
+def _model(ib, spec, step, seed=7):
+    old = os.environ.get("IFB_STEP")
+    os.environ["IFB_STEP"] = "1" if step else "0"
+    try:
+        m = ib.Model(spec)
+    finally:
+        if old is None:
+            del os.environ["IFB_STEP"]
+        else:
+            os.environ["IFB_STEP"] = old
+    m.init_synthetic(seed=seed)
+    return m
+
+
+# head_dim 64 / 128, MHA and GQA groups 2/4/8, both cache types, every dp4a weight format + fp16 weights
+CONFIGS = [
+    dict(weight_dtype=orc.Q4_B32T1A, kv_dtype=orc.Q8_B32T2, heads=4, kv_heads=4, d_model=512, d_ffn=1024),    # hd 128, vec4
+    dict(weight_dtype=orc.Q4_B32T1A, kv_dtype=orc.F16, heads=8, kv_heads=2, d_model=512, d_ffn=1376),         # hd 64, G 4, d_ffn not /128
+    dict(weight_dtype=orc.Q3H_B64T1, kv_dtype=orc.Q8_B32T2, heads=8, kv_heads=1, d_model=512, d_ffn=1024),    # G 8
+    dict(weight_dtype=orc.Q8_B32T2, kv_dtype=orc.Q8_B32T2, heads=4, kv_heads=2, d_model=256, d_ffn=512, rope_order=0),
+    dict(weight_dtype=orc.Q6_B64T1, kv_dtype=orc.F16, heads=2, kv_heads=2, d_model=256, d_ffn=512, lm_head_dtype=orc.Q6_B64T1),
+    dict(weight_dtype=orc.Q5_B64T1, kv_dtype=orc.Q8_B32T2, heads=4, kv_heads=4, d_model=256, d_ffn=768),
+    dict(weight_dtype=orc.Q4_B64T1, kv_dtype=orc.Q8_B32T2, heads=2, kv_heads=1, d_model=256, d_ffn=512),
+    dict(weight_dtype=orc.F16, kv_dtype=orc.F16, heads=4, kv_heads=4, d_model=256, d_ffn=512),
+]
+IDS = [f"{orc.NAMES[c['weight_dtype']]}-kv{orc.NAMES[c['kv_dtype']]}-h{c['heads']}g{c['heads'] // c['kv_heads']}d{c['d_model']}"
+       for c in CONFIGS]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=IDS)
+def test_step_kernel_matches_oracle(cfg):
+    import inferflow_b200 as ib
+    torch.zeros(1, device="cuda")
+    spec = ib.ModelSpec(layers=2, vocab=512, max_ctx=128, **cfg)
+    m = _model(ib, spec, step=True)
+    orcm = OracleModel(spec, _tensors(m, spec))
+    tok = 5
+    for pos in range(70):          # crosses the 32- and 64-position tile edges of the cache
+        m.decode(tok, pos)
+        logits, nxt = _read(ib, m, spec)
+        on, rec = m.step_status()
+        assert on and rec[0] == 0, f"persistent step kernel not in use or failed: {on} {rec} {ib.lib.ifb_last_error()}"
+        assert m.launches_per_step == 1
+        want = orcm.step(tok, pos)
+        scale = np.abs(want).max()
+        err = np.abs(logits.astype(np.float64) - want).max()
+        assert err <= 2 ** -7 * scale, f"pos {pos}: logits differ by {err:.3e} (range {scale:.3e})"
+        assert nxt == int(np.argmax(logits.astype(np.float32))), "device argmax != argmax of device logits"
+        srt = np.sort(want)
+        if srt[-1] - srt[-2] > 4 * err:
+            assert nxt == int(np.argmax(want))
+        tok = nxt
+    m.close()
+
+
+@pytest.mark.parametrize("cfg", CONFIGS[:4], ids=IDS[:4])
+def test_step_kernel_matches_multi_launch_path(cfg):
+    """same weights, same synthetic 500-row cache: one persistent launch == the chain of operator kernels"""
+    import inferflow_b200 as ib
+    spec = ib.ModelSpec(layers=3, vocab=1024, max_ctx=640, **cfg)
+    a, b = _model(ib, spec, step=True, seed=3), _model(ib, spec, step=False, seed=3)
+    for m in (a, b):
+        m.kv_reset(500, fill_synthetic=True, seed=5)
+    ta = tb = 11
+    for pos in range(500, 520):
+        a.decode(ta, pos)
+        b.decode(tb, pos)
+        la, na = _read(ib, a, spec)
+        lb, nb = _read(ib, b, spec)
+        assert a.step_status()[0] and not b.step_status()[0]
+        scale = np.abs(lb.astype(np.float64)).max()
+        err = np.abs(la.astype(np.float64) - lb.astype(np.float64)).max()
+        assert err <= 2 ** -9 * scale, f"pos {pos}: step kernel vs multi-launch logits differ by {err:.3e} (range {scale:.3e})"
+        srt = np.sort(lb.astype(np.float64))
+        if srt[-1] - srt[-2] > 4 * err:
+            assert na == nb
+        # layer 0's new cache row depends on the token's embedding only: the reference's Q8_B32T2 / fp16 row, bit for bit
+        for name in ("layers.0.kcache", "layers.0.vcache"):
+            assert np.array_equal(a.read_tensor(name), b.read_tensor(name)), f"{name} differs at pos {pos}"
+        ta = tb = nb
+    a.close(); b.close()
+
+
+def test_step_kernel_replay_and_position_guard():
+    """decode_next (device-side position / token) continues the host-driven stream; it refuses to run past max_ctx"""
+    import inferflow_b200 as ib
+    spec = ib.ModelSpec(layers=2, d_model=256, d_ffn=512, heads=2, kv_heads=2, vocab=512, max_ctx=24)
+    m = _model(ib, spec, step=True)
+    toks, tok = [], 1
+    for pos in range(12):
+        m.decode(tok, pos)
+        _, tok = _read(ib, m, spec)
+        toks.append(tok)
+    m.kv_reset(0)
+    m.decode(1, 0)
+    replay = []
+    for _ in range(11):
+        _, t = _read(ib, m, spec)
+        replay.append(t)
+        m.decode_next()
+    _, t = _read(ib, m, spec)
+    replay.append(t)
+    assert replay == toks
+    for _ in range(12):                       # positions 12..23 are still inside the cache
+        m.decode_next()
+    ib.check(ib.lib.ifb_device_synchronize(), "sync")
+    with pytest.raises(ib.IfbError):
+        m.decode_next()                       # position 24 == max_ctx
+    with pytest.raises(ib.IfbError):
+        m.decode(spec.vocab, 0)               # token outside the vocabulary
+    m.close()
