@@ -793,6 +793,14 @@ static int step_prepare(ifb_model *m) {
         const long long ms = e ? atoll(e) : 2000;
         P.timeout_ns = (unsigned long long)(ms > 0 ? ms : 2000) * 1000000ull;
     }
+    {
+        const char *e = getenv("IFB_STEP_BATCH");
+        P.claim_batch = e ? atoi(e) : 4;
+        if (P.claim_batch < 1) P.claim_batch = 1;
+        const char *f = getenv("IFB_STEP_INFLIGHT");
+        P.max_inflight = f ? atoi(f) : 0;
+        if (P.max_inflight >= P.nslots || P.max_inflight < 0) P.max_inflight = 0;
+    }
     if (m->trace_on) {
         // [n_ops][grid][4] stamps; the multi-launch trace buffer is large enough for models up to ~800 ops
         if ((size_t)P.n_ops * sm_count() * 4 * 8 <= m->trace.bytes) P.trace = (unsigned long long *)m->trace.p;

@@ -271,76 +271,79 @@ __device__ __noinline__ void stage_att(const StepParams &P, int layer, int ctx, 
     const int hd = P.hd, nb = hd / 32;
     const AttLayout L = att_layout(P.heads, P.kv_heads, hd, Q8);
     const __half *q = P.qkv, *k = P.qkv + P.q_dim, *v = P.qkv + P.q_dim + P.kv_dim;
-    // ---- q: RoPE, round to half, scale; Q8 cache: two int8 terms per block, q ~= s1*qh + s2*ql (s2 <= s1/254)
-    const int nq = P.q_dim >> 3;
-    for (int base = 0; base < nq; base += GEMV_CTHREADS) {
+    const int nq = P.q_dim >> 3, nkv = P.kv_dim >> 3;
+    const int pos = ctx - 1;
+    const StepLayer &lw = P.layers[layer];
+    const bool half_split = P.rope_order == 2;
+    for (int base = 0; base < max(nq, nkv); base += GEMV_CTHREADS) {
         const int g8 = base + tid;
-        const bool act = g8 < nq;
-        const int e0 = act ? g8 * 8 : 0, hq = e0 / hd, d0 = e0 - hq * hd;
-        float x[8], o[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) { x[i] = 0.f; o[i] = 0.f; }
-        if (act) {
-            unpack8(ld_cg128(q + e0), x);
-            if (P.rope_order == 2) unpack8(ld_cg128(q + hq * hd + (d0 < hd / 2 ? d0 + hd / 2 : d0 - hd / 2)), o);
-            rope8(x, o, d0, hd, P.rope_order, s_cos, s_sin);
+        const bool aq = g8 < nq, akv = g8 < nkv;
+        const int e0 = g8 * 8;
+        // ---- all loads of this pass first: they share one round trip to the L2
+        uint4 wq_ = make_uint4(0, 0, 0, 0), wqo = wq_, wk_ = wq_, wko = wq_, wv_ = wq_;
+        const int hq = aq ? e0 / hd : 0, dq = aq ? e0 - hq * hd : 0;
+        const int hk = akv ? e0 / hd : 0, dk = akv ? e0 - hk * hd : 0;
+        if (aq) {
+            wq_ = ld_cg128(q + e0);
+            if (half_split) wqo = ld_cg128(q + hq * hd + (dq < hd / 2 ? dq + hd / 2 : dq - hd / 2));
+        }
+        if (akv) {
+            wk_ = ld_cg128(k + e0);
+            if (half_split) wko = ld_cg128(k + hk * hd + (dk < hd / 2 ? dk + hd / 2 : dk - hd / 2));
+            wv_ = ld_cg128(v + e0);
+        }
+        // ---- q: RoPE, round to half, scale; Q8 cache: two int8 terms per block, q ~= s1*qh + s2*ql (s2 <= s1/254)
+        {
+            float x[8], o[8];
+            unpack8(wq_, x);
+            unpack8(wqo, o);
+            rope8(x, o, dq, hd, P.rope_order, s_cos, s_sin);
 #pragma unroll
             for (int i = 0; i < 8; i++) x[i] *= P.softmax_scale;
-        }
-        if (Q8) {
-            float m = 0.f;
+            if (Q8) {
+                float m = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; i++) m = fmaxf(m, fabsf(x[i]));
-            const float s1 = quad_max(m) * (1.0f / 127.0f);
-            int qh[8], ql[8];
-            float r[8], m2 = 0.f;
+                for (int i = 0; i < 8; i++) m = fmaxf(m, fabsf(x[i]));
+                const float s1 = quad_max(m) * (1.0f / 127.0f);
+                int qh[8], ql[8];
+                float r[8], m2 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const float t = s1 > 0.f ? rintf(x[i] / s1) : 0.f;
-                qh[i] = (int)t;
-                r[i] = x[i] - t * s1;
-                m2 = fmaxf(m2, fabsf(r[i]));
-            }
-            const float s2 = quad_max(m2) * (1.0f / 127.0f);
-#pragma unroll
-            for (int i = 0; i < 8; i++) ql[i] = (int)(s2 > 0.f ? rintf(r[i] / s2) : 0.f);
-            if (act) {
-                *reinterpret_cast<uint2 *>(xst + L.qh + e0) = pack8_s8(qh);
-                *reinterpret_cast<uint2 *>(xst + L.ql + e0) = pack8_s8(ql);
-                if ((d0 & 31) == 0) reinterpret_cast<float2 *>(xst + L.qs)[hq * nb + (d0 >> 5)] = make_float2(s1, s2);
-            }
-        } else if (act) {
-            float *dst = reinterpret_cast<float *>(xst) + ((size_t)hq * (hd / 16) + (d0 >> 4)) * 20 + (d0 & 15);
-            *reinterpret_cast<float4 *>(dst) = make_float4(x[0], x[1], x[2], x[3]);
-            *reinterpret_cast<float4 *>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
-        }
-    }
-    // ---- the new K row (RoPE) and V row of every kv head, as the cache stores them (SetKRows / SetVRows,
-    // kv_cache.cc:104-183; Q8: Tensor_QuantizeQ8_B32T2_Alg2_Kernel, tensor_quant.h:45-82). Every CTA keeps them in
-    // shared memory (a tile that holds position ctx-1 is patched there: its bulk copy may have been issued before
-    // this row existed); the CTA h % grid writes head h's row to the cache itself.
-    const int pos = ctx - 1;
-    const int nkv = P.kv_dim >> 3;
-    const StepLayer &lw = P.layers[layer];
-    for (int which = 0; which < 2; which++) {
-        const __half *src = which == 0 ? k : v;
-        uint8_t *cache = which == 0 ? lw.kcache : lw.vcache;
-        for (int base = 0; base < nkv; base += GEMV_CTHREADS) {
-            const int g8 = base + tid;
-            const bool act = g8 < nkv;
-            const int e0 = act ? g8 * 8 : 0, h = e0 / hd, d0 = e0 - h * hd;
-            float x[8], o[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) { x[i] = 0.f; o[i] = 0.f; }
-            if (act) {
-                unpack8(ld_cg128(src + e0), x);
-                if (which == 0) {
-                    if (P.rope_order == 2) unpack8(ld_cg128(src + h * hd + (d0 < hd / 2 ? d0 + hd / 2 : d0 - hd / 2)), o);
-                    rope8(x, o, d0, hd, P.rope_order, s_cos, s_sin);
+                for (int i = 0; i < 8; i++) {
+                    const float t = s1 > 0.f ? rintf(x[i] / s1) : 0.f;
+                    qh[i] = (int)t;
+                    r[i] = x[i] - t * s1;
+                    m2 = fmaxf(m2, fabsf(r[i]));
                 }
+                const float s2 = quad_max(m2) * (1.0f / 127.0f);
+#pragma unroll
+                for (int i = 0; i < 8; i++) ql[i] = (int)(s2 > 0.f ? rintf(r[i] / s2) : 0.f);
+                if (aq) {
+                    *reinterpret_cast<uint2 *>(xst + L.qh + e0) = pack8_s8(qh);
+                    *reinterpret_cast<uint2 *>(xst + L.ql + e0) = pack8_s8(ql);
+                    if ((dq & 31) == 0) reinterpret_cast<float2 *>(xst + L.qs)[hq * nb + (dq >> 5)] = make_float2(s1, s2);
+                }
+            } else if (aq) {
+                float *dst = reinterpret_cast<float *>(xst) + ((size_t)hq * (hd / 16) + (dq >> 4)) * 20 + (dq & 15);
+                *reinterpret_cast<float4 *>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<float4 *>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
             }
-            const bool mine = act && (h % (int)gridDim.x) == (int)blockIdx.x;
-            const int64_t row = (int64_t)h * P.max_ctx_pad + pos;
+        }
+        // ---- the new K row (RoPE) and V row of every kv head, as the cache stores them (SetKRows / SetVRows,
+        // kv_cache.cc:104-183; Q8: Tensor_QuantizeQ8_B32T2_Alg2_Kernel, tensor_quant.h:45-82). Every CTA keeps them in
+        // shared memory (a tile that holds position ctx-1 is patched there: its bulk copy may have been issued before
+        // this row existed); the CTA h % grid writes head h's row to the cache itself.
+        const bool mine = akv && (hk % (int)gridDim.x) == (int)blockIdx.x;
+        const int64_t row = (int64_t)hk * P.max_ctx_pad + pos;
+#pragma unroll
+        for (int which = 0; which < 2; which++) {
+            uint8_t *cache = which == 0 ? lw.kcache : lw.vcache;
+            float x[8];
+            unpack8(which == 0 ? wk_ : wv_, x);
+            if (which == 0) {
+                float o[8];
+                unpack8(wko, o);
+                rope8(x, o, dk, hd, P.rope_order, s_cos, s_sin);
+            }
             if (Q8) {
                 float m = 0.f;
 #pragma unroll
@@ -352,24 +355,24 @@ __device__ __noinline__ void stage_att(const StepParams &P, int layer, int ctx, 
                     int t = scale <= 0.000001f ? 0 : (int)roundf(__fdiv_rn(x[i], scale));
                     qv[i] = min(max(t, -128), 127);
                 }
-                if (act) {
+                if (akv) {
                     const uint2 pk = pack8_s8(qv);
                     *reinterpret_cast<uint2 *>(xst + (which == 0 ? L.newk : L.newv) + e0) = pk;
                     const __half hs = __float2half_rn(scale);
-                    if ((d0 & 31) == 0) reinterpret_cast<__half *>(xst + (which == 0 ? L.newks : L.newvs))[h * nb + (d0 >> 5)] = hs;
+                    if ((dk & 31) == 0) reinterpret_cast<__half *>(xst + (which == 0 ? L.newks : L.newvs))[hk * nb + (dk >> 5)] = hs;
                     if (mine) {
-                        *reinterpret_cast<uint2 *>(cache + row * hd + d0) = pk;
-                        if ((d0 & 31) == 0)
-                            reinterpret_cast<__half *>(cache + (int64_t)P.kv_heads * P.max_ctx_pad * hd)[row * nb + (d0 >> 5)] = hs;
+                        *reinterpret_cast<uint2 *>(cache + row * hd + dk) = pk;
+                        if ((dk & 31) == 0)
+                            reinterpret_cast<__half *>(cache + (int64_t)P.kv_heads * P.max_ctx_pad * hd)[row * nb + (dk >> 5)] = hs;
                     }
                 }
-            } else if (act) {
+            } else if (akv) {
                 uint4 pk;
                 __half2 *ph = reinterpret_cast<__half2 *>(&pk);
 #pragma unroll
                 for (int i = 0; i < 4; i++) ph[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
                 *reinterpret_cast<uint4 *>(xst + (which == 0 ? L.newk : L.newv) + (size_t)e0 * 2) = pk;
-                if (mine) *reinterpret_cast<uint4 *>(cache + (row * hd + d0) * 2) = pk;
+                if (mine) *reinterpret_cast<uint4 *>(cache + (row * hd + dk) * 2) = pk;
             }
         }
     }
@@ -561,16 +564,35 @@ __device__ __forceinline__ void att_task_any(const StepParams &P, uint8_t *slot,
 __device__ __noinline__ void att_merge(const StepParams &P, int ctx, float *scratch, int tid) {
     const int hd = P.hd, ngrp = GEMV_CTHREADS / hd, grp = tid / hd, dd = tid - grp * hd;
     const int ntile = (ctx + 31) >> 5;
+    constexpr int NB = 8;      // tiles per batch: all of a batch's loads are in flight together (one L2 round trip)
     for (int hq = (int)blockIdx.x; hq < P.heads; hq += (int)gridDim.x) {
         const float *pb = P.partials + (size_t)hq * P.max_tiles * (hd + 4);
-        float M = -INFINITY;
-        for (int t = grp; t < ntile; t += ngrp) M = fmaxf(M, ld_cg_f32(pb + (size_t)t * (hd + 4)));
-        float num = 0.f, den = 0.f;
-        for (int t = grp; t < ntile; t += ngrp) {
-            const float *pt = pb + (size_t)t * (hd + 4);
-            const float w = __expf(ld_cg_f32(pt) - M);
-            num = fmaf(w, ld_cg_f32(pt + 4 + dd), num);
-            den = fmaf(w, ld_cg_f32(pt + 1), den);
+        float M = -INFINITY, num = 0.f, den = 0.f;
+        for (int t0 = grp; t0 < ntile; t0 += ngrp * NB) {
+            float m[NB], l[NB], a[NB];
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                const int t = t0 + i * ngrp;
+                m[i] = -INFINITY; l[i] = 0.f; a[i] = 0.f;
+                if (t < ntile) {
+                    const float *pt = pb + (size_t)t * (hd + 4);
+                    m[i] = ld_cg_f32(pt);
+                    l[i] = ld_cg_f32(pt + 1);
+                    a[i] = ld_cg_f32(pt + 4 + dd);
+                }
+            }
+            float Mn = M;
+#pragma unroll
+            for (int i = 0; i < NB; i++) Mn = fmaxf(Mn, m[i]);
+            const float c = (M == -INFINITY) ? 0.f : __expf(M - Mn);
+            num *= c; den *= c;
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                const float w = (m[i] == -INFINITY) ? 0.f : __expf(m[i] - Mn);
+                num = fmaf(w, a[i], num);
+                den = fmaf(w, l[i], den);
+            }
+            M = Mn;
         }
         scratch[(grp * hd + dd) * 3 + 0] = M;
         scratch[(grp * hd + dd) * 3 + 1] = num;
@@ -677,17 +699,55 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
         const uint64_t pol = l2_policy_evict_first();   // weights and cache tiles are read once per token
         int op = 0, pos = 0;
         uint32_t phase = 1;                              // a fresh mbarrier passes a wait on parity 1
-        int next = atomicAdd(&P.cursors[0], 1);
+        // Units are handed out by per-op global cursors (SMs do not get equal shares of the HBM bandwidth). One claim is
+        // a global atomic round trip (~1 us while the memory system is busy): claiming unit by unit caps a CTA's stream
+        // at unit_bytes / latency (measured: every op ran at ~3 TB/s). So a claim takes a BATCH of consecutive units,
+        // sized by what is left (guided self-scheduling: remaining / (2 * grid), at most claim_batch, down to 1 at
+        // the tail), and the claim of the next batch is in flight while this one is copied.
+        auto batch_of = [&](int units, int from) {
+            const int b = (units - from) / (2 * (int)gridDim.x);
+            return max(1, min(b, P.claim_batch));
+        };
+        auto units_of = [&](int o) {
+            const int kind = o == head_op ? OPK_HEAD : o % 5;
+            return kind == OPK_ATT ? att_units : ((P.parts & STEP_PART_GEMV) ? P.op[kind].units : 0);
+        };
+        unsigned issued = 0;                             // copies (ring fills) issued so far
+        int units = units_of(0);
+        int bsz = batch_of(units, 0);
+        int bcur = atomicAdd(&P.cursors[0], bsz), bend = bcur + bsz;
+        int nsz = 0, nstart = 0;
+        bool have_next = false;
         while (op < n_ops) {
             const int kind = op == head_op ? OPK_HEAD : op % 5, layer = op / 5;
             const StepOpShape &s = P.op[kind];
-            const int units = kind == OPK_ATT ? att_units : ((P.parts & STEP_PART_GEMV) ? s.units : 0);
-            const int u = next;
-            if (u >= units) {
-                if (++op < n_ops) next = atomicAdd(&P.cursors[op], 1);
+            if (bcur >= units || bcur >= bend) {
+                if (bcur < units && have_next) {         // this batch is copied: take the one requested behind it
+                    bcur = nstart; bend = nstart + nsz; have_next = false;
+                    continue;
+                }
+                // the op is handed out (a claim at or past `units`, or a batch that reached the end): next op
+                if (++op < n_ops) {
+                    units = units_of(op);
+                    bsz = batch_of(units, 0);
+                    bcur = atomicAdd(&P.cursors[op], bsz); bend = bcur + bsz;
+                    have_next = false;
+                }
                 continue;
             }
-            next = atomicAdd(&P.cursors[op], 1);         // in flight while we wait for the slot
+            if (!have_next && bend < units) {            // request the following batch now: in flight while we copy this one
+                nsz = batch_of(units, bend);
+                nstart = atomicAdd(&P.cursors[op], nsz);
+                have_next = true;
+            }
+            const int u = bcur++;
+            // bounded run-ahead: at most max_inflight copies outstanding per SM. More only queues in the memory system
+            // and every demand load of the staging code (activations, norm weights, completion counts) waits behind it.
+            if (P.max_inflight > 0 && issued >= (unsigned)P.max_inflight) {
+                const unsigned w = issued - (unsigned)P.max_inflight;
+                mbar_wait_bounded(&full_bar[w % (unsigned)P.nslots], (w / (unsigned)P.nslots) & 1u, P, op);
+            }
+            issued++;
             mbar_wait_bounded(&empty_bar[pos], phase, P, op);
             slot_meta[pos] = make_int2(op, u);
             uint8_t *dst = ring + (size_t)pos * P.slot_bytes;

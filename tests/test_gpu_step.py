@@ -61,8 +61,11 @@ CONFIGS = [
     dict(weight_dtype=orc.Q4_B64T1, kv_dtype=orc.Q8_B32T2, heads=2, kv_heads=1, d_model=256, d_ffn=512),
     dict(weight_dtype=orc.F16, kv_dtype=orc.F16, heads=4, kv_heads=4, d_model=256, d_ffn=512),
 ]
-IDS = [f"{orc.NAMES[c['weight_dtype']]}-kv{orc.NAMES[c['kv_dtype']]}-h{c['heads']}g{c['heads'] // c['kv_heads']}d{c['d_model']}"
-       for c in CONFIGS]
+def _n(dt):
+    return "F16" if dt == orc.F16 else orc.NAMES[dt]
+
+
+IDS = [f"{_n(c['weight_dtype'])}-kv{_n(c['kv_dtype'])}-h{c['heads']}g{c['heads'] // c['kv_heads']}d{c['d_model']}" for c in CONFIGS]
 
 
 @pytest.mark.parametrize("cfg", CONFIGS, ids=IDS)
