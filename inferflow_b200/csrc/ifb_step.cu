@@ -266,14 +266,13 @@ __device__ __forceinline__ uint2 pack8_s8(const int *q) {
 
 // One thread = 8 consecutive dims, four neighbouring lanes = one 32-dim block (its max by two shuffles).
 template <bool Q8>
-__device__ __noinline__ void stage_att(const StepParams &P, int layer, int ctx, uint8_t *xst, const float *s_cos,
+__device__ __noinline__ void stage_att(const StepParams &P, const StepLayer &lw, int ctx, uint8_t *xst, const float *s_cos,
                                        const float *s_sin, int tid) {
     const int hd = P.hd, nb = hd / 32;
     const AttLayout L = att_layout(P.heads, P.kv_heads, hd, Q8);
     const __half *q = P.qkv, *k = P.qkv + P.q_dim, *v = P.qkv + P.q_dim + P.kv_dim;
     const int nq = P.q_dim >> 3, nkv = P.kv_dim >> 3;
     const int pos = ctx - 1;
-    const StepLayer &lw = P.layers[layer];
     const bool half_split = P.rope_order == 2;
     for (int base = 0; base < max(nq, nkv); base += GEMV_CTHREADS) {
         const int g8 = base + tid;
@@ -663,6 +662,13 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
     uint8_t *xst = smem + P.x_off;
     uint4 *resid = reinterpret_cast<uint4 *>(smem + P.resid_off);
     float *s_cos = reinterpret_cast<float *>(smem + P.rope_off), *s_sin = s_cos + P.hd / 2;
+    // the per-layer pointer table lives in shared memory: with the whole SM carved out as shared memory there is next
+    // to no L1, and a table lookup in global memory costs a full L2 round trip (~1 us while the weight stream runs) --
+    // measured: the producer's stream was bound by exactly that, every op ran at unit_bytes / 1 us
+    const StepLayer *s_layers = reinterpret_cast<const StepLayer *>(smem + P.lay_off);
+    uint4 *s_norm = reinterpret_cast<uint4 *>(smem + P.norm_off);
+    for (int i = tid; i < P.n_layers * (int)(sizeof(StepLayer) / 16); i += STEP_THREADS)
+        reinterpret_cast<uint4 *>(smem + P.lay_off)[i] = reinterpret_cast<const uint4 *>(P.layers)[i];
     const int n_ops = P.n_ops, head_op = n_ops - 1;
 
     if (tid == 0) {
@@ -713,13 +719,25 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             return kind == OPK_ATT ? att_units : ((P.parts & STEP_PART_GEMV) ? P.op[kind].units : 0);
         };
         unsigned issued = 0;                             // copies (ring fills) issued so far
+        const uint8_t *src0 = nullptr, *src1 = nullptr, *src2 = nullptr;   // this op's matrices / cache planes
+        auto bind_op = [&](int o) {
+            const int kind = o == head_op ? OPK_HEAD : o % 5;
+            if (kind == OPK_HEAD) { src0 = P.lm_head; return; }
+            const StepLayer &lw = s_layers[o / 5];
+            if (kind == OPK_QKV) { src0 = lw.wq; src1 = lw.wk; src2 = lw.wv; }
+            else if (kind == OPK_ATT) { src0 = lw.kcache; src1 = lw.vcache; }
+            else if (kind == OPK_WO) src0 = lw.wo;
+            else if (kind == OPK_GLU) { src0 = lw.w1; src1 = lw.w3; }
+            else src0 = lw.w2;
+        };
+        bind_op(0);
         int units = units_of(0);
         int bsz = batch_of(units, 0);
         int bcur = atomicAdd(&P.cursors[0], bsz), bend = bcur + bsz;
         int nsz = 0, nstart = 0;
         bool have_next = false;
         while (op < n_ops) {
-            const int kind = op == head_op ? OPK_HEAD : op % 5, layer = op / 5;
+            const int kind = op == head_op ? OPK_HEAD : op % 5;
             const StepOpShape &s = P.op[kind];
             if (bcur >= units || bcur >= bend) {
                 if (bcur < units && have_next) {         // this batch is copied: take the one requested behind it
@@ -728,6 +746,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                 }
                 // the op is handed out (a claim at or past `units`, or a batch that reached the end): next op
                 if (++op < n_ops) {
+                    bind_op(op);
                     units = units_of(op);
                     bsz = batch_of(units, 0);
                     bcur = atomicAdd(&P.cursors[op], bsz); bend = bcur + bsz;
@@ -753,7 +772,6 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             uint8_t *dst = ring + (size_t)pos * P.slot_bytes;
             const uint32_t ub = (uint32_t)s.unit_bytes;
             if (kind == OPK_ATT) {
-                const StepLayer &lw = P.layers[layer];
                 const int h = u / tiles_per_head, t = u - h * tiles_per_head;
                 const int64_t row0 = (int64_t)h * P.max_ctx_pad + (int64_t)t * P.att_pos;
                 const int hd = P.hd, nb = hd / 32, UP = P.att_pos;
@@ -761,29 +779,23 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                     const uint32_t kb = (uint32_t)(UP * hd), sb = (uint32_t)(UP * nb * 2);
                     const int64_t soff = (int64_t)P.kv_heads * P.max_ctx_pad * hd;
                     mbar_arrive_expect_tx(&full_bar[pos], 2 * (kb + sb));
-                    bulk_g2s_hint(dst, lw.kcache + row0 * hd, kb, &full_bar[pos], pol);
-                    bulk_g2s_hint(dst + kb, lw.kcache + soff + row0 * nb * 2, sb, &full_bar[pos], pol);
-                    bulk_g2s_hint(dst + kb + sb, lw.vcache + row0 * hd, kb, &full_bar[pos], pol);
-                    bulk_g2s_hint(dst + 2 * kb + sb, lw.vcache + soff + row0 * nb * 2, sb, &full_bar[pos], pol);
+                    bulk_g2s_hint(dst, src0 + row0 * hd, kb, &full_bar[pos], pol);
+                    bulk_g2s_hint(dst + kb, src0 + soff + row0 * nb * 2, sb, &full_bar[pos], pol);
+                    bulk_g2s_hint(dst + kb + sb, src1 + row0 * hd, kb, &full_bar[pos], pol);
+                    bulk_g2s_hint(dst + 2 * kb + sb, src1 + soff + row0 * nb * 2, sb, &full_bar[pos], pol);
                 } else {
                     const uint32_t kb = (uint32_t)(UP * hd * 2);
                     mbar_arrive_expect_tx(&full_bar[pos], 2 * kb);
-                    bulk_g2s_hint(dst, lw.kcache + row0 * hd * 2, kb, &full_bar[pos], pol);
-                    bulk_g2s_hint(dst + kb, lw.vcache + row0 * hd * 2, kb, &full_bar[pos], pol);
+                    bulk_g2s_hint(dst, src0 + row0 * hd * 2, kb, &full_bar[pos], pol);
+                    bulk_g2s_hint(dst + kb, src1 + row0 * hd * 2, kb, &full_bar[pos], pol);
                 }
             } else if (kind == OPK_GLU) {
-                const StepLayer &lw = P.layers[layer];
                 mbar_arrive_expect_tx(&full_bar[pos], 2 * ub);
-                bulk_g2s_hint(dst, lw.w1 + (size_t)u * ub, ub, &full_bar[pos], pol);
-                bulk_g2s_hint(dst + ub, lw.w3 + (size_t)u * ub, ub, &full_bar[pos], pol);
+                bulk_g2s_hint(dst, src0 + (size_t)u * ub, ub, &full_bar[pos], pol);
+                bulk_g2s_hint(dst + ub, src1 + (size_t)u * ub, ub, &full_bar[pos], pol);
             } else {
-                const uint8_t *src;
-                if (kind == OPK_HEAD) src = P.lm_head + (size_t)u * ub;
-                else {
-                    const StepLayer &lw = P.layers[layer];
-                    if (kind == OPK_QKV) src = u >= s.seg2 ? lw.wv + (size_t)(u - s.seg2) * ub : (u >= s.seg1 ? lw.wk + (size_t)(u - s.seg1) * ub : lw.wq + (size_t)u * ub);
-                    else src = (kind == OPK_WO ? lw.wo : lw.w2) + (size_t)u * ub;
-                }
+                const uint8_t *src = src0 + (size_t)u * ub;
+                if (kind == OPK_QKV && u >= s.seg1) src = u >= s.seg2 ? src2 + (size_t)(u - s.seg2) * ub : src1 + (size_t)(u - s.seg1) * ub;
                 mbar_arrive_expect_tx(&full_bar[pos], ub);
                 bulk_g2s_hint(dst, src, ub, &full_bar[pos], pol);
             }
@@ -805,6 +817,12 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
         const int kind = op == head_op ? OPK_HEAD : op % 5, layer = op / 5;
         trace_op(P, op, 0, tid);
         if (kind == OPK_QKV || kind == OPK_GLU || kind == OPK_HEAD) {
+            // the RMSNorm weights do not depend on the previous op: their (DRAM) round trip runs under the wait
+            const __half *nw_g = kind == OPK_HEAD ? P.out_norm : (kind == OPK_QKV ? s_layers[layer].attn_norm : s_layers[layer].ffn_norm);
+            uint4 nwv[2];
+            const int ngd = P.d >> 3;
+#pragma unroll
+            for (int i = 0; i < 2; i++) nwv[i] = (tid + i * GEMV_CTHREADS < ngd) ? reinterpret_cast<const uint4 *>(nw_g)[tid + i * GEMV_CTHREADS] : make_uint4(0, 0, 0, 0);
             if (op == 0) {
                 // GetEmbdTensor (inference_engine.cc:1324-1350): the token's embedding row starts the residual stream
                 int tok = P.scalars[1];
@@ -819,9 +837,12 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                 dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
                 resid_add_local(P, resid, tid);
             }
+#pragma unroll
+            for (int i = 0; i < 2; i++) if (tid + i * GEMV_CTHREADS < ngd) s_norm[tid + i * GEMV_CTHREADS] = nwv[i];
+            for (int g = tid + 2 * GEMV_CTHREADS; g < ngd; g += GEMV_CTHREADS) s_norm[g] = reinterpret_cast<const uint4 *>(nw_g)[g];   // d > 8192
             trace_op(P, op, 1, tid);
             named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
-            const __half *nw = kind == OPK_HEAD ? P.out_norm : (kind == OPK_QKV ? P.layers[layer].attn_norm : P.layers[layer].ffn_norm);
+            const __half *nw = reinterpret_cast<const __half *>(s_norm);
             if (kind == OPK_HEAD && P.head_f16) {
                 const XStage a = {P.d, nullptr, nw, P.eps, 0.f};
                 stage_x_f16<0>(a, resid, reinterpret_cast<__half *>(xst), red, tid);
@@ -831,8 +852,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
         } else if (kind == OPK_ATT) {
             dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
             trace_op(P, op, 1, tid);
-            if (P.kv_q8) stage_att<true>(P, layer, ctx, xst, s_cos, s_sin, tid);
-            else stage_att<false>(P, layer, ctx, xst, s_cos, s_sin, tid);
+            if (P.kv_q8) stage_att<true>(P, s_layers[layer], ctx, xst, s_cos, s_sin, tid);
+            else stage_att<false>(P, s_layers[layer], ctx, xst, s_cos, s_sin, tid);
         } else if (kind == OPK_WO) {
             dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
             att_merge(P, ctx, reinterpret_cast<float *>(xst), tid);
@@ -1107,8 +1128,10 @@ int step_build(StepParams &P, int kv_dtype, int head_dtype, int sms) {
     const int64_t resid_b = ((int64_t)P.d * 2 + 127) / 128 * 128;
     const int64_t sp_b = ((int64_t)GEMV_CWARPS * P.group * 32 * 4 + 127) / 128 * 128;
     const int64_t rope_b = ((int64_t)P.hd * 4 + 127) / 128 * 128;
+    const int64_t lay_b = ((int64_t)P.n_layers * (int64_t)sizeof(StepLayer) + 127) / 128 * 128;
+    const int64_t norm_b = resid_b;
     const int64_t smem_max = 232448 - 1536;     // opt-in maximum per CTA minus this kernel's static shared memory
-    int64_t nslots = (smem_max - xb - resid_b - sp_b - rope_b) / slot;
+    int64_t nslots = (smem_max - xb - resid_b - sp_b - rope_b - lay_b - norm_b) / slot;
     if (nslots > STEP_MAX_SLOTS) nslots = STEP_MAX_SLOTS;
     IFB_CHECK_ARG(nslots >= 3, "step kernel: only %lld ring slots of %lld bytes fit beside %lld bytes of staging", (long long)nslots, (long long)slot, (long long)(xb + resid_b));
     P.nslots = (int)nslots;
@@ -1117,7 +1140,9 @@ int step_build(StepParams &P, int kv_dtype, int head_dtype, int sms) {
     P.resid_off = P.x_off + (int)xb;
     P.sp_off = P.resid_off + (int)resid_b;
     P.rope_off = P.sp_off + (int)sp_b;
-    P.smem_bytes = P.rope_off + (int)rope_b;
+    P.lay_off = P.rope_off + (int)rope_b;
+    P.norm_off = P.lay_off + (int)lay_b;
+    P.smem_bytes = P.norm_off + (int)norm_b;
     return IFB_OK;
 }
 

@@ -30,7 +30,9 @@ struct StepLayer {
     const uint8_t *wq, *wk, *wv, *wo, *w1, *w3, *w2;
     const __half *attn_norm, *ffn_norm;
     uint8_t *kcache, *vcache;
+    const void *pad_;            // 96 bytes: the table is copied to shared memory with 16-byte accesses
 };
+static_assert(sizeof(StepLayer) == 96, "StepLayer must stay a multiple of 16 bytes");
 
 struct StepParams {
     StepOpShape op[OPK_COUNT];
@@ -50,7 +52,7 @@ struct StepParams {
     unsigned int *done;          // [n_ops] + merge_done[n_layers] + 1 }
     unsigned long long *amax;    // argmax key                         }
     // shared-memory layout (bytes from the start of dynamic shared memory)
-    int nslots, slot_bytes, x_off, resid_off, sp_off, rope_off, smem_bytes;
+    int nslots, slot_bytes, x_off, resid_off, sp_off, rope_off, lay_off, norm_off, smem_bytes;
     int att_pos;                 // positions per ATT unit (64 for a Q8_B32T2 cache, 32 for fp16)
     int parts, advance;
     int claim_batch;             // most units one cursor claim takes (guided self-scheduling)
