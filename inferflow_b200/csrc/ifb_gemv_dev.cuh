@@ -50,13 +50,14 @@ __device__ __forceinline__ int x_slot(int b) {
 
 // RMS scale of the whole vector, computed by the consumer threads (128-bit loads).
 // Tensor_RmsNorm_Kernel (unary_tensor_opr.h:217): scale = 1/sqrt(mean(x^2) + eps)
-template <int LD = 0>
+template <int LD = 0, int NW = GEMV_CWARPS>
 __device__ __forceinline__ float rms_scale(const __half *x, int cx, float eps, float *red, int tid) {
+    constexpr int NT = NW * 32;   // consumer threads taking part (the stand-alone kernel: 16 warps; the step kernel: 15)
     const uint4 *x4 = reinterpret_cast<const uint4 *>(x);
     const int ng = cx >> 3;
     float s = 0.f;
 #pragma unroll 4
-    for (int g = tid; g < ng; g += GEMV_CTHREADS) {
+    for (int g = tid; g < ng; g += NT) {
         const uint4 v = ld_x128<LD>(x4 + g);
         const __half2 *h = reinterpret_cast<const __half2 *>(&v);
 #pragma unroll
@@ -68,10 +69,10 @@ __device__ __forceinline__ float rms_scale(const __half *x, int cx, float eps, f
     }
     s = warp_sum(s);
     if ((tid & 31) == 0) red[tid >> 5] = s;
-    named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+    named_bar_sync(BAR_CONSUMERS, NT);
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < GEMV_CWARPS; i++) t += red[i];
+    for (int i = 0; i < NW; i++) t += red[i];
     const float mean = t / (float)cx;
     return 1.0f / sqrtf(mean + eps);
 }
@@ -81,13 +82,14 @@ __device__ __forceinline__ float rms_scale(const __half *x, int cx, float eps, f
 // absmax/127, q = roundf(v/scale), scale <= 1e-6 -> 0. Mapping: one thread = 8 consecutive
 // elements (ONE 128-bit load), four neighbouring lanes = one block; all of a thread's loads are
 // issued before any is used, so the prologue costs one memory round trip, not one per block.
-template <bool XSPLIT, bool VEC4, int LD = 0>
+template <bool XSPLIT, bool VEC4, int LD = 0, int NW = GEMV_CWARPS>
 __device__ __forceinline__ void stage_x_q8(const XStage &a, const void *xsrc, uint8_t *xlo, uint8_t *xhi,
                                            float2 *xs, float *red, int tid) {
+    constexpr int NT = NW * 32;
     const int warp = tid >> 5, lane = tid & 31;
     const int nxb = a.cx >> 5;
     if (a.xq != nullptr) {  // already quantized by the caller (TensorMul::Gemv_AX with a Q8 X)
-        for (int b = warp; b < nxb; b += GEMV_CWARPS) {
+        for (int b = warp; b < nxb; b += NW) {
             const uint8_t *blk = a.xq + (size_t)b * 34;
             const int q = (int)(int8_t)blk[2 + lane];
             const int p = x_pos<XSPLIT>(lane), sl = x_slot<VEC4>(b);
@@ -105,14 +107,14 @@ __device__ __forceinline__ void stage_x_q8(const XStage &a, const void *xsrc, ui
     const uint4 *w4 = reinterpret_cast<const uint4 *>(a.norm_w);
     const int ng = a.cx >> 3;                 // groups of 8 elements; ng % 4 == 0
     constexpr int KPT = 3;                    // groups per thread per round
-    const bool one_round = ng <= GEMV_CTHREADS * KPT;   // cx <= 12288: x is read from memory exactly once
+    const bool one_round = ng <= NT * KPT;   // cx <= 12288: x is read from memory exactly once
     float rs = 1.f;
-    if (norm && !one_round) rs = rms_scale<LD>(reinterpret_cast<const __half *>(xsrc), a.cx, a.eps, red, tid);
-    for (int g0 = 0; g0 < ng; g0 += GEMV_CTHREADS * KPT) {
+    if (norm && !one_round) rs = rms_scale<LD, NW>(reinterpret_cast<const __half *>(xsrc), a.cx, a.eps, red, tid);
+    for (int g0 = 0; g0 < ng; g0 += NT * KPT) {
         uint4 xv[KPT], wv[KPT];
 #pragma unroll
         for (int k = 0; k < KPT; k++) {
-            const int g = g0 + k * GEMV_CTHREADS + tid;
+            const int g = g0 + k * NT + tid;
             xv[k] = make_uint4(0, 0, 0, 0);
             wv[k] = make_uint4(0, 0, 0, 0);
             if (g < ng) {
@@ -135,16 +137,16 @@ __device__ __forceinline__ void stage_x_q8(const XStage &a, const void *xsrc, ui
             }
             ss = warp_sum(ss);
             if (lane == 0) red[warp] = ss;
-            named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+            named_bar_sync(BAR_CONSUMERS, NT);
             float t = 0.f;
 #pragma unroll
-            for (int i = 0; i < GEMV_CWARPS; i++) t += red[i];
+            for (int i = 0; i < NW; i++) t += red[i];
             rs = 1.0f / sqrtf(t / (float)a.cx + a.eps);
         }
 #pragma unroll
         for (int k = 0; k < KPT; k++) {
-            const int g = g0 + k * GEMV_CTHREADS + tid;   // a quad of lanes shares one block
-            if (g0 + k * GEMV_CTHREADS >= ng) break;      // uniform: the whole sub-round is past the end
+            const int g = g0 + k * NT + tid;   // a quad of lanes shares one block
+            if (g0 + k * NT >= ng) break;      // uniform: the whole sub-round is past the end
             float v[8];
             {
                 const __half2 *h = reinterpret_cast<const __half2 *>(&xv[k]);
@@ -201,17 +203,18 @@ __device__ __forceinline__ void stage_x_q8(const XStage &a, const void *xsrc, ui
 }
 
 // Stage x as fp16 (optionally RMS-normalised) for the fp16-activation paths.
-template <int LD = 0>
+template <int LD = 0, int NW = GEMV_CWARPS>
 __device__ __forceinline__ void stage_x_f16(const XStage &a, const void *xsrc, __half *xh, float *red, int tid) {
+    constexpr int NT = NW * 32;
     const bool norm = a.norm_w != nullptr;
     float rs = 1.f;
-    if (norm) rs = rms_scale<LD>(reinterpret_cast<const __half *>(xsrc), a.cx, a.eps, red, tid);
+    if (norm) rs = rms_scale<LD, NW>(reinterpret_cast<const __half *>(xsrc), a.cx, a.eps, red, tid);
     const uint4 *x4 = reinterpret_cast<const uint4 *>(xsrc);
     const uint4 *w4 = reinterpret_cast<const uint4 *>(a.norm_w);
     uint4 *o4 = reinterpret_cast<uint4 *>(xh);
     const int ng = a.cx >> 3;
 #pragma unroll 4
-    for (int g = tid; g < ng; g += GEMV_CTHREADS) {
+    for (int g = tid; g < ng; g += NT) {
         uint4 xv = ld_x128<LD>(x4 + g);
         if (norm) {
             const uint4 wv = w4[g];

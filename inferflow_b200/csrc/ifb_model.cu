@@ -803,7 +803,7 @@ static int step_prepare(ifb_model *m) {
     }
     if (m->trace_on) {
         // [n_ops][grid][4] stamps; the multi-launch trace buffer is large enough for models up to ~800 ops
-        if ((size_t)P.n_ops * sm_count() * 4 * 8 <= m->trace.bytes) P.trace = (unsigned long long *)m->trace.p;
+        if ((size_t)P.n_ops * sm_count() * 8 * 8 <= m->trace.bytes) P.trace = (unsigned long long *)m->trace.p;
     }
     m->step_ok = true;
     return IFB_OK;
@@ -814,6 +814,7 @@ static int issue_step_kernel(ifb_model *m, cudaStream_t st, int *launches, int p
     P.parts = ((parts & PART_GEMV) ? STEP_PART_GEMV : 0) | ((parts & PART_ATTN) ? STEP_PART_ATT : 0);
     P.advance = parts == PART_ALL ? 1 : 0;
     IFB_CUDA(cudaMemsetAsync(m->step_ctr.p, 0, m->step_ctr.bytes, st));
+    if (P.trace != nullptr) IFB_CUDA(cudaMemsetAsync(m->trace.p, 0, (size_t)P.n_ops * sm_count() * 8 * 8, st));
     TRY(step_launch(P, sm_count(), st));
     if (launches) *launches = 1;
     return IFB_OK;

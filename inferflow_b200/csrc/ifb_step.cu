@@ -8,14 +8,14 @@
 // staging behind a cold ring, ring refill after the grid dependency, tail): 4-5 us on launches whose weight stream
 // takes 1.6-8.6 us. Here the launch boundaries are gone:
 //
-//  * grid = one CTA per SM, resident for the whole token: 16 consumer warps + 1 producer warp;
+//  * grid = one CTA per SM, resident for the whole token: 15 consumer warps + 1 producer warp;
 //  * the PRODUCER (one elected thread) walks every op of the token in order -- per layer wq|wk|wv, the KV cache,
 //    wo, w1|w3, w2, then the lm_head -- claiming units from per-op global cursors and streaming them with 1-D TMA
 //    bulk copies into a shared-memory ring. It never waits for an activation: while the consumers of all SMs
 //    synchronise at an op boundary, the HBM pipe keeps filling the rings with the NEXT op's weights (the rings of
 //    148 SMs hold ~27 MB = 4 us of HBM time; a boundary costs ~1 us);
 //  * the CONSUMERS take ring slots in order; a slot's tasks (2 adjacent rows / one w1,w3 row pair / 32 cache
-//    positions) are dealt round-robin to the 16 warps. When the next slot belongs to a new op, the CTA signals
+//    positions) are dealt round-robin to the 15 warps. When the next slot belongs to a new op, the CTA signals
 //    "my part of op k is stored" (one release add on a global counter), waits until all CTAs have, and stages the
 //    new op's input into shared memory: residual add (fp16, the reference's order), RMSNorm, Q8_B32T2
 //    quantization (the reference's alg-2 arithmetic), or RoPE + two-term int8 q + the new K/V cache row for
@@ -37,7 +37,12 @@
 
 namespace ifb {
 
-constexpr int STEP_THREADS = GEMV_CTHREADS + 32;
+// 15 consumer warps + 1 producer warp = 16 warps, four per SM sub-partition: 128 registers per thread are available.
+// (16 + 1 warps put five warps on one sub-partition: 96 registers, and the compiler kept the ring-walk state of the
+// consumer loop in local memory -- reloaded for every slot, with next to no L1 behind it.)
+constexpr int STEP_CWARPS = 15;
+constexpr int STEP_CTHREADS = STEP_CWARPS * 32;
+constexpr int STEP_THREADS = STEP_CTHREADS + 32;
 constexpr int STEP_MAX_SLOTS = 16;
 constexpr int STEP_TARGET_UNIT = 20480;   // bytes per ring slot the unit sizes aim for
 
@@ -82,7 +87,7 @@ __device__ __forceinline__ void st_relaxed_sys_v2(void *p, uint2 v) {
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __noinline__ void step_abort(const StepParams &P, int code, int op, int detail) {
+__device__ __forceinline__ void step_abort(const StepParams &P, int code, int op, int detail) {
     if (P.err != nullptr) {
         P.err[1] = op; P.err[2] = detail; P.err[3] = (int)blockIdx.x;
         P.err[0] = code;
@@ -113,10 +118,10 @@ __device__ __forceinline__ void dep_wait(const unsigned int *ctr, unsigned int t
             }
         }
     }
-    named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+    named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);
 }
 __device__ __forceinline__ void dep_signal(unsigned int *ctr, int tid) {
-    named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);     // every consumer thread's stores are ordered before thread 0's fence
+    named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);     // every consumer thread's stores are ordered before thread 0's fence
     if (tid == 0) {
         __threadfence();
         atomicAdd(ctr, 1u);
@@ -124,10 +129,20 @@ __device__ __forceinline__ void dep_signal(unsigned int *ctr, int tid) {
 }
 
 __device__ __forceinline__ void trace_op(const StepParams &P, int op, int k, int tid) {
-    if (P.trace != nullptr && tid == 0) P.trace[((size_t)op * gridDim.x + blockIdx.x) * 4 + k] = globaltimer_ns();
+    if (P.trace != nullptr && tid == 0) P.trace[((size_t)op * gridDim.x + blockIdx.x) * 8 + k] = globaltimer_ns();
 }
 
 // monotone key of (logit, index): larger logit wins, ties go to the smaller index (argmax: first max wins)
+// profile counters of the timeline probe (IFB_TRACE=1): entries 4..7 of an (op, CTA) record
+__device__ __forceinline__ void trace_add(const StepParams &P, int op, int k, unsigned long long v) {
+    if (P.trace != nullptr) P.trace[((size_t)op * gridDim.x + blockIdx.x) * 8 + k] += v;
+}
+__device__ __forceinline__ long long clk() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
+
 __device__ __forceinline__ unsigned long long amax_key(float v, int idx) {
     uint32_t u = __float_as_uint(v);
     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -139,9 +154,9 @@ __device__ __forceinline__ unsigned long long amax_key(float v, int idx) {
 // ---------------------------------------------------------------------------------------
 // single GPU: y = round_h(W x) was stored by the consumers of all CTAs (half tensor, as the reference's GEMV
 // output), x_new = round_h(y + resid) (TensorOpr::Add, inference_worker.cc:849)
-__device__ __noinline__ void resid_add_local(const StepParams &P, uint4 *resid, int tid) {
+__device__ __forceinline__ void resid_add_local(const StepParams &P, uint4 *resid, int tid) {
     const int ng = P.d >> 3;
-    for (int g = tid; g < ng; g += GEMV_CTHREADS) {
+    for (int g = tid; g < ng; g += STEP_CTHREADS) {
         const uint4 yv = ld_cg128(reinterpret_cast<const uint4 *>(P.ybuf) + g);
         const uint4 rv = resid[g];
         uint4 out;
@@ -159,11 +174,11 @@ __device__ __noinline__ void resid_add_local(const StepParams &P, uint4 *resid, 
 // tensor parallel: the partial sums of all ranks arrive in this rank's exchange region as flag-in-data words
 // {half2, flag}; they are added in rank order with fp16 rounding after every add, the residual last
 // (MergeTensors adds worker 1..n-1 onto worker 0 with TensorOpr::Add, inference_worker.cc:2264-2289, then :849)
-__device__ __noinline__ void resid_add_gather(const StepParams &P, uint4 *resid, uint32_t idx, uint32_t seq, int op, int tid) {
+__device__ __forceinline__ void resid_add_gather(const StepParams &P, uint4 *resid, uint32_t idx, uint32_t seq, int op, int tid) {
     const uint32_t flag = (seq << 8) | idx;
     const uint8_t *base = reinterpret_cast<const uint8_t *>(P.peer[P.tp_rank]) + P.x_recv + (long long)(idx & 1u) * P.x_recv_parity;
     const int ng = P.d >> 3;
-    for (int g = tid; g < ng; g += GEMV_CTHREADS) {
+    for (int g = tid; g < ng; g += STEP_CTHREADS) {
         float acc[8];
         for (int p = 0; p < P.tp_size; p++) {
             const uint4 *src = reinterpret_cast<const uint4 *>(base + (size_t)p * P.x_recv_rank) + 2 * g;
@@ -266,7 +281,7 @@ __device__ __forceinline__ uint2 pack8_s8(const int *q) {
 
 // One thread = 8 consecutive dims, four neighbouring lanes = one 32-dim block (its max by two shuffles).
 template <bool Q8>
-__device__ __noinline__ void stage_att(const StepParams &P, const StepLayer &lw, int ctx, uint8_t *xst, const float *s_cos,
+__device__ __forceinline__ void stage_att(const StepParams &P, const StepLayer &lw, int ctx, uint8_t *xst, const float *s_cos,
                                        const float *s_sin, int tid) {
     const int hd = P.hd, nb = hd / 32;
     const AttLayout L = att_layout(P.heads, P.kv_heads, hd, Q8);
@@ -274,7 +289,7 @@ __device__ __noinline__ void stage_att(const StepParams &P, const StepLayer &lw,
     const int nq = P.q_dim >> 3, nkv = P.kv_dim >> 3;
     const int pos = ctx - 1;
     const bool half_split = P.rope_order == 2;
-    for (int base = 0; base < max(nq, nkv); base += GEMV_CTHREADS) {
+    for (int base = 0; base < max(nq, nkv); base += STEP_CTHREADS) {
         const int g8 = base + tid;
         const bool aq = g8 < nq, akv = g8 < nkv;
         const int e0 = g8 * 8;
@@ -383,17 +398,19 @@ __device__ __forceinline__ float s8f_(uint32_t w_biased, int k) {
     return __uint_as_float(bits) - 8388736.0f;
 }
 
-// One task = the 32 positions [pbase, pbase+32) of kv head kvh against the G q heads of its group; the warp writes
-// the tile's (m, l, acc[HD]) partial of each q head. The arithmetic is the scan body of attn_decode_kernel
-// (ifb_attention.cu): dp4a scores with the two-term int8 q for a Q8 cache, fp32 softmax, lane-owns-4-dims P.V.
-template <int HD, int G, bool Q8>
-__device__ __noinline__ void att_task(const StepParams &P, uint8_t *slot, int tt, int kvh, int p0, int ctx,
-                                      const uint8_t *xst, float *sp, int lane) {
+// One task = the 32 positions [pbase, pbase+32) of kv head kvh against the q heads of its group, one q head after the
+// other (the tile is read from shared memory once per q head: grouped-query models have little cache to stream, the
+// op stays HBM-bound); the warp writes the tile's (m, l, acc[HD]) partial of each q head. The arithmetic is the scan
+// body of attn_decode_kernel (ifb_attention.cu): dp4a scores with the two-term int8 q for a Q8 cache, fp32 softmax,
+// lane-owns-4-dims P.V.
+template <int HD, bool Q8>
+__device__ __forceinline__ void att_task(const StepParams &P, uint8_t *slot, int tt, int kvh, int p0, int ctx,
+                                         const uint8_t *xst, float *sp, int lane) {
     constexpr int NB = HD / 32;
     const int pbase = p0 + tt * 32;
     if (pbase >= ctx) return;
     const AttLayout L = att_layout(P.heads, P.kv_heads, HD, Q8);
-    const int UP = P.att_pos;
+    const int UP = P.att_pos, G = P.group;
     uint8_t *tK, *tKs = nullptr, *tV, *tVs = nullptr;
     if (Q8) {
         tK = slot + tt * 32 * HD;
@@ -421,153 +438,128 @@ __device__ __noinline__ void att_task(const StepParams &P, uint8_t *slot, int tt
         fence_proxy_async_smem();   // generic-proxy writes into a buffer the next bulk copy (async proxy) will overwrite
         __syncwarp();
     }
-
-    // ---- scores
-    if (Q8) {
-        constexpr int C = HD / 16;
-        constexpr int RPL = (C >= 8) ? 1 : 8 / C;
-        const int rot = lane / RPL;
-        float sc[G];
+    const int tile = pbase >> 5;
+    const int npos = min(32, ctx - pbase);
+    for (int g = 0; g < G; g++) {
+        const int hq = kvh * G + g;
+        // ---- scores
+        if (Q8) {
+            constexpr int C = HD / 16;
+            constexpr int RPL = (C >= 8) ? 1 : 8 / C;
+            const int rot = lane / RPL;
+            float sc = 0.f;
+            const float2 *qs = reinterpret_cast<const float2 *>(xst + L.qs) + hq * NB;
+            const uint8_t *qh_ = xst + L.qh + (size_t)hq * HD, *ql_ = xst + L.ql + (size_t)hq * HD;
 #pragma unroll
-        for (int g = 0; g < G; g++) sc[g] = 0.f;
-        const float2 *qs = reinterpret_cast<const float2 *>(xst + L.qs);
-#pragma unroll
-        for (int j = 0; j < C; j++) {
-            const int ci = (j + rot) & (C - 1);
-            const uint4 kw = *reinterpret_cast<const uint4 *>(tK + lane * HD + ci * 16);
-            const float ksc = __half2float(reinterpret_cast<const __half *>(tKs)[lane * NB + (ci >> 1)]);
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                const int hq = kvh * G + g;
-                const uint4 qh = *reinterpret_cast<const uint4 *>(xst + L.qh + (size_t)hq * HD + ci * 16);
-                const uint4 ql = *reinterpret_cast<const uint4 *>(xst + L.ql + (size_t)hq * HD + ci * 16);
+            for (int j = 0; j < C; j++) {
+                const int ci = (j + rot) & (C - 1);
+                const uint4 kw = *reinterpret_cast<const uint4 *>(tK + lane * HD + ci * 16);
+                const float ksc = __half2float(reinterpret_cast<const __half *>(tKs)[lane * NB + (ci >> 1)]);
+                const uint4 qh = *reinterpret_cast<const uint4 *>(qh_ + ci * 16);
+                const uint4 ql = *reinterpret_cast<const uint4 *>(ql_ + ci * 16);
                 int dh = dp4a_ss(kw.x, qh.x, 0), dl = dp4a_ss(kw.x, ql.x, 0);
                 dh = dp4a_ss(kw.y, qh.y, dh); dl = dp4a_ss(kw.y, ql.y, dl);
                 dh = dp4a_ss(kw.z, qh.z, dh); dl = dp4a_ss(kw.z, ql.z, dl);
                 dh = dp4a_ss(kw.w, qh.w, dh); dl = dp4a_ss(kw.w, ql.w, dl);
-                const float2 s12 = qs[hq * NB + (ci >> 1)];
+                const float2 s12 = qs[ci >> 1];
                 const float t = fmaf(s12.x, (float)dh, s12.y * (float)dl);
-                sc[g] = fmaf(ksc, t, sc[g]);
+                sc = fmaf(ksc, t, sc);
             }
-        }
-#pragma unroll
-        for (int g = 0; g < G; g++) sp[g * 32 + lane] = (pbase + lane < ctx) ? sc[g] : -INFINITY;
-    } else {
-        constexpr int LPP = HD / 16, PPW = 32 / LPP;
-        const int sub = lane % LPP, pl = lane / LPP;
-        const float *sq = reinterpret_cast<const float *>(xst);
+            sp[lane] = (pbase + lane < ctx) ? sc : -INFINITY;
+        } else {
+            constexpr int LPP = HD / 16, PPW = 32 / LPP;
+            const int sub = lane % LPP, pl = lane / LPP;
+            const float4 *qv = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(xst) + ((size_t)hq * (HD / 16) + sub) * 20);
+            const float4 q0 = qv[0], q1 = qv[1], q2 = qv[2], q3 = qv[3];
 #pragma unroll 2
-        for (int pp = pl; pp < 32; pp += PPW) {
-            float kf[16];
-            const uint4 w0 = *reinterpret_cast<const uint4 *>(tK + (pp * HD + sub * 16) * 2);
-            const uint4 w1 = *reinterpret_cast<const uint4 *>(tK + (pp * HD + sub * 16) * 2 + 16);
-            unpack8(w0, kf);
-            unpack8(w1, kf + 8);
+            for (int pp = pl; pp < 32; pp += PPW) {
+                float kf[16];
+                unpack8(*reinterpret_cast<const uint4 *>(tK + (pp * HD + sub * 16) * 2), kf);
+                unpack8(*reinterpret_cast<const uint4 *>(tK + (pp * HD + sub * 16) * 2 + 16), kf + 8);
+                float s0 = 0.f, s1 = 0.f;   // two chains, in the order of attn_decode_kernel
+                s0 = fmaf(kf[0], q0.x, s0); s1 = fmaf(kf[4], q1.x, s1);
+                s0 = fmaf(kf[1], q0.y, s0); s1 = fmaf(kf[5], q1.y, s1);
+                s0 = fmaf(kf[2], q0.z, s0); s1 = fmaf(kf[6], q1.z, s1);
+                s0 = fmaf(kf[3], q0.w, s0); s1 = fmaf(kf[7], q1.w, s1);
+                s0 = fmaf(kf[8], q2.x, s0); s1 = fmaf(kf[12], q3.x, s1);
+                s0 = fmaf(kf[9], q2.y, s0); s1 = fmaf(kf[13], q3.y, s1);
+                s0 = fmaf(kf[10], q2.z, s0); s1 = fmaf(kf[14], q3.z, s1);
+                s0 = fmaf(kf[11], q2.w, s0); s1 = fmaf(kf[15], q3.w, s1);
+                float sv = s0 + s1;
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                const float4 *qv = reinterpret_cast<const float4 *>(sq + ((size_t)(kvh * G + g) * (HD / 16) + sub) * 20);
-                float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; j += 2) {
-                    const float4 qa = qv[j], qb = qv[j + 1];
-                    s0 = fmaf(kf[4 * j], qa.x, s0);
-                    s1 = fmaf(kf[4 * j + 4], qb.x, s1);
-                    s0 = fmaf(kf[4 * j + 1], qa.y, s0);
-                    s1 = fmaf(kf[4 * j + 5], qb.y, s1);
-                    s0 = fmaf(kf[4 * j + 2], qa.z, s0);
-                    s1 = fmaf(kf[4 * j + 6], qb.z, s1);
-                    s0 = fmaf(kf[4 * j + 3], qa.w, s0);
-                    s1 = fmaf(kf[4 * j + 7], qb.w, s1);
-                }
-                float s = s0 + s1;
-#pragma unroll
-                for (int of = LPP / 2; of > 0; of >>= 1) s += __shfl_xor_sync(0xffffffffu, s, of);
-                if (sub == 0) sp[g * 32 + pp] = (pbase + pp < ctx) ? s : -INFINITY;
+                for (int of = LPP / 2; of > 0; of >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, of);
+                if (sub == 0) sp[pp] = (pbase + pp < ctx) ? sv : -INFINITY;
             }
         }
-    }
-    __syncwarp();
-
-    // ---- softmax of the tile (fp32), then P.V: lane owns 4 dims
-    float mrun[G], lrun[G], acc[G][4];
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-        const float v0 = sp[g * 32 + lane];
+        __syncwarp();
+        // ---- softmax of the tile (fp32), then P.V: lane owns 4 dims
+        const float v0 = sp[lane];
         const float cm = warp_max(v0);
         const float e0 = (v0 == -INFINITY) ? 0.f : __expf(v0 - cm);
-        lrun[g] = warp_sum(e0);
-        mrun[g] = cm;
-        sp[g * 32 + lane] = e0;
-        acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f;
-    }
-    __syncwarp();
-    if (lane < HD / 4) {
-        const int npos = min(32, ctx - pbase);
+        const float lsum = warp_sum(e0);
+        __syncwarp();
+        sp[lane] = e0;
+        __syncwarp();
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (lane < HD / 4) {
 #pragma unroll 4
-        for (int pp = 0; pp < npos; pp++) {
-            float vf[4], vsc = 1.f;
-            if (Q8) {
-                const uint32_t w = reinterpret_cast<const uint32_t *>(tV + pp * HD)[lane] ^ 0x80808080u;
-                vsc = __half2float(reinterpret_cast<const __half *>(tVs)[pp * NB + lane / 8]);
+            for (int pp = 0; pp < npos; pp++) {
+                float vf[4], vsc = 1.f;
+                if (Q8) {
+                    const uint32_t w = reinterpret_cast<const uint32_t *>(tV + pp * HD)[lane] ^ 0x80808080u;
+                    vsc = __half2float(reinterpret_cast<const __half *>(tVs)[pp * NB + lane / 8]);
 #pragma unroll
-                for (int k = 0; k < 4; k++) vf[k] = s8f_(w, k);
-            } else {
-                const uint2 w = reinterpret_cast<const uint2 *>(tV + pp * HD * 2)[lane];
-                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&w.x));
-                const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w.y));
-                vf[0] = f0.x; vf[1] = f0.y; vf[2] = f1.x; vf[3] = f1.y;
-            }
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                const float p = sp[g * 32 + pp] * vsc;
-                acc[g][0] = fmaf(p, vf[0], acc[g][0]);
-                acc[g][1] = fmaf(p, vf[1], acc[g][1]);
-                acc[g][2] = fmaf(p, vf[2], acc[g][2]);
-                acc[g][3] = fmaf(p, vf[3], acc[g][3]);
+                    for (int k = 0; k < 4; k++) vf[k] = s8f_(w, k);
+                } else {
+                    const uint2 w = reinterpret_cast<const uint2 *>(tV + pp * HD * 2)[lane];
+                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&w.x));
+                    const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w.y));
+                    vf[0] = f0.x; vf[1] = f0.y; vf[2] = f1.x; vf[3] = f1.y;
+                }
+                const float p = sp[pp] * vsc;     // the block scale rides on the probability
+                a0 = fmaf(p, vf[0], a0);
+                a1 = fmaf(p, vf[1], a1);
+                a2 = fmaf(p, vf[2], a2);
+                a3 = fmaf(p, vf[3], a3);
             }
         }
+        float *o = P.partials + ((size_t)hq * P.max_tiles + tile) * (HD + 4);
+        if (lane == 0) *reinterpret_cast<float2 *>(o) = make_float2(cm, lsum);
+        if (lane < HD / 4) *reinterpret_cast<float4 *>(o + 4 + lane * 4) = make_float4(a0, a1, a2, a3);
+        __syncwarp();
     }
-    const int tile = pbase >> 5;
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-        float *o = P.partials + ((size_t)(kvh * G + g) * P.max_tiles + tile) * (HD + 4);
-        if (lane == 0) *reinterpret_cast<float2 *>(o) = make_float2(mrun[g], lrun[g]);
-        if (lane < HD / 4) *reinterpret_cast<float4 *>(o + 4 + lane * 4) = make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
-    }
-    __syncwarp();
 }
 
-template <int HD, bool Q8>
-__device__ __forceinline__ void att_task_g(const StepParams &P, uint8_t *slot, int tt, int kvh, int p0, int ctx,
-                                           const uint8_t *xst, float *sp, int lane) {
-    switch (P.group) {
-        case 1: att_task<HD, 1, Q8>(P, slot, tt, kvh, p0, ctx, xst, sp, lane); break;
-        case 2: att_task<HD, 2, Q8>(P, slot, tt, kvh, p0, ctx, xst, sp, lane); break;
-        case 4: att_task<HD, 4, Q8>(P, slot, tt, kvh, p0, ctx, xst, sp, lane); break;
-        default: att_task<HD, 8, Q8>(P, slot, tt, kvh, p0, ctx, xst, sp, lane); break;
-    }
-}
+// position in the ring as the consumer warps walk it: slot, mbarrier parity of its current fill, and the rotating
+// task -> warp offset (task t of a slot goes to warp (tbase + t) % 15)
+struct RingPos {
+    int pos;
+    uint32_t phase;
+    int tbase;
+};
+
 __device__ __forceinline__ void att_task_any(const StepParams &P, uint8_t *slot, int tt, int kvh, int p0, int ctx,
                                              const uint8_t *xst, float *sp, int lane) {
     if (P.hd == 128) {
-        if (P.kv_q8) att_task_g<128, true>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
-        else att_task_g<128, false>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        if (P.kv_q8) att_task<128, true>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        else att_task<128, false>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
     } else {
-        if (P.kv_q8) att_task_g<64, true>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
-        else att_task_g<64, false>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        if (P.kv_q8) att_task<64, true>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        else att_task<64, false>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
     }
 }
 
 // log-sum-exp merge of the tiles' partials: q head hq -> attn_out[hq][hd] (half, as the reference's attention output
 // tensor). 512 threads = (512/hd) tile groups x hd dims; scratch = the (idle) staging area.
-__device__ __noinline__ void att_merge(const StepParams &P, int ctx, float *scratch, int tid) {
-    const int hd = P.hd, ngrp = GEMV_CTHREADS / hd, grp = tid / hd, dd = tid - grp * hd;
+__device__ __forceinline__ void att_merge(const StepParams &P, int ctx, float *scratch, int tid) {
+    const int hd = P.hd, ngrp = STEP_CTHREADS / hd, grp = tid / hd, dd = tid - grp * hd;
+    const bool part = grp < ngrp;      // 480 threads = 3 groups of 128 (+ 96 idle) or 7 groups of 64 (+ 32 idle)
     const int ntile = (ctx + 31) >> 5;
     constexpr int NB = 8;      // tiles per batch: all of a batch's loads are in flight together (one L2 round trip)
     for (int hq = (int)blockIdx.x; hq < P.heads; hq += (int)gridDim.x) {
         const float *pb = P.partials + (size_t)hq * P.max_tiles * (hd + 4);
         float M = -INFINITY, num = 0.f, den = 0.f;
-        for (int t0 = grp; t0 < ntile; t0 += ngrp * NB) {
+        for (int t0 = grp; part && t0 < ntile; t0 += ngrp * NB) {
             float m[NB], l[NB], a[NB];
 #pragma unroll
             for (int i = 0; i < NB; i++) {
@@ -593,10 +585,12 @@ __device__ __noinline__ void att_merge(const StepParams &P, int ctx, float *scra
             }
             M = Mn;
         }
-        scratch[(grp * hd + dd) * 3 + 0] = M;
-        scratch[(grp * hd + dd) * 3 + 1] = num;
-        scratch[(grp * hd + dd) * 3 + 2] = den;
-        named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+        if (part) {
+            scratch[(grp * hd + dd) * 3 + 0] = M;
+            scratch[(grp * hd + dd) * 3 + 1] = num;
+            scratch[(grp * hd + dd) * 3 + 2] = den;
+        }
+        named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);
         if (tid < hd) {
             float MM = -INFINITY;
             for (int g = 0; g < ngrp; g++) MM = fmaxf(MM, scratch[(g * hd + tid) * 3]);
@@ -609,7 +603,7 @@ __device__ __noinline__ void att_merge(const StepParams &P, int ctx, float *scra
             }
             P.attn_out[(size_t)hq * hd + tid] = __float2half_rn(n2 / d2);
         }
-        named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+        named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);
     }
 }
 
@@ -621,14 +615,14 @@ __device__ __forceinline__ void stage_gemv_x(const StepParams &P, const StepOpSh
                                              uint8_t *xst, float *red, int tid) {
     const XStage a = {s.cx, nullptr, norm_w, P.eps, 0.f};
     if constexpr (is_f16_fmt<Fmt>::value) {
-        stage_x_f16<LD>(a, src, reinterpret_cast<__half *>(xst), red, tid);
+        stage_x_f16<LD, STEP_CWARPS>(a, src, reinterpret_cast<__half *>(xst), red, tid);
     } else {
         uint8_t *xlo = xst, *xhi = xst + (size_t)s.nxb * 16;
         float2 *xs = reinterpret_cast<float2 *>(xst + (size_t)s.nxb * 32);
         if constexpr (is_q4b32_fmt<Fmt>::value) {
-            if (s.vec4) { stage_x_q8<true, true, LD>(a, src, xlo, xhi, xs, red, tid); return; }
+            if (s.vec4) { stage_x_q8<true, true, LD, STEP_CWARPS>(a, src, xlo, xhi, xs, red, tid); return; }
         }
-        stage_x_q8<Fmt::XSPLIT, false, LD>(a, src, xlo, xhi, xs, red, tid);
+        stage_x_q8<Fmt::XSPLIT, false, LD, STEP_CWARPS>(a, src, xlo, xhi, xs, red, tid);
     }
 }
 
@@ -654,8 +648,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t full_bar[STEP_MAX_SLOTS], empty_bar[STEP_MAX_SLOTS];
     __shared__ int2 slot_meta[STEP_MAX_SLOTS];   // (op, unit) of what sits in each ring slot
-    __shared__ float red[GEMV_CWARPS];
-    __shared__ unsigned long long s_key[GEMV_CWARPS];
+    __shared__ float red[STEP_CWARPS];
+    __shared__ unsigned long long s_key[STEP_CWARPS];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *ring = smem;
@@ -674,7 +668,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
     if (tid == 0) {
         for (int i = 0; i < P.nslots; i++) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], GEMV_CWARPS);
+            mbar_init(&empty_bar[i], STEP_CWARPS);
         }
         mbar_fence_init();
     }
@@ -699,7 +693,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
     const int att_units = (P.parts & STEP_PART_ATT) ? P.kv_heads * ((ctx + P.att_pos - 1) / P.att_pos) : 0;
     const int tiles_per_head = (ctx + P.att_pos - 1) / P.att_pos;
 
-    if (warp == GEMV_CWARPS) {
+    if (warp == STEP_CWARPS) {
         // ===== producer: depends on nothing but free ring slots =====
         if (lane != 0) return;
         const uint64_t pol = l2_policy_evict_first();   // weights and cache tiles are read once per token
@@ -767,6 +761,12 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                 mbar_wait_bounded(&full_bar[w % (unsigned)P.nslots], (w / (unsigned)P.nslots) & 1u, P, op);
             }
             issued++;
+            if (P.trace != nullptr) {
+                const long long t0 = clk();
+                mbar_wait_bounded(&empty_bar[pos], phase, P, op);
+                trace_add(P, op, 6, (unsigned long long)(clk() - t0));
+                trace_add(P, op, 7, 1ull);
+            } else
             mbar_wait_bounded(&empty_bar[pos], phase, P, op);
             slot_meta[pos] = make_int2(op, u);
             uint8_t *dst = ring + (size_t)pos * P.slot_bytes;
@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
     }
 
     // ===== consumers =====
-    float *sp = reinterpret_cast<float *>(smem + P.sp_off) + (size_t)warp * P.group * 32;
+    float *sp = reinterpret_cast<float *>(smem + P.sp_off) + (size_t)warp * 32;
     const int tp = P.tp_size;
 
     // staging of op `op`'s input (every CTA runs it for every op, in order: the residual stream lives in each CTA's
@@ -822,13 +822,13 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             uint4 nwv[2];
             const int ngd = P.d >> 3;
 #pragma unroll
-            for (int i = 0; i < 2; i++) nwv[i] = (tid + i * GEMV_CTHREADS < ngd) ? reinterpret_cast<const uint4 *>(nw_g)[tid + i * GEMV_CTHREADS] : make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < 2; i++) nwv[i] = (tid + i * STEP_CTHREADS < ngd) ? reinterpret_cast<const uint4 *>(nw_g)[tid + i * STEP_CTHREADS] : make_uint4(0, 0, 0, 0);
             if (op == 0) {
                 // GetEmbdTensor (inference_engine.cc:1324-1350): the token's embedding row starts the residual stream
                 int tok = P.scalars[1];
                 tok = max(0, min(tok, P.vocab - 1));
                 const uint4 *row = reinterpret_cast<const uint4 *>(P.tok_emb + (size_t)tok * P.d);
-                for (int g = tid; g < (P.d >> 3); g += GEMV_CTHREADS) resid[g] = row[g];
+                for (int g = tid; g < (P.d >> 3); g += STEP_CTHREADS) resid[g] = row[g];
             } else if (tp > 1) {
                 // exchange index: wo of layer l -> 2l+1, w2 of layer l -> 2l+2 (two buffers, alternating)
                 const uint32_t idx = kind == OPK_GLU ? (uint32_t)(2 * layer + 1) : (uint32_t)(2 * (kind == OPK_HEAD ? P.n_layers : layer));
@@ -838,14 +838,14 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                 resid_add_local(P, resid, tid);
             }
 #pragma unroll
-            for (int i = 0; i < 2; i++) if (tid + i * GEMV_CTHREADS < ngd) s_norm[tid + i * GEMV_CTHREADS] = nwv[i];
-            for (int g = tid + 2 * GEMV_CTHREADS; g < ngd; g += GEMV_CTHREADS) s_norm[g] = reinterpret_cast<const uint4 *>(nw_g)[g];   // d > 8192
+            for (int i = 0; i < 2; i++) if (tid + i * STEP_CTHREADS < ngd) s_norm[tid + i * STEP_CTHREADS] = nwv[i];
+            for (int g = tid + 2 * STEP_CTHREADS; g < ngd; g += STEP_CTHREADS) s_norm[g] = reinterpret_cast<const uint4 *>(nw_g)[g];   // d > 8192
             trace_op(P, op, 1, tid);
-            named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+            named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);
             const __half *nw = reinterpret_cast<const __half *>(s_norm);
             if (kind == OPK_HEAD && P.head_f16) {
                 const XStage a = {P.d, nullptr, nw, P.eps, 0.f};
-                stage_x_f16<0>(a, resid, reinterpret_cast<__half *>(xst), red, tid);
+                stage_x_f16<0, STEP_CWARPS>(a, resid, reinterpret_cast<__half *>(xst), red, tid);
             } else {
                 stage_gemv_x<Fmt, 0>(P, P.op[kind], resid, nw, xst, red, tid);
             }
@@ -866,21 +866,24 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             trace_op(P, op, 1, tid);
             stage_gemv_x<Fmt, 1>(P, P.op[kind], P.hbuf, nullptr, xst, red, tid);
         }
-        named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+        named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);
         trace_op(P, op, 2, tid);
     };
 
     float best_v = -INFINITY;
     int best_i = 0x7fffffff;
-    int traced_op = -1;
     int cur_op = -1;            // nothing staged yet: the first pass stages op 0 while the first units are in flight
-    int pos = 0, tbase = 0;
-    uint32_t phase = 0;
+    RingPos rp = {0, 0u, 0};
     for (;;) {
         int2 meta = make_int2(0, -1);
         if (cur_op >= 0) {
-            mbar_wait_bounded(&full_bar[pos], phase, P, cur_op);
-            meta = slot_meta[pos];
+            if (P.trace != nullptr && tid == 0) {
+                const long long t0 = clk();
+                mbar_wait_bounded(&full_bar[rp.pos], rp.phase, P, cur_op);
+                trace_add(P, cur_op, 4, (unsigned long long)(clk() - t0));
+            } else
+            mbar_wait_bounded(&full_bar[rp.pos], rp.phase, P, cur_op);
+            meta = slot_meta[rp.pos];
         }
         if (meta.x != cur_op) {
             for (int k = cur_op; k < meta.x; k++) {
@@ -892,15 +895,16 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             }
             cur_op = meta.x;
             if (cur_op >= n_ops) break;
+            trace_op(P, cur_op, 3, tid);             // first unit of the op in hand (none yet on the very first pass)
         }
         if (meta.y < 0) continue;   // first pass: no slot in hand yet
         const int kind = cur_op == head_op ? OPK_HEAD : cur_op % 5, layer = cur_op / 5;
         const StepOpShape &s = P.op[kind];
-        uint8_t *slot = ring + (size_t)pos * P.slot_bytes;
+        uint8_t *slot = ring + (size_t)rp.pos * P.slot_bytes;
         const int u = meta.y;
         const int ntask = s.tasks;
-        if (P.trace != nullptr && traced_op != cur_op) { trace_op(P, cur_op, 3, tid); traced_op = cur_op; }   // first unit of the op in hand
-        for (int t = (warp - tbase) & 15; t < ntask; t += GEMV_CWARPS) {
+        const long long t_task0 = (P.trace != nullptr && tid == 0) ? clk() : 0ll;
+        for (int t = warp >= rp.tbase ? warp - rp.tbase : warp - rp.tbase + STEP_CWARPS; t < ntask; t += STEP_CWARPS) {
             if (kind == OPK_ATT) {
                 const int h = u / tiles_per_head, tl = u - h * tiles_per_head;
                 att_task_any(P, slot, t, h, tl * P.att_pos, ctx, xst, sp, lane);
@@ -956,10 +960,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                 }
             }
         }
-        tbase = (tbase + ntask) & 15;
+        if (P.trace != nullptr && tid == 0) trace_add(P, cur_op, 5, (unsigned long long)(clk() - t_task0));
+        rp.tbase = (rp.tbase + ntask) % STEP_CWARPS;
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[pos]);
-        if (++pos == P.nslots) { pos = 0; phase ^= 1u; }
+        if (lane == 0) mbar_arrive(&empty_bar[rp.pos]);
+        if (++rp.pos == P.nslots) { rp.pos = 0; rp.phase ^= 1u; }
     }
 
     // ===== end of the token: next token id, position += 1 =====
@@ -973,7 +978,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
         const int w0 = (int)blockIdx.x * per, w1 = min(nw, w0 + per);
         float bv = -INFINITY;
         int bi = 0x7fffffff;
-        for (int w = w0 + tid; w < w1; w += GEMV_CTHREADS) {
+        for (int w = w0 + tid; w < w1; w += STEP_CTHREADS) {
             uint2 v = ld_relaxed_sys_v2(ll + w);
             if (v.y != flag) {
                 const unsigned long long t0 = globaltimer_ns();
@@ -995,16 +1000,16 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             key = ok > key ? ok : key;
         }
         if (lane == 0) s_key[warp] = key;
-        named_bar_sync(BAR_CONSUMERS, GEMV_CTHREADS);
+        named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);
         if (tid == 0) {
-            for (int i = 1; i < GEMV_CWARPS; i++) key = s_key[i] > key ? s_key[i] : key;
+            for (int i = 1; i < STEP_CWARPS; i++) key = s_key[i] > key ? s_key[i] : key;
             if (key != 0ull) atomicMax(P.amax, key);
         }
         dep_signal(&P.done[n_ops + P.n_layers], tid);
     }
     if (blockIdx.x == 0) {
         dep_wait(&P.done[tp > 1 ? n_ops + P.n_layers : head_op], gridDim.x, P, n_ops, tid);
-        for (int g = tid; g < (P.d >> 3); g += GEMV_CTHREADS) reinterpret_cast<uint4 *>(P.x_out)[g] = resid[g];
+        for (int g = tid; g < (P.d >> 3); g += STEP_CTHREADS) reinterpret_cast<uint4 *>(P.x_out)[g] = resid[g];
         if (tid == 0) {
             const unsigned long long key = ld_cg_u64(P.amax);
             const int tok = key == 0ull ? 0 : (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
@@ -1122,11 +1127,11 @@ int step_build(StepParams &P, int kv_dtype, int head_dtype, int sms) {
         const int64_t b = f16x ? (int64_t)P.op[k].cx * 2 : (int64_t)P.op[k].nxb * 40;
         if (b > xb) xb = b;
     }
-    const int64_t merge_b = (int64_t)GEMV_CTHREADS * 3 * 4;
+    const int64_t merge_b = (int64_t)STEP_CTHREADS * 3 * 4;
     if (merge_b > xb) xb = merge_b;
     xb = (xb + 127) / 128 * 128;
     const int64_t resid_b = ((int64_t)P.d * 2 + 127) / 128 * 128;
-    const int64_t sp_b = ((int64_t)GEMV_CWARPS * P.group * 32 * 4 + 127) / 128 * 128;
+    const int64_t sp_b = ((int64_t)STEP_CWARPS * 32 * 4 + 127) / 128 * 128;
     const int64_t rope_b = ((int64_t)P.hd * 4 + 127) / 128 * 128;
     const int64_t lay_b = ((int64_t)P.n_layers * (int64_t)sizeof(StepLayer) + 127) / 128 * 128;
     const int64_t norm_b = resid_b;

@@ -17,7 +17,7 @@ on, rec = m.step_status()
 print("step kernel:", on, rec)
 n_ops = 5 * spec.layers + 1
 grid = 148
-raw = m.read_tensor("trace").view(np.uint64)[: n_ops * grid * 4].reshape(n_ops, grid, 4).astype(np.int64)
+raw = m.read_tensor("trace").view(np.uint64)[: n_ops * grid * 8].reshape(n_ops, grid, 8).astype(np.int64)
 names = ["QKV", "ATT", "WO", "GLU", "W2"]
 t_first = raw[0, :, 0].min()
 t_last = raw[n_ops - 1, :, 3].max()
@@ -31,6 +31,9 @@ for L in (1, 16):
             v = r[:, c]
             return f"{v.min():7.2f}/{np.median(v):7.2f}/{v.max():7.2f}"
         print(f"{names[k]:4s} enter {f(0)}  dep {f(1)}  staged {f(2)}  first_unit {f(3)}")
+        c = raw[5 * L + k]
+        mhz = 1965.0
+        print(f"       warp0: wait-for-data med {np.median(c[:, 4]) / mhz:6.2f} us  in-tasks med {np.median(c[:, 5]) / mhz:6.2f} us | producer: wait-for-free-slot med {np.median(c[:, 6]) / mhz:6.2f} us  units/CTA min {c[:, 7].min()} med {int(np.median(c[:, 7]))} max {c[:, 7].max()}")
 r = (raw[n_ops - 1] - raw[n_ops - 1, :, 0].min()) / 1000.0
 print("HEAD enter %.2f/%.2f dep %.2f staged %.2f first_unit %.2f" % (r[:, 0].min(), r[:, 0].max(), np.median(r[:, 1]), np.median(r[:, 2]), np.median(r[:, 3])))
 # per-layer period
