@@ -202,6 +202,135 @@ __device__ __forceinline__ void stage_x_q8(const XStage &a, const void *xsrc, ui
     }
 }
 
+// The same staging, small: ONE instantiation serves every layout / source (vec4 and ldcg are run-time flags) and the
+// per-group quantization is a rolled loop. For the persistent step kernel, where this code runs once per op boundary and
+// is cold every time (the unrolled form above is ~30 KB of SASS per instantiation; the instruction fetch, not the
+// arithmetic, was what a boundary cost). Bit-for-bit the arithmetic of stage_x_q8.
+template <bool XSPLIT, int NW>
+__device__ __forceinline__ void stage_x_q8_compact(const XStage &a, const void *xsrc, uint8_t *xlo, uint8_t *xhi,
+                                                   float2 *xs, float *red, int tid, bool vec4, bool ldcg) {
+    constexpr int NT = NW * 32;
+    const int warp = tid >> 5, lane = tid & 31;
+    const bool norm = a.norm_w != nullptr;
+    const uint4 *x4 = reinterpret_cast<const uint4 *>(xsrc);
+    const uint4 *w4 = reinterpret_cast<const uint4 *>(a.norm_w);
+    const int ng = a.cx >> 3;
+    constexpr int KPT = 3;
+    float ss_total = 0.f;
+    float rs = 1.f;
+    const bool one_round = ng <= NT * KPT;
+    if (norm && !one_round) {
+        // Tensor_RmsNorm_Kernel (unary_tensor_opr.h:217): scale = 1/sqrt(mean(x^2) + eps), a pass of its own
+        float sq = 0.f;
+        for (int g = tid; g < ng; g += NT) {
+            const uint4 v = ldcg ? ld_x128<1>(x4 + g) : x4[g];
+            const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float2 f = __half22float2(h[k]);
+                sq = fmaf(f.x, f.x, sq);
+                sq = fmaf(f.y, f.y, sq);
+            }
+        }
+        sq = warp_sum(sq);
+        if (lane == 0) red[warp] = sq;
+        named_bar_sync(BAR_CONSUMERS, NT);
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < NW; i++) t += red[i];
+        rs = 1.0f / sqrtf(t / (float)a.cx + a.eps);
+    }
+    (void)ss_total;
+    for (int g0 = 0; g0 < ng; g0 += NT * KPT) {
+        uint4 xv0 = make_uint4(0, 0, 0, 0), xv1 = xv0, xv2 = xv0, wv0 = xv0, wv1 = xv0, wv2 = xv0;
+        {   // all loads of the round first: one memory round trip
+            const int ga = g0 + tid, gb = ga + NT, gc = gb + NT;
+            if (ga < ng) { xv0 = ldcg ? ld_x128<1>(x4 + ga) : x4[ga]; if (norm) wv0 = w4[ga]; }
+            if (gb < ng) { xv1 = ldcg ? ld_x128<1>(x4 + gb) : x4[gb]; if (norm) wv1 = w4[gb]; }
+            if (gc < ng) { xv2 = ldcg ? ld_x128<1>(x4 + gc) : x4[gc]; if (norm) wv2 = w4[gc]; }
+        }
+        if (norm && one_round) {
+            float ss = 0.f;
+            const uint4 xs3[3] = {xv0, xv1, xv2};
+#pragma unroll
+            for (int k = 0; k < KPT; k++) {
+                const __half2 *h = reinterpret_cast<const __half2 *>(&xs3[k]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float2 f = __half22float2(h[i]);
+                    ss = fmaf(f.x, f.x, ss);
+                    ss = fmaf(f.y, f.y, ss);
+                }
+            }
+            ss = warp_sum(ss);
+            if (lane == 0) red[warp] = ss;
+            named_bar_sync(BAR_CONSUMERS, NT);
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < NW; i++) t += red[i];
+            rs = 1.0f / sqrtf(t / (float)a.cx + a.eps);
+        }
+#pragma unroll 1
+        for (int k = 0; k < KPT; k++) {
+            const int g = g0 + k * NT + tid;   // a quad of lanes shares one block
+            if (g0 + k * NT >= ng) break;      // uniform: the whole sub-round is past the end
+            const uint4 xk = k == 0 ? xv0 : (k == 1 ? xv1 : xv2);
+            const uint4 wk = k == 0 ? wv0 : (k == 1 ? wv1 : wv2);
+            float v[8];
+            {
+                const __half2 *h = reinterpret_cast<const __half2 *>(&xk);
+                const __half2 *hw = reinterpret_cast<const __half2 *>(&wk);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    float2 f = __half22float2(h[i]);
+                    if (norm) {  // v = x*scale*(multi_base + w), stored as half by the reference's RmsNorm
+                        const float2 fw = __half22float2(hw[i]);
+                        f.x = round_h(f.x * rs * (a.norm_base + fw.x));
+                        f.y = round_h(f.y * rs * (a.norm_base + fw.y));
+                    }
+                    v[2 * i] = f.x;
+                    v[2 * i + 1] = f.y;
+                }
+            }
+            float m = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) m = fmaxf(m, fabsf(v[i]));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            const float scale = m / 127.0f;
+            const bool dead = scale <= 0.000001f;
+            const float inv = dead ? 0.f : __frcp_rn(scale);
+            int q[8], qs = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int t = dead ? 0 : q8_round_div(v[i], scale, inv);
+                q[i] = min(max(t, -128), 127);
+                qs += q[i];
+            }
+            qs += __shfl_xor_sync(0xffffffffu, qs, 1);
+            qs += __shfl_xor_sync(0xffffffffu, qs, 2);
+            if (g < ng) {
+                uint32_t w0, w1;
+                if (XSPLIT) {
+                    w0 = (q[0] & 0xff) | ((q[2] & 0xff) << 8) | ((q[4] & 0xff) << 16) | ((uint32_t)(q[6] & 0xff) << 24);
+                    w1 = (q[1] & 0xff) | ((q[3] & 0xff) << 8) | ((q[5] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
+                } else {
+                    w0 = (q[0] & 0xff) | ((q[1] & 0xff) << 8) | ((q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
+                    w1 = (q[4] & 0xff) | ((q[5] & 0xff) << 8) | ((q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
+                }
+                const int b = g >> 2, j = g & 3;   // block, group-in-block (elements 8j..8j+7 = words 2j,2j+1)
+                const int sl = vec4 ? x_slot<true>(b) : b;
+                uint2 *dst = reinterpret_cast<uint2 *>((j < 2 ? xlo : xhi) + (size_t)sl * 16 + (j & 1) * 8);
+                *dst = make_uint2(w0, w1);
+                if (j == 0) {
+                    const float sh = round_h(scale);  // the GEMV reads the fp16 scale back (gemv.h:1631)
+                    xs[sl] = make_float2(sh, sh * (float)qs);
+                }
+            }
+        }
+    }
+}
+
 // Stage x as fp16 (optionally RMS-normalised) for the fp16-activation paths.
 template <int LD = 0, int NW = GEMV_CWARPS>
 __device__ __forceinline__ void stage_x_f16(const XStage &a, const void *xsrc, __half *xh, float *red, int tid) {

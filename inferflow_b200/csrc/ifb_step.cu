@@ -318,19 +318,24 @@ __device__ __forceinline__ void stage_att(const StepParams &P, const StepLayer &
                 float m = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; i++) m = fmaxf(m, fabsf(x[i]));
+                // (the two-term split is this kernel's own representation of q, not a reference format: any rounding
+                // of x/s1 within the int8 range serves -- the second term carries the remainder -- so a reciprocal
+                // multiply replaces the 16 IEEE divisions per thread the first version spent here)
                 const float s1 = quad_max(m) * (1.0f / 127.0f);
+                const float i1 = s1 > 0.f ? __frcp_rn(s1) : 0.f;
                 int qh[8], ql[8];
                 float r[8], m2 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const float t = s1 > 0.f ? rintf(x[i] / s1) : 0.f;
+                    const float t = fminf(fmaxf(rintf(x[i] * i1), -127.f), 127.f);
                     qh[i] = (int)t;
                     r[i] = x[i] - t * s1;
                     m2 = fmaxf(m2, fabsf(r[i]));
                 }
                 const float s2 = quad_max(m2) * (1.0f / 127.0f);
+                const float i2 = s2 > 0.f ? __frcp_rn(s2) : 0.f;
 #pragma unroll
-                for (int i = 0; i < 8; i++) ql[i] = (int)(s2 > 0.f ? rintf(r[i] / s2) : 0.f);
+                for (int i = 0; i < 8; i++) ql[i] = (int)fminf(fmaxf(rintf(r[i] * i2), -127.f), 127.f);
                 if (aq) {
                     *reinterpret_cast<uint2 *>(xst + L.qh + e0) = pack8_s8(qh);
                     *reinterpret_cast<uint2 *>(xst + L.ql + e0) = pack8_s8(ql);
@@ -363,10 +368,12 @@ __device__ __forceinline__ void stage_att(const StepParams &P, const StepLayer &
 #pragma unroll
                 for (int i = 0; i < 8; i++) m = fmaxf(m, fabsf(x[i]));
                 const float scale = __fdiv_rn(quad_max(m), 127.0f);
+                const bool dead = scale <= 0.000001f;
+                const float inv = dead ? 0.f : __frcp_rn(scale);
                 int qv[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    int t = scale <= 0.000001f ? 0 : (int)roundf(__fdiv_rn(x[i], scale));
+                    const int t = dead ? 0 : q8_round_div(x[i], scale, inv);   // == (int)roundf(x / scale), see ifb_common.cuh
                     qv[i] = min(max(t, -128), 127);
                 }
                 if (akv) {
@@ -610,19 +617,17 @@ __device__ __forceinline__ void att_merge(const StepParams &P, int ctx, float *s
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
-template <class Fmt, int LD>
-__device__ __forceinline__ void stage_gemv_x(const StepParams &P, const StepOpShape &s, const void *src, const __half *norm_w,
+template <class Fmt>
+__device__ __forceinline__ void stage_gemv_x(const StepParams &P, const StepOpShape &s, const void *src, bool ldcg, const __half *norm_w,
                                              uint8_t *xst, float *red, int tid) {
     const XStage a = {s.cx, nullptr, norm_w, P.eps, 0.f};
     if constexpr (is_f16_fmt<Fmt>::value) {
-        stage_x_f16<LD, STEP_CWARPS>(a, src, reinterpret_cast<__half *>(xst), red, tid);
+        if (ldcg) stage_x_f16<1, STEP_CWARPS>(a, src, reinterpret_cast<__half *>(xst), red, tid);
+        else stage_x_f16<0, STEP_CWARPS>(a, src, reinterpret_cast<__half *>(xst), red, tid);
     } else {
         uint8_t *xlo = xst, *xhi = xst + (size_t)s.nxb * 16;
         float2 *xs = reinterpret_cast<float2 *>(xst + (size_t)s.nxb * 32);
-        if constexpr (is_q4b32_fmt<Fmt>::value) {
-            if (s.vec4) { stage_x_q8<true, true, LD, STEP_CWARPS>(a, src, xlo, xhi, xs, red, tid); return; }
-        }
-        stage_x_q8<Fmt::XSPLIT, false, LD, STEP_CWARPS>(a, src, xlo, xhi, xs, red, tid);
+        stage_x_q8_compact<Fmt::XSPLIT, STEP_CWARPS>(a, src, xlo, xhi, xs, red, tid, s.vec4 != 0, ldcg);
     }
 }
 
@@ -650,6 +655,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
     __shared__ int2 slot_meta[STEP_MAX_SLOTS];   // (op, unit) of what sits in each ring slot
     __shared__ float red[STEP_CWARPS];
     __shared__ unsigned long long s_key[STEP_CWARPS];
+    __shared__ int s_prof[4];   // timeline probe (IFB_TRACE=1): warp 0's cycles waiting for data / in tasks, the producer's waiting for a free slot / its units
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *ring = smem;
@@ -665,6 +671,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
         reinterpret_cast<uint4 *>(smem + P.lay_off)[i] = reinterpret_cast<const uint4 *>(P.layers)[i];
     const int n_ops = P.n_ops, head_op = n_ops - 1;
 
+    if (tid < 4) s_prof[tid] = 0;
     if (tid == 0) {
         for (int i = 0; i < P.nslots; i++) {
             mbar_init(&full_bar[i], 1);
@@ -739,6 +746,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                     continue;
                 }
                 // the op is handed out (a claim at or past `units`, or a batch that reached the end): next op
+                if (P.trace != nullptr) {
+                    trace_add(P, op, 6, (unsigned long long)s_prof[2]);
+                    trace_add(P, op, 7, (unsigned long long)s_prof[3]);
+                    s_prof[2] = s_prof[3] = 0;
+                }
                 if (++op < n_ops) {
                     bind_op(op);
                     units = units_of(op);
@@ -764,8 +776,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             if (P.trace != nullptr) {
                 const long long t0 = clk();
                 mbar_wait_bounded(&empty_bar[pos], phase, P, op);
-                trace_add(P, op, 6, (unsigned long long)(clk() - t0));
-                trace_add(P, op, 7, 1ull);
+                s_prof[2] += (int)(clk() - t0);
+                s_prof[3]++;
             } else
             mbar_wait_bounded(&empty_bar[pos], phase, P, op);
             slot_meta[pos] = make_int2(op, u);
@@ -816,6 +828,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
     auto stage_for = [&](int op) {
         const int kind = op == head_op ? OPK_HEAD : op % 5, layer = op / 5;
         trace_op(P, op, 0, tid);
+        // input of the GEMV staging below (one call site: the staging code is inlined once)
+        const void *xsrc = resid;
+        const __half *xnorm = nullptr;
+        bool xcg = false;
         if (kind == OPK_QKV || kind == OPK_GLU || kind == OPK_HEAD) {
             // the RMSNorm weights do not depend on the previous op: their (DRAM) round trip runs under the wait
             const __half *nw_g = kind == OPK_HEAD ? P.out_norm : (kind == OPK_QKV ? s_layers[layer].attn_norm : s_layers[layer].ffn_norm);
@@ -839,16 +855,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             }
 #pragma unroll
             for (int i = 0; i < 2; i++) if (tid + i * STEP_CTHREADS < ngd) s_norm[tid + i * STEP_CTHREADS] = nwv[i];
-            for (int g = tid + 2 * STEP_CTHREADS; g < ngd; g += STEP_CTHREADS) s_norm[g] = reinterpret_cast<const uint4 *>(nw_g)[g];   // d > 8192
+            for (int g = tid + 2 * STEP_CTHREADS; g < ngd; g += STEP_CTHREADS) s_norm[g] = reinterpret_cast<const uint4 *>(nw_g)[g];   // d > 7680
             trace_op(P, op, 1, tid);
             named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);
-            const __half *nw = reinterpret_cast<const __half *>(s_norm);
-            if (kind == OPK_HEAD && P.head_f16) {
-                const XStage a = {P.d, nullptr, nw, P.eps, 0.f};
-                stage_x_f16<0, STEP_CWARPS>(a, resid, reinterpret_cast<__half *>(xst), red, tid);
-            } else {
-                stage_gemv_x<Fmt, 0>(P, P.op[kind], resid, nw, xst, red, tid);
-            }
+            xnorm = reinterpret_cast<const __half *>(s_norm);
         } else if (kind == OPK_ATT) {
             dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
             trace_op(P, op, 1, tid);
@@ -860,11 +870,19 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             dep_signal(&P.done[n_ops + layer], tid);
             dep_wait(&P.done[n_ops + layer], gridDim.x, P, op, tid);
             trace_op(P, op, 1, tid);
-            stage_gemv_x<Fmt, 1>(P, P.op[kind], P.attn_out, nullptr, xst, red, tid);
+            xsrc = P.attn_out; xcg = true;
         } else {   // OPK_W2
             dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
             trace_op(P, op, 1, tid);
-            stage_gemv_x<Fmt, 1>(P, P.op[kind], P.hbuf, nullptr, xst, red, tid);
+            xsrc = P.hbuf; xcg = true;
+        }
+        if (kind != OPK_ATT) {
+            if (kind == OPK_HEAD && P.head_f16) {
+                const XStage a = {P.d, nullptr, xnorm, P.eps, 0.f};
+                stage_x_f16<0, STEP_CWARPS>(a, resid, reinterpret_cast<__half *>(xst), red, tid);
+            } else {
+                stage_gemv_x<Fmt>(P, P.op[kind], xsrc, xcg, xnorm, xst, red, tid);
+            }
         }
         named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);
         trace_op(P, op, 2, tid);
@@ -880,7 +898,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             if (P.trace != nullptr && tid == 0) {
                 const long long t0 = clk();
                 mbar_wait_bounded(&full_bar[rp.pos], rp.phase, P, cur_op);
-                trace_add(P, cur_op, 4, (unsigned long long)(clk() - t0));
+                s_prof[0] += (int)(clk() - t0);
             } else
             mbar_wait_bounded(&full_bar[rp.pos], rp.phase, P, cur_op);
             meta = slot_meta[rp.pos];
@@ -888,6 +906,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
         if (meta.x != cur_op) {
             for (int k = cur_op; k < meta.x; k++) {
                 if (k >= 0) {
+                    if (P.trace != nullptr && tid == 0) {
+                        trace_add(P, k, 4, (unsigned long long)s_prof[0]);
+                        trace_add(P, k, 5, (unsigned long long)s_prof[1]);
+                        s_prof[0] = s_prof[1] = 0;
+                    }
                     if (k == head_op && tp == 1 && lane == 0 && best_i != 0x7fffffff) atomicMax(P.amax, amax_key(best_v, best_i));
                     dep_signal(&P.done[k], tid);     // this CTA's rows of op k are stored (and its staging of op k is long done)
                 }
@@ -960,7 +983,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                 }
             }
         }
-        if (P.trace != nullptr && tid == 0) trace_add(P, cur_op, 5, (unsigned long long)(clk() - t_task0));
+        if (P.trace != nullptr && tid == 0) s_prof[1] += (int)(clk() - t_task0);
         rp.tbase = (rp.tbase + ntask) % STEP_CWARPS;
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[rp.pos]);
