@@ -96,13 +96,14 @@ __device__ __forceinline__ void step_abort(const StepParams &P, int code, int op
     __trap();
 }
 
-// every wait of this kernel is bounded: past the deadline the kernel leaves an error record and traps
+// every wait of this kernel is bounded: past the deadline the kernel leaves an error record and traps. The threads
+// sleep in the barrier unit (suspend-time hint) rather than spin: a spinning consumer warp costs the working warps issue
+// slots (ncu: the first version spent 5 % of all executed instructions in this loop).
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity, const StepParams &P, int op) {
     if (mbar_try_wait(bar, parity)) return;
     const unsigned long long t0 = globaltimer_ns();
-    for (unsigned it = 0;; it++) {
-        if (mbar_try_wait(bar, parity)) return;
-        if ((it & 63u) == 63u && globaltimer_ns() - t0 > P.timeout_ns) step_abort(P, STEP_ERR_RING, op, (int)parity);
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if (globaltimer_ns() - t0 > P.timeout_ns) step_abort(P, STEP_ERR_RING, op, (int)parity);
     }
 }
 
@@ -888,80 +889,97 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
         trace_op(P, op, 2, tid);
     };
 
+    // The slot walk. Every consumer warp passes every slot (it arrives on the slot's "empty" barrier whether it had a
+    // task in it or not), so what a pass costs is paid 15 x slots-per-token times: everything that is constant for an
+    // op is computed once per op, and each op kind has its own tight slot loop (ncu on the first version: dp4a was 4 % of
+    // the executed instructions, the generic per-slot bookkeeping ~45 %).
     float best_v = -INFINITY;
     int best_i = 0x7fffffff;
     int cur_op = -1;            // nothing staged yet: the first pass stages op 0 while the first units are in flight
-    RingPos rp = {0, 0u, 0};
+    int next_op = 0;
+    int pos = 0, tbase = 0;
+    uint32_t phase = 0;
+    const int nslots = P.nslots, slot_bytes = P.slot_bytes;
+    // one pass over a slot: wait for its data; false when it belongs to another op (left in place for the transition)
+#define IFB_SLOT_BEGIN()                                                            \
+        mbar_wait_bounded(&full_bar[pos], phase, P, cur_op);                        \
+        const int2 meta = slot_meta[pos];                                           \
+        if (meta.x != cur_op) { next_op = meta.x; break; }                          \
+        uint8_t *slot = ring + (size_t)pos * slot_bytes;                            \
+        const int u = meta.y;                                                       \
+        int t = warp - tbase;                                                       \
+        if (t < 0) t += STEP_CWARPS;
+#define IFB_SLOT_END()                                                              \
+        tbase += ntask_mod;                                                         \
+        if (tbase >= STEP_CWARPS) tbase -= STEP_CWARPS;                             \
+        __syncwarp();                                                               \
+        if (lane == 0) mbar_arrive(&empty_bar[pos]);                                \
+        if (++pos == nslots) { pos = 0; phase ^= 1u; }
     for (;;) {
-        int2 meta = make_int2(0, -1);
-        if (cur_op >= 0) {
-            if (P.trace != nullptr && tid == 0) {
-                const long long t0 = clk();
-                mbar_wait_bounded(&full_bar[rp.pos], rp.phase, P, cur_op);
-                s_prof[0] += (int)(clk() - t0);
-            } else
-            mbar_wait_bounded(&full_bar[rp.pos], rp.phase, P, cur_op);
-            meta = slot_meta[rp.pos];
-        }
-        if (meta.x != cur_op) {
-            for (int k = cur_op; k < meta.x; k++) {
-                if (k >= 0) {
-                    if (P.trace != nullptr && tid == 0) {
-                        trace_add(P, k, 4, (unsigned long long)s_prof[0]);
-                        trace_add(P, k, 5, (unsigned long long)s_prof[1]);
-                        s_prof[0] = s_prof[1] = 0;
-                    }
-                    if (k == head_op && tp == 1 && lane == 0 && best_i != 0x7fffffff) atomicMax(P.amax, amax_key(best_v, best_i));
-                    dep_signal(&P.done[k], tid);     // this CTA's rows of op k are stored (and its staging of op k is long done)
-                }
-                if (k + 1 < n_ops) stage_for(k + 1);
+        // ---- op boundary: signal what is done, stage what comes
+        for (int k = cur_op; k < next_op; k++) {
+            if (k >= 0) {
+                if (k == head_op && tp == 1 && lane == 0 && best_i != 0x7fffffff) atomicMax(P.amax, amax_key(best_v, best_i));
+                dep_signal(&P.done[k], tid);     // this CTA's rows of op k are stored (and its staging of op k is long done)
             }
-            cur_op = meta.x;
-            if (cur_op >= n_ops) break;
-            trace_op(P, cur_op, 3, tid);             // first unit of the op in hand (none yet on the very first pass)
+            if (k + 1 < n_ops) stage_for(k + 1);
         }
-        if (meta.y < 0) continue;   // first pass: no slot in hand yet
+        cur_op = next_op;
+        if (cur_op >= n_ops) break;
+        trace_op(P, cur_op, 3, tid);
         const int kind = cur_op == head_op ? OPK_HEAD : cur_op % 5, layer = cur_op / 5;
         const StepOpShape &s = P.op[kind];
-        uint8_t *slot = ring + (size_t)rp.pos * P.slot_bytes;
-        const int u = meta.y;
-        const int ntask = s.tasks;
-        const long long t_task0 = (P.trace != nullptr && tid == 0) ? clk() : 0ll;
-        for (int t = warp >= rp.tbase ? warp - rp.tbase : warp - rp.tbase + STEP_CWARPS; t < ntask; t += STEP_CWARPS) {
-            if (kind == OPK_ATT) {
-                const int h = u / tiles_per_head, tl = u - h * tiles_per_head;
-                att_task_any(P, slot, t, h, tl * P.att_pos, ctx, xst, sp, lane);
-                continue;
-            }
-            float acc[2];
-            int o;
-            if (kind == OPK_GLU) {
-                o = u * s.R + t;
-                dot2<Fmt>(s, slot + (size_t)t * s.row_bytes, (size_t)s.unit_bytes, xst, lane, acc);
-            } else {
-                o = u * s.R + 2 * t;
-                const uint8_t *row = slot + (size_t)(2 * t) * s.row_bytes;
-                if (kind == OPK_HEAD && P.head_f16) {
-                    acc[0] = row_dot_f16(row, s.cx, reinterpret_cast<const __half *>(xst), lane);
-                    acc[1] = row_dot_f16(row + s.row_bytes, s.cx, reinterpret_cast<const __half *>(xst), lane);
-                } else {
-                    dot2<Fmt>(s, row, (size_t)s.row_bytes, xst, lane, acc);
+        const int ntask = s.tasks, ntask_mod = s.tasks % STEP_CWARPS;
+        const long long t_op0 = (P.trace != nullptr && tid == 0) ? clk() : 0ll;
+        if (kind == OPK_ATT) {
+            for (;;) {
+                IFB_SLOT_BEGIN()
+                if (t < ntask) {
+                    const int h = u / tiles_per_head, tl = u - h * tiles_per_head;
+                    for (; t < ntask; t += STEP_CWARPS) att_task_any(P, slot, t, h, tl * P.att_pos, ctx, xst, sp, lane);
                 }
+                IFB_SLOT_END()
             }
-            acc[0] = warp_sum(acc[0]);
-            acc[1] = warp_sum(acc[1]);
-            if (lane == 0) {
-                const float v0 = round_h(acc[0]), v1 = round_h(acc[1]);   // GEMV output tensors are half
-                if (kind == OPK_GLU) {
-                    // SiluActivation_Kernel (unary_tensor_opr.h:553) then Mul, each stored as half
-                    const float g = round_h(v0 / (1.0f + expf(-v0)));
-                    P.hbuf[o] = __float2half_rn(g * v1);
-                } else {
-                    const __half2 hv = __floats2half2_rn(v0, v1);
-                    const uint32_t bits = *reinterpret_cast<const uint32_t *>(&hv);
-                    if (kind == OPK_QKV) {
-                        reinterpret_cast<uint32_t *>(P.qkv)[o >> 1] = bits;
-                    } else if (kind == OPK_HEAD) {
+        } else if (kind == OPK_GLU) {
+            const int R = s.R, row_bytes_ = s.row_bytes;
+            const size_t stride = (size_t)s.unit_bytes;
+            for (;;) {
+                IFB_SLOT_BEGIN()
+                for (; t < ntask; t += STEP_CWARPS) {
+                    float acc[2];
+                    dot2<Fmt>(s, slot + (size_t)t * row_bytes_, stride, xst, lane, acc);
+                    acc[0] = warp_sum(acc[0]);
+                    acc[1] = warp_sum(acc[1]);
+                    if (lane == 0) {
+                        // SiluActivation_Kernel (unary_tensor_opr.h:553) then Mul, each stored as half
+                        const float v0 = round_h(acc[0]), v1 = round_h(acc[1]);   // GEMV output tensors are half
+                        const float g = round_h(v0 / (1.0f + expf(-v0)));
+                        P.hbuf[u * R + t] = __float2half_rn(g * v1);
+                    }
+                }
+                IFB_SLOT_END()
+            }
+        } else if (kind == OPK_HEAD) {
+            const int R = s.R, row_bytes_ = s.row_bytes;
+            const bool f16 = P.head_f16 != 0;
+            for (;;) {
+                IFB_SLOT_BEGIN()
+                for (; t < ntask; t += STEP_CWARPS) {
+                    float acc[2];
+                    const uint8_t *row = slot + (size_t)(2 * t) * row_bytes_;
+                    if (f16) {
+                        acc[0] = row_dot_f16(row, s.cx, reinterpret_cast<const __half *>(xst), lane);
+                        acc[1] = row_dot_f16(row + row_bytes_, s.cx, reinterpret_cast<const __half *>(xst), lane);
+                    } else {
+                        dot2<Fmt>(s, row, (size_t)row_bytes_, xst, lane, acc);
+                    }
+                    acc[0] = warp_sum(acc[0]);
+                    acc[1] = warp_sum(acc[1]);
+                    if (lane == 0) {
+                        const int o = u * R + 2 * t;
+                        const float v0 = round_h(acc[0]), v1 = round_h(acc[1]);
+                        const __half2 hv = __floats2half2_rn(v0, v1);
+                        const uint32_t bits = *reinterpret_cast<const uint32_t *>(&hv);
                         if (tp == 1) {
                             reinterpret_cast<uint32_t *>(P.logits)[o >> 1] = bits;
                             if (v0 == v0 && (v0 > best_v || (v0 == best_v && o < best_i))) { best_v = v0; best_i = o; }
@@ -971,24 +989,43 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                             const size_t off = (size_t)P.x_logits + ((size_t)(P.tp_rank * P.vocab_l + o) >> 1) * 8;
                             for (int p = 0; p < tp; p++) st_relaxed_sys_v2(reinterpret_cast<uint8_t *>(P.peer[p]) + off, wd);
                         }
-                    } else if (tp == 1) {
-                        reinterpret_cast<uint32_t *>(P.ybuf)[o >> 1] = bits;
-                    } else {
-                        // row-parallel partial sums go straight into every rank's exchange region over NVLink
-                        const uint32_t idx = kind == OPK_WO ? (uint32_t)(2 * layer + 1) : (uint32_t)(2 * layer + 2);
-                        const uint2 wd = make_uint2(bits, (seq << 8) | idx);
-                        const size_t off = (size_t)P.x_recv + (size_t)(idx & 1u) * P.x_recv_parity + (size_t)P.tp_rank * P.x_recv_rank + (size_t)(o >> 1) * 8;
-                        for (int p = 0; p < tp; p++) st_relaxed_sys_v2(reinterpret_cast<uint8_t *>(P.peer[p]) + off, wd);
                     }
                 }
+                IFB_SLOT_END()
+            }
+        } else {   // QKV, WO, W2: two adjacent rows per task, plain half outputs
+            const int R = s.R, row_bytes_ = s.row_bytes;
+            uint32_t *out32 = reinterpret_cast<uint32_t *>(kind == OPK_QKV ? P.qkv : P.ybuf);
+            const bool push = kind != OPK_QKV && tp > 1;
+            // row-parallel partial sums go straight into every rank's exchange region over NVLink
+            const uint32_t xidx = kind == OPK_WO ? (uint32_t)(2 * layer + 1) : (uint32_t)(2 * layer + 2);
+            const size_t xoff = (size_t)P.x_recv + (size_t)(xidx & 1u) * P.x_recv_parity + (size_t)P.tp_rank * P.x_recv_rank;
+            for (;;) {
+                IFB_SLOT_BEGIN()
+                for (; t < ntask; t += STEP_CWARPS) {
+                    float acc[2];
+                    dot2<Fmt>(s, slot + (size_t)(2 * t) * row_bytes_, (size_t)row_bytes_, xst, lane, acc);
+                    acc[0] = warp_sum(acc[0]);
+                    acc[1] = warp_sum(acc[1]);
+                    if (lane == 0) {
+                        const int o = u * R + 2 * t;
+                        const __half2 hv = __floats2half2_rn(acc[0], acc[1]);      // GEMV output tensors are half
+                        const uint32_t bits = *reinterpret_cast<const uint32_t *>(&hv);
+                        if (!push) {
+                            out32[o >> 1] = bits;
+                        } else {
+                            const uint2 wd = make_uint2(bits, (seq << 8) | xidx);
+                            for (int p = 0; p < tp; p++) st_relaxed_sys_v2(reinterpret_cast<uint8_t *>(P.peer[p]) + xoff + (size_t)(o >> 1) * 8, wd);
+                        }
+                    }
+                }
+                IFB_SLOT_END()
             }
         }
-        if (P.trace != nullptr && tid == 0) s_prof[1] += (int)(clk() - t_task0);
-        rp.tbase = (rp.tbase + ntask) % STEP_CWARPS;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[rp.pos]);
-        if (++rp.pos == P.nslots) { rp.pos = 0; rp.phase ^= 1u; }
+        if (P.trace != nullptr && tid == 0) trace_add(P, cur_op, 5, (unsigned long long)(clk() - t_op0));   // slot walk of this op, warp 0
     }
+#undef IFB_SLOT_BEGIN
+#undef IFB_SLOT_END
 
     // ===== end of the token: next token id, position += 1 =====
     if (tp > 1) {

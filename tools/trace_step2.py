@@ -33,7 +33,7 @@ for L in (1, 16):
         print(f"{names[k]:4s} enter {f(0)}  dep {f(1)}  staged {f(2)}  first_unit {f(3)}")
         c = raw[5 * L + k]
         mhz = 1965.0
-        print(f"       warp0: wait-for-data med {np.median(c[:, 4]) / mhz:6.2f} us  in-tasks med {np.median(c[:, 5]) / mhz:6.2f} us | producer: wait-for-free-slot med {np.median(c[:, 6]) / mhz:6.2f} us  units/CTA min {c[:, 7].min()} med {int(np.median(c[:, 7]))} max {c[:, 7].max()}")
+        print(f"       warp0 slot walk med {np.median(c[:, 5]) / mhz:6.2f} us | producer: wait-for-free-slot med {np.median(c[:, 6]) / mhz:6.2f} us  units/CTA min {c[:, 7].min()} med {int(np.median(c[:, 7]))} max {c[:, 7].max()}")
 r = (raw[n_ops - 1] - raw[n_ops - 1, :, 0].min()) / 1000.0
 print("HEAD enter %.2f/%.2f dep %.2f staged %.2f first_unit %.2f" % (r[:, 0].min(), r[:, 0].max(), np.median(r[:, 1]), np.median(r[:, 2]), np.median(r[:, 3])))
 # per-layer period
