@@ -273,7 +273,8 @@ __device__ __forceinline__ void stage_x_q8_compact(const XStage &a, const void *
 #pragma unroll 1
         for (int k = 0; k < KPT; k++) {
             const int g = g0 + k * NT + tid;   // a quad of lanes shares one block
-            if (g0 + k * NT >= ng) break;      // uniform: the whole sub-round is past the end
+            if (g0 + k * NT + warp * 32 >= ng) break;   // warp-uniform (ng % 32 == 0 for cx % 256 == 0; else the tail warp
+                                                        // runs with idle lanes): nothing left for this warp
             const uint4 xk = k == 0 ? xv0 : (k == 1 ? xv1 : xv2);
             const uint4 wk = k == 0 ? wv0 : (k == 1 ? wv1 : wv2);
             float v[8];

@@ -201,7 +201,8 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     }
     A(m->lm_head, wbytes(ldt, m->vocab_l, d));
     wsum += wbytes(ldt, m->vocab_l, d);
-    if (tp > 1) {
+    {   // the exchange region: under tensor parallelism the peers store into it; on one GPU the step kernel's own
+        // row-parallel GEMVs do (flag-in-data words instead of a completion count, see ifb_step.cu)
         auto up = [](int64_t v) { return (v + 255) / 256 * 256; };
         m->x_recv = 0;
         m->x_recv_rank = (int64_t)d * 4;             // d/2 words of 8 bytes
@@ -783,8 +784,12 @@ static int step_prepare(ifb_model *m) {
     if (s.tp_size > 1) {
         if (m->peer_xchg.empty()) { m->step_built = false; return IFB_OK; }   // not connected yet: decide at the first decode
         for (int p = 0; p < s.tp_size; p++) P.peer[p] = m->peer_xchg[p];
-        P.x_recv = m->x_recv; P.x_recv_parity = m->x_recv_parity; P.x_recv_rank = m->x_recv_rank; P.x_logits = m->x_logits;
+    } else {
+        P.peer[0] = m->xchg.p;
+        const char *e = getenv("IFB_STEP_LOCAL_LL");
+        P.local_ll = e ? (atoi(e) ? 1 : 0) : 1;
     }
+    P.x_recv = m->x_recv; P.x_recv_parity = m->x_recv_parity; P.x_recv_rank = m->x_recv_rank; P.x_logits = m->x_logits;
     void *dev_err = nullptr;
     IFB_CUDA(cudaHostGetDevicePointer(&dev_err, m->step_err, 0));
     P.err = (int *)dev_err;

@@ -99,11 +99,13 @@ __device__ __forceinline__ void step_abort(const StepParams &P, int code, int op
 // every wait of this kernel is bounded: past the deadline the kernel leaves an error record and traps. The threads
 // sleep in the barrier unit (suspend-time hint) rather than spin: a spinning consumer warp costs the working warps issue
 // slots (ncu: the first version spent 5 % of all executed instructions in this loop).
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity, const StepParams &P, int op) {
-    if (mbar_try_wait(bar, parity)) return;
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar_addr, uint32_t parity, const StepParams &P, int op) {
+    if (mbar_try_wait_a(bar_addr, parity)) return;
     const unsigned long long t0 = globaltimer_ns();
-    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-        if (globaltimer_ns() - t0 > P.timeout_ns) step_abort(P, STEP_ERR_RING, op, (int)parity);
+    unsigned it = 0;
+    while (!mbar_try_wait_a(bar_addr, parity)) {
+        __nanosleep(32);
+        if ((++it & 1023u) == 0u && globaltimer_ns() - t0 > P.timeout_ns) step_abort(P, STEP_ERR_RING, op, (int)parity);
     }
 }
 
@@ -218,25 +220,20 @@ __device__ __forceinline__ void resid_add_gather(const StepParams &P, uint4 *res
 // attention: staging of q and the new K/V row, the 32-position task, the merge
 // ---------------------------------------------------------------------------------------
 // staged layout inside the x area (HD = head_dim, NB = HD/32):
-//   Q8 cache : int8 qh[heads][HD] | int8 ql[heads][HD] | float qs[heads][NB][2] | int8 newk[kvh][HD] | int8 newv[kvh][HD]
-//              | half newks[kvh][NB] | half newvs[kvh][NB]
-//   F16 cache: float q[heads][HD/16][20] | half newk[kvh][HD] | half newv[kvh][HD]
+//   Q8 cache : int8 qh[heads][HD] | int8 ql[heads][HD] | float qs[heads][NB][2]
+//   F16 cache: float q[heads][HD/16][20]
 struct AttLayout {
-    int qh, ql, qs, newk, newv, newks, newvs, total;
+    int qh, ql, qs, total;
 };
-__host__ __device__ inline AttLayout att_layout(int heads, int kvh, int hd, bool q8) {
+__host__ __device__ inline AttLayout att_layout(int heads, int hd, bool q8) {
     AttLayout a;
     const int nb = hd / 32;
     if (q8) {
         a.qh = 0; a.ql = heads * hd; a.qs = 2 * heads * hd;
-        a.newk = a.qs + heads * nb * 8; a.newv = a.newk + kvh * hd;
-        a.newks = a.newv + kvh * hd; a.newvs = a.newks + kvh * nb * 2;
-        a.total = a.newvs + kvh * nb * 2;
+        a.total = a.qs + heads * nb * 8;
     } else {
         a.qh = 0; a.ql = 0; a.qs = 0;
-        a.newk = heads * (hd / 16) * 20 * 4; a.newv = a.newk + kvh * hd * 2;
-        a.newks = a.newvs = 0;
-        a.total = a.newv + kvh * hd * 2;
+        a.total = heads * (hd / 16) * 20 * 4;
     }
     a.total = (a.total + 127) / 128 * 128;
     return a;
@@ -280,122 +277,63 @@ __device__ __forceinline__ uint2 pack8_s8(const int *q) {
                       (q[4] & 0xff) | ((q[5] & 0xff) << 8) | ((q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24));
 }
 
-// One thread = 8 consecutive dims, four neighbouring lanes = one 32-dim block (its max by two shuffles).
+// q of every head of this rank: RoPE, round to half (PositionEmbedding stores half), scale; for a Q8 cache the two
+// int8 terms per 32-dim block, q ~= s1*qh + s2*ql (s2 <= s1/254). One thread = 8 consecutive dims, four neighbouring
+// lanes = one block (its max by two shuffles).
 template <bool Q8>
-__device__ __forceinline__ void stage_att(const StepParams &P, const StepLayer &lw, int ctx, uint8_t *xst, const float *s_cos,
-                                       const float *s_sin, int tid) {
+__device__ __forceinline__ void stage_att(const StepParams &P, uint8_t *xst, const float *s_cos, const float *s_sin, int tid) {
     const int hd = P.hd, nb = hd / 32;
-    const AttLayout L = att_layout(P.heads, P.kv_heads, hd, Q8);
-    const __half *q = P.qkv, *k = P.qkv + P.q_dim, *v = P.qkv + P.q_dim + P.kv_dim;
-    const int nq = P.q_dim >> 3, nkv = P.kv_dim >> 3;
-    const int pos = ctx - 1;
+    const AttLayout L = att_layout(P.heads, hd, Q8);
+    const __half *q = P.qkv;
+    const int nq = P.q_dim >> 3;
     const bool half_split = P.rope_order == 2;
-    for (int base = 0; base < max(nq, nkv); base += STEP_CTHREADS) {
+    for (int base = 0; base < nq; base += STEP_CTHREADS) {
+        if (base + (tid & ~31) >= nq) break;          // nothing left for this warp
         const int g8 = base + tid;
-        const bool aq = g8 < nq, akv = g8 < nkv;
-        const int e0 = g8 * 8;
-        // ---- all loads of this pass first: they share one round trip to the L2
-        uint4 wq_ = make_uint4(0, 0, 0, 0), wqo = wq_, wk_ = wq_, wko = wq_, wv_ = wq_;
-        const int hq = aq ? e0 / hd : 0, dq = aq ? e0 - hq * hd : 0;
-        const int hk = akv ? e0 / hd : 0, dk = akv ? e0 - hk * hd : 0;
+        const bool aq = g8 < nq;
+        const int e0 = aq ? g8 * 8 : 0;
+        const int hq = e0 / hd, dq = e0 - hq * hd;
+        uint4 wq_ = make_uint4(0, 0, 0, 0), wqo = wq_;
         if (aq) {
             wq_ = ld_cg128(q + e0);
             if (half_split) wqo = ld_cg128(q + hq * hd + (dq < hd / 2 ? dq + hd / 2 : dq - hd / 2));
         }
-        if (akv) {
-            wk_ = ld_cg128(k + e0);
-            if (half_split) wko = ld_cg128(k + hk * hd + (dk < hd / 2 ? dk + hd / 2 : dk - hd / 2));
-            wv_ = ld_cg128(v + e0);
-        }
-        // ---- q: RoPE, round to half, scale; Q8 cache: two int8 terms per block, q ~= s1*qh + s2*ql (s2 <= s1/254)
-        {
-            float x[8], o[8];
-            unpack8(wq_, x);
-            unpack8(wqo, o);
-            rope8(x, o, dq, hd, P.rope_order, s_cos, s_sin);
+        float x[8], o[8];
+        unpack8(wq_, x);
+        unpack8(wqo, o);
+        rope8(x, o, dq, hd, P.rope_order, s_cos, s_sin);
 #pragma unroll
-            for (int i = 0; i < 8; i++) x[i] *= P.softmax_scale;
-            if (Q8) {
-                float m = 0.f;
+        for (int i = 0; i < 8; i++) x[i] *= P.softmax_scale;
+        if (Q8) {
+            float m = 0.f;
 #pragma unroll
-                for (int i = 0; i < 8; i++) m = fmaxf(m, fabsf(x[i]));
-                // (the two-term split is this kernel's own representation of q, not a reference format: any rounding
-                // of x/s1 within the int8 range serves -- the second term carries the remainder -- so a reciprocal
-                // multiply replaces the 16 IEEE divisions per thread the first version spent here)
-                const float s1 = quad_max(m) * (1.0f / 127.0f);
-                const float i1 = s1 > 0.f ? __frcp_rn(s1) : 0.f;
-                int qh[8], ql[8];
-                float r[8], m2 = 0.f;
+            for (int i = 0; i < 8; i++) m = fmaxf(m, fabsf(x[i]));
+            // (the two-term split is this kernel's own representation of q, not a reference format: any rounding of
+            // x/s1 within the int8 range serves -- the second term carries the remainder -- so reciprocal multiplies)
+            const float s1 = quad_max(m) * (1.0f / 127.0f);
+            const float i1 = s1 > 0.f ? __frcp_rn(s1) : 0.f;
+            int qh[8], ql[8];
+            float r[8], m2 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const float t = fminf(fmaxf(rintf(x[i] * i1), -127.f), 127.f);
-                    qh[i] = (int)t;
-                    r[i] = x[i] - t * s1;
-                    m2 = fmaxf(m2, fabsf(r[i]));
-                }
-                const float s2 = quad_max(m2) * (1.0f / 127.0f);
-                const float i2 = s2 > 0.f ? __frcp_rn(s2) : 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; i++) ql[i] = (int)fminf(fmaxf(rintf(r[i] * i2), -127.f), 127.f);
-                if (aq) {
-                    *reinterpret_cast<uint2 *>(xst + L.qh + e0) = pack8_s8(qh);
-                    *reinterpret_cast<uint2 *>(xst + L.ql + e0) = pack8_s8(ql);
-                    if ((dq & 31) == 0) reinterpret_cast<float2 *>(xst + L.qs)[hq * nb + (dq >> 5)] = make_float2(s1, s2);
-                }
-            } else if (aq) {
-                float *dst = reinterpret_cast<float *>(xst) + ((size_t)hq * (hd / 16) + (dq >> 4)) * 20 + (dq & 15);
-                *reinterpret_cast<float4 *>(dst) = make_float4(x[0], x[1], x[2], x[3]);
-                *reinterpret_cast<float4 *>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
+            for (int i = 0; i < 8; i++) {
+                const float t = fminf(fmaxf(rintf(x[i] * i1), -127.f), 127.f);
+                qh[i] = (int)t;
+                r[i] = x[i] - t * s1;
+                m2 = fmaxf(m2, fabsf(r[i]));
             }
-        }
-        // ---- the new K row (RoPE) and V row of every kv head, as the cache stores them (SetKRows / SetVRows,
-        // kv_cache.cc:104-183; Q8: Tensor_QuantizeQ8_B32T2_Alg2_Kernel, tensor_quant.h:45-82). Every CTA keeps them in
-        // shared memory (a tile that holds position ctx-1 is patched there: its bulk copy may have been issued before
-        // this row existed); the CTA h % grid writes head h's row to the cache itself.
-        const bool mine = akv && (hk % (int)gridDim.x) == (int)blockIdx.x;
-        const int64_t row = (int64_t)hk * P.max_ctx_pad + pos;
+            const float s2 = quad_max(m2) * (1.0f / 127.0f);
+            const float i2 = s2 > 0.f ? __frcp_rn(s2) : 0.f;
 #pragma unroll
-        for (int which = 0; which < 2; which++) {
-            uint8_t *cache = which == 0 ? lw.kcache : lw.vcache;
-            float x[8];
-            unpack8(which == 0 ? wk_ : wv_, x);
-            if (which == 0) {
-                float o[8];
-                unpack8(wko, o);
-                rope8(x, o, dk, hd, P.rope_order, s_cos, s_sin);
+            for (int i = 0; i < 8; i++) ql[i] = (int)fminf(fmaxf(rintf(r[i] * i2), -127.f), 127.f);
+            if (aq) {
+                *reinterpret_cast<uint2 *>(xst + L.qh + e0) = pack8_s8(qh);
+                *reinterpret_cast<uint2 *>(xst + L.ql + e0) = pack8_s8(ql);
+                if ((dq & 31) == 0) reinterpret_cast<float2 *>(xst + L.qs)[hq * nb + (dq >> 5)] = make_float2(s1, s2);
             }
-            if (Q8) {
-                float m = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; i++) m = fmaxf(m, fabsf(x[i]));
-                const float scale = __fdiv_rn(quad_max(m), 127.0f);
-                const bool dead = scale <= 0.000001f;
-                const float inv = dead ? 0.f : __frcp_rn(scale);
-                int qv[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int t = dead ? 0 : q8_round_div(x[i], scale, inv);   // == (int)roundf(x / scale), see ifb_common.cuh
-                    qv[i] = min(max(t, -128), 127);
-                }
-                if (akv) {
-                    const uint2 pk = pack8_s8(qv);
-                    *reinterpret_cast<uint2 *>(xst + (which == 0 ? L.newk : L.newv) + e0) = pk;
-                    const __half hs = __float2half_rn(scale);
-                    if ((dk & 31) == 0) reinterpret_cast<__half *>(xst + (which == 0 ? L.newks : L.newvs))[hk * nb + (dk >> 5)] = hs;
-                    if (mine) {
-                        *reinterpret_cast<uint2 *>(cache + row * hd + dk) = pk;
-                        if ((dk & 31) == 0)
-                            reinterpret_cast<__half *>(cache + (int64_t)P.kv_heads * P.max_ctx_pad * hd)[row * nb + (dk >> 5)] = hs;
-                    }
-                }
-            } else if (akv) {
-                uint4 pk;
-                __half2 *ph = reinterpret_cast<__half2 *>(&pk);
-#pragma unroll
-                for (int i = 0; i < 4; i++) ph[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
-                *reinterpret_cast<uint4 *>(xst + (which == 0 ? L.newk : L.newv) + (size_t)e0 * 2) = pk;
-                if (mine) *reinterpret_cast<uint4 *>(cache + (row * hd + dk) * 2) = pk;
-            }
+        } else if (aq) {
+            float *dst = reinterpret_cast<float *>(xst) + ((size_t)hq * (hd / 16) + (dq >> 4)) * 20 + (dq & 15);
+            *reinterpret_cast<float4 *>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+            *reinterpret_cast<float4 *>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
         }
     }
 }
@@ -412,12 +350,12 @@ __device__ __forceinline__ float s8f_(uint32_t w_biased, int k) {
 // body of attn_decode_kernel (ifb_attention.cu): dp4a scores with the two-term int8 q for a Q8 cache, fp32 softmax,
 // lane-owns-4-dims P.V.
 template <int HD, bool Q8>
-__device__ __forceinline__ void att_task(const StepParams &P, uint8_t *slot, int tt, int kvh, int p0, int ctx,
-                                         const uint8_t *xst, float *sp, int lane) {
+__device__ __forceinline__ void att_task(const StepParams &P, const StepLayer &lw, const float *s_cos, const float *s_sin,
+                                         uint8_t *slot, int tt, int kvh, int p0, int ctx, const uint8_t *xst, float *sp, int lane) {
     constexpr int NB = HD / 32;
     const int pbase = p0 + tt * 32;
     if (pbase >= ctx) return;
-    const AttLayout L = att_layout(P.heads, P.kv_heads, HD, Q8);
+    const AttLayout L = att_layout(P.heads, HD, Q8);
     const int UP = P.att_pos, G = P.group;
     uint8_t *tK, *tKs = nullptr, *tV, *tVs = nullptr;
     if (Q8) {
@@ -430,18 +368,90 @@ __device__ __forceinline__ void att_task(const StepParams &P, uint8_t *slot, int
         tV = slot + 32 * HD * 2;
     }
     if (ctx - 1 >= pbase && ctx - 1 < pbase + 32) {
-        // the copy raced with (or preceded) the store of this token's K/V row: put the row in place here
-        const int r = (ctx - 1) - pbase;
-        constexpr int ROWB = Q8 ? HD : HD * 2;
-        const uint32_t *nk = reinterpret_cast<const uint32_t *>(xst + L.newk + (size_t)kvh * ROWB);
-        const uint32_t *nv = reinterpret_cast<const uint32_t *>(xst + L.newv + (size_t)kvh * ROWB);
-        for (int i = lane; i < ROWB / 4; i += 32) {
-            reinterpret_cast<uint32_t *>(tK + r * ROWB)[i] = nk[i];
-            reinterpret_cast<uint32_t *>(tV + r * ROWB)[i] = nv[i];
+        // This tile holds the position being decoded. Its bulk copy was issued before this token's K/V row existed
+        // (or raced with it): the warp builds the row here -- RoPE on k, then the cache's storage form (SetKRows /
+        // SetVRows, kv_cache.cc:104-183; Q8: Tensor_QuantizeQ8_B32T2_Alg2_Kernel, tensor_quant.h:45-82) -- stores
+        // it to the cache and puts it in place in the staged tile. One task per kv head and token does this.
+        constexpr int DPL = HD / 32;                       // dims per lane
+        const int r = (ctx - 1) - pbase, d0 = lane * DPL;
+        const __half *kn = P.qkv + P.q_dim + (size_t)kvh * HD, *vn = kn + P.kv_dim;
+        float kx[DPL], vx[DPL];
+        {
+            uint32_t kw[DPL / 2], vw[DPL / 2];
+#pragma unroll
+            for (int i = 0; i < DPL / 2; i++) {
+                asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(kw[i]) : "l"(kn + d0 + 2 * i) : "memory");
+                asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(vw[i]) : "l"(vn + d0 + 2 * i) : "memory");
+            }
+#pragma unroll
+            for (int i = 0; i < DPL / 2; i++) {
+                const float2 fk = __half22float2(*reinterpret_cast<const __half2 *>(&kw[i]));
+                const float2 fv = __half22float2(*reinterpret_cast<const __half2 *>(&vw[i]));
+                kx[2 * i] = fk.x; kx[2 * i + 1] = fk.y;
+                vx[2 * i] = fv.x; vx[2 * i + 1] = fv.y;
+            }
         }
-        if (Q8 && lane < NB) {
-            reinterpret_cast<__half *>(tKs)[r * NB + lane] = reinterpret_cast<const __half *>(xst + L.newks)[kvh * NB + lane];
-            reinterpret_cast<__half *>(tVs)[r * NB + lane] = reinterpret_cast<const __half *>(xst + L.newvs)[kvh * NB + lane];
+        if (P.rope_order == 2) {
+            // half-split pairs (d, d + HD/2): the partner sits 16 lanes away
+            const bool first = d0 < HD / 2;
+#pragma unroll
+            for (int i = 0; i < DPL; i++) {
+                const float o = __shfl_xor_sync(0xffffffffu, kx[i], 16);
+                const int pi = (first ? d0 : d0 - HD / 2) + i;
+                const float cs = s_cos[pi], sn = s_sin[pi];
+                kx[i] = first ? round_h(kx[i] * cs - o * sn) : round_h(o * sn + kx[i] * cs);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < DPL; i += 2) {
+                const float cs = s_cos[(d0 + i) >> 1], sn = s_sin[(d0 + i) >> 1];
+                const float a_ = kx[i], b_ = kx[i + 1];
+                kx[i] = round_h(a_ * cs - b_ * sn);
+                kx[i + 1] = round_h(a_ * sn + b_ * cs);
+            }
+        }
+        const int64_t row = (int64_t)kvh * P.max_ctx_pad + (ctx - 1);
+#pragma unroll
+        for (int which = 0; which < 2; which++) {
+            float *x = which == 0 ? kx : vx;
+            uint8_t *cache = which == 0 ? lw.kcache : lw.vcache;
+            uint8_t *trow = (which == 0 ? tK : tV) + r * (Q8 ? HD : HD * 2);
+            if (Q8) {
+                float m = 0.f;
+#pragma unroll
+                for (int i = 0; i < DPL; i++) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+                for (int of = 1; of < 32 / DPL; of <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, of));   // the block's 32/DPL lanes
+                const float scale = __fdiv_rn(m, 127.0f);
+                const bool dead = scale <= 0.000001f;
+                const float inv = dead ? 0.f : __frcp_rn(scale);
+                uint32_t pk = 0;
+#pragma unroll
+                for (int i = 0; i < DPL; i++) {
+                    const int t = dead ? 0 : q8_round_div(x[i], scale, inv);   // == (int)roundf(x / scale), see ifb_common.cuh
+                    pk |= (uint32_t)(min(max(t, -128), 127) & 0xff) << (8 * i);
+                }
+                const __half hs = __float2half_rn(scale);
+                if (DPL == 4) {
+                    reinterpret_cast<uint32_t *>(trow)[lane] = pk;
+                    reinterpret_cast<uint32_t *>(cache + row * HD)[lane] = pk;
+                } else {
+                    reinterpret_cast<uint16_t *>(trow)[lane] = (uint16_t)pk;
+                    reinterpret_cast<uint16_t *>(cache + row * HD)[lane] = (uint16_t)pk;
+                }
+                if ((d0 & 31) == 0) {
+                    reinterpret_cast<__half *>(which == 0 ? tKs : tVs)[r * NB + (d0 >> 5)] = hs;
+                    reinterpret_cast<__half *>(cache + (int64_t)P.kv_heads * P.max_ctx_pad * HD)[row * NB + (d0 >> 5)] = hs;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < DPL; i += 2) {
+                    const __half2 hv = __floats2half2_rn(x[i], x[i + 1]);
+                    const uint32_t bits = *reinterpret_cast<const uint32_t *>(&hv);
+                    reinterpret_cast<uint32_t *>(trow)[(d0 + i) >> 1] = bits;
+                    reinterpret_cast<uint32_t *>(cache + row * HD * 2)[(d0 + i) >> 1] = bits;
+                }
+            }
         }
         fence_proxy_async_smem();   // generic-proxy writes into a buffer the next bulk copy (async proxy) will overwrite
         __syncwarp();
@@ -546,68 +556,69 @@ struct RingPos {
     int tbase;
 };
 
-__device__ __forceinline__ void att_task_any(const StepParams &P, uint8_t *slot, int tt, int kvh, int p0, int ctx,
-                                             const uint8_t *xst, float *sp, int lane) {
+__device__ __forceinline__ void att_task_any(const StepParams &P, const StepLayer &lw, const float *s_cos, const float *s_sin,
+                                             uint8_t *slot, int tt, int kvh, int p0, int ctx, const uint8_t *xst, float *sp, int lane) {
     if (P.hd == 128) {
-        if (P.kv_q8) att_task<128, true>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
-        else att_task<128, false>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        if (P.kv_q8) att_task<128, true>(P, lw, s_cos, s_sin, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        else att_task<128, false>(P, lw, s_cos, s_sin, slot, tt, kvh, p0, ctx, xst, sp, lane);
     } else {
-        if (P.kv_q8) att_task<64, true>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
-        else att_task<64, false>(P, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        if (P.kv_q8) att_task<64, true>(P, lw, s_cos, s_sin, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        else att_task<64, false>(P, lw, s_cos, s_sin, slot, tt, kvh, p0, ctx, xst, sp, lane);
     }
 }
 
 // log-sum-exp merge of the tiles' partials: q head hq -> attn_out[hq][hd] (half, as the reference's attention output
-// tensor). 512 threads = (512/hd) tile groups x hd dims; scratch = the (idle) staging area.
+// tensor). Thread = (4 dims, tile group): hd/4 dim quads x 480/(hd/4) tile groups; a thread's tiles are all loaded
+// before any is used (one L2 round trip for a 2k context), the tile groups meet in shared memory (the idle staging area).
 __device__ __forceinline__ void att_merge(const StepParams &P, int ctx, float *scratch, int tid) {
-    const int hd = P.hd, ngrp = STEP_CTHREADS / hd, grp = tid / hd, dd = tid - grp * hd;
-    const bool part = grp < ngrp;      // 480 threads = 3 groups of 128 (+ 96 idle) or 7 groups of 64 (+ 32 idle)
+    const int hd = P.hd, nq4 = hd >> 2, ngrp = STEP_CTHREADS / nq4, tg = tid / nq4, q4 = tid - tg * nq4;
     const int ntile = (ctx + 31) >> 5;
-    constexpr int NB = 8;      // tiles per batch: all of a batch's loads are in flight together (one L2 round trip)
+    constexpr int NB = 6;      // tiles per batch and thread
     for (int hq = (int)blockIdx.x; hq < P.heads; hq += (int)gridDim.x) {
         const float *pb = P.partials + (size_t)hq * P.max_tiles * (hd + 4);
-        float M = -INFINITY, num = 0.f, den = 0.f;
-        for (int t0 = grp; part && t0 < ntile; t0 += ngrp * NB) {
-            float m[NB], l[NB], a[NB];
+        float M = -INFINITY, den = 0.f;
+        float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t0 = tg; t0 < ntile; t0 += ngrp * NB) {
+            float2 ml[NB];
+            float4 a[NB];
 #pragma unroll
             for (int i = 0; i < NB; i++) {
                 const int t = t0 + i * ngrp;
-                m[i] = -INFINITY; l[i] = 0.f; a[i] = 0.f;
+                ml[i] = make_float2(-INFINITY, 0.f);
+                a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (t < ntile) {
                     const float *pt = pb + (size_t)t * (hd + 4);
-                    m[i] = ld_cg_f32(pt);
-                    l[i] = ld_cg_f32(pt + 1);
-                    a[i] = ld_cg_f32(pt + 4 + dd);
+                    asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(ml[i].x), "=f"(ml[i].y) : "l"(pt) : "memory");
+                    a[i] = ld_cg_f32x4(pt + 4 + 4 * q4);
                 }
             }
             float Mn = M;
 #pragma unroll
-            for (int i = 0; i < NB; i++) Mn = fmaxf(Mn, m[i]);
+            for (int i = 0; i < NB; i++) Mn = fmaxf(Mn, ml[i].x);
             const float c = (M == -INFINITY) ? 0.f : __expf(M - Mn);
-            num *= c; den *= c;
+            num.x *= c; num.y *= c; num.z *= c; num.w *= c; den *= c;
 #pragma unroll
             for (int i = 0; i < NB; i++) {
-                const float w = (m[i] == -INFINITY) ? 0.f : __expf(m[i] - Mn);
-                num = fmaf(w, a[i], num);
-                den = fmaf(w, l[i], den);
+                const float w = (ml[i].x == -INFINITY) ? 0.f : __expf(ml[i].x - Mn);
+                num.x = fmaf(w, a[i].x, num.x); num.y = fmaf(w, a[i].y, num.y);
+                num.z = fmaf(w, a[i].z, num.z); num.w = fmaf(w, a[i].w, num.w);
+                den = fmaf(w, ml[i].y, den);
             }
             M = Mn;
         }
-        if (part) {
-            scratch[(grp * hd + dd) * 3 + 0] = M;
-            scratch[(grp * hd + dd) * 3 + 1] = num;
-            scratch[(grp * hd + dd) * 3 + 2] = den;
-        }
+        float *rowp = scratch + (size_t)tg * (hd + 4);
+        if (q4 == 0) { rowp[0] = M; rowp[1] = den; }
+        *reinterpret_cast<float4 *>(rowp + 4 + 4 * q4) = num;
         named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);
         if (tid < hd) {
             float MM = -INFINITY;
-            for (int g = 0; g < ngrp; g++) MM = fmaxf(MM, scratch[(g * hd + tid) * 3]);
+            for (int g = 0; g < ngrp; g++) MM = fmaxf(MM, scratch[(size_t)g * (hd + 4)]);
             float n2 = 0.f, d2 = 0.f;
             for (int g = 0; g < ngrp; g++) {
-                const float mg = scratch[(g * hd + tid) * 3];
+                const float mg = scratch[(size_t)g * (hd + 4)];
                 const float w = (mg == -INFINITY) ? 0.f : __expf(mg - MM);
-                n2 = fmaf(w, scratch[(g * hd + tid) * 3 + 1], n2);
-                d2 = fmaf(w, scratch[(g * hd + tid) * 3 + 2], d2);
+                n2 = fmaf(w, scratch[(size_t)g * (hd + 4) + 4 + tid], n2);
+                d2 = fmaf(w, scratch[(size_t)g * (hd + 4) + 1], d2);
             }
             P.attn_out[(size_t)hq * hd + tid] = __float2half_rn(n2 / d2);
         }
@@ -721,6 +732,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             return kind == OPK_ATT ? att_units : ((P.parts & STEP_PART_GEMV) ? P.op[kind].units : 0);
         };
         unsigned issued = 0;                             // copies (ring fills) issued so far
+        const uint32_t pfull0 = smem_u32(full_bar), pempty0 = smem_u32(empty_bar), ring0 = smem_u32(ring);
         const uint8_t *src0 = nullptr, *src1 = nullptr, *src2 = nullptr;   // this op's matrices / cache planes
         auto bind_op = [&](int o) {
             const int kind = o == head_op ? OPK_HEAD : o % 5;
@@ -771,18 +783,18 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             // and every demand load of the staging code (activations, norm weights, completion counts) waits behind it.
             if (P.max_inflight > 0 && issued >= (unsigned)P.max_inflight) {
                 const unsigned w = issued - (unsigned)P.max_inflight;
-                mbar_wait_bounded(&full_bar[w % (unsigned)P.nslots], (w / (unsigned)P.nslots) & 1u, P, op);
+                mbar_wait_bounded(pfull0 + 8u * (w % (unsigned)P.nslots), (w / (unsigned)P.nslots) & 1u, P, op);
             }
             issued++;
             if (P.trace != nullptr) {
                 const long long t0 = clk();
-                mbar_wait_bounded(&empty_bar[pos], phase, P, op);
+                mbar_wait_bounded(pempty0 + 8u * (uint32_t)pos, phase, P, op);
                 s_prof[2] += (int)(clk() - t0);
                 s_prof[3]++;
             } else
-            mbar_wait_bounded(&empty_bar[pos], phase, P, op);
+            mbar_wait_bounded(pempty0 + 8u * (uint32_t)pos, phase, P, op);
             slot_meta[pos] = make_int2(op, u);
-            uint8_t *dst = ring + (size_t)pos * P.slot_bytes;
+            const uint32_t dst = ring0 + (uint32_t)pos * (uint32_t)P.slot_bytes, fb = pfull0 + 8u * (uint32_t)pos;
             const uint32_t ub = (uint32_t)s.unit_bytes;
             if (kind == OPK_ATT) {
                 const int h = u / tiles_per_head, t = u - h * tiles_per_head;
@@ -791,38 +803,42 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                 if (P.kv_q8) {
                     const uint32_t kb = (uint32_t)(UP * hd), sb = (uint32_t)(UP * nb * 2);
                     const int64_t soff = (int64_t)P.kv_heads * P.max_ctx_pad * hd;
-                    mbar_arrive_expect_tx(&full_bar[pos], 2 * (kb + sb));
-                    bulk_g2s_hint(dst, src0 + row0 * hd, kb, &full_bar[pos], pol);
-                    bulk_g2s_hint(dst + kb, src0 + soff + row0 * nb * 2, sb, &full_bar[pos], pol);
-                    bulk_g2s_hint(dst + kb + sb, src1 + row0 * hd, kb, &full_bar[pos], pol);
-                    bulk_g2s_hint(dst + 2 * kb + sb, src1 + soff + row0 * nb * 2, sb, &full_bar[pos], pol);
+                    mbar_arrive_expect_tx_a(fb, 2 * (kb + sb));
+                    bulk_g2s_hint_a(dst, src0 + row0 * hd, kb, fb, pol);
+                    bulk_g2s_hint_a(dst + kb, src0 + soff + row0 * nb * 2, sb, fb, pol);
+                    bulk_g2s_hint_a(dst + kb + sb, src1 + row0 * hd, kb, fb, pol);
+                    bulk_g2s_hint_a(dst + 2 * kb + sb, src1 + soff + row0 * nb * 2, sb, fb, pol);
                 } else {
                     const uint32_t kb = (uint32_t)(UP * hd * 2);
-                    mbar_arrive_expect_tx(&full_bar[pos], 2 * kb);
-                    bulk_g2s_hint(dst, src0 + row0 * hd * 2, kb, &full_bar[pos], pol);
-                    bulk_g2s_hint(dst + kb, src1 + row0 * hd * 2, kb, &full_bar[pos], pol);
+                    mbar_arrive_expect_tx_a(fb, 2 * kb);
+                    bulk_g2s_hint_a(dst, src0 + row0 * hd * 2, kb, fb, pol);
+                    bulk_g2s_hint_a(dst + kb, src1 + row0 * hd * 2, kb, fb, pol);
                 }
             } else if (kind == OPK_GLU) {
-                mbar_arrive_expect_tx(&full_bar[pos], 2 * ub);
-                bulk_g2s_hint(dst, src0 + (size_t)u * ub, ub, &full_bar[pos], pol);
-                bulk_g2s_hint(dst + ub, src1 + (size_t)u * ub, ub, &full_bar[pos], pol);
+                mbar_arrive_expect_tx_a(fb, 2 * ub);
+                bulk_g2s_hint_a(dst, src0 + (size_t)u * ub, ub, fb, pol);
+                bulk_g2s_hint_a(dst + ub, src1 + (size_t)u * ub, ub, fb, pol);
             } else {
                 const uint8_t *src = src0 + (size_t)u * ub;
                 if (kind == OPK_QKV && u >= s.seg1) src = u >= s.seg2 ? src2 + (size_t)(u - s.seg2) * ub : src1 + (size_t)(u - s.seg1) * ub;
-                mbar_arrive_expect_tx(&full_bar[pos], ub);
-                bulk_g2s_hint(dst, src, ub, &full_bar[pos], pol);
+                mbar_arrive_expect_tx_a(fb, ub);
+                bulk_g2s_hint_a(dst, src, ub, fb, pol);
             }
             if (++pos == P.nslots) { pos = 0; phase ^= 1u; }
         }
-        mbar_wait_bounded(&empty_bar[pos], phase, P, n_ops);
+        mbar_wait_bounded(pempty0 + 8u * (uint32_t)pos, phase, P, n_ops);
         slot_meta[pos] = make_int2(n_ops, 0);            // end of the token
-        mbar_arrive(&full_bar[pos]);
+        mbar_arrive_a(pfull0 + 8u * (uint32_t)pos);
         return;
     }
 
     // ===== consumers =====
     float *sp = reinterpret_cast<float *>(smem + P.sp_off) + (size_t)warp * 32;
     const int tp = P.tp_size;
+    // The outputs of the row-parallel GEMVs (wo, w2) travel as flag-in-data words {half2, flag}: under tensor parallelism
+    // into every rank's exchange region, on one GPU into this GPU's own (local_ll). The reader polls the words it needs
+    // -- no completion count, fence or atomic on that path, one L2 round trip instead of three.
+    const bool ll = tp > 1 || P.local_ll != 0;
 
     // staging of op `op`'s input (every CTA runs it for every op, in order: the residual stream lives in each CTA's
     // shared memory, and "this CTA has staged op k" is part of what its completion count of op k tells the peers)
@@ -846,7 +862,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                 tok = max(0, min(tok, P.vocab - 1));
                 const uint4 *row = reinterpret_cast<const uint4 *>(P.tok_emb + (size_t)tok * P.d);
                 for (int g = tid; g < (P.d >> 3); g += STEP_CTHREADS) resid[g] = row[g];
-            } else if (tp > 1) {
+            } else if (ll) {
                 // exchange index: wo of layer l -> 2l+1, w2 of layer l -> 2l+2 (two buffers, alternating)
                 const uint32_t idx = kind == OPK_GLU ? (uint32_t)(2 * layer + 1) : (uint32_t)(2 * (kind == OPK_HEAD ? P.n_layers : layer));
                 resid_add_gather(P, resid, idx, seq, op, tid);
@@ -863,8 +879,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
         } else if (kind == OPK_ATT) {
             dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
             trace_op(P, op, 1, tid);
-            if (P.kv_q8) stage_att<true>(P, s_layers[layer], ctx, xst, s_cos, s_sin, tid);
-            else stage_att<false>(P, s_layers[layer], ctx, xst, s_cos, s_sin, tid);
+            if (P.kv_q8) stage_att<true>(P, xst, s_cos, s_sin, tid);
+            else stage_att<false>(P, xst, s_cos, s_sin, tid);
         } else if (kind == OPK_WO) {
             dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
             att_merge(P, ctx, reinterpret_cast<float *>(xst), tid);
@@ -900,9 +916,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
     int pos = 0, tbase = 0;
     uint32_t phase = 0;
     const int nslots = P.nslots, slot_bytes = P.slot_bytes;
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
     // one pass over a slot: wait for its data; false when it belongs to another op (left in place for the transition)
 #define IFB_SLOT_BEGIN()                                                            \
-        mbar_wait_bounded(&full_bar[pos], phase, P, cur_op);                        \
+        mbar_wait_bounded(full0 + 8u * (uint32_t)pos, phase, P, cur_op);            \
         const int2 meta = slot_meta[pos];                                           \
         if (meta.x != cur_op) { next_op = meta.x; break; }                          \
         uint8_t *slot = ring + (size_t)pos * slot_bytes;                            \
@@ -913,7 +930,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
         tbase += ntask_mod;                                                         \
         if (tbase >= STEP_CWARPS) tbase -= STEP_CWARPS;                             \
         __syncwarp();                                                               \
-        if (lane == 0) mbar_arrive(&empty_bar[pos]);                                \
+        if (lane == 0) mbar_arrive_a(empty0 + 8u * (uint32_t)pos);                  \
         if (++pos == nslots) { pos = 0; phase ^= 1u; }
     for (;;) {
         // ---- op boundary: signal what is done, stage what comes
@@ -936,7 +953,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                 IFB_SLOT_BEGIN()
                 if (t < ntask) {
                     const int h = u / tiles_per_head, tl = u - h * tiles_per_head;
-                    for (; t < ntask; t += STEP_CWARPS) att_task_any(P, slot, t, h, tl * P.att_pos, ctx, xst, sp, lane);
+                    for (; t < ntask; t += STEP_CWARPS) att_task_any(P, s_layers[layer], s_cos, s_sin, slot, t, h, tl * P.att_pos, ctx, xst, sp, lane);
                 }
                 IFB_SLOT_END()
             }
@@ -996,7 +1013,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
         } else {   // QKV, WO, W2: two adjacent rows per task, plain half outputs
             const int R = s.R, row_bytes_ = s.row_bytes;
             uint32_t *out32 = reinterpret_cast<uint32_t *>(kind == OPK_QKV ? P.qkv : P.ybuf);
-            const bool push = kind != OPK_QKV && tp > 1;
+            const bool push = kind != OPK_QKV && ll;
             // row-parallel partial sums go straight into every rank's exchange region over NVLink
             const uint32_t xidx = kind == OPK_WO ? (uint32_t)(2 * layer + 1) : (uint32_t)(2 * layer + 2);
             const size_t xoff = (size_t)P.x_recv + (size_t)(xidx & 1u) * P.x_recv_parity + (size_t)P.tp_rank * P.x_recv_rank;
@@ -1180,14 +1197,14 @@ int step_build(StepParams &P, int kv_dtype, int head_dtype, int sms) {
         if (ub > slot) slot = ub;
     }
     slot = (slot + 16 + 127) / 128 * 128;        // + 16: Q8_B32T2 block decode reads one word past its block
-    int64_t xb = att_layout(P.heads, P.kv_heads, P.hd, P.kv_q8 != 0).total;
+    int64_t xb = att_layout(P.heads, P.hd, P.kv_q8 != 0).total;
     for (int k = 0; k < OPK_COUNT; k++) {
         if (k == OPK_ATT) continue;
         const bool f16x = (k == OPK_HEAD ? head_dtype : wdt) == DT_F16;
         const int64_t b = f16x ? (int64_t)P.op[k].cx * 2 : (int64_t)P.op[k].nxb * 40;
         if (b > xb) xb = b;
     }
-    const int64_t merge_b = (int64_t)STEP_CTHREADS * 3 * 4;
+    const int64_t merge_b = (int64_t)(STEP_CTHREADS / (P.hd / 4)) * (P.hd + 4) * 4;
     if (merge_b > xb) xb = merge_b;
     xb = (xb + 127) / 128 * 128;
     const int64_t resid_b = ((int64_t)P.d * 2 + 127) / 128 * 128;

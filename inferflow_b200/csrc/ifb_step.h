@@ -59,6 +59,7 @@ struct StepParams {
     int max_inflight;            // bulk copies outstanding per SM (0: as many as the ring has slots)
     // tensor parallelism (size 1: unused) -- exchange regions as in ifb_model.cu
     int tp_size, tp_rank;
+    int local_ll;                // one GPU: wo / w2 outputs as flag-in-data words in this GPU's own exchange region
     void *peer[8];
     long long x_recv, x_recv_parity, x_recv_rank, x_logits;
     unsigned long long *trace;   // optional [n_ops][grid][4] globaltimer stamps
