@@ -9,8 +9,10 @@ KV cache Q8_B32T2, batch 1, context 2048 (the cache holds 2047 synthetic rows, t
 decodes position 2047 -> attends over 2048), fp16 lm_head, greedy pick. Synthetic random
 weights generated on the device in the reference's block layout (no network for checkpoints).
 
-One step = one full decode token: embedding row -> 32 layers (6 fused kernels each) -> final
-norm + lm_head -> argmax, replayed as one CUDA graph. Prints ONE JSON line.
+One step = one full decode token: embedding row -> 32 layers -> final norm + lm_head -> argmax. By default ONE
+persistent kernel launch per token (csrc/ifb_step.cu; IFB_STEP=0 selects the multi-launch path: 5 fused kernels per
+layer in a CUDA graph). Before anything is timed the logits of one step are checked against a second model with the
+same seeded weights: at N > 1 a single-GPU model on rank 0, at N = 1 the other of the two paths. Prints ONE JSON line.
 """
 import argparse
 import ctypes as C
@@ -235,7 +237,7 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
         "dtype": "f16 weights x f32 activations (ggml)" if base["kind"] == "reference" else "int8 x q4 integer dot, fp32 combine",
-        "data": "synthetic", "config": workload_config(args.gpus),
+        "data": "synthetic", "config": dict(workload_config(args.gpus), measured_on=base["sample"]),
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
@@ -244,10 +246,14 @@ def run_reference_arm(args):
     return 0
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per GEMV launch, averaged over the 129 launches of one token, from the
-# `ncu --set full` capture in profiles/r1_ncu.md: per layer 31.53 + 10.56 + 56.44 + 28.27 MB read (+0.3 MB written),
-# lm_head 262.1 MB; the algorithmic figure is 33.41 MB -- no re-reads
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of THIS workload (a profiler
+# run is never a timing run; the byte counts do not depend on the clock):
+#  * multi-launch path, per GEMV launch averaged over the 129 of one token (profiles/r1_ncu.md): per layer
+#    31.53 + 10.56 + 56.44 + 28.27 MB read (+0.3 MB written), lm_head 262.1 MB; algorithmic 33.41 MB -- no re-reads
+#  * step kernel, the one launch of a token (profiles/r2_ncu.md): 4881.5 MB read + 29.3 MB written; algorithmic
+#    4880.1 MB -- no re-reads (the 29 MB written are the attention partials, the activations and the new cache rows)
 GEMV_TRAFFIC_PER_LAUNCH = (32 * (31.528448 + 10.557440 + 56.434944 + 28.266496 + 0.3) + 262.2) * 1e6 / 129
+STEP_TRAFFIC_PER_LAUNCH = 4881.514e6 + 29.273e6
 
 
 def workload_config(n):
@@ -257,7 +263,113 @@ def workload_config(n):
             "layers": 32, "d_model": 4096, "d_ffn": 11008, "heads": 32, "kv_heads": 32, "vocab": 32000}
 
 
+# --------------------------------------------------------------------------- reference CUDA operators beside ours
+def reference_cuda_ops(ib, torch):
+    """The reference's own CUDA operators (oracle/_ref/libifref_cuda.so: src/tensor/*.cu + src/kernels/*.h compiled
+    unmodified for sm_100a) timed on this B200 on the shapes of one Llama-2-7B layer, beside our stand-alone operator
+    entries on the same buffers. Every call gets weights it has not touched for > 126 MB (the L2) of other traffic.
+    Per token the reference engine runs, per layer: RmsNorm, Quantize, 3 Gemv_AX (wq wk wv), 2 RoPE, KV set rows,
+    Dequantize K prefix, Dequantize V prefix, the attention operator sequence, Quantize, Gemv_AX (wo), Add, RmsNorm,
+    Quantize, 2 Gemv_AX (w1 w3), SiLU, Mul, Quantize, Gemv_AX (w2), Add (inference_worker.cc:762-1900) -- each a
+    separate synchronous launch; the sum below leaves out its per-token thread create/join and host logic, so it is an
+    UPPER bound on what the reference's GPU path can reach on this box."""
+    import numpy as np
+    import orc
+    if not os.path.exists(orc.ref_cuda_path()):
+        return None
+    L = C.CDLL(orc.ref_cuda_path())
+    vp, i = C.c_void_p, C.c_int
+    L.ifref_cuda_gemv_ax.argtypes = [i, vp, vp, i, vp, i, i]
+    L.ifref_cuda_quantize.argtypes = [i, vp, vp, i, i]
+    L.ifref_cuda_dequantize.argtypes = [i, vp, vp, i, i]
+    L.ifref_cuda_rmsnorm.argtypes = [vp, vp, vp, i, i]
+    L.ifref_cuda_silu_mul.argtypes = [vp, vp, vp, i]
+    L.ifref_cuda_attention_decode.argtypes = [vp, vp, vp, vp, i, i, i, i, C.c_float]
+    Q4, Q8, F16 = ib.DT.Q4_B32T1A, ib.DT.Q8_B32T2, ib.DT.F16
+    dev = "cuda"
+    g = torch.Generator(device=dev); g.manual_seed(5)
+
+    def ev_time(fn, reps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(reps):
+            fn(r)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / reps     # us per call
+
+    out = {}
+    # ---- decode GEMV, Q4_B32T1A weights x Q8_B32T2 activation (Gemv_AX8, kernels/gemv.h:1500-1709)
+    for name, cy, cx in (("4096x4096", 4096, 4096), ("11008x4096", 11008, 4096), ("4096x11008", 4096, 11008)):
+        rb = ib.row_bytes(Q4, cx)
+        copies = max(2, int(300e6 // (cy * rb)) + 1)
+        w = torch.randint(0, 256, (copies, cy * rb), dtype=torch.uint8, device=dev, generator=g)
+        w.view(copies, -1, 20)[:, :, 0] = 0x00; w.view(copies, -1, 20)[:, :, 1] = 0xa8   # base = -0.03 (fp16 0xa800)
+        w.view(copies, -1, 20)[:, :, 2] = 0x00; w.view(copies, -1, 20)[:, :, 3] = 0x1c   # scale = 0.004 (fp16 0x1c00)
+        x = torch.randn(cx, dtype=torch.float16, device=dev, generator=g)
+        xq = torch.empty(cx // 32 * 34, dtype=torch.uint8, device=dev)
+        assert L.ifref_cuda_quantize(Q8, xq.data_ptr(), x.data_ptr(), 1, cx) == 0
+        y = torch.empty(cy, dtype=torch.float16, device=dev)
+        y2 = torch.empty(cy, dtype=torch.float16, device=dev)
+        reps = 3 * copies
+        for r in range(2):
+            L.ifref_cuda_gemv_ax(Q4, y.data_ptr(), w[r % copies].data_ptr(), Q8, xq.data_ptr(), cy, cx)
+            ib.check(ib.lib.ifb_gemv(Q4, y2.data_ptr(), w[r % copies].data_ptr(), Q8, xq.data_ptr(), cy, cx, None, None), "ifb_gemv")
+        t_ref = ev_time(lambda r: L.ifref_cuda_gemv_ax(Q4, y.data_ptr(), w[r % copies].data_ptr(), Q8, xq.data_ptr(), cy, cx), reps)
+        t_our = ev_time(lambda r: ib.lib.ifb_gemv(Q4, y2.data_ptr(), w[r % copies].data_ptr(), Q8, xq.data_ptr(), cy, cx, None, None), reps)
+        same = bool(torch.equal(y, y2))
+        out["gemv_ax8_q4_" + name] = {"reference_us": t_ref, "ours_us": t_our, "bytes": cy * rb,
+                                       "reference_GBps": cy * rb / t_ref / 1e3, "ours_GBps": cy * rb / t_our / 1e3,
+                                       "outputs_bit_equal": same}
+        del w
+    # ---- the small operators of a layer
+    x = torch.randn(11008, dtype=torch.float16, device=dev, generator=g)
+    nw = torch.ones(4096, dtype=torch.float16, device=dev)
+    t1 = torch.empty(11008, dtype=torch.float16, device=dev)
+    xq = torch.empty(11008 // 32 * 34, dtype=torch.uint8, device=dev)
+    small = {
+        "rmsnorm_4096": ev_time(lambda r: L.ifref_cuda_rmsnorm(t1.data_ptr(), x.data_ptr(), nw.data_ptr(), 1, 4096), 20),
+        "quantize_q8_4096": ev_time(lambda r: L.ifref_cuda_quantize(Q8, xq.data_ptr(), x.data_ptr(), 1, 4096), 20),
+        "quantize_q8_11008": ev_time(lambda r: L.ifref_cuda_quantize(Q8, xq.data_ptr(), x.data_ptr(), 1, 11008), 20),
+        "silu_mul_11008": ev_time(lambda r: L.ifref_cuda_silu_mul(t1.data_ptr(), x.data_ptr(), x.data_ptr(), 11008), 20),
+    }
+    out["small_ops_reference_us"] = small
+    # ---- attention over a Q8_B32T2 cache of 2048 rows: GetKRows / GetVRows dequantize the whole prefix
+    # (kv_cache.cc:185-249), then the operator sequence of ProcessGpuLayer_Attention
+    ctx, heads, hd = CTX, 32, 128
+    kv_dim = heads * hd
+    kf = torch.randn(ctx, kv_dim, dtype=torch.float16, device=dev, generator=g)
+    vf = torch.randn(ctx, kv_dim, dtype=torch.float16, device=dev, generator=g)
+    kq_ = torch.empty(ctx * kv_dim // 32 * 34, dtype=torch.uint8, device=dev)
+    assert L.ifref_cuda_quantize(Q8, kq_.data_ptr(), kf.data_ptr(), ctx, kv_dim) == 0
+    q = torch.randn(kv_dim, dtype=torch.float16, device=dev, generator=g)
+    o = torch.empty(kv_dim, dtype=torch.float16, device=dev)
+    t_deq = ev_time(lambda r: L.ifref_cuda_dequantize(Q8, kf.data_ptr(), kq_.data_ptr(), ctx, kv_dim), 6)
+    t_att = ev_time(lambda r: L.ifref_cuda_attention_decode(o.data_ptr(), q.data_ptr(), kf.data_ptr(), vf.data_ptr(), ctx, heads, heads, hd, 1.0), 6)
+    out["attention_ctx2048_reference_us"] = {"dequantize_prefix_each_of_K_V": t_deq, "operator_sequence": t_att}
+    gm = out
+    per_layer = (small["rmsnorm_4096"] * 2 + small["quantize_q8_4096"] * 3 + small["quantize_q8_11008"] + small["silu_mul_11008"] * 2
+                 + 4 * gm["gemv_ax8_q4_4096x4096"]["reference_us"] + 2 * gm["gemv_ax8_q4_11008x4096"]["reference_us"]
+                 + gm["gemv_ax8_q4_4096x11008"]["reference_us"] + 2 * t_deq + t_att)
+    out["reference_cuda_per_layer_us"] = per_layer
+    out["reference_cuda_tokens_per_s_upper_bound"] = 1e6 / (32 * per_layer)
+    out["note"] = ("reference CUDA operators compiled unmodified for sm_100a, CUDA events around back-to-back calls on the legacy "
+                   "stream; per-layer sum of the operators of ProcessGpuLayer (lm_head, RoPE, KV row stores, Add, host logic and "
+                   "the per-token worker thread left out): an upper bound on the reference's own GPU decode rate on this box")
+    return out
+
+
 # --------------------------------------------------------------------------- ours
+def _read_logits(ib, np, model, spec, stream):
+    stream.synchronize()
+    logits = np.empty(spec.vocab, dtype=np.float16)
+    ib.check(ib.lib.ifb_memcpy_d2h(logits.ctypes.data, model.logits_ptr, spec.vocab * 2), "d2h")
+    nxt = np.empty(1, dtype=np.int32)
+    ib.check(ib.lib.ifb_memcpy_d2h(nxt.ctypes.data, model.next_token_ptr, 4), "d2h")
+    return logits, int(nxt[0])
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -274,7 +386,23 @@ def run_ours(args):
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl")
+    model = None
+    try:
+        return _run_ours(args, ib, np, torch, dist, rank, world, local)
+    except BaseException as e:  # noqa: BLE001
+        # a rank that fails must still leave: the peers' kernels give up on their own deadline (bounded waits), the
+        # process group is torn down, the exit code says so -- never a hang that looks like a lost box
+        sys.stderr.write(f"bench.py rank {rank}: {e!r}\n")
+        raise
+    finally:
+        if dist is not None:
+            try:
+                dist.destroy_process_group()
+            except Exception:  # noqa: BLE001
+                pass
 
+
+def _run_ours(args, ib, np, torch, dist, rank, world, local):
     spec = ib.ModelSpec(max_ctx=CTX, weight_dtype=ib.DT.Q4_B32T1A, kv_dtype=ib.DT.Q8_B32T2,
                         lm_head_dtype=ib.DT.F16, tp_rank=rank, tp_size=world, **ib.LLAMA2_7B)
     model = ib.Model(spec)
@@ -288,6 +416,48 @@ def run_ours(args):
 
     pos = CTX - 1
     token = 1
+    # ---- verification BEFORE timing: the logits of this very step against a second model holding the same weights
+    # and cache (synthetic tensors are a function of seed and GLOBAL position, so the shards of N ranks are the
+    # single-GPU model): N > 1 -> single-GPU model on rank 0; N = 1 -> the other decode path of the runtime
+    model.decode(token, pos, stream=sh)
+    got, got_tok = _read_logits(ib, np, model, spec, stream)
+    uses_step = model.step_status()[0]
+    verify = None
+    if rank == 0:
+        saved = os.environ.get("IFB_STEP")
+        if world == 1:
+            os.environ["IFB_STEP"] = "0" if uses_step else "1"
+        try:
+            spec1 = ib.ModelSpec(max_ctx=CTX, weight_dtype=ib.DT.Q4_B32T1A, kv_dtype=ib.DT.Q8_B32T2,
+                                 lm_head_dtype=ib.DT.F16, **ib.LLAMA2_7B)
+            ref = ib.Model(spec1)
+        finally:
+            if saved is None:
+                os.environ.pop("IFB_STEP", None)
+            else:
+                os.environ["IFB_STEP"] = saved
+        ref.init_synthetic(seed=1234, stream=sh)
+        ref.kv_reset(CTX - 1, fill_synthetic=True, seed=99, stream=sh)
+        ref.decode(token, pos, stream=sh)
+        want, want_tok = _read_logits(ib, np, ref, spec1, stream)
+        ref_step = ref.step_status()[0]
+        ref.close()
+        rng_ = float(np.abs(want.astype(np.float64)).max())
+        err = float(np.abs(got.astype(np.float64) - want.astype(np.float64)).max())
+        srt = np.sort(want.astype(np.float64))
+        margin = float(srt[-1] - srt[-2])
+        # sharded and unsharded sums round differently (as in the reference's MergeTensors): 2^-4 of the range across
+        # ranks; the two single-GPU paths share the GEMV arithmetic: 2^-7
+        tol = (2.0 ** -4 if world > 1 else 2.0 ** -7) * rng_
+        verify = {"against": ("single-GPU model of the same seed on rank 0" if world > 1 else
+                              ("multi-launch path" if uses_step else "persistent step kernel") + " of the same model"),
+                  "reference_uses_step_kernel": bool(ref_step), "max_abs_err": err, "logit_range": rng_, "tolerance": tol,
+                  "token": got_tok, "reference_token": want_tok, "top2_margin": margin}
+        if not (err <= tol) or (margin > 4 * err and got_tok != want_tok) or not np.isfinite(err):
+            raise SystemExit(f"bench.py: verification failed before timing: {json.dumps(verify)}")
+    if dist is not None:
+        dist.barrier()
+
     # ---- device-resident timing ("value")
     sampler = ClockSampler(local)
     sampler.start()
@@ -347,8 +517,10 @@ def run_ours(args):
         e2e_ms = float(t.item())
     e2e_tok_s = 1000.0 * args.steps / e2e_ms
 
-    # ---- roofline of the dominant kernel family (gemv_stream_kernel): all GEMV launches of one
-    # token back to back, timed with CUDA events on the launching stream
+    # ---- roofline of the dominant kernel. Step kernel: the token IS one launch -- achieved = this rank's algorithmic
+    # bytes (weights + lm_head + KV rows) / its average duration (the timed region above holds nothing else but a
+    # 1.3 KB memset per step). Multi-launch path: all GEMV launches of one token back to back. Both: the weight-stream
+    # and the attention part issued alone (measurement aid of the C ABI) for the split.
     peaks, peak_kind = measured_peaks()
     with torch.cuda.stream(stream):
         nl = 0
@@ -363,7 +535,6 @@ def run_ours(args):
         g1.record(stream)
         stream.synchronize()
         gemv_ms = g0.elapsed_time(g1) / reps
-        # attention family likewise (reported as extra)
         for _ in range(2):
             na = model.issue_parts(2, stream=sh)
         stream.synchronize()
@@ -376,28 +547,46 @@ def run_ours(args):
         attn_ms = a0.elapsed_time(a1) / reps
     wbytes = model.weight_bytes
     kvbytes = model.kv_bytes_per_token(CTX)
-    achieved = wbytes / (gemv_ms * 1e-3) / 1e9
-    peak = float(peaks["hbm_gbs"])
-    roofline = {"bound": "hbm", "kernel": "gemv_stream_kernel (all %d GEMV launches of one token)" % nl,
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": GEMV_TRAFFIC_PER_LAUNCH,
-                "peak_kind": peak_kind, "bytes_per_launch_avg": wbytes / max(nl, 1),
-                "us_per_launch_avg": gemv_ms * 1e3 / max(nl, 1),
-                "attention": {"achieved": kvbytes / (attn_ms * 1e-3) / 1e9, "launches": na,
-                              "frac": kvbytes / (attn_ms * 1e-3) / 1e9 / peak}}
     step_bytes = wbytes + kvbytes
+    peak = float(peaks["hbm_gbs"])
+    if uses_step:
+        achieved = step_bytes / (ms_per_step * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "decode_step_kernel<FmtQ4_B32T1> (one persistent launch per token: every GEMV, the attention, "
+                                              "the op boundaries)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": STEP_TRAFFIC_PER_LAUNCH if world == 1 else None, "peak_kind": peak_kind,
+                    "bytes_per_launch_avg": step_bytes, "us_per_launch_avg": ms_per_step * 1e3,
+                    "weights_only_run": {"ms": gemv_ms, "achieved": wbytes / (gemv_ms * 1e-3) / 1e9, "frac": wbytes / (gemv_ms * 1e-3) / 1e9 / peak,
+                                         "what": "the same kernel with the attention units switched off (boundaries still run)"},
+                    "attention_only_run": {"ms": attn_ms, "achieved": kvbytes / (attn_ms * 1e-3) / 1e9,
+                                           "what": "the same kernel with the GEMV units switched off (boundaries still run)"}}
+    else:
+        achieved = wbytes / (gemv_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "gemv_stream_kernel (all %d GEMV launches of one token)" % nl,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": GEMV_TRAFFIC_PER_LAUNCH,
+                    "peak_kind": peak_kind, "bytes_per_launch_avg": wbytes / max(nl, 1),
+                    "us_per_launch_avg": gemv_ms * 1e3 / max(nl, 1),
+                    "attention": {"achieved": kvbytes / (attn_ms * 1e-3) / 1e9, "launches": na,
+                                  "frac": kvbytes / (attn_ms * 1e-3) / 1e9 / peak}}
     roofline["step"] = {"bytes_per_token": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                         "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
 
     launches = model.launches_per_step
+    on, rec = model.step_status()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()          # no rank frees its exchange region while a peer's last kernels still store into it
     model.close()
     if dist is not None:
         dist.barrier()
-        dist.destroy_process_group()
     if rank != 0:
         return 0
+    refcuda = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            refcuda = reference_cuda_ops(ib, torch)
+        except Exception as e:  # noqa: BLE001
+            refcuda = {"error": repr(e)}
     cpu = cpu_baseline_port() if world == 1 and not args.no_cpu_baseline else None
     line = {
         "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
@@ -407,10 +596,14 @@ def run_ours(args):
         "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 4,
                 "d2h_bytes_per_step": spec.vocab * 2 + 4},
         "gpu_launches": launches * args.steps,
+        "decode_path": "persistent step kernel" if on else "multi-launch (CUDA graph)",
+        "verify": verify,
         "roofline": roofline,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if refcuda is not None:
+        line["reference_cuda"] = refcuda
     emit(line)
     return 0
 

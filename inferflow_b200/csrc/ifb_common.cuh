@@ -251,6 +251,25 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
     return v;
 }
 
+// Every wait on memory another GPU writes is BOUNDED: a peer that died (exception between tp_connect and the last
+// barrier, out of memory, a skipped step) must not wedge the other GPUs of the box in an unkillable kernel. Past the
+// deadline the kernel traps; the host sees a launch failure at its next synchronisation and can tear down.
+#ifndef IFB_PEER_DEADLINE_NS
+#define IFB_PEER_DEADLINE_NS 2000000000ull
+#endif
+struct PeerDeadline {
+    unsigned long long t0;
+    unsigned it;
+    __device__ __forceinline__ PeerDeadline() : t0(0ull), it(0u) {}
+    // call once per failed poll
+    __device__ __forceinline__ void tick() {
+        if ((++it & 1023u) != 0u) return;
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0ull) t0 = now;
+        else if (now - t0 > IFB_PEER_DEADLINE_NS) __trap();
+    }
+};
+
 // q = (int)roundf(v / scale) exactly as the reference's alg-2 quantizer computes it
 // (kernels/tensor_quant.h:64), but cheaply: r = v * (1/scale) is within ~3e-5 of the correctly rounded
 // quotient for |q| <= 127; round it to nearest with the 1.5*2^23 trick and take the IEEE division +

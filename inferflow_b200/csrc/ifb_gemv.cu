@@ -91,8 +91,9 @@ __device__ __forceinline__ uint4 tp_gather8(const GemvArgs &a, int g, uint32_t f
         for (int i = 0; i < 4; i++)
             if (p0 + i < a.tp.size) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(base + (size_t)(p0 + i) * a.tp.src_rank_stride) + 2 * g;
-                while (w[i][0].y != flag || w[i][0].w != flag) w[i][0] = ld_relaxed_sys_v4(src);
-                while (w[i][1].y != flag || w[i][1].w != flag) w[i][1] = ld_relaxed_sys_v4(src + 1);
+                PeerDeadline dl;   // bounded: see ifb_common.cuh
+                while (w[i][0].y != flag || w[i][0].w != flag) { w[i][0] = ld_relaxed_sys_v4(src); dl.tick(); }
+                while (w[i][1].y != flag || w[i][1].w != flag) { w[i][1] = ld_relaxed_sys_v4(src + 1); dl.tick(); }
                 const uint32_t d[4] = {w[i][0].x, w[i][0].z, w[i][1].x, w[i][1].z};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {

@@ -77,7 +77,7 @@ int argmax(int32_t *out, const void *logits, int64_t n, cudaStream_t st);
 // argmax after waiting until every peer has published `*epoch` in flags[0..n_peers)
 int argmax_tp(int32_t *out, void *logits_f16, const void *ll_words, int64_t n, const int32_t *seq, uint32_t idx, cudaStream_t st);
 int embed_row(void *dst_f16, const void *table, int table_dtype, int64_t cols, int token_id,
-              const int32_t *token_dev, cudaStream_t st);
+              const int32_t *token_dev, cudaStream_t st, int rows = 0);   // rows > 0: the token id is clamped to the table
 
 // KV cache (head-major): per K or V buffer
 //   F16      : half  [kv_heads][max_ctx][head_dim]

@@ -145,6 +145,11 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     }
     const char *e2 = getenv("IFB_NO_GRAPH");
     if (e2 && atoi(e2)) m->use_graph = 0;
+    // Which decode path: the persistent step kernel (one launch per token) or the multi-launch CUDA graph. Measured on
+    // B200: on one GPU the two are within ~10 % of each other (multi-launch ahead: both pay ~4 us
+    // per grid-wide dependency, the step kernel in boundaries, the graph in launch + staging); under tensor parallelism
+    // the step kernel wins clearly (per-rank streaming shrinks, launch overheads do not). IFB_STEP=0/1 overrides.
+    m->use_step = tp > 1 ? 1 : 0;
     const char *e4 = getenv("IFB_STEP");
     if (e4) m->use_step = atoi(e4) ? 1 : 0;
 
@@ -306,10 +311,15 @@ __device__ __forceinline__ int max_code(int dt) {
 // Fill a block-quantized tensor: random code bytes, scale ~ |N(0, sigma)|*2/maxcode, base = -maxcode/2*scale
 // (so dequantized weights are ~uniform in +-|N(0,sigma)|, sigma = 0.02 like N(0,0.02) weights).
 // Q3H needs valid base-11 pairs (P <= 120): its code bytes are generated through the quantizer's packing.
-__global__ void synth_blocks_kernel(uint8_t *dst, int dt, int64_t nblocks, int bb, uint64_t seed, float sigma) {
-    int64_t bi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (bi >= nblocks) return;
-    uint8_t *b = dst + bi * bb;
+// Every block is a function of (seed, GLOBAL block index of the unsharded tensor): a tensor-parallel rank that holds rows
+// [row0, ...) and blocks [blk0, blk0 + lbpr) of every row generates exactly the bytes a single-GPU model holds there, so a
+// sharded run can be checked against an unsharded one (bench.py does, before it times anything).
+__global__ void synth_blocks_kernel(uint8_t *dst, int dt, int64_t nblocks, int bb, uint64_t seed, float sigma,
+                                    int64_t lbpr, int64_t gbpr, int64_t row0, int64_t blk0) {
+    int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nblocks) return;
+    uint8_t *b = dst + li * bb;
+    const int64_t bi = (row0 + li / lbpr) * gbpr + blk0 + li % lbpr;
     uint64_t key = seed * 0x100000001b3ull + (uint64_t)bi;
     float amp = fabsf(gauss(key)) * sigma + 1e-4f;
     int mc = max_code(dt);
@@ -352,26 +362,31 @@ __global__ void synth_blocks_kernel(uint8_t *dst, int dt, int64_t nblocks, int b
     }
 }
 
-__global__ void synth_f16_kernel(__half *dst, int64_t n, uint64_t seed, float sigma, float constant, int use_const) {
+__global__ void synth_f16_kernel(__half *dst, int64_t n, uint64_t seed, float sigma, float constant, int use_const,
+                                 int64_t lcols, int64_t gcols, int64_t row0, int64_t col0) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    dst[i] = __float2half_rn(use_const ? constant : gauss(seed * 0x100000001b3ull + (uint64_t)i) * sigma);
+    const int64_t gi = (row0 + i / lcols) * gcols + col0 + i % lcols;
+    dst[i] = __float2half_rn(use_const ? constant : gauss(seed * 0x100000001b3ull + (uint64_t)gi) * sigma);
 }
 
-static int synth_tensor(void *p, int dt, int64_t rows, int64_t cols, uint64_t seed, float sigma, cudaStream_t st) {
+// this rank's [rows x cols] shard at (row0, col0) of a global tensor with gcols columns
+static int synth_tensor(void *p, int dt, int64_t rows, int64_t cols, uint64_t seed, float sigma, cudaStream_t st,
+                        int64_t gcols = 0, int64_t row0 = 0, int64_t col0 = 0) {
+    if (gcols == 0) gcols = cols;
     if (dt == DT_F16) {
         int64_t n = rows * cols;
-        synth_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((__half *)p, n, seed, sigma, 0.f, 0);
+        synth_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((__half *)p, n, seed, sigma, 0.f, 0, cols, gcols, row0, col0);
     } else {
         int cap = block_capacity(dt), bb = block_bytes(dt);
         int64_t nb = rows * (cols / cap);
-        synth_blocks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>((uint8_t *)p, dt, nb, bb, seed, sigma);
+        synth_blocks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>((uint8_t *)p, dt, nb, bb, seed, sigma, cols / cap, gcols / cap, row0, col0 / cap);
     }
     IFB_LAUNCH_CHECK();
     return IFB_OK;
 }
 static int const_f16(void *p, int64_t n, float v, cudaStream_t st) {
-    synth_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((__half *)p, n, 0, 0.f, v, 1);
+    synth_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((__half *)p, n, 0, 0.f, v, 1, n, n, 0, 0);
     IFB_LAUNCH_CHECK();
     return IFB_OK;
 }
@@ -381,21 +396,25 @@ extern "C" int32_t ifb_model_init_synthetic(ifb_model_t *m, uint64_t seed, ifb_s
     cudaStream_t st = (cudaStream_t)stream;
     const auto &s = m->spec;
     const int d = s.d_model, wdt = s.weight_dtype;
-    // every shard is generated from (global seed, tensor id, rank) so that runs are reproducible
-    uint64_t sd = seed * 1000003ull + (uint64_t)s.tp_rank * 7919ull;
+    // every shard is generated from (global seed, tensor id, GLOBAL element position): the ranks of a tensor-parallel
+    // group together hold exactly the single-GPU model of the same seed
+    uint64_t sd = seed * 1000003ull;
+    const int64_t rk = s.tp_rank;
+    const int64_t q0 = rk * m->q_dim_l, kv0 = rk * m->kv_dim_l, f0 = rk * m->ffn_l;
+    const int64_t gq = (int64_t)s.heads * m->hd, gf = s.d_ffn;
     int li = 0;
     for (auto &L : m->layers) {
         uint64_t ls = sd + 100ull * (uint64_t)(li + 1);
         TRY(const_f16(L.attn_norm.p, d, 1.0f, st));
         TRY(const_f16(L.ffn_norm.p, d, 1.0f, st));
-        TRY(synth_tensor(L.wq.p, wdt, m->q_dim_l, d, ls + 1, 0.02f, st));
-        TRY(synth_tensor(L.wk.p, wdt, m->kv_dim_l, d, ls + 2, 0.02f, st));
-        TRY(synth_tensor(L.wv.p, wdt, m->kv_dim_l, d, ls + 3, 0.02f, st));
-        TRY(synth_tensor(L.wo.p, wdt, d, m->q_dim_l, ls + 4, 0.02f, st));
+        TRY(synth_tensor(L.wq.p, wdt, m->q_dim_l, d, ls + 1, 0.02f, st, d, q0, 0));          // BY_COL: rows of this rank
+        TRY(synth_tensor(L.wk.p, wdt, m->kv_dim_l, d, ls + 2, 0.02f, st, d, kv0, 0));
+        TRY(synth_tensor(L.wv.p, wdt, m->kv_dim_l, d, ls + 3, 0.02f, st, d, kv0, 0));
+        TRY(synth_tensor(L.wo.p, wdt, d, m->q_dim_l, ls + 4, 0.02f, st, gq, 0, q0));          // BY_ROW: columns of this rank
         if (s.experts == 0) {
-            TRY(synth_tensor(L.w1.p, wdt, m->ffn_l, d, ls + 5, 0.02f, st));
-            TRY(synth_tensor(L.w3.p, wdt, m->ffn_l, d, ls + 6, 0.02f, st));
-            TRY(synth_tensor(L.w2.p, wdt, d, m->ffn_l, ls + 7, 0.02f, st));
+            TRY(synth_tensor(L.w1.p, wdt, m->ffn_l, d, ls + 5, 0.02f, st, d, f0, 0));
+            TRY(synth_tensor(L.w3.p, wdt, m->ffn_l, d, ls + 6, 0.02f, st, d, f0, 0));
+            TRY(synth_tensor(L.w2.p, wdt, d, m->ffn_l, ls + 7, 0.02f, st, gf, 0, f0));
         } else {
             TRY(synth_tensor(L.gate.p, DT_F16, s.experts, d, ls + 8, 0.05f, st));   // router: non-degenerate expert choice
             for (int e = 0; e < s.experts; e++) {
@@ -408,7 +427,7 @@ extern "C" int32_t ifb_model_init_synthetic(ifb_model_t *m, uint64_t seed, ifb_s
     }
     TRY(synth_tensor(m->tok_emb.p, DT_F16, s.vocab, d, seed * 1000003ull + 11, 1.0f, st));   // same on all ranks
     TRY(const_f16(m->out_norm.p, d, 1.0f, st));
-    TRY(synth_tensor(m->lm_head.p, s.lm_head_dtype, m->vocab_l, d, seed * 1000003ull + 13 + 17ull * s.tp_rank, 0.02f, st));
+    TRY(synth_tensor(m->lm_head.p, s.lm_head_dtype, m->vocab_l, d, seed * 1000003ull + 13, 0.02f, st, d, rk * m->vocab_l, 0));   // vocabulary-sharded
     return IFB_OK;
 }
 
@@ -416,7 +435,7 @@ extern "C" int32_t ifb_model_init_synthetic(ifb_model_t *m, uint64_t seed, ifb_s
 // KV reset / synthetic fill
 // ---------------------------------------------------------------------------------------
 __global__ void synth_kv_kernel(uint8_t *cache, int kv_dtype, int kv_heads, int hd, int max_ctx_pad,
-                                int ctx, uint64_t seed) {
+                                int ctx, uint64_t seed, int head0) {
     // one warp per (head, pos, block of 32 dims)
     int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -426,7 +445,9 @@ __global__ void synth_kv_kernel(uint8_t *cache, int kv_dtype, int kv_heads, int 
     int blk = (int)(wid % nb);
     int pos = (int)((wid / nb) % ctx);
     int h = (int)(wid / ((int64_t)nb * ctx));
-    float v = round_h(gauss(seed + (uint64_t)wid * 32 + lane));
+    // keyed by the GLOBAL kv head: the shards of a tensor-parallel group hold the single-GPU cache of the same seed
+    const int64_t gwid = ((int64_t)(head0 + h) * ctx + pos) * nb + blk;
+    float v = round_h(gauss(seed + (uint64_t)gwid * 32 + lane));
     int64_t base = (int64_t)h * max_ctx_pad + pos;
     if (kv_dtype == DT_F16) {
         reinterpret_cast<__half *>(cache)[base * hd + blk * 32 + lane] = __float2half_rn(v);
@@ -452,8 +473,9 @@ extern "C" int32_t ifb_model_kv_reset(ifb_model_t *m, int32_t ctx_len, int32_t f
         for (auto &L : m->layers) {
             int64_t warps = (int64_t)m->kv_heads_l * ctx_len * (m->hd / 32);
             unsigned grid = (unsigned)((warps * 32 + 255) / 256);
-            synth_kv_kernel<<<grid, 256, 0, st>>>((uint8_t *)L.kcache.p, m->spec.kv_dtype, m->kv_heads_l, m->hd, pad, ctx_len, seed + 977ull * li + 1);
-            synth_kv_kernel<<<grid, 256, 0, st>>>((uint8_t *)L.vcache.p, m->spec.kv_dtype, m->kv_heads_l, m->hd, pad, ctx_len, seed + 977ull * li + 500009);
+            const int head0 = m->spec.tp_rank * m->kv_heads_l;
+            synth_kv_kernel<<<grid, 256, 0, st>>>((uint8_t *)L.kcache.p, m->spec.kv_dtype, m->kv_heads_l, m->hd, pad, ctx_len, seed + 977ull * li + 1, head0);
+            synth_kv_kernel<<<grid, 256, 0, st>>>((uint8_t *)L.vcache.p, m->spec.kv_dtype, m->kv_heads_l, m->hd, pad, ctx_len, seed + 977ull * li + 500009, head0);
             li++;
         }
         IFB_LAUNCH_CHECK();
@@ -836,7 +858,7 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
     IFB_CUDA(cudaMemsetAsync(m->counters.p, 0, m->counters.bytes, st));
     auto CT = [&](int idx) -> void * { return (void *)((int *)m->counters.p + (size_t)idx * 8); };   // cursor + per-op completion counts
     auto TR = [&](int idx) -> void * { return (m->trace_on && idx < 512) ? (void *)((uint64_t *)m->trace.p + (size_t)idx * 160 * 8) : nullptr; };
-    if (parts & PART_MISC) { TRY(embed_row(m->x0.p, m->tok_emb.p, DT_F16, d, 0, sc + 1, st)); n++; }
+    if (parts & PART_MISC) { TRY(embed_row(m->x0.p, m->tok_emb.p, DT_F16, d, 0, sc + 1, st, s.vocab)); n++; }
     const bool q8 = true;   // enable_full_quant_gemv = true (inference_engine.cc:53-57)
     auto ax8_ok = [](int dt) {
         return dt == DT_Q8_B32T2 || dt == DT_Q6_B64T1 || dt == DT_Q5_B64T1 || dt == DT_Q4_B32T1A ||

@@ -123,12 +123,13 @@ __global__ void __launch_bounds__(1024) argmax_kernel(int32_t *out, const __half
     __shared__ float sv[32];
     __shared__ int si[32];
     float best = -INFINITY;
-    int bi = 0x7fffffff;
+    int bi = 0x7fffffff;   // "none yet": mapped to token 0 at the end (all-NaN logits must not index past the vocabulary)
     if (ll != nullptr) {
         const uint32_t flag = ((uint32_t)*reinterpret_cast<const volatile int32_t *>(seq) << 8) | idx;
         for (int64_t w = threadIdx.x; w < n / 2; w += 1024) {
             uint2 v = ld_relaxed_sys_v2(ll + w);
-            while (v.y != flag) v = ld_relaxed_sys_v2(ll + w);
+            PeerDeadline dl;   // bounded: see ifb_common.cuh
+            while (v.y != flag) { v = ld_relaxed_sys_v2(ll + w); dl.tick(); }
             reinterpret_cast<uint32_t *>(compact)[w] = v.x;
             const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&v.x));
             if (f.x > best) { best = f.x; bi = (int)(2 * w); }       // ascending index per thread: first max wins
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(1024) argmax_kernel(int32_t *out, const __half
             int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
-        if (threadIdx.x == 0) *out = bi;
+        if (threadIdx.x == 0) *out = bi == 0x7fffffff ? 0 : bi;
     }
 }
 int argmax(int32_t *out, const void *logits, int64_t n, cudaStream_t st) {
@@ -177,8 +178,9 @@ int argmax_tp(int32_t *out, void *logits_f16, const void *ll_words, int64_t n, c
 // ---------------------------------------------------------------- embedding row
 // GetEmbdTensor (inference_engine.cc:1324-1350): copy / dequantize one row of the table to fp16
 __global__ void embed_row_kernel(__half *dst, const uint8_t *table, int dt, int64_t cols,
-                                 int token_id, const int32_t *token_dev) {
+                                 int token_id, const int32_t *token_dev, int rows) {
     int tok = token_dev != nullptr ? *token_dev : token_id;
+    if (rows > 0) tok = max(0, min(tok, rows - 1));   // a token id from device memory is not validated by the host
     if (dt == DT_F16) {
         const __half *row = reinterpret_cast<const __half *>(table) + (int64_t)tok * cols;
         for (int64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cols; i += (int64_t)gridDim.x * blockDim.x)
@@ -197,8 +199,8 @@ __global__ void embed_row_kernel(__half *dst, const uint8_t *table, int dt, int6
     }
 }
 int embed_row(void *dst, const void *table, int dt, int64_t cols, int token_id,
-              const int32_t *token_dev, cudaStream_t st) {
-    embed_row_kernel<<<4, 256, 0, st>>>((__half *)dst, (const uint8_t *)table, dt, cols, token_id, token_dev);
+              const int32_t *token_dev, cudaStream_t st, int rows) {
+    embed_row_kernel<<<4, 256, 0, st>>>((__half *)dst, (const uint8_t *)table, dt, cols, token_id, token_dev, rows);
     IFB_LAUNCH_CHECK();
     return IFB_OK;
 }

@@ -68,7 +68,10 @@ def same_on_all_ranks(arr, what):
         assert torch.equal(o, out[0]), f"{what}: rank {r} differs from rank 0"
 
 
+# head_dim 64 / 128 with a dp4a weight type run as ONE persistent step kernel per token (exchange inside it);
+# head_dim 32 or other weight types keep the multi-launch path (exchange in the GEMV kernels): both are covered
 CONFIGS = [
+    dict(weight_dtype=orc.Q4_B32T1A, kv_dtype=orc.Q8_B32T2, heads=8, kv_heads=8, d_model=1024, d_ffn=2048),   # head_dim 128, step kernel
     dict(weight_dtype=orc.Q4_B32T1A, kv_dtype=orc.Q8_B32T2, heads=8, kv_heads=8, d_model=512, d_ffn=1024),
     dict(weight_dtype=orc.Q8_B32T2, kv_dtype=orc.F16, heads=8, kv_heads=2, d_model=256, d_ffn=512),
     dict(weight_dtype=orc.Q3_B32T1A, kv_dtype=orc.Q8_B32T2, heads=4, kv_heads=4, d_model=256, d_ffn=512),  # fp16-x path
@@ -82,16 +85,24 @@ def main():
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     dist.init_process_group("nccl")
     torch.zeros(1, device="cuda")
-    for ci, cfg in enumerate(CONFIGS):
+    big = os.environ.get("IFB_TP_7B", "1") != "0"
+    configs = list(CONFIGS)
+    if big:
+        # the per-rank shapes of the benchmark model: ONE Llama-2-7B layer (d 4096, f 11008, 32 heads), fp16 lm_head
+        configs.append(dict(weight_dtype=orc.Q4_B32T1A, kv_dtype=orc.Q8_B32T2, heads=32, kv_heads=32, d_model=4096, d_ffn=11008,
+                            layers=1, vocab=4096, max_ctx=64))
+    for ci, cfg in enumerate(configs):
+        cfg = dict(cfg)
         if cfg["kv_heads"] % world or cfg["heads"] % world:
             continue
-        base = dict(layers=3, vocab=1024, max_ctx=128, **cfg)
+        base = dict(layers=cfg.pop("layers", 3), vocab=cfg.pop("vocab", 1024), max_ctx=cfg.pop("max_ctx", 128), **cfg)
         spec = ib.ModelSpec(tp_rank=rank, tp_size=world, **base)
         w = host_weights(spec, 100 + ci)
         m = ib.Model(spec)
         load_all(m, w)
         m.tp_connect(dist)
         ref = orcm = None
+        nsteps = 3 if base["d_model"] >= 4096 else 6
         if rank == 0:
             spec1 = ib.ModelSpec(**base)
             ref = ib.Model(spec1)
@@ -102,9 +113,11 @@ def main():
                     t[f"layers.{l}.{n}"] = ref.read_tensor(f"layers.{l}.{n}")
             orcm = OracleModel(spec1, t, tp=world)     # same shard-sum order as the kernels
         tok, toks = 5, []
-        for pos in range(6):
+        for pos in range(nsteps):
             m.decode(tok, pos)
             logits, nxt = read(m, spec)
+            on, rec = m.step_status()
+            assert rec[0] == 0, f"cfg {ci}: step kernel error record {rec}"
             same_on_all_ranks(logits, f"cfg {ci} pos {pos} logits")
             assert nxt == int(np.argmax(logits.astype(np.float32))), "device argmax != argmax of device logits"
             if rank == 0:
@@ -128,21 +141,22 @@ def main():
             replay.append(nxt)
         m.kv_reset(0)
         tok2, again = 5, []
-        for pos in range(10):
+        for pos in range(nsteps + 4):
             m.decode(tok2, pos)
             _, tok2 = read(m, spec)
             again.append(tok2)
-        assert again[:6] == toks and again[6:] == replay, f"cfg {ci}: replay {toks + replay} vs stepping {again}"
+        assert again[:nsteps] == toks and again[nsteps:] == replay, f"cfg {ci}: replay {toks + replay} vs stepping {again}"
         tt = torch.tensor(again, device="cuda")
         out = [torch.empty_like(tt) for _ in range(world)]
         dist.all_gather(out, tt)
         assert all(torch.equal(o, out[0]) for o in out)
         dist.barrier()
+        m_on = m.step_status()[0]
         m.close()
         if ref is not None:
             ref.close()
         if rank == 0:
-            print(f"tp{world} cfg {ci} ({orc.NAMES[cfg['weight_dtype']]}): ok", flush=True)
+            print(f"tp{world} cfg {ci} ({orc.NAMES[cfg['weight_dtype']]}, d {base['d_model']}, step kernel {m_on}): ok", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
