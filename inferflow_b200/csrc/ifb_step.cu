@@ -153,6 +153,139 @@ __device__ __forceinline__ unsigned long long amax_key(float v, int idx) {
 }
 
 // ---------------------------------------------------------------------------------------
+// flag-in-data vectors: every 8-byte word is {two fp16 values, 32-bit flag}; a word is valid for (step, tag) when its
+// flag equals (step sequence number << 8 | tag). 8-byte stores are atomic: the writer needs no fence, the reader polls
+// the words it needs -- the data IS the signal (one L2 round trip where a completion count costs three: the writer's
+// release add, the reader's poll, then the load).
+// ---------------------------------------------------------------------------------------
+// 8 consecutive fp16 values = words 4g..4g+3 of `words`, polled until valid
+// (poll = false: a partial issue -- measurement aid -- in which nobody writes the words: take what is there)
+__device__ __forceinline__ uint4 ll_load8(const uint4 *words, int g, uint32_t flag, const StepParams &P, int op, bool poll = true) {
+    const uint4 *src = words + 2 * g;
+    uint4 w0 = ld_relaxed_sys_v4(src), w1 = ld_relaxed_sys_v4(src + 1);
+    if (poll && (w0.y != flag || w0.w != flag || w1.y != flag || w1.w != flag)) {
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned it = 0;
+        while (w0.y != flag || w0.w != flag || w1.y != flag || w1.w != flag) {
+            w0 = ld_relaxed_sys_v4(src);
+            w1 = ld_relaxed_sys_v4(src + 1);
+            if ((++it & 255u) == 0u && globaltimer_ns() - t0 > P.timeout_ns) step_abort(P, STEP_ERR_PEER, op, g);
+        }
+    }
+    return make_uint4(w0.x, w0.z, w1.x, w1.z);
+}
+
+// Staging of a GEMV input from values that arrive in REGISTERS (load(g) -> the 8 fp16 values of group g, already final):
+// [RMSNorm with the sum of squares taken from the registers] -> Q8_B32T2 quantization -> the staged layout. Two
+// barriers (sum of squares, done) and no shared-memory round trip of the vector. Bit-for-bit the arithmetic of
+// stage_x_q8 (ifb_gemv_dev.cuh). A thread owns groups tid, tid + 480, tid + 960 of a round; vectors with a norm fit
+// one round (cx <= 11520, checked when the plan is built).
+template <bool XSPLIT, class LoadF>
+__device__ __forceinline__ void stage_fused_q8(const StepOpShape &s, const __half *norm_w, float eps, uint8_t *xst, float *red,
+                                               int tid, LoadF load) {
+    constexpr int NT = STEP_CTHREADS, KPT = 3;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ng = s.cx >> 3;
+    uint8_t *xlo = xst, *xhi = xst + (size_t)s.nxb * 16;
+    float2 *xs = reinterpret_cast<float2 *>(xst + (size_t)s.nxb * 32);
+    const bool norm = norm_w != nullptr, vec4 = s.vec4 != 0;
+    const uint4 *w4 = reinterpret_cast<const uint4 *>(norm_w);
+    float rs = 1.f;
+    for (int g0 = 0; g0 < ng; g0 += NT * KPT) {
+        const int ga = g0 + tid, gb = ga + NT, gc = gb + NT;
+        uint4 wv0 = make_uint4(0, 0, 0, 0), wv1 = wv0, wv2 = wv0, xv0 = wv0, xv1 = wv0, xv2 = wv0;
+        if (norm) {   // the norm weights do not depend on the previous op: their round trip runs under the wait for x
+            if (ga < ng) wv0 = w4[ga];
+            if (gb < ng) wv1 = w4[gb];
+            if (gc < ng) wv2 = w4[gc];
+        }
+        if (ga < ng) xv0 = load(ga);
+        if (gb < ng) xv1 = load(gb);
+        if (gc < ng) xv2 = load(gc);
+        if (norm) {
+            // Tensor_RmsNorm_Kernel (unary_tensor_opr.h:217): scale = 1/sqrt(mean(x^2) + eps)
+            float ss = 0.f;
+            const uint4 xs3[3] = {xv0, xv1, xv2};
+#pragma unroll
+            for (int k = 0; k < KPT; k++) {
+                const __half2 *h = reinterpret_cast<const __half2 *>(&xs3[k]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float2 f = __half22float2(h[i]);
+                    ss = fmaf(f.x, f.x, ss);
+                    ss = fmaf(f.y, f.y, ss);
+                }
+            }
+            ss = warp_sum(ss);
+            if (lane == 0) red[warp] = ss;
+            named_bar_sync(BAR_CONSUMERS, NT);
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < STEP_CWARPS; i++) t += red[i];
+            rs = 1.0f / sqrtf(t / (float)s.cx + eps);
+        }
+#pragma unroll 1
+        for (int k = 0; k < KPT; k++) {
+            const int g = g0 + k * NT + tid;   // a quad of lanes shares one block
+            if (g0 + k * NT + warp * 32 >= ng) break;   // warp-uniform: nothing left for this warp
+            const uint4 xk = k == 0 ? xv0 : (k == 1 ? xv1 : xv2);
+            const uint4 wk = k == 0 ? wv0 : (k == 1 ? wv1 : wv2);
+            float v[8];
+            {
+                const __half2 *h = reinterpret_cast<const __half2 *>(&xk);
+                const __half2 *hw = reinterpret_cast<const __half2 *>(&wk);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    float2 f = __half22float2(h[i]);
+                    if (norm) {  // v = x*scale*(multi_base + w), stored as half by the reference's RmsNorm (multi_base 0)
+                        const float2 fw = __half22float2(hw[i]);
+                        f.x = round_h(f.x * rs * (0.f + fw.x));
+                        f.y = round_h(f.y * rs * (0.f + fw.y));
+                    }
+                    v[2 * i] = f.x;
+                    v[2 * i + 1] = f.y;
+                }
+            }
+            float m = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) m = fmaxf(m, fabsf(v[i]));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            const float scale = m / 127.0f;
+            const bool dead = scale <= 0.000001f;
+            const float inv = dead ? 0.f : __frcp_rn(scale);
+            int q[8], qs = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int t = dead ? 0 : q8_round_div(v[i], scale, inv);
+                q[i] = min(max(t, -128), 127);
+                qs += q[i];
+            }
+            qs += __shfl_xor_sync(0xffffffffu, qs, 1);
+            qs += __shfl_xor_sync(0xffffffffu, qs, 2);
+            if (g < ng) {
+                uint32_t w0, w1;
+                if (XSPLIT) {
+                    w0 = (q[0] & 0xff) | ((q[2] & 0xff) << 8) | ((q[4] & 0xff) << 16) | ((uint32_t)(q[6] & 0xff) << 24);
+                    w1 = (q[1] & 0xff) | ((q[3] & 0xff) << 8) | ((q[5] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
+                } else {
+                    w0 = (q[0] & 0xff) | ((q[1] & 0xff) << 8) | ((q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
+                    w1 = (q[4] & 0xff) | ((q[5] & 0xff) << 8) | ((q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
+                }
+                const int b = g >> 2, j = g & 3;
+                const int sl = vec4 ? x_slot<true>(b) : b;
+                uint2 *dst = reinterpret_cast<uint2 *>((j < 2 ? xlo : xhi) + (size_t)sl * 16 + (j & 1) * 8);
+                *dst = make_uint2(w0, w1);
+                if (j == 0) {
+                    const float sh = round_h(scale);  // the GEMV reads the fp16 scale back (gemv.h:1631)
+                    xs[sl] = make_float2(sh, sh * (float)qs);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // residual stream: resid (shared memory, fp16 [d]) += the row-parallel GEMV's output
 // ---------------------------------------------------------------------------------------
 // single GPU: y = round_h(W x) was stored by the consumers of all CTAs (half tensor, as the reference's GEMV
@@ -281,10 +414,11 @@ __device__ __forceinline__ uint2 pack8_s8(const int *q) {
 // int8 terms per 32-dim block, q ~= s1*qh + s2*ql (s2 <= s1/254). One thread = 8 consecutive dims, four neighbouring
 // lanes = one block (its max by two shuffles).
 template <bool Q8>
-__device__ __forceinline__ void stage_att(const StepParams &P, uint8_t *xst, const float *s_cos, const float *s_sin, int tid) {
+__device__ __forceinline__ void stage_att(const StepParams &P, uint8_t *xst, const float *s_cos, const float *s_sin, int tid,
+                                          uint32_t flag, int op) {
     const int hd = P.hd, nb = hd / 32;
     const AttLayout L = att_layout(P.heads, hd, Q8);
-    const __half *q = P.qkv;
+    const uint4 *qw = reinterpret_cast<const uint4 *>(P.qkvw);     // the wq|wk|wv GEMV wrote {half2, flag} words
     const int nq = P.q_dim >> 3;
     const bool half_split = P.rope_order == 2;
     for (int base = 0; base < nq; base += STEP_CTHREADS) {
@@ -295,8 +429,9 @@ __device__ __forceinline__ void stage_att(const StepParams &P, uint8_t *xst, con
         const int hq = e0 / hd, dq = e0 - hq * hd;
         uint4 wq_ = make_uint4(0, 0, 0, 0), wqo = wq_;
         if (aq) {
-            wq_ = ld_cg128(q + e0);
-            if (half_split) wqo = ld_cg128(q + hq * hd + (dq < hd / 2 ? dq + hd / 2 : dq - hd / 2));
+            const bool poll = (P.parts & STEP_PART_GEMV) != 0;
+            wq_ = ll_load8(qw, g8, flag, P, op, poll);
+            if (half_split) wqo = ll_load8(qw, (hq * hd + (dq < hd / 2 ? dq + hd / 2 : dq - hd / 2)) >> 3, flag, P, op, poll);
         }
         float x[8], o[8];
         unpack8(wq_, x);
@@ -350,7 +485,7 @@ __device__ __forceinline__ float s8f_(uint32_t w_biased, int k) {
 // body of attn_decode_kernel (ifb_attention.cu): dp4a scores with the two-term int8 q for a Q8 cache, fp32 softmax,
 // lane-owns-4-dims P.V.
 template <int HD, bool Q8>
-__device__ __forceinline__ void att_task(const StepParams &P, const StepLayer &lw, const float *s_cos, const float *s_sin,
+__device__ __forceinline__ void att_task(const StepParams &P, const StepLayer &lw, const float *s_cos, const float *s_sin, uint32_t qflag,
                                          uint8_t *slot, int tt, int kvh, int p0, int ctx, const uint8_t *xst, float *sp, int lane) {
     constexpr int NB = HD / 32;
     const int pbase = p0 + tt * 32;
@@ -374,14 +509,24 @@ __device__ __forceinline__ void att_task(const StepParams &P, const StepLayer &l
         // it to the cache and puts it in place in the staged tile. One task per kv head and token does this.
         constexpr int DPL = HD / 32;                       // dims per lane
         const int r = (ctx - 1) - pbase, d0 = lane * DPL;
-        const __half *kn = P.qkv + P.q_dim + (size_t)kvh * HD, *vn = kn + P.kv_dim;
         float kx[DPL], vx[DPL];
         {
+            // this token's k and v of the head, as the wq|wk|wv GEMV left them: {half2, flag} words, polled
+            const uint2 *kwp = P.qkvw + ((P.q_dim + kvh * HD + d0) >> 1), *vwp = kwp + (P.kv_dim >> 1);
             uint32_t kw[DPL / 2], vw[DPL / 2];
 #pragma unroll
             for (int i = 0; i < DPL / 2; i++) {
-                asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(kw[i]) : "l"(kn + d0 + 2 * i) : "memory");
-                asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(vw[i]) : "l"(vn + d0 + 2 * i) : "memory");
+                uint2 a_ = ld_relaxed_sys_v2(kwp + i), b_ = ld_relaxed_sys_v2(vwp + i);
+                if ((P.parts & STEP_PART_GEMV) && (a_.y != qflag || b_.y != qflag)) {
+                    const unsigned long long t0 = globaltimer_ns();
+                    unsigned it = 0;
+                    while (a_.y != qflag || b_.y != qflag) {
+                        a_ = ld_relaxed_sys_v2(kwp + i);
+                        b_ = ld_relaxed_sys_v2(vwp + i);
+                        if ((++it & 255u) == 0u && globaltimer_ns() - t0 > P.timeout_ns) step_abort(P, STEP_ERR_PEER, -1, kvh);
+                    }
+                }
+                kw[i] = a_.x; vw[i] = b_.x;
             }
 #pragma unroll
             for (int i = 0; i < DPL / 2; i++) {
@@ -556,21 +701,21 @@ struct RingPos {
     int tbase;
 };
 
-__device__ __forceinline__ void att_task_any(const StepParams &P, const StepLayer &lw, const float *s_cos, const float *s_sin,
+__device__ __forceinline__ void att_task_any(const StepParams &P, const StepLayer &lw, const float *s_cos, const float *s_sin, uint32_t qflag,
                                              uint8_t *slot, int tt, int kvh, int p0, int ctx, const uint8_t *xst, float *sp, int lane) {
     if (P.hd == 128) {
-        if (P.kv_q8) att_task<128, true>(P, lw, s_cos, s_sin, slot, tt, kvh, p0, ctx, xst, sp, lane);
-        else att_task<128, false>(P, lw, s_cos, s_sin, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        if (P.kv_q8) att_task<128, true>(P, lw, s_cos, s_sin, qflag, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        else att_task<128, false>(P, lw, s_cos, s_sin, qflag, slot, tt, kvh, p0, ctx, xst, sp, lane);
     } else {
-        if (P.kv_q8) att_task<64, true>(P, lw, s_cos, s_sin, slot, tt, kvh, p0, ctx, xst, sp, lane);
-        else att_task<64, false>(P, lw, s_cos, s_sin, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        if (P.kv_q8) att_task<64, true>(P, lw, s_cos, s_sin, qflag, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        else att_task<64, false>(P, lw, s_cos, s_sin, qflag, slot, tt, kvh, p0, ctx, xst, sp, lane);
     }
 }
 
 // log-sum-exp merge of the tiles' partials: q head hq -> attn_out[hq][hd] (half, as the reference's attention output
 // tensor). Thread = (4 dims, tile group): hd/4 dim quads x 480/(hd/4) tile groups; a thread's tiles are all loaded
 // before any is used (one L2 round trip for a 2k context), the tile groups meet in shared memory (the idle staging area).
-__device__ __forceinline__ void att_merge(const StepParams &P, int ctx, float *scratch, int tid) {
+__device__ __forceinline__ void att_merge(const StepParams &P, int ctx, float *scratch, int tid, uint32_t flag) {
     const int hd = P.hd, nq4 = hd >> 2, ngrp = STEP_CTHREADS / nq4, tg = tid / nq4, q4 = tid - tg * nq4;
     const int ntile = (ctx + 31) >> 5;
     constexpr int NB = 6;      // tiles per batch and thread
@@ -620,7 +765,13 @@ __device__ __forceinline__ void att_merge(const StepParams &P, int ctx, float *s
                 n2 = fmaf(w, scratch[(size_t)g * (hd + 4) + 4 + tid], n2);
                 d2 = fmaf(w, scratch[(size_t)g * (hd + 4) + 1], d2);
             }
-            P.attn_out[(size_t)hq * hd + tid] = __float2half_rn(n2 / d2);
+            // out as {half2, flag} words: the wo staging of every CTA polls them (no second completion count)
+            const float mine = n2 / d2;
+            const float nxt = __shfl_down_sync(0xffffffffu, mine, 1);
+            if ((tid & 1) == 0) {
+                const __half2 hv = __floats2half2_rn(mine, nxt);
+                st_relaxed_sys_v2(P.attw + (((size_t)hq * hd + tid) >> 1), make_uint2(*reinterpret_cast<const uint32_t *>(&hv), flag));
+            }
         }
         named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);
     }
@@ -845,60 +996,91 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
     auto stage_for = [&](int op) {
         const int kind = op == head_op ? OPK_HEAD : op % 5, layer = op / 5;
         trace_op(P, op, 0, tid);
-        // input of the GEMV staging below (one call site: the staging code is inlined once)
-        const void *xsrc = resid;
-        const __half *xnorm = nullptr;
-        bool xcg = false;
-        if (kind == OPK_QKV || kind == OPK_GLU || kind == OPK_HEAD) {
-            // the RMSNorm weights do not depend on the previous op: their (DRAM) round trip runs under the wait
-            const __half *nw_g = kind == OPK_HEAD ? P.out_norm : (kind == OPK_QKV ? s_layers[layer].attn_norm : s_layers[layer].ffn_norm);
-            uint4 nwv[2];
-            const int ngd = P.d >> 3;
-#pragma unroll
-            for (int i = 0; i < 2; i++) nwv[i] = (tid + i * STEP_CTHREADS < ngd) ? reinterpret_cast<const uint4 *>(nw_g)[tid + i * STEP_CTHREADS] : make_uint4(0, 0, 0, 0);
-            if (op == 0) {
-                // GetEmbdTensor (inference_engine.cc:1324-1350): the token's embedding row starts the residual stream
-                int tok = P.scalars[1];
-                tok = max(0, min(tok, P.vocab - 1));
-                const uint4 *row = reinterpret_cast<const uint4 *>(P.tok_emb + (size_t)tok * P.d);
-                for (int g = tid; g < (P.d >> 3); g += STEP_CTHREADS) resid[g] = row[g];
-            } else if (ll) {
-                // exchange index: wo of layer l -> 2l+1, w2 of layer l -> 2l+2 (two buffers, alternating)
-                const uint32_t idx = kind == OPK_GLU ? (uint32_t)(2 * layer + 1) : (uint32_t)(2 * (kind == OPK_HEAD ? P.n_layers : layer));
-                resid_add_gather(P, resid, idx, seq, op, tid);
-            } else {
-                dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
-                resid_add_local(P, resid, tid);
+        const uint32_t lflag = (seq << 8) | (uint32_t)(layer + 1);      // tag of this layer's qkv / attention-output words
+        if (kind == OPK_ATT) {
+            // q of every head: polled from the words the wq|wk|wv GEMV wrote (no completion count on this path)
+            trace_op(P, op, 1, tid);
+            if (P.kv_q8) stage_att<true>(P, xst, s_cos, s_sin, tid, lflag, op);
+            else stage_att<false>(P, xst, s_cos, s_sin, tid, lflag, op);
+        } else {
+            if (kind == OPK_WO) {
+                dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);      // every tile's partial is stored
+                att_merge(P, ctx, reinterpret_cast<float *>(xst), tid, lflag);
+            } else if (kind == OPK_W2) {
+                dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);      // h = silu(w1 x) * (w3 x) is stored
             }
+            // where the 8 values of group g come from (and, for the ops that start from the residual stream, the
+            // residual update itself: x_new = resid + row-parallel output, stored back to the shared-memory stream)
+            const bool from_resid = kind == OPK_QKV || kind == OPK_GLU || kind == OPK_HEAD;
+            const uint32_t xidx = kind == OPK_GLU ? (uint32_t)(2 * layer + 1) : (uint32_t)(2 * (kind == OPK_HEAD ? P.n_layers : layer));
+            const uint32_t xflag = (seq << 8) | xidx;
+            const uint8_t *xbase = reinterpret_cast<const uint8_t *>(P.peer[P.tp_rank]) + P.x_recv + (long long)(xidx & 1u) * P.x_recv_parity;
+            const bool gather = ll && (P.parts & STEP_PART_GEMV);
+            if (from_resid && op != 0 && !ll) dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
+            auto load = [&](int g) -> uint4 {
+                if (kind == OPK_WO) return ll_load8(reinterpret_cast<const uint4 *>(P.attw), g, lflag, P, op);   // written by this step's merge in any case
+                if (kind == OPK_W2) return ld_cg128(reinterpret_cast<const uint4 *>(P.hbuf) + g);
+                if (op == 0) {
+                    // GetEmbdTensor (inference_engine.cc:1324-1350): the token's embedding row starts the residual stream
+                    int tok = P.scalars[1];
+                    tok = max(0, min(tok, P.vocab - 1));
+                    const uint4 v = reinterpret_cast<const uint4 *>(P.tok_emb + (size_t)tok * P.d)[g];
+                    resid[g] = v;
+                    return v;
+                }
+                float acc[8];
+                if (gather) {
+                    // partial sums of all ranks, added in rank order with fp16 rounding after every add (MergeTensors,
+                    // inference_worker.cc:2264-2289); one GPU: the single "rank" is this GPU's own wo / w2 output
+                    for (int p = 0; p < P.tp_size; p++) {
+                        const uint4 d4 = ll_load8(reinterpret_cast<const uint4 *>(xbase + (size_t)p * P.x_recv_rank), g, xflag, P, op);
+                        const uint32_t dw[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-            for (int i = 0; i < 2; i++) if (tid + i * STEP_CTHREADS < ngd) s_norm[tid + i * STEP_CTHREADS] = nwv[i];
-            for (int g = tid + 2 * STEP_CTHREADS; g < ngd; g += STEP_CTHREADS) s_norm[g] = reinterpret_cast<const uint4 *>(nw_g)[g];   // d > 7680
-            trace_op(P, op, 1, tid);
-            named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);
-            xnorm = reinterpret_cast<const __half *>(s_norm);
-        } else if (kind == OPK_ATT) {
-            dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
-            trace_op(P, op, 1, tid);
-            if (P.kv_q8) stage_att<true>(P, xst, s_cos, s_sin, tid);
-            else stage_att<false>(P, xst, s_cos, s_sin, tid);
-        } else if (kind == OPK_WO) {
-            dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
-            att_merge(P, ctx, reinterpret_cast<float *>(xst), tid);
-            dep_signal(&P.done[n_ops + layer], tid);
-            dep_wait(&P.done[n_ops + layer], gridDim.x, P, op, tid);
-            trace_op(P, op, 1, tid);
-            xsrc = P.attn_out; xcg = true;
-        } else {   // OPK_W2
-            dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
-            trace_op(P, op, 1, tid);
-            xsrc = P.hbuf; xcg = true;
-        }
-        if (kind != OPK_ATT) {
-            if (kind == OPK_HEAD && P.head_f16) {
-                const XStage a = {P.d, nullptr, xnorm, P.eps, 0.f};
-                stage_x_f16<0, STEP_CWARPS>(a, resid, reinterpret_cast<__half *>(xst), red, tid);
+                        for (int k = 0; k < 4; k++) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&dw[k]));
+                            if (p == 0) { acc[2 * k] = f.x; acc[2 * k + 1] = f.y; }
+                            else { acc[2 * k] = round_h(acc[2 * k] + f.x); acc[2 * k + 1] = round_h(acc[2 * k + 1] + f.y); }
+                        }
+                    }
+                } else {
+                    float t8[8];
+                    unpack8(ll ? make_uint4(0, 0, 0, 0) : ld_cg128(reinterpret_cast<const uint4 *>(P.ybuf) + g), t8);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) acc[k] = t8[k];
+                }
+                // + residual, the last add (TensorOpr::Add, inference_worker.cc:849)
+                const uint4 rv = resid[g];
+                uint4 out;
+                __half2 *o = reinterpret_cast<__half2 *>(&out);
+                const __half2 *r = reinterpret_cast<const __half2 *>(&rv);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float2 rf = __half22float2(r[i]);
+                    o[i] = __floats2half2_rn(acc[2 * i] + rf.x, acc[2 * i + 1] + rf.y);
+                }
+                resid[g] = out;
+                return out;
+            };
+            const __half *nw = !from_resid ? nullptr : (kind == OPK_HEAD ? P.out_norm : (kind == OPK_QKV ? s_layers[layer].attn_norm : s_layers[layer].ffn_norm));
+            bool fp16_x = kind == OPK_HEAD && P.head_f16;
+            if constexpr (is_f16_fmt<Fmt>::value) fp16_x = true;
+            if (fp16_x) {
+                // fp16 activation (fp16 weights / fp16 lm_head): without a norm the staged form IS the vector; with one,
+                // the residual stream (just updated in shared memory) goes through the fp16 staging
+                const int ngx = P.op[kind].cx >> 3;
+                for (int g = tid; g < ngx; g += STEP_CTHREADS) {
+                    const uint4 v = load(g);
+                    if (!from_resid) reinterpret_cast<uint4 *>(xst)[g] = v;
+                }
+                trace_op(P, op, 1, tid);
+                if (from_resid) {
+                    named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);
+                    const XStage a = {P.op[kind].cx, nullptr, nw, P.eps, 0.f};
+                    stage_x_f16<0, STEP_CWARPS>(a, resid, reinterpret_cast<__half *>(xst), red, tid);
+                }
             } else {
-                stage_gemv_x<Fmt>(P, P.op[kind], xsrc, xcg, xnorm, xst, red, tid);
+                if constexpr (!is_f16_fmt<Fmt>::value) stage_fused_q8<Fmt::XSPLIT>(P.op[kind], nw, P.eps, xst, red, tid, load);
+                trace_op(P, op, 1, tid);
             }
         }
         named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);
@@ -937,7 +1119,16 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
         for (int k = cur_op; k < next_op; k++) {
             if (k >= 0) {
                 if (k == head_op && tp == 1 && lane == 0 && best_i != 0x7fffffff) atomicMax(P.amax, amax_key(best_v, best_i));
-                dep_signal(&P.done[k], tid);     // this CTA's rows of op k are stored (and its staging of op k is long done)
+                // "this CTA's part of op k is stored (and its staging of op k is long done)": counted where somebody waits
+                // for the count -- the attention tiles (merge), h (w2 staging), the lm_head (end of the token), and the
+                // row-parallel outputs when they do not travel as flag-in-data words. The q|k|v and attention-output words
+                // are their own signal. (The counts of ATT and GLU are also what keeps the two exchange buffers safe: no
+                // rank can be two exchanges ahead of a CTA that has not read the older one.)
+                const int kk = k == head_op ? OPK_HEAD : k % 5;
+                if (kk == OPK_ATT || kk == OPK_GLU || kk == OPK_HEAD || (!ll && (kk == OPK_WO || kk == OPK_W2)))
+                    dep_signal(&P.done[k], tid);
+                else
+                    named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);   // the staging below overwrites what the slowest warp may still read
             }
             if (k + 1 < n_ops) stage_for(k + 1);
         }
@@ -947,13 +1138,14 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
         const int kind = cur_op == head_op ? OPK_HEAD : cur_op % 5, layer = cur_op / 5;
         const StepOpShape &s = P.op[kind];
         const int ntask = s.tasks, ntask_mod = s.tasks % STEP_CWARPS;
+        const uint32_t lflag_op = (seq << 8) | (uint32_t)(layer + 1);
         const long long t_op0 = (P.trace != nullptr && tid == 0) ? clk() : 0ll;
         if (kind == OPK_ATT) {
             for (;;) {
                 IFB_SLOT_BEGIN()
                 if (t < ntask) {
                     const int h = u / tiles_per_head, tl = u - h * tiles_per_head;
-                    for (; t < ntask; t += STEP_CWARPS) att_task_any(P, s_layers[layer], s_cos, s_sin, slot, t, h, tl * P.att_pos, ctx, xst, sp, lane);
+                    for (; t < ntask; t += STEP_CWARPS) att_task_any(P, s_layers[layer], s_cos, s_sin, lflag_op, slot, t, h, tl * P.att_pos, ctx, xst, sp, lane);
                 }
                 IFB_SLOT_END()
             }
@@ -1012,8 +1204,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             }
         } else {   // QKV, WO, W2: two adjacent rows per task, plain half outputs
             const int R = s.R, row_bytes_ = s.row_bytes;
-            uint32_t *out32 = reinterpret_cast<uint32_t *>(kind == OPK_QKV ? P.qkv : P.ybuf);
-            const bool push = kind != OPK_QKV && ll;
+            uint32_t *out32 = reinterpret_cast<uint32_t *>(P.ybuf);
+            const bool qkv = kind == OPK_QKV;
+            const bool push = !qkv && ll;
             // row-parallel partial sums go straight into every rank's exchange region over NVLink
             const uint32_t xidx = kind == OPK_WO ? (uint32_t)(2 * layer + 1) : (uint32_t)(2 * layer + 2);
             const size_t xoff = (size_t)P.x_recv + (size_t)(xidx & 1u) * P.x_recv_parity + (size_t)P.tp_rank * P.x_recv_rank;
@@ -1028,7 +1221,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                         const int o = u * R + 2 * t;
                         const __half2 hv = __floats2half2_rn(acc[0], acc[1]);      // GEMV output tensors are half
                         const uint32_t bits = *reinterpret_cast<const uint32_t *>(&hv);
-                        if (!push) {
+                        if (qkv) {
+                            st_relaxed_sys_v2(P.qkvw + (o >> 1), make_uint2(bits, lflag_op));   // q|k|v as {half2, flag} words
+                        } else if (!push) {
                             out32[o >> 1] = bits;
                         } else {
                             const uint2 wd = make_uint2(bits, (seq << 8) | xidx);
@@ -1045,7 +1240,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
 #undef IFB_SLOT_END
 
     // ===== end of the token: next token id, position += 1 =====
-    if (tp > 1) {
+    if (tp > 1 && (P.parts & STEP_PART_GEMV)) {
         // the vocabulary-sharded lm_head of every rank pushed its logits here as flag-in-data words: each CTA
         // compacts a slice to fp16 and folds it into the argmax key
         const uint2 *ll = reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(P.peer[P.tp_rank]) + P.x_logits);
@@ -1085,7 +1280,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
         dep_signal(&P.done[n_ops + P.n_layers], tid);
     }
     if (blockIdx.x == 0) {
-        dep_wait(&P.done[tp > 1 ? n_ops + P.n_layers : head_op], gridDim.x, P, n_ops, tid);
+        dep_wait(&P.done[(tp > 1 && (P.parts & STEP_PART_GEMV)) ? n_ops + P.n_layers : head_op], gridDim.x, P, n_ops, tid);
         for (int g = tid; g < (P.d >> 3); g += STEP_CTHREADS) reinterpret_cast<uint4 *>(P.x_out)[g] = resid[g];
         if (tid == 0) {
             const unsigned long long key = ld_cg_u64(P.amax);
