@@ -68,7 +68,7 @@ struct ifb_model {
     int use_step = 1;               // IFB_STEP=0 keeps the multi-launch path
     bool step_built = false, step_ok = false;
     StepParams step;
-    DevBuf step_layers, step_ctr, partials, ybuf, qkvw, attw;
+    DevBuf step_layers, step_ctr, partials, ybuf, qkvw, attw, hbufw;
     int *step_err = nullptr;        // pinned host memory: error record of a step kernel that hit its deadline
     int host_pos = -1;              // host mirror of the device-side position (decode_next must not run past max_ctx)
     int64_t smem_kb[5] = {0, 0, 0, 0, 0};   // per-CTA shared-memory budget of the QKV / wo / GLU / w2 / lm_head GEMVs (KB, 0 = kernel default)
@@ -238,7 +238,8 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     A(m->ybuf, d * 2);
     A(m->qkvw, (size_t)(m->q_dim_l + 2 * m->kv_dim_l) * 4);     // {half2, flag} words
     A(m->attw, (size_t)m->q_dim_l * 4);
-    if (rc == IFB_OK) { cudaMemset(m->qkvw.p, 0, m->qkvw.bytes); cudaMemset(m->attw.p, 0, m->attw.bytes); }
+    A(m->hbufw, (size_t)m->ffn_l * 4);
+    if (rc == IFB_OK) { cudaMemset(m->qkvw.p, 0, m->qkvw.bytes); cudaMemset(m->attw.p, 0, m->attw.bytes); cudaMemset(m->hbufw.p, 0, m->hbufw.bytes); }
     A(m->partials, (size_t)m->heads_l * ((s.max_ctx + 31) / 32) * (m->hd + 4) * sizeof(float));
     { const char *e3 = getenv("IFB_TRACE"); if (e3 && atoi(e3)) m->trace_on = 1; }
     if (m->trace_on) A(m->trace, (size_t)512 * 160 * 8 * 8);
@@ -801,7 +802,7 @@ static int step_prepare(ifb_model *m) {
     P.qkv = (__half *)m->qkv.p; P.attn_out = (__half *)m->attn_out.p; P.hbuf = (__half *)m->hbuf.p;
     P.ybuf = (__half *)m->ybuf.p; P.logits = (__half *)m->logits.p; P.x_out = (__half *)m->x0.p;
     P.partials = (float *)m->partials.p;
-    P.qkvw = (uint2 *)m->qkvw.p; P.attw = (uint2 *)m->attw.p;
+    P.qkvw = (uint2 *)m->qkvw.p; P.attw = (uint2 *)m->attw.p; P.hbufw = (uint2 *)m->hbufw.p;
     P.scalars = (int32_t *)m->scalars.p;
     P.cursors = (int *)m->step_ctr.p;
     P.done = (unsigned int *)((int *)m->step_ctr.p + P.n_ops);

@@ -1006,8 +1006,6 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             if (kind == OPK_WO) {
                 dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);      // every tile's partial is stored
                 att_merge(P, ctx, reinterpret_cast<float *>(xst), tid, lflag);
-            } else if (kind == OPK_W2) {
-                dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);      // h = silu(w1 x) * (w3 x) is stored
             }
             // where the 8 values of group g come from (and, for the ops that start from the residual stream, the
             // residual update itself: x_new = resid + row-parallel output, stored back to the shared-memory stream)
@@ -1019,7 +1017,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             if (from_resid && op != 0 && !ll) dep_wait(&P.done[op - 1], gridDim.x, P, op, tid);
             auto load = [&](int g) -> uint4 {
                 if (kind == OPK_WO) return ll_load8(reinterpret_cast<const uint4 *>(P.attw), g, lflag, P, op);   // written by this step's merge in any case
-                if (kind == OPK_W2) return ld_cg128(reinterpret_cast<const uint4 *>(P.hbuf) + g);
+                if (kind == OPK_W2) return ll_load8(reinterpret_cast<const uint4 *>(P.hbufw), g, lflag, P, op, (P.parts & STEP_PART_GEMV) != 0);
                 if (op == 0) {
                     // GetEmbdTensor (inference_engine.cc:1324-1350): the token's embedding row starts the residual stream
                     int tok = P.scalars[1];
@@ -1120,12 +1118,13 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             if (k >= 0) {
                 if (k == head_op && tp == 1 && lane == 0 && best_i != 0x7fffffff) atomicMax(P.amax, amax_key(best_v, best_i));
                 // "this CTA's part of op k is stored (and its staging of op k is long done)": counted where somebody waits
-                // for the count -- the attention tiles (merge), h (w2 staging), the lm_head (end of the token), and the
-                // row-parallel outputs when they do not travel as flag-in-data words. The q|k|v and attention-output words
-                // are their own signal. (The counts of ATT and GLU are also what keeps the two exchange buffers safe: no
-                // rank can be two exchanges ahead of a CTA that has not read the older one.)
+                // for the count -- the attention tiles (merge), the lm_head (end of the token), and the row-parallel
+                // outputs when they do not travel as flag-in-data words. The q|k|v, attention-output and h words are their
+                // own signal. The count of ATT is the ONE grid-wide barrier of a layer, and it is what keeps every reused
+                // buffer safe: the words / partials / exchange buffers of layer l+1 are written behind it, and a CTA counts
+                // itself only after all its stagings up to ATT(l+1) -- i.e. after its last read of the layer-l contents.
                 const int kk = k == head_op ? OPK_HEAD : k % 5;
-                if (kk == OPK_ATT || kk == OPK_GLU || kk == OPK_HEAD || (!ll && (kk == OPK_WO || kk == OPK_W2)))
+                if (kk == OPK_ATT || kk == OPK_HEAD || (!ll && (kk == OPK_WO || kk == OPK_W2)))
                     dep_signal(&P.done[k], tid);
                 else
                     named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);   // the staging below overwrites what the slowest warp may still read
@@ -1150,20 +1149,27 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                 IFB_SLOT_END()
             }
         } else if (kind == OPK_GLU) {
+            // a task = two consecutive (w1, w3) row pairs: its two outputs h[o], h[o+1] leave as ONE {half2, flag} word
             const int R = s.R, row_bytes_ = s.row_bytes;
             const size_t stride = (size_t)s.unit_bytes;
             for (;;) {
                 IFB_SLOT_BEGIN()
                 for (; t < ntask; t += STEP_CWARPS) {
-                    float acc[2];
-                    dot2<Fmt>(s, slot + (size_t)t * row_bytes_, stride, xst, lane, acc);
-                    acc[0] = warp_sum(acc[0]);
-                    acc[1] = warp_sum(acc[1]);
-                    if (lane == 0) {
+                    float h2[2];
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        float acc[2];
+                        dot2<Fmt>(s, slot + (size_t)(2 * t + j) * row_bytes_, stride, xst, lane, acc);
+                        acc[0] = warp_sum(acc[0]);
+                        acc[1] = warp_sum(acc[1]);
                         // SiluActivation_Kernel (unary_tensor_opr.h:553) then Mul, each stored as half
                         const float v0 = round_h(acc[0]), v1 = round_h(acc[1]);   // GEMV output tensors are half
                         const float g = round_h(v0 / (1.0f + expf(-v0)));
-                        P.hbuf[u * R + t] = __float2half_rn(g * v1);
+                        h2[j] = g * v1;
+                    }
+                    if (lane == 0) {
+                        const __half2 hv = __floats2half2_rn(h2[0], h2[1]);
+                        st_relaxed_sys_v2(P.hbufw + ((u * R + 2 * t) >> 1), make_uint2(*reinterpret_cast<const uint32_t *>(&hv), lflag_op));
                     }
                 }
                 IFB_SLOT_END()
@@ -1313,7 +1319,7 @@ static int pick_rows(const int *seg_rows, int nseg, int row_bytes_, int nmat, bo
     int total = 0;
     for (int i = 0; i < nseg; i++) total += seg_rows[i];
     const int byte_cap = target / (row_bytes_ * nmat);
-    const int fair = total / grid;
+    const int fair = total / (4 * grid);       // aim for >= 4 units per CTA: a short op is all tail otherwise
     for (int pass = 0; pass < 2; pass++) {
         int cap = byte_cap;
         if (pass == 0) {                       // first choice: at least one unit per CTA
@@ -1353,11 +1359,11 @@ int step_build(StepParams &P, int kv_dtype, int head_dtype, int sms) {
         s.row_bytes = (int)(dt == DT_F16 ? (int64_t)cx * 2 : row_bytes(dt, cx));
         s.nblk = dt == DT_F16 ? cx / 32 : cx / block_capacity(dt);
         int target = STEP_TARGET_UNIT;
-        int R = pick_rows(segs, nseg, s.row_bytes, nmat, nmat == 1, sms, target);
-        if (R == 0) { target = 2 * STEP_TARGET_UNIT; R = pick_rows(segs, nseg, s.row_bytes, nmat, nmat == 1, sms, target); }
+        int R = pick_rows(segs, nseg, s.row_bytes, nmat, true, sms, target);
+        if (R == 0) { target = 2 * STEP_TARGET_UNIT; R = pick_rows(segs, nseg, s.row_bytes, nmat, true, sms, target); }
         IFB_CHECK_ARG(R > 0, "step kernel: rows of op %d (row_bytes %d) cannot be tiled into ring units", kind, s.row_bytes);
         s.R = R;
-        s.tasks = nmat == 2 ? R : R / 2;
+        s.tasks = R / 2;                         // two adjacent rows (two adjacent w1,w3 row pairs for GLU) per task
         s.unit_bytes = R * s.row_bytes;
         int units = 0;
         s.seg1 = s.seg2 = 0x7fffffff;

@@ -45,7 +45,7 @@ struct StepParams {
     const __half *tok_emb, *out_norm;
     const uint8_t *lm_head;
     __half *qkv, *attn_out, *hbuf, *ybuf, *logits, *x_out;
-    uint2 *qkvw, *attw;          // q|k|v of the layer in hand and the attention output as flag-in-data words {half2, flag}
+    uint2 *qkvw, *attw, *hbufw;  // q|k|v of the layer in hand, the attention output and h = silu(w1 x)*(w3 x) as flag-in-data words {half2, flag}
     float *partials;             // attention partials [heads][max_tiles][hd + 4]: m, l, -, -, acc[hd]
     int max_tiles;
     int32_t *scalars;            // [0] position [1] token [2] next token [3] step sequence number
