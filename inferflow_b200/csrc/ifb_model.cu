@@ -830,6 +830,8 @@ static int step_prepare(ifb_model *m) {
         const char *e = getenv("IFB_STEP_BATCH");
         P.claim_batch = e ? atoi(e) : 4;
         if (P.claim_batch < 1) P.claim_batch = 1;
+        const char *dbg = getenv("IFB_STEP_DEBUG");
+        P.debug = dbg ? atoi(dbg) : 0;
         const char *f = getenv("IFB_STEP_INFLIGHT");
         P.max_inflight = f ? atoi(f) : 0;
         if (P.max_inflight >= P.nslots || P.max_inflight < 0) P.max_inflight = 0;

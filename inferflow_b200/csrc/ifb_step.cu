@@ -99,13 +99,13 @@ __device__ __forceinline__ void step_abort(const StepParams &P, int code, int op
 // every wait of this kernel is bounded: past the deadline the kernel leaves an error record and traps. The threads
 // sleep in the barrier unit (suspend-time hint) rather than spin: a spinning consumer warp costs the working warps issue
 // slots (ncu: the first version spent 5 % of all executed instructions in this loop).
-__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar_addr, uint32_t parity, const StepParams &P, int op) {
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar_addr, uint32_t parity, const StepParams &P, int op, unsigned pause_ns = 100u) {
     if (mbar_try_wait_a(bar_addr, parity)) return;
     const unsigned long long t0 = globaltimer_ns();
     unsigned it = 0;
     while (!mbar_try_wait_a(bar_addr, parity)) {
-        __nanosleep(32);
-        if ((++it & 1023u) == 0u && globaltimer_ns() - t0 > P.timeout_ns) step_abort(P, STEP_ERR_RING, op, (int)parity);
+        __nanosleep(pause_ns);     // a waiting warp must not eat the working warps' issue slots (ncu: 8 % of all instructions)
+        if ((++it & 255u) == 0u && globaltimer_ns() - t0 > P.timeout_ns) step_abort(P, STEP_ERR_RING, op, (int)parity);
     }
 }
 
@@ -939,11 +939,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
             issued++;
             if (P.trace != nullptr) {
                 const long long t0 = clk();
-                mbar_wait_bounded(pempty0 + 8u * (uint32_t)pos, phase, P, op);
+                mbar_wait_bounded(pempty0 + 8u * (uint32_t)pos, phase, P, op, 200u);
                 s_prof[2] += (int)(clk() - t0);
                 s_prof[3]++;
             } else
-            mbar_wait_bounded(pempty0 + 8u * (uint32_t)pos, phase, P, op);
+            mbar_wait_bounded(pempty0 + 8u * (uint32_t)pos, phase, P, op, 200u);
             slot_meta[pos] = make_int2(op, u);
             const uint32_t dst = ring0 + (uint32_t)pos * (uint32_t)P.slot_bytes, fb = pfull0 + 8u * (uint32_t)pos;
             const uint32_t ub = (uint32_t)s.unit_bytes;
@@ -1136,7 +1136,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
         trace_op(P, cur_op, 3, tid);
         const int kind = cur_op == head_op ? OPK_HEAD : cur_op % 5, layer = cur_op / 5;
         const StepOpShape &s = P.op[kind];
-        const int ntask = s.tasks, ntask_mod = s.tasks % STEP_CWARPS;
+        const int ntask = (P.debug & 1) ? 0 : s.tasks, ntask_mod = s.tasks % STEP_CWARPS;
         const uint32_t lflag_op = (seq << 8) | (uint32_t)(layer + 1);
         const long long t_op0 = (P.trace != nullptr && tid == 0) ? clk() : 0ll;
         if (kind == OPK_ATT) {

@@ -56,6 +56,7 @@ struct StepParams {
     int nslots, slot_bytes, x_off, resid_off, sp_off, rope_off, lay_off, norm_off, smem_bytes;
     int att_pos;                 // positions per ATT unit (64 for a Q8_B32T2 cache, 32 for fp16)
     int parts, advance;
+    int debug;                   // measurement aid (IFB_STEP_DEBUG): bit 0 = the tasks skip their arithmetic (pure streaming + boundaries)
     int claim_batch;             // most units one cursor claim takes (guided self-scheduling)
     int max_inflight;            // bulk copies outstanding per SM (0: as many as the ring has slots)
     // tensor parallelism (size 1: unused) -- exchange regions as in ifb_model.cu
