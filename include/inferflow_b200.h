@@ -85,6 +85,16 @@ int32_t ifb_dequantize_rows(int32_t dtype, void *dst_f16, const void *src, int64
 int32_t ifb_gemv(int32_t w_dtype, void *y_f16, const void *w, int32_t x_dtype, const void *x,
                  int64_t cy, int64_t cx, const void *bias_f16, ifb_stream_t stream);
 
+/* ------------------------------------------------------------------ GEMM (rows > 1: prefill, batched decode)
+ * GpuInferenceWorker::MatrixMultiplication for more than one row (inference_worker.cc:2364-2432): the reference
+ * dequantizes the WHOLE weight tensor to fp16 (:2375-2380), calls cublasGemmEx (:2413, cublas_engine.cu:425-505) and
+ * transposes the result. Here:  Y[tokens][cy] = X[tokens][cx] . W[cy][cx]^T (+ bias), fp16 in / fp32 accumulate /
+ * fp16 out, with W dequantized tile by tile in shared memory (value = fp16(q * scale + base), the bytes
+ * TensorOpr::Dequantize writes) and multiplied on the 5th-generation tensor cores (tcgen05.mma, accumulator in tensor
+ * memory). w_dtype: IFB_F16 or any block format of the dp4a family. cy % 128 == 0, cx % 64 == 0. */
+int32_t ifb_gemm_q(int32_t w_dtype, void *y_f16, const void *w, const void *x_f16, int64_t tokens, int64_t cy,
+                   int64_t cx, const void *bias_f16, ifb_stream_t stream);
+
 /* Fused decode GEMV used by our layer runtime: one launch replaces
  *   [RmsNorm] -> Quantize(Q8_B32T2) -> 1..3 Gemv_AX sharing x -> [SiLU, Mul] -> [Add residual]
  * (inference_worker.cc:1038,1442-1444,1555-1571,1726-1900). */

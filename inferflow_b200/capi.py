@@ -63,6 +63,7 @@ def _load():
     L.ifb_dequantize_rows.argtypes = [i32, vp, vp, i64, i64, vp]
     L.ifb_gemv.argtypes = [i32, vp, vp, i32, vp, i64, i64, vp, vp]
     L.ifb_gemv_fused.argtypes = [C.POINTER(GemvDesc), vp]
+    L.ifb_gemm_q.argtypes = [i32, vp, vp, vp, i64, i64, i64, vp, vp]
     L.ifb_rmsnorm.argtypes = [vp, vp, vp, i64, i64, f32, f32, vp]
     L.ifb_rope.argtypes = [vp, i32, i32, i32, i32, i32, f32, i32, vp]
     L.ifb_silu_mul.argtypes = [vp, vp, vp, i64, vp]
@@ -120,7 +121,7 @@ lib = _load()
 # every symbol include/inferflow_b200.h declares (checked by tests/test_capi_symbols.py)
 DECLARED = [
     "ifb_version", "ifb_last_error", "ifb_block_capacity", "ifb_block_bytes", "ifb_row_bytes",
-    "ifb_dtype_from_name", "ifb_quantize_rows", "ifb_dequantize_rows", "ifb_gemv", "ifb_gemv_fused",
+    "ifb_dtype_from_name", "ifb_quantize_rows", "ifb_dequantize_rows", "ifb_gemv", "ifb_gemv_fused", "ifb_gemm_q",
     "ifb_rmsnorm", "ifb_rope", "ifb_silu_mul", "ifb_add", "ifb_argmax", "ifb_kv_cache_bytes",
     "ifb_kv_append", "ifb_kv_get_rows", "ifb_attn_workspace_bytes", "ifb_attn_decode", "ifb_attn_decode_append", "ifb_moe_topk", "ifb_moe_route", "ifb_moe_combine",
     "ifb_engine_resolve", "ifb_engine_create", "ifb_engine_destroy", "ifb_engine_vocab_size", "ifb_engine_add_query",

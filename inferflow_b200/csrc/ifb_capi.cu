@@ -96,6 +96,13 @@ int32_t ifb_gemv(int32_t w_dtype, void *y, const void *w, int32_t x_dtype, const
     return gemv_launch(g, (cudaStream_t)st);
 }
 
+int32_t ifb_gemm_q(int32_t w_dtype, void *y, const void *w, const void *x, int64_t tokens, int64_t cy, int64_t cx,
+                   const void *bias, ifb_stream_t st) {
+    IFB_CHECK_ARG(y && w && x, "MatrixMultiplication: null tensor");
+    IFB_CHECK_ARG(cy > 0 && cy < (1ll << 31) && cx > 0 && cx < (1ll << 31) && tokens > 0 && tokens < (1ll << 31), "MatrixMultiplication: bad shape");
+    return gemm_q(w_dtype, y, w, x, tokens, cy, cx, bias, (cudaStream_t)st);
+}
+
 int32_t ifb_gemv_fused(const ifb_gemv_desc_t *d, ifb_stream_t st) {
     IFB_CHECK_ARG(d != nullptr, "gemv_fused: null descriptor");
     IFB_CHECK_ARG(d->x_f16 && d->y_f16, "gemv_fused: null tensor");

@@ -1,0 +1,277 @@
+// Dequant-fused tensor-core GEMM for rows > 1: prefill and batched decode, sm_100a (tcgen05 + TMEM).
+//
+// Replaces the rows > 1 branch of GpuInferenceWorker::MatrixMultiplication (reference
+// src/transformer/inference_worker.cc:2364-2432): Dequantize the whole weight tensor to fp16 (:2375-2380) ->
+// cublas_engine_.GemmEx (:2413, src/tensor/cublas_engine.cu:425-505) -> Transpose. Here the weight never exists in
+// fp16 in global memory:
+//
+//   Y[tokens][cy] = X[tokens][cx] . W[cy][cx]^T        (fp16 in, fp32 accumulate in TMEM, fp16 out)
+//
+//  * a CTA owns 128 weight rows x up to 128 tokens; the K loop walks 64 columns at a time through a 3-stage ring;
+//  * the 4 producer warps (thread = one weight row / one token) fetch their row's quantized blocks of the k-slice,
+//    decode them with the same Fmt::decode the GEMV uses, compute value = fp16(q * scale + base) -- the bytes
+//    TensorOpr::Dequantize would have written -- and store them straight into the A tile in shared memory; the same
+//    threads copy their token's 64 activations into the B tile. Both tiles are laid out as UMMA "core matrices"
+//    (8 rows x 16 bytes, contiguous), K-major, no swizzle;
+//  * ONE elected thread of the MMA warp issues tcgen05.mma (M = 128, N = token tile, K = 16 per instruction) with the
+//    accumulator in tensor memory; tcgen05.commit hands the shared-memory stage back to the producers;
+//  * after the last k-slice the producer warps become the epilogue: tcgen05.ld (32 lanes x 32 bit, lane = weight row)
+//    -> fp16 -> Y. The output is written in its final [tokens][cy] orientation (no transpose pass).
+//  * two CTAs fit an SM (96 KB of shared memory, 128 TMEM columns each): one CTA's block fetch latency hides behind the
+//    other's MMAs.
+#include "ifb_formats.cuh"
+#include "ifb_kernels.h"
+
+namespace ifb {
+
+constexpr int GQ_ROWS = 128;        // weight rows per CTA = UMMA M
+constexpr int GQ_BK = 64;           // k-slice per stage
+constexpr int GQ_STAGES = 3;
+constexpr int GQ_NT_MAX = 128;      // tokens per CTA = UMMA N (multiple of 16)
+constexpr int GQ_THREADS = 160;     // 4 producer / epilogue warps + the MMA warp
+constexpr int GQ_A_BYTES = GQ_ROWS * GQ_BK * 2;      // 16 KB
+constexpr int GQ_B_BYTES = GQ_NT_MAX * GQ_BK * 2;    // 16 KB
+constexpr int GQ_STAGE_BYTES = GQ_A_BYTES + GQ_B_BYTES;
+constexpr int GQ_STRIP = 80;        // per-thread scratch for the raw blocks of one k-slice (<= 2 x 36 B + slack)
+
+// ---- tcgen05 / TMEM wrappers (PTX; SASS: UTCHMMA, LDTM, UTCBAR ...)
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the mbarrier receives one arrival when every tcgen05 operation this thread issued so far has completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 bit x 16 columns: thread (lane) i of the warp gets columns c..c+15 of TMEM lane (warp%4)*32 + i
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major, no swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (K-adjacent core matrices), [32,46) stride byte
+// offset >> 4 (8-row groups), [46,48) version = 1, [61,64) layout type 0.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+struct GemmArgs {
+    const uint8_t *w;        // [cy][cx / cap] blocks (or fp16 [cy][cx])
+    const __half *x;         // [tokens][cx]
+    __half *y;               // [tokens][cy]
+    const __half *bias;      // [cy] or null
+    int tokens, cy, cx, row_bytes, w_dtype;
+    int nt;                  // token tile (multiple of 16, <= 128)
+};
+
+// element (r, k) of a tile: core matrices of 8 rows x 8 halves (128 contiguous bytes); K-adjacent core matrices 128 B
+// apart (LBO), 8-row groups (BK/8) * 128 B apart (SBO)
+constexpr int GQ_LBO = 128, GQ_SBO = (GQ_BK / 8) * 128;
+
+template <class Fmt, bool F16W>
+__global__ void __launch_bounds__(GQ_THREADS, 2) gemm_q_kernel(const GemmArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full_bar[GQ_STAGES], empty_bar[GQ_STAGES], done_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * GQ_ROWS, tok0 = blockIdx.y * a.nt;
+    const int nk = a.cx / GQ_BK;
+    uint8_t *strips = smem + GQ_STAGES * GQ_STAGE_BYTES;     // [128][GQ_STRIP]
+
+    if (tid == 0) {
+        for (int i = 0; i < GQ_STAGES; i++) { mbar_init(&full_bar[i], 128); mbar_init(&empty_bar[i], 1); }
+        mbar_init(&done_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4) tmem_alloc(&tmem_base_s, 128);             // 128 columns of fp32 accumulators (power of two >= 32)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == 4) {
+        // ===== MMA issuer: one thread =====
+        if (lane == 0) {
+            // instruction descriptor (InstrDescriptor): c_format F32 (bits 4-5 = 1), a/b fp16 K-major (0), N >> 3 at bit 17,
+            // M >> 4 at bit 24
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(a.nt >> 3) << 17) | ((uint32_t)(GQ_ROWS >> 4) << 24);
+            for (int kb = 0; kb < nk; kb++) {
+                const int s = kb % GQ_STAGES;
+                mbar_wait(&full_bar[s], (uint32_t)(kb / GQ_STAGES) & 1u);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * GQ_STAGE_BYTES), b_addr = a_addr + GQ_A_BYTES;
+#pragma unroll
+                for (int k = 0; k < GQ_BK / 16; k++) {
+                    // one instruction consumes K = 16: two K-adjacent core matrices = 2 * LBO bytes further
+                    const uint64_t ad = umma_desc(a_addr + k * 2 * GQ_LBO, GQ_LBO, GQ_SBO);
+                    const uint64_t bd = umma_desc(b_addr + k * 2 * GQ_LBO, GQ_LBO, GQ_SBO);
+                    umma_f16(tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);          // the stage is free once these MMAs have read it
+            }
+            umma_commit(&done_bar);                  // accumulator complete
+        }
+    } else {
+        // ===== producers: thread = weight row `tid` of the tile, and token `tid` of the token tile =====
+        const int r = tid;
+        const uint8_t *wrow = a.w + (size_t)(row0 + r) * a.row_bytes;
+        const bool tok_ok = tid < a.nt && tok0 + tid < a.tokens;
+        const __half *xrow = a.x + (size_t)(tok0 + tid) * a.cx;
+        uint8_t *strip = strips + r * GQ_STRIP;
+        for (int kb = 0; kb < nk; kb++) {
+            const int s = kb % GQ_STAGES;
+            mbar_wait(&empty_bar[s], ((uint32_t)(kb / GQ_STAGES) & 1u) ^ 1u);
+            uint8_t *At = smem + s * GQ_STAGE_BYTES, *Bt = At + GQ_A_BYTES;
+            uint8_t *arow = At + (r >> 3) * GQ_SBO + (r & 7) * 16;         // + k8 * LBO
+            const int k0 = kb * GQ_BK;
+            if (F16W) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(wrow + (size_t)k0 * 2);
+#pragma unroll
+                for (int k8 = 0; k8 < GQ_BK / 8; k8++) *reinterpret_cast<uint4 *>(arow + k8 * GQ_LBO) = src[k8];
+            } else {
+                // the row's blocks of this k-slice: raw bytes -> this thread's strip (blocks are only 2- or 4-byte aligned)
+                constexpr int NBLK = GQ_BK / Fmt::CAP, SEG = NBLK * Fmt::BYTES;
+                const uint8_t *seg = wrow + (size_t)(k0 / Fmt::CAP) * Fmt::BYTES;
+                const uint32_t mis = (uint32_t)((uintptr_t)seg & 3u);       // 0 or 2
+                const uint32_t *seg4 = reinterpret_cast<const uint32_t *>(seg - mis);
+                uint32_t *strip4 = reinterpret_cast<uint32_t *>(strip);
+#pragma unroll
+                for (int i = 0; i < (SEG + 3 + 3) / 4; i++) strip4[i] = seg4[i];
+                __syncwarp();
+#pragma unroll
+                for (int b = 0; b < NBLK; b++) {
+                    uint32_t codes[Fmt::NW];
+                    float sc, ba;
+                    Fmt::decode(strip + mis + b * Fmt::BYTES, codes, sc, ba);
+#pragma unroll
+                    for (int c8 = 0; c8 < Fmt::CAP / 8; c8++) {          // 8 elements = one 16-byte chunk of the A tile
+                        uint4 out;
+                        __half2 *oh = reinterpret_cast<__half2 *>(&out);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            // element e of the block sits in byte e%4 of codes[e/4] ... except for the nibble-split formats,
+                            // whose staged order is (x0,x2,x4,x6)(x1,x3,x5,x7) per group of 8 (see x_pos in ifb_gemv_dev.cuh)
+                            int q0, q1;
+                            if (Fmt::XSPLIT) {
+                                q0 = (codes[2 * c8] >> (8 * j)) & 0xff;          // element 8*c8 + 2j
+                                q1 = (codes[2 * c8 + 1] >> (8 * j)) & 0xff;      // element 8*c8 + 2j + 1
+                            } else {
+                                const int e = 8 * c8 + 2 * j;
+                                q0 = (codes[e >> 2] >> (8 * (e & 3))) & 0xff;
+                                q1 = (codes[(e + 1) >> 2] >> (8 * ((e + 1) & 3))) & 0xff;
+                            }
+                            if (Fmt::SIGNED) { q0 = (int)(int8_t)q0; q1 = (int)(int8_t)q1; }
+                            // TensorOpr::Dequantize: value = q * scale + base in fp32, stored as half
+                            oh[j] = __floats2half2_rn(fmaf((float)q0, sc, ba), fmaf((float)q1, sc, ba));
+                        }
+                        *reinterpret_cast<uint4 *>(arow + (b * (Fmt::CAP / 8) + c8) * GQ_LBO) = out;
+                    }
+                }
+            }
+            // this thread's token: 64 activations = 8 chunks
+            {
+                uint8_t *brow = Bt + (tid >> 3) * GQ_SBO + (tid & 7) * 16;
+                const uint4 *src = reinterpret_cast<const uint4 *>(xrow + k0);
+#pragma unroll
+                for (int k8 = 0; k8 < GQ_BK / 8; k8++)
+                    *reinterpret_cast<uint4 *>(brow + k8 * GQ_LBO) = tok_ok ? src[k8] : make_uint4(0, 0, 0, 0);
+            }
+            fence_async_smem();                      // generic-proxy stores -> visible to the tensor core (async proxy)
+            mbar_arrive(&full_bar[s]);
+        }
+        // ===== epilogue: TMEM lane = weight row =====
+        mbar_wait(&done_bar, 0);
+        tc_fence_after();
+        const float bias = a.bias != nullptr ? __half2float(a.bias[row0 + r]) : 0.f;
+        for (int c0 = 0; c0 < a.nt; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                const int t = tok0 + c0 + c;
+                if (t < a.tokens) {
+                    float f = __uint_as_float(v[c]);
+                    if (a.bias != nullptr) f = __half2float(__float2half_rn(f)) + bias;     // GEMM output is half, then + bias
+                    a.y[(size_t)t * a.cy + row0 + r] = __float2half_rn(f);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 128);
+    }
+}
+
+template <class Fmt, bool F16W>
+static int launch_gemm(const GemmArgs &a, cudaStream_t st) {
+    auto kern = gemm_q_kernel<Fmt, F16W>;
+    const size_t smem = (size_t)GQ_STAGES * GQ_STAGE_BYTES + 128 * GQ_STRIP;
+    static int attr_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+        IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_dev = dev;
+    }
+    dim3 grid(a.cy / GQ_ROWS, (a.tokens + a.nt - 1) / a.nt);
+    kern<<<grid, GQ_THREADS, smem, st>>>(a);
+    IFB_LAUNCH_CHECK();
+    return IFB_OK;
+}
+
+// Y[tokens][cy] = X[tokens][cx] . W[cy][cx]^T (+ bias). W: any dp4a-capable block format (or fp16).
+int gemm_q(int w_dtype, void *y_f16, const void *w, const void *x_f16, int64_t tokens, int64_t cy, int64_t cx,
+           const void *bias_f16, cudaStream_t st) {
+    IFB_CHECK_ARG(tokens >= 1 && cy >= 1 && cx >= 1, "gemm: empty shape");
+    IFB_CHECK_ARG(cy % GQ_ROWS == 0, "gemm: rows of W (%lld) must be a multiple of %d", (long long)cy, GQ_ROWS);
+    IFB_CHECK_ARG(cx % GQ_BK == 0, "gemm: cx (%lld) must be a multiple of %d", (long long)cx, GQ_BK);
+    IFB_CHECK_ARG((((uintptr_t)x_f16 | (uintptr_t)w) & 15) == 0 || w_dtype != DT_F16, "gemm: fp16 operands must be 16-byte aligned");
+    IFB_CHECK_ARG(((uintptr_t)x_f16 & 15) == 0, "gemm: x must be 16-byte aligned");
+    GemmArgs a;
+    a.w = (const uint8_t *)w; a.x = (const __half *)x_f16; a.y = (__half *)y_f16; a.bias = (const __half *)bias_f16;
+    a.tokens = (int)tokens; a.cy = (int)cy; a.cx = (int)cx; a.w_dtype = w_dtype;
+    a.row_bytes = (int)(w_dtype == DT_F16 ? cx * 2 : row_bytes(w_dtype, cx));
+    int nt = (int)((tokens + 15) / 16 * 16);
+    a.nt = nt > GQ_NT_MAX ? GQ_NT_MAX : nt;
+    switch (w_dtype) {
+        case DT_F16: return launch_gemm<FmtQ4_B32T1, true>(a, st);
+        case DT_Q4_B32T1A:
+        case DT_Q4_B32T1B: return launch_gemm<FmtQ4_B32T1, false>(a, st);
+        case DT_Q4_B64T1: return launch_gemm<FmtQ4_B64T1, false>(a, st);
+        case DT_Q8_B32T2: return launch_gemm<FmtQ8_B32T2, false>(a, st);
+        case DT_Q6_B64T1: return launch_gemm<FmtQ6_B64T1, false>(a, st);
+        case DT_Q5_B64T1: return launch_gemm<FmtQ5_B64T1, false>(a, st);
+        case DT_Q3H_B64T1: return launch_gemm<FmtQ3H_B64T1, false>(a, st);
+        default:
+            set_last_error("gemm: weight type %d has no tensor-core path (reference: Dequantize + cublasGemmEx)", w_dtype);
+            return IFB_ERR_TYPE;
+    }
+}
+
+}  // namespace ifb
