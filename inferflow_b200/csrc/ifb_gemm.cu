@@ -24,15 +24,17 @@
 
 namespace ifb {
 
-constexpr int GQ_ROWS = 128;        // weight rows per CTA = UMMA M
+constexpr int GQ_ROWS = 128;        // weight rows per accumulator = UMMA M
 constexpr int GQ_BK = 64;           // k-slice per stage
 constexpr int GQ_STAGES = 3;
-constexpr int GQ_NT_MAX = 128;      // tokens per CTA = UMMA N (multiple of 16)
-constexpr int GQ_THREADS = 160;     // 4 producer / epilogue warps + the MMA warp
-constexpr int GQ_A_BYTES = GQ_ROWS * GQ_BK * 2;      // 16 KB
-constexpr int GQ_B_BYTES = GQ_NT_MAX * GQ_BK * 2;    // 16 KB
-constexpr int GQ_STAGE_BYTES = GQ_A_BYTES + GQ_B_BYTES;
+constexpr int GQ_A_BYTES = GQ_ROWS * GQ_BK * 2;      // 16 KB per 128-row block
 constexpr int GQ_STRIP = 80;        // per-thread scratch for the raw blocks of one k-slice (<= 2 x 36 B + slack)
+// Two tile configurations (template parameters RB = 128-row blocks per CTA, NT = token tile):
+//   small (RB 1, NT <= 128): 128 rows x 128 tokens, 4 producer warps, 96 KB of shared memory -> two CTAs per SM hide
+//         each other's fetch latency; for few tokens (batched decode), where the weight stream is the cost;
+//   large (RB 2, NT 256):   256 rows x 256 tokens, 8 producer warps, both accumulators fill the 512 TMEM columns; a
+//         weight element is dequantized once per 256 tokens (the dequantization is ALU work that competes with nothing
+//         the tensor core needs, but at 128 tokens per pass it was what bound the first version: ~190 TFLOP/s).
 
 // ---- tcgen05 / TMEM wrappers (PTX; SASS: UTCHMMA, LDTM, UTCBAR ...)
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
@@ -83,36 +85,42 @@ struct GemmArgs {
     __half *y;               // [tokens][cy]
     const __half *bias;      // [cy] or null
     int tokens, cy, cx, row_bytes, w_dtype;
-    int nt;                  // token tile (multiple of 16, <= 128)
+    int nt;                  // token tile (multiple of 16)
 };
 
 // element (r, k) of a tile: core matrices of 8 rows x 8 halves (128 contiguous bytes); K-adjacent core matrices 128 B
 // apart (LBO), 8-row groups (BK/8) * 128 B apart (SBO)
 constexpr int GQ_LBO = 128, GQ_SBO = (GQ_BK / 8) * 128;
 
-template <class Fmt, bool F16W>
-__global__ void __launch_bounds__(GQ_THREADS, 2) gemm_q_kernel(const GemmArgs a) {
+template <class Fmt, bool F16W, int RB, int NTMAX>
+__global__ void __launch_bounds__(128 * RB + 32, RB == 1 ? 2 : 1) gemm_q_kernel(const GemmArgs a) {
+    constexpr int NPROD = 128 * RB;                       // producer threads: thread = weight row and token of the tile
+    constexpr int PW = NPROD / 32;                        // producer warps; warp PW issues the MMAs
+    constexpr int B_BYTES = NTMAX * GQ_BK * 2;
+    constexpr int STAGE_BYTES = RB * GQ_A_BYTES + B_BYTES;
+    constexpr int TMEM_COLS = RB * NTMAX < 32 ? 32 : RB * NTMAX;
+    static_assert(NTMAX <= NPROD, "a producer thread copies one token");
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t full_bar[GQ_STAGES], empty_bar[GQ_STAGES], done_bar;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row0 = blockIdx.x * GQ_ROWS, tok0 = blockIdx.y * a.nt;
+    const int row0 = blockIdx.x * (GQ_ROWS * RB), tok0 = blockIdx.y * a.nt;
     const int nk = a.cx / GQ_BK;
-    uint8_t *strips = smem + GQ_STAGES * GQ_STAGE_BYTES;     // [128][GQ_STRIP]
+    uint8_t *strips = smem + GQ_STAGES * STAGE_BYTES;     // [NPROD][GQ_STRIP]
 
     if (tid == 0) {
-        for (int i = 0; i < GQ_STAGES; i++) { mbar_init(&full_bar[i], 128); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < GQ_STAGES; i++) { mbar_init(&full_bar[i], NPROD); mbar_init(&empty_bar[i], 1); }
         mbar_init(&done_bar, 1);
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc(&tmem_base_s, 128);             // 128 columns of fp32 accumulators (power of two >= 32)
+    if (warp == PW) tmem_alloc(&tmem_base_s, TMEM_COLS);  // fp32 accumulators: RB x nt columns (power of two >= 32)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
 
-    if (warp == 4) {
+    if (warp == PW) {
         // ===== MMA issuer: one thread =====
         if (lane == 0) {
             // instruction descriptor (InstrDescriptor): c_format F32 (bits 4-5 = 1), a/b fp16 K-major (0), N >> 3 at bit 17,
@@ -122,44 +130,73 @@ __global__ void __launch_bounds__(GQ_THREADS, 2) gemm_q_kernel(const GemmArgs a)
                 const int s = kb % GQ_STAGES;
                 mbar_wait(&full_bar[s], (uint32_t)(kb / GQ_STAGES) & 1u);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * GQ_STAGE_BYTES), b_addr = a_addr + GQ_A_BYTES;
+                const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES), b_addr = a_addr + RB * GQ_A_BYTES;
 #pragma unroll
                 for (int k = 0; k < GQ_BK / 16; k++) {
                     // one instruction consumes K = 16: two K-adjacent core matrices = 2 * LBO bytes further
-                    const uint64_t ad = umma_desc(a_addr + k * 2 * GQ_LBO, GQ_LBO, GQ_SBO);
                     const uint64_t bd = umma_desc(b_addr + k * 2 * GQ_LBO, GQ_LBO, GQ_SBO);
-                    umma_f16(tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+                    for (int rb = 0; rb < RB; rb++) {
+                        const uint64_t ad = umma_desc(a_addr + rb * GQ_A_BYTES + k * 2 * GQ_LBO, GQ_LBO, GQ_SBO);
+                        umma_f16(tmem + (uint32_t)(rb * a.nt), ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit(&empty_bar[s]);          // the stage is free once these MMAs have read it
             }
-            umma_commit(&done_bar);                  // accumulator complete
+            umma_commit(&done_bar);                  // accumulators complete
         }
     } else {
-        // ===== producers: thread = weight row `tid` of the tile, and token `tid` of the token tile =====
-        const int r = tid;
+        // ===== producers: thread = weight row `tid` of the CTA's rows, and token `tid` of the token tile =====
+        const int r = tid, rb = r >> 7, rr = r & 127;
         const uint8_t *wrow = a.w + (size_t)(row0 + r) * a.row_bytes;
-        const bool tok_ok = tid < a.nt && tok0 + tid < a.tokens;
-        const __half *xrow = a.x + (size_t)(tok0 + tid) * a.cx;
+        const bool tok_in = tid < a.nt;                          // this thread copies a token of the tile
+        const bool tok_ok = tok_in && tok0 + tid < a.tokens;
+        const __half *xrow = a.x + (size_t)(tok_ok ? tok0 + tid : 0) * a.cx;
         uint8_t *strip = strips + r * GQ_STRIP;
-        for (int kb = 0; kb < nk; kb++) {
-            const int s = kb % GQ_STAGES;
-            mbar_wait(&empty_bar[s], ((uint32_t)(kb / GQ_STAGES) & 1u) ^ 1u);
-            uint8_t *At = smem + s * GQ_STAGE_BYTES, *Bt = At + GQ_A_BYTES;
-            uint8_t *arow = At + (r >> 3) * GQ_SBO + (r & 7) * 16;         // + k8 * LBO
+        constexpr int NBLK = F16W ? 1 : GQ_BK / Fmt::CAP, SEG = F16W ? GQ_BK * 2 : NBLK * Fmt::BYTES;
+        constexpr int NRAW = F16W ? GQ_BK * 2 / 4 : (SEG + 3 + 3) / 4;     // 32-bit words fetched per k-slice
+        uint32_t raw[NRAW], raw_n[NRAW];
+        uint4 xv[GQ_BK / 8], xv_n[GQ_BK / 8];
+        uint32_t mis = 0;
+        // fetch of k-slice kb into registers (issued one slice ahead: the L2 / HBM latency runs under the previous slice's
+        // dequantization and under the MMAs)
+        auto fetch = [&](int kb, uint32_t *rw, uint4 *xr) {
             const int k0 = kb * GQ_BK;
             if (F16W) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(wrow + (size_t)k0 * 2);
 #pragma unroll
-                for (int k8 = 0; k8 < GQ_BK / 8; k8++) *reinterpret_cast<uint4 *>(arow + k8 * GQ_LBO) = src[k8];
+                for (int i = 0; i < GQ_BK / 8; i++) {
+                    const uint4 v = src[i];
+                    rw[4 * i] = v.x; rw[4 * i + 1] = v.y; rw[4 * i + 2] = v.z; rw[4 * i + 3] = v.w;
+                }
             } else {
-                // the row's blocks of this k-slice: raw bytes -> this thread's strip (blocks are only 2- or 4-byte aligned)
-                constexpr int NBLK = GQ_BK / Fmt::CAP, SEG = NBLK * Fmt::BYTES;
                 const uint8_t *seg = wrow + (size_t)(k0 / Fmt::CAP) * Fmt::BYTES;
-                const uint32_t mis = (uint32_t)((uintptr_t)seg & 3u);       // 0 or 2
-                const uint32_t *seg4 = reinterpret_cast<const uint32_t *>(seg - mis);
+                const uint32_t m = (uint32_t)((uintptr_t)seg & 3u);       // blocks are only 2- or 4-byte aligned
+                const uint32_t *seg4 = reinterpret_cast<const uint32_t *>(seg - m);
+#pragma unroll
+                for (int i = 0; i < NRAW; i++) rw[i] = seg4[i];
+            }
+            const uint4 *xs = reinterpret_cast<const uint4 *>(xrow + k0);
+#pragma unroll
+            for (int i = 0; i < GQ_BK / 8; i++) xr[i] = tok_ok ? xs[i] : make_uint4(0, 0, 0, 0);
+        };
+        fetch(0, raw, xv);
+        for (int kb = 0; kb < nk; kb++) {
+            const int s = kb % GQ_STAGES;
+            if (kb + 1 < nk) fetch(kb + 1, raw_n, xv_n);
+            if (!F16W) mis = (uint32_t)((uintptr_t)(wrow + (size_t)(kb * GQ_BK / Fmt::CAP) * Fmt::BYTES) & 3u);
+            mbar_wait(&empty_bar[s], ((uint32_t)(kb / GQ_STAGES) & 1u) ^ 1u);
+            uint8_t *At = smem + s * STAGE_BYTES + rb * GQ_A_BYTES, *Bt = smem + s * STAGE_BYTES + RB * GQ_A_BYTES;
+            uint8_t *arow = At + (rr >> 3) * GQ_SBO + (rr & 7) * 16;         // + k8 * LBO
+            if (F16W) {
+#pragma unroll
+                for (int k8 = 0; k8 < GQ_BK / 8; k8++)
+                    *reinterpret_cast<uint4 *>(arow + k8 * GQ_LBO) = make_uint4(raw[4 * k8], raw[4 * k8 + 1], raw[4 * k8 + 2], raw[4 * k8 + 3]);
+            } else {
+                // raw bytes -> this thread's strip, decoded with the GEMV's Fmt::decode
                 uint32_t *strip4 = reinterpret_cast<uint32_t *>(strip);
 #pragma unroll
-                for (int i = 0; i < (SEG + 3 + 3) / 4; i++) strip4[i] = seg4[i];
+                for (int i = 0; i < NRAW; i++) strip4[i] = raw[i];
                 __syncwarp();
 #pragma unroll
                 for (int b = 0; b < NBLK; b++) {
@@ -191,24 +228,25 @@ __global__ void __launch_bounds__(GQ_THREADS, 2) gemm_q_kernel(const GemmArgs a)
                     }
                 }
             }
-            // this thread's token: 64 activations = 8 chunks
-            {
+            if (tid < NTMAX) {       // this thread's token: 64 activations = 8 chunks (zeros beyond the tile / the input)
                 uint8_t *brow = Bt + (tid >> 3) * GQ_SBO + (tid & 7) * 16;
-                const uint4 *src = reinterpret_cast<const uint4 *>(xrow + k0);
 #pragma unroll
-                for (int k8 = 0; k8 < GQ_BK / 8; k8++)
-                    *reinterpret_cast<uint4 *>(brow + k8 * GQ_LBO) = tok_ok ? src[k8] : make_uint4(0, 0, 0, 0);
+                for (int k8 = 0; k8 < GQ_BK / 8; k8++) *reinterpret_cast<uint4 *>(brow + k8 * GQ_LBO) = xv[k8];
             }
             fence_async_smem();                      // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(&full_bar[s]);
+#pragma unroll
+            for (int i = 0; i < NRAW; i++) raw[i] = raw_n[i];
+#pragma unroll
+            for (int i = 0; i < GQ_BK / 8; i++) xv[i] = xv_n[i];
         }
-        // ===== epilogue: TMEM lane = weight row =====
+        // ===== epilogue: TMEM lane = weight row; warp w reads lane quadrant w % 4 of accumulator w / 4 =====
         mbar_wait(&done_bar, 0);
         tc_fence_after();
         const float bias = a.bias != nullptr ? __half2float(a.bias[row0 + r]) : 0.f;
         for (int c0 = 0; c0 < a.nt; c0 += 16) {
             uint32_t v[16];
-            tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(rb * a.nt + c0), v);
 #pragma unroll
             for (int c = 0; c < 16; c++) {
                 const int t = tok0 + c0 + c;
@@ -222,16 +260,16 @@ __global__ void __launch_bounds__(GQ_THREADS, 2) gemm_q_kernel(const GemmArgs a)
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == PW) {
         tc_fence_after();
-        tmem_dealloc(tmem, 128);
+        tmem_dealloc(tmem, TMEM_COLS);
     }
 }
 
-template <class Fmt, bool F16W>
-static int launch_gemm(const GemmArgs &a, cudaStream_t st) {
-    auto kern = gemm_q_kernel<Fmt, F16W>;
-    const size_t smem = (size_t)GQ_STAGES * GQ_STAGE_BYTES + 128 * GQ_STRIP;
+template <class Fmt, bool F16W, int RB, int NTMAX>
+static int launch_gemm_cfg(const GemmArgs &a, cudaStream_t st) {
+    auto kern = gemm_q_kernel<Fmt, F16W, RB, NTMAX>;
+    const size_t smem = (size_t)GQ_STAGES * (RB * GQ_A_BYTES + NTMAX * GQ_BK * 2) + (size_t)128 * RB * GQ_STRIP;
     static int attr_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -239,10 +277,21 @@ static int launch_gemm(const GemmArgs &a, cudaStream_t st) {
         IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_dev = dev;
     }
-    dim3 grid(a.cy / GQ_ROWS, (a.tokens + a.nt - 1) / a.nt);
-    kern<<<grid, GQ_THREADS, smem, st>>>(a);
+    dim3 grid(a.cy / (GQ_ROWS * RB), (a.tokens + a.nt - 1) / a.nt);
+    kern<<<grid, 128 * RB + 32, smem, st>>>(a);
     IFB_LAUNCH_CHECK();
     return IFB_OK;
+}
+
+template <class Fmt, bool F16W>
+static int launch_gemm(GemmArgs a, cudaStream_t st) {
+    const int t16 = (a.tokens + 15) / 16 * 16;
+    if (a.tokens > 128 && a.cy % 256 == 0) {
+        a.nt = t16 > 256 ? 256 : t16;
+        return launch_gemm_cfg<Fmt, F16W, 2, 256>(a, st);
+    }
+    a.nt = t16 > 128 ? 128 : t16;
+    return launch_gemm_cfg<Fmt, F16W, 1, 128>(a, st);
 }
 
 // Y[tokens][cy] = X[tokens][cx] . W[cy][cx]^T (+ bias). W: any dp4a-capable block format (or fp16).
@@ -257,8 +306,7 @@ int gemm_q(int w_dtype, void *y_f16, const void *w, const void *x_f16, int64_t t
     a.w = (const uint8_t *)w; a.x = (const __half *)x_f16; a.y = (__half *)y_f16; a.bias = (const __half *)bias_f16;
     a.tokens = (int)tokens; a.cy = (int)cy; a.cx = (int)cx; a.w_dtype = w_dtype;
     a.row_bytes = (int)(w_dtype == DT_F16 ? cx * 2 : row_bytes(w_dtype, cx));
-    int nt = (int)((tokens + 15) / 16 * 16);
-    a.nt = nt > GQ_NT_MAX ? GQ_NT_MAX : nt;
+    a.nt = 0;
     switch (w_dtype) {
         case DT_F16: return launch_gemm<FmtQ4_B32T1, true>(a, st);
         case DT_Q4_B32T1A:
