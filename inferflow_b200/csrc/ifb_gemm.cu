@@ -19,6 +19,8 @@
 //    -> fp16 -> Y. The output is written in its final [tokens][cy] orientation (no transpose pass).
 //  * two CTAs fit an SM (96 KB of shared memory, 128 TMEM columns each): one CTA's block fetch latency hides behind the
 //    other's MMAs.
+#include <cuda.h>      // CUtensorMap + the driver's encode function (fetched through cudaGetDriverEntryPoint: no libcuda link)
+
 #include "ifb_formats.cuh"
 #include "ifb_kernels.h"
 
@@ -70,6 +72,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 2-D TMA tile load (SASS UTMALDG): box of the tensor map at (c0, c1) -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+// unsigned byte -> float without the conversion unit: drop the byte into the mantissa of 2^23, subtract 2^23 (exact).
+// (ncu on the first version: the XU pipe, where I2F lives, was 77 % busy -- one I2F per weight element.)
+__device__ __forceinline__ float u8f(uint32_t word, int k) {
+    return __uint_as_float(__byte_perm(word, 0x4b000000u, 0x7650u + (uint32_t)k)) - 8388608.0f;
+}
 
 // Shared-memory matrix descriptor, K-major, no swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (K-adjacent core matrices), [32,46) stride byte
@@ -92,14 +106,16 @@ struct GemmArgs {
 // apart (LBO), 8-row groups (BK/8) * 128 B apart (SBO)
 constexpr int GQ_LBO = 128, GQ_SBO = (GQ_BK / 8) * 128;
 
+// B tile (activations), written by TMA: chunk k8 (8 halves of every token) is one [NTMAX][16 B] box, boxes 16*NTMAX apart:
+//   element (t, k) at (k / 8) * 16 * NTMAX + t * 16 + (k % 8) * 2   ->   LBO = 16 * NTMAX, SBO = 128 (8 tokens x 16 B)
 template <class Fmt, bool F16W, int RB, int NTMAX>
-__global__ void __launch_bounds__(128 * RB + 32, RB == 1 ? 2 : 1) gemm_q_kernel(const GemmArgs a) {
-    constexpr int NPROD = 128 * RB;                       // producer threads: thread = weight row and token of the tile
-    constexpr int PW = NPROD / 32;                        // producer warps; warp PW issues the MMAs
+__global__ void __launch_bounds__(128 * RB + 64, RB == 1 ? 2 : 1) gemm_q_kernel(const GemmArgs a, const __grid_constant__ CUtensorMap xmap) {
+    constexpr int NPROD = 128 * RB;                       // producer threads: thread = one weight row of the CTA's rows
+    constexpr int PW = NPROD / 32;                        // producer warps; warp PW issues the MMAs, warp PW+1 the TMA loads of X
     constexpr int B_BYTES = NTMAX * GQ_BK * 2;
     constexpr int STAGE_BYTES = RB * GQ_A_BYTES + B_BYTES;
     constexpr int TMEM_COLS = RB * NTMAX < 32 ? 32 : RB * NTMAX;
-    static_assert(NTMAX <= NPROD, "a producer thread copies one token");
+    constexpr uint32_t B_LBO = 16 * NTMAX, B_SBO = 128;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t full_bar[GQ_STAGES], empty_bar[GQ_STAGES], done_bar;
     __shared__ uint32_t tmem_base_s;
@@ -110,7 +126,8 @@ __global__ void __launch_bounds__(128 * RB + 32, RB == 1 ? 2 : 1) gemm_q_kernel(
     uint8_t *strips = smem + GQ_STAGES * STAGE_BYTES;     // [NPROD][GQ_STRIP]
 
     if (tid == 0) {
-        for (int i = 0; i < GQ_STAGES; i++) { mbar_init(&full_bar[i], NPROD); mbar_init(&empty_bar[i], 1); }
+        // a stage is full when every producer warp has delivered its rows of A (PW arrivals) and the TMA bytes of B landed
+        for (int i = 0; i < GQ_STAGES; i++) { mbar_init(&full_bar[i], PW + 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(&done_bar, 1);
         mbar_fence_init();
     }
@@ -120,7 +137,20 @@ __global__ void __launch_bounds__(128 * RB + 32, RB == 1 ? 2 : 1) gemm_q_kernel(
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
 
-    if (warp == PW) {
+    if (warp == PW + 1) {
+        // ===== activation loader: one thread, runs up to GQ_STAGES slices ahead =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nk; kb++) {
+                const int s = kb % GQ_STAGES;
+                mbar_wait(&empty_bar[s], ((uint32_t)(kb / GQ_STAGES) & 1u) ^ 1u);
+                uint8_t *Bt = smem + s * STAGE_BYTES + RB * GQ_A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)B_BYTES);
+#pragma unroll
+                for (int k8 = 0; k8 < GQ_BK / 8; k8++)           // tokens beyond the input are zero-filled by the TMA unit
+                    tma_load_2d(Bt + k8 * B_LBO, &xmap, kb * GQ_BK + k8 * 8, tok0, &full_bar[s]);
+            }
+        }
+    } else if (warp == PW) {
         // ===== MMA issuer: one thread =====
         if (lane == 0) {
             // instruction descriptor (InstrDescriptor): c_format F32 (bits 4-5 = 1), a/b fp16 K-major (0), N >> 3 at bit 17,
@@ -134,7 +164,7 @@ __global__ void __launch_bounds__(128 * RB + 32, RB == 1 ? 2 : 1) gemm_q_kernel(
 #pragma unroll
                 for (int k = 0; k < GQ_BK / 16; k++) {
                     // one instruction consumes K = 16: two K-adjacent core matrices = 2 * LBO bytes further
-                    const uint64_t bd = umma_desc(b_addr + k * 2 * GQ_LBO, GQ_LBO, GQ_SBO);
+                    const uint64_t bd = umma_desc(b_addr + k * 2 * B_LBO, B_LBO, B_SBO);
 #pragma unroll
                     for (int rb = 0; rb < RB; rb++) {
                         const uint64_t ad = umma_desc(a_addr + rb * GQ_A_BYTES + k * 2 * GQ_LBO, GQ_LBO, GQ_SBO);
@@ -146,21 +176,17 @@ __global__ void __launch_bounds__(128 * RB + 32, RB == 1 ? 2 : 1) gemm_q_kernel(
             umma_commit(&done_bar);                  // accumulators complete
         }
     } else {
-        // ===== producers: thread = weight row `tid` of the CTA's rows, and token `tid` of the token tile =====
+        // ===== producers: thread = weight row `tid` of the CTA's rows =====
         const int r = tid, rb = r >> 7, rr = r & 127;
         const uint8_t *wrow = a.w + (size_t)(row0 + r) * a.row_bytes;
-        const bool tok_in = tid < a.nt;                          // this thread copies a token of the tile
-        const bool tok_ok = tok_in && tok0 + tid < a.tokens;
-        const __half *xrow = a.x + (size_t)(tok_ok ? tok0 + tid : 0) * a.cx;
         uint8_t *strip = strips + r * GQ_STRIP;
         constexpr int NBLK = F16W ? 1 : GQ_BK / Fmt::CAP, SEG = F16W ? GQ_BK * 2 : NBLK * Fmt::BYTES;
         constexpr int NRAW = F16W ? GQ_BK * 2 / 4 : (SEG + 3 + 3) / 4;     // 32-bit words fetched per k-slice
-        uint32_t raw[NRAW], raw_n[NRAW];
-        uint4 xv[GQ_BK / 8], xv_n[GQ_BK / 8];
-        uint32_t mis = 0;
-        // fetch of k-slice kb into registers (issued one slice ahead: the L2 / HBM latency runs under the previous slice's
-        // dequantization and under the MMAs)
-        auto fetch = [&](int kb, uint32_t *rw, uint4 *xr) {
+        // the row's blocks of a k-slice are fetched into registers TWO slices ahead: the L2 / HBM round trip (the
+        // first version stalled ~3 us per slice on it) runs under two slices of dequantization and MMAs
+        uint32_t raw0[NRAW], raw1[NRAW], raw2[NRAW];
+        auto fetch = [&](int kb, uint32_t *rw) {
+            if (kb >= nk) return;
             const int k0 = kb * GQ_BK;
             if (F16W) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(wrow + (size_t)k0 * 2);
@@ -176,17 +202,11 @@ __global__ void __launch_bounds__(128 * RB + 32, RB == 1 ? 2 : 1) gemm_q_kernel(
 #pragma unroll
                 for (int i = 0; i < NRAW; i++) rw[i] = seg4[i];
             }
-            const uint4 *xs = reinterpret_cast<const uint4 *>(xrow + k0);
-#pragma unroll
-            for (int i = 0; i < GQ_BK / 8; i++) xr[i] = tok_ok ? xs[i] : make_uint4(0, 0, 0, 0);
         };
-        fetch(0, raw, xv);
-        for (int kb = 0; kb < nk; kb++) {
+        auto produce = [&](int kb, const uint32_t *raw) {
             const int s = kb % GQ_STAGES;
-            if (kb + 1 < nk) fetch(kb + 1, raw_n, xv_n);
-            if (!F16W) mis = (uint32_t)((uintptr_t)(wrow + (size_t)(kb * GQ_BK / Fmt::CAP) * Fmt::BYTES) & 3u);
             mbar_wait(&empty_bar[s], ((uint32_t)(kb / GQ_STAGES) & 1u) ^ 1u);
-            uint8_t *At = smem + s * STAGE_BYTES + rb * GQ_A_BYTES, *Bt = smem + s * STAGE_BYTES + RB * GQ_A_BYTES;
+            uint8_t *At = smem + s * STAGE_BYTES + rb * GQ_A_BYTES;
             uint8_t *arow = At + (rr >> 3) * GQ_SBO + (rr & 7) * 16;         // + k8 * LBO
             if (F16W) {
 #pragma unroll
@@ -194,6 +214,7 @@ __global__ void __launch_bounds__(128 * RB + 32, RB == 1 ? 2 : 1) gemm_q_kernel(
                     *reinterpret_cast<uint4 *>(arow + k8 * GQ_LBO) = make_uint4(raw[4 * k8], raw[4 * k8 + 1], raw[4 * k8 + 2], raw[4 * k8 + 3]);
             } else {
                 // raw bytes -> this thread's strip, decoded with the GEMV's Fmt::decode
+                const uint32_t mis = (uint32_t)((uintptr_t)(wrow + (size_t)(kb * GQ_BK / Fmt::CAP) * Fmt::BYTES) & 3u);
                 uint32_t *strip4 = reinterpret_cast<uint32_t *>(strip);
 #pragma unroll
                 for (int i = 0; i < NRAW; i++) strip4[i] = raw[i];
@@ -211,34 +232,37 @@ __global__ void __launch_bounds__(128 * RB + 32, RB == 1 ? 2 : 1) gemm_q_kernel(
                         for (int j = 0; j < 4; j++) {
                             // element e of the block sits in byte e%4 of codes[e/4] ... except for the nibble-split formats,
                             // whose staged order is (x0,x2,x4,x6)(x1,x3,x5,x7) per group of 8 (see x_pos in ifb_gemv_dev.cuh)
-                            int q0, q1;
+                            float q0, q1;
                             if (Fmt::XSPLIT) {
-                                q0 = (codes[2 * c8] >> (8 * j)) & 0xff;          // element 8*c8 + 2j
-                                q1 = (codes[2 * c8 + 1] >> (8 * j)) & 0xff;      // element 8*c8 + 2j + 1
+                                q0 = u8f(codes[2 * c8], j);                  // element 8*c8 + 2j
+                                q1 = u8f(codes[2 * c8 + 1], j);              // element 8*c8 + 2j + 1
+                            } else if (Fmt::SIGNED) {
+                                const int e = 8 * c8 + 2 * j;                // signed codes: bias by 128, take it back exactly
+                                q0 = u8f(codes[e >> 2] ^ 0x80808080u, e & 3) - 128.0f;
+                                q1 = u8f(codes[(e + 1) >> 2] ^ 0x80808080u, (e + 1) & 3) - 128.0f;
                             } else {
                                 const int e = 8 * c8 + 2 * j;
-                                q0 = (codes[e >> 2] >> (8 * (e & 3))) & 0xff;
-                                q1 = (codes[(e + 1) >> 2] >> (8 * ((e + 1) & 3))) & 0xff;
+                                q0 = u8f(codes[e >> 2], e & 3);
+                                q1 = u8f(codes[(e + 1) >> 2], (e + 1) & 3);
                             }
-                            if (Fmt::SIGNED) { q0 = (int)(int8_t)q0; q1 = (int)(int8_t)q1; }
                             // TensorOpr::Dequantize: value = q * scale + base in fp32, stored as half
-                            oh[j] = __floats2half2_rn(fmaf((float)q0, sc, ba), fmaf((float)q1, sc, ba));
+                            oh[j] = __floats2half2_rn(fmaf(q0, sc, ba), fmaf(q1, sc, ba));
                         }
                         *reinterpret_cast<uint4 *>(arow + (b * (Fmt::CAP / 8) + c8) * GQ_LBO) = out;
                     }
                 }
             }
-            if (tid < NTMAX) {       // this thread's token: 64 activations = 8 chunks (zeros beyond the tile / the input)
-                uint8_t *brow = Bt + (tid >> 3) * GQ_SBO + (tid & 7) * 16;
-#pragma unroll
-                for (int k8 = 0; k8 < GQ_BK / 8; k8++) *reinterpret_cast<uint4 *>(brow + k8 * GQ_LBO) = xv[k8];
-            }
             fence_async_smem();                      // generic-proxy stores -> visible to the tensor core (async proxy)
-            mbar_arrive(&full_bar[s]);
-#pragma unroll
-            for (int i = 0; i < NRAW; i++) raw[i] = raw_n[i];
-#pragma unroll
-            for (int i = 0; i < GQ_BK / 8; i++) xv[i] = xv_n[i];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[s]);
+        };
+        fetch(0, raw0);
+        fetch(1, raw1);
+        for (int kb = 0; kb < nk; kb += 3) {         // register sets rotate by name: the loop is unrolled by three
+            fetch(kb + 2, raw2);
+            produce(kb, raw0);
+            if (kb + 1 < nk) { fetch(kb + 3, raw0); produce(kb + 1, raw1); }
+            if (kb + 2 < nk) { fetch(kb + 4, raw1); produce(kb + 2, raw2); }
         }
         // ===== epilogue: TMEM lane = weight row; warp w reads lane quadrant w % 4 of accumulator w / 4 =====
         mbar_wait(&done_bar, 0);
@@ -266,6 +290,34 @@ __global__ void __launch_bounds__(128 * RB + 32, RB == 1 ? 2 : 1) gemm_q_kernel(
     }
 }
 
+// the activation matrix [tokens][cx] fp16 as a 2-D tensor map with a box of NTMAX tokens x 8 halves (16 bytes): one
+// TMA load lands chunk k8 of every token of the tile contiguously -- the UMMA core-matrix layout of the B operand
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_xmap(CUtensorMap *map, const void *x, int64_t tokens, int64_t cx, int ntmax) {
+    static EncodeTiledFn encode = nullptr;
+    if (encode == nullptr) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        IFB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        IFB_CHECK_ARG(fn != nullptr && qres == cudaDriverEntryPointSuccess, "gemm: the driver does not export cuTensorMapEncodeTiled");
+        encode = (EncodeTiledFn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)cx, (cuuint64_t)tokens};
+    const cuuint64_t strides[1] = {(cuuint64_t)cx * 2};
+    const cuuint32_t box[2] = {8, (cuuint32_t)ntmax};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(x), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("gemm: cuTensorMapEncodeTiled failed (%d) for x [%lld][%lld]", (int)r, (long long)tokens, (long long)cx);
+        return IFB_ERR_CUDA;
+    }
+    return IFB_OK;
+}
+
 template <class Fmt, bool F16W, int RB, int NTMAX>
 static int launch_gemm_cfg(const GemmArgs &a, cudaStream_t st) {
     auto kern = gemm_q_kernel<Fmt, F16W, RB, NTMAX>;
@@ -277,8 +329,11 @@ static int launch_gemm_cfg(const GemmArgs &a, cudaStream_t st) {
         IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_dev = dev;
     }
+    CUtensorMap xmap;
+    int rc = make_xmap(&xmap, a.x, a.tokens, a.cx, NTMAX);
+    if (rc != IFB_OK) return rc;
     dim3 grid(a.cy / (GQ_ROWS * RB), (a.tokens + a.nt - 1) / a.nt);
-    kern<<<grid, 128 * RB + 32, smem, st>>>(a);
+    kern<<<grid, 128 * RB + 64, smem, st>>>(a, xmap);
     IFB_LAUNCH_CHECK();
     return IFB_OK;
 }
