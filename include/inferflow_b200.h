@@ -169,6 +169,15 @@ int32_t ifb_attn_decode_append(int32_t kv_dtype, void *out_f16, const void *q_f1
                                float kq_scale, int32_t rope_order, int32_t rope_dims, float rope_theta,
                                void *workspace, ifb_stream_t stream);
 
+/* Attention for q_tokens > 1 (the prompt): T query tokens at positions pos0..pos0+T-1, whose K/V rows are already in the
+ * cache (ifb_kv_append), attend causally over positions 0..pos0+T-1. Replaces ProcessGpuLayer_Attention with rows > 1
+ * (inference_worker.cc:1130-1320, :1639-1724: dequantize prefix, RepeatKV, Gemm_Alg2, SoftMax, Gemm_Alg2) without the
+ * [heads][T][ctx] score tensor -- any prompt the cache holds works (the reference refuses beyond its scratch size,
+ * :2612-2618). q / out fp16 [T][heads*head_dim], q with RoPE applied. head_dim 64 or 128. */
+int32_t ifb_attn_prefill(int32_t kv_dtype, void *out_f16, const void *q_f16, const void *kcache, const void *vcache,
+                         int32_t tokens, int32_t pos0, int32_t heads, int32_t kv_heads, int32_t head_dim,
+                         int32_t max_ctx, ifb_stream_t stream);
+
 /* ------------------------------------------------------------------ MoE router
  * HostTensorOpr::BuildRowsForMoE (src/tensor/host_tensor_opr.cc:190-244) on device:
  * scores fp16 [rows][experts] (softmax over all experts already applied, as in
@@ -247,6 +256,13 @@ int32_t ifb_model_kv_reset(ifb_model_t *m, int32_t ctx_len, int32_t fill_synthet
  * next token (int32, device). Captured as a CUDA graph internally; async on stream. */
 int32_t ifb_model_decode(ifb_model_t *m, int32_t token_id, const int32_t *token_dev, int32_t pos,
                          ifb_stream_t stream);
+/* The prompt in ONE pass (the reference's inference step with q_tokens = n): n tokens (host array) at positions
+ * pos0..pos0+n-1 through every layer with the tensor-core GEMM and the prefill attention, K/V rows appended, logits and
+ * greedy next token of the LAST prompt token left where ifb_model_decode leaves them; ifb_model_decode_next continues.
+ * ifb_model_prefill_supported() == 0 (tensor parallel, MoE, dims not multiples of 128, weight types without a
+ * tensor-core path): feed the prompt token by token with ifb_model_decode instead. */
+int32_t ifb_model_prefill_supported(const ifb_model_t *m);
+int32_t ifb_model_prefill(ifb_model_t *m, const int32_t *tokens_host, int32_t n, int32_t pos0, ifb_stream_t stream);
 /* replay the step graph from the position / token the previous step left in device memory
  * (back-to-back generation without host round trips) */
 int32_t ifb_model_decode_next(ifb_model_t *m, ifb_stream_t stream);

@@ -93,6 +93,9 @@ def _load():
     L.ifb_model_kv_reset.argtypes = [vp, i32, i32, C.c_uint64, vp]
     L.ifb_model_decode.argtypes = [vp, i32, vp, i32, vp]
     L.ifb_model_decode_next.argtypes = [vp, vp]
+    L.ifb_model_prefill.argtypes = [vp, vp, i32, i32, vp]
+    L.ifb_model_prefill_supported.argtypes = [vp]
+    L.ifb_attn_prefill.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.ifb_model_issue_parts.argtypes = [vp, i32, vp]
     L.ifb_model_logits.restype = vp
     L.ifb_model_logits.argtypes = [vp]
@@ -129,7 +132,7 @@ DECLARED = [
     "ifb_model_init_synthetic", "ifb_model_load_tensor", "ifb_model_kv_reset", "ifb_model_decode",
     "ifb_model_logits", "ifb_model_next_token", "ifb_model_kernel_launches_per_step",
     "ifb_model_tp_export", "ifb_model_tp_import", "ifb_model_decode_next", "ifb_model_tensor_ptr",
-    "ifb_memcpy_d2h", "ifb_memcpy_h2d", "ifb_device_synchronize", "ifb_model_issue_parts", "ifb_memcpy_d2h_async", "ifb_memcpy_h2d_async", "ifb_model_step_status",
+    "ifb_memcpy_d2h", "ifb_memcpy_h2d", "ifb_device_synchronize", "ifb_model_issue_parts", "ifb_memcpy_d2h_async", "ifb_memcpy_h2d_async", "ifb_model_step_status", "ifb_model_prefill", "ifb_model_prefill_supported", "ifb_attn_prefill",
 ]
 
 

@@ -165,6 +165,12 @@ int32_t ifb_attn_decode(int32_t kv_dtype, void *out, const void *q, const void *
     return attn_decode(a, (cudaStream_t)st);
 }
 
+int32_t ifb_attn_prefill(int32_t kv_dtype, void *out, const void *q, const void *kc, const void *vc, int32_t tokens, int32_t pos0,
+                         int32_t heads, int32_t kv_heads, int32_t hd, int32_t max_ctx, ifb_stream_t st) {
+    IFB_CHECK_ARG(out && q && kc && vc, "prefill attention: null tensor");
+    return attn_prefill(kv_dtype, out, q, kc, vc, tokens, pos0, heads, kv_heads, hd, max_ctx, (cudaStream_t)st);
+}
+
 int32_t ifb_attn_decode_append(int32_t kv_dtype, void *out, const void *q, const void *k_new, const void *v_new,
                                void *kc, void *vc, int32_t heads, int32_t kv_heads, int32_t hd, int32_t max_ctx,
                                int32_t ctx_len, float kq_scale, int32_t rope_order, int32_t rope_dims,

@@ -68,6 +68,11 @@ int gemv_chain_launch(const GemvLaunch *ops, int nops, cudaStream_t st);
 int gemm_q(int w_dtype, void *y_f16, const void *w, const void *x_f16, int64_t tokens, int64_t cy, int64_t cx,
            const void *bias_f16, cudaStream_t st);
 
+// rows > 1 attention: T query tokens at positions pos0.. (K/V rows already appended) over cache positions 0..pos0+T-1
+int attn_prefill(int kv_dtype, void *out_f16, const void *q_f16, const void *kcache, const void *vcache, int tokens, int pos0,
+                 int heads, int kv_heads, int head_dim, int max_ctx, cudaStream_t st);
+int embed_rows(void *dst_f16, const void *table_f16, const int32_t *tokens_dev, int n, int64_t cols, int vocab, cudaStream_t st);
+
 int quantize_rows(int dt, void *dst, const void *src_f16, int64_t rows, int64_t cx, cudaStream_t st);
 int dequantize_rows(int dt, void *dst_f16, const void *src, int64_t rows, int64_t cx, cudaStream_t st);
 

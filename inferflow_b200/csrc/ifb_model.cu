@@ -71,6 +71,10 @@ struct ifb_model {
     DevBuf step_layers, step_ctr, partials, ybuf, qkvw, attw, hbufw;
     int *step_err = nullptr;        // pinned host memory: error record of a step kernel that hit its deadline
     int host_pos = -1;              // host mirror of the device-side position (decode_next must not run past max_ctx)
+    // prompt pass (ifb_model_prefill): activations of T tokens, grown on demand
+    int pf_cap = 0;
+    void *pf_x = nullptr, *pf_xn = nullptr, *pf_q = nullptr, *pf_k = nullptr, *pf_v = nullptr, *pf_att = nullptr, *pf_h1 = nullptr,
+         *pf_h3 = nullptr, *pf_tmp = nullptr, *pf_tok = nullptr;
     int64_t smem_kb[5] = {0, 0, 0, 0, 0};   // per-CTA shared-memory budget of the QKV / wo / GLU / w2 / lm_head GEMVs (KB, 0 = kernel default)
 };
 
@@ -271,6 +275,8 @@ extern "C" void ifb_model_destroy(ifb_model_t *m) {
         if ((int)p != m->spec.tp_rank && m->peer_xchg[p] != nullptr) cudaIpcCloseMemHandle(m->peer_xchg[p]);
     for (void *p : m->allocs) cudaFree(p);
     if (m->step_err) cudaFreeHost(m->step_err);
+    for (void *p : {m->pf_x, m->pf_xn, m->pf_q, m->pf_k, m->pf_v, m->pf_att, m->pf_h1, m->pf_h3, m->pf_tmp, m->pf_tok})
+        if (p) cudaFree(p);
     delete m;
 }
 
@@ -1078,6 +1084,85 @@ extern "C" int32_t ifb_model_issue_parts(ifb_model_t *m, int32_t parts, ifb_stre
 extern "C" const void *ifb_model_logits(const ifb_model_t *m) { return m ? m->logits.p : nullptr; }
 extern "C" const int32_t *ifb_model_next_token(const ifb_model_t *m) { return m ? (const int32_t *)m->scalars.p + 2 : nullptr; }
 extern "C" int32_t ifb_model_kernel_launches_per_step(const ifb_model_t *m) { return m ? m->launches_per_step : 0; }
+
+// ---------------------------------------------------------------------------------------
+// prompt pass: T tokens through every layer at once (rows > 1)
+// ---------------------------------------------------------------------------------------
+// The reference runs a prompt as ONE inference step with q_tokens = T (GpuInferenceWorker::Run, ProcessGpuLayer with
+// rows > 1): RmsNorm rows, MatrixMultiplication rows > 1 = Dequantize + cuBLAS GEMM on the fp16 activations (no Q8
+// activation quantization on this branch, inference_worker.cc:2364-2432), PositionEmbedding, SetK/VRows, batched attention,
+// ... and the lm_head on the last row. Same here: ifb_gemm_q (tensor cores, weights dequantized tile by tile),
+// kv_append (RoPE + cache rows), attn_prefill, elementwise kernels; then the decode machinery for the last row's logits.
+static bool prefill_supported(const ifb_model *m) {
+    const auto &s = m->spec;
+    auto ok_w = [](int dt) { return dt == DT_F16 || dt == DT_Q8_B32T2 || dt == DT_Q6_B64T1 || dt == DT_Q5_B64T1 || dt == DT_Q4_B32T1A ||
+                                    dt == DT_Q4_B32T1B || dt == DT_Q4_B64T1 || dt == DT_Q3H_B64T1; };
+    return s.tp_size == 1 && s.experts == 0 && ok_w(s.weight_dtype) && (m->hd == 64 || m->hd == 128) && s.d_model % 128 == 0 &&
+           m->q_dim_l % 128 == 0 && m->kv_dim_l % 128 == 0 && s.d_ffn % 128 == 0 && (s.rope_order == 0 || s.rope_order == 2);
+}
+
+extern "C" int32_t ifb_model_prefill_supported(const ifb_model_t *m) { return (m != nullptr && prefill_supported(m)) ? 1 : 0; }
+
+extern "C" int32_t ifb_model_prefill(ifb_model_t *m, const int32_t *tokens_host, int32_t n, int32_t pos0, ifb_stream_t stream) {
+    IFB_CHECK_ARG(m != nullptr && tokens_host != nullptr, "prefill: null argument");
+    IFB_CHECK_ARG(n >= 1 && pos0 >= 0 && pos0 + n <= m->spec.max_ctx, "prefill: positions %d..%d outside max_context_len %d", pos0, pos0 + n, m->spec.max_ctx);
+    IFB_CHECK_ARG(prefill_supported(m), "prefill: this model runs its prompt token by token (tensor parallel, mixture of experts, "
+                  "a weight type without a tensor-core path, or dimensions that are not multiples of 128)");
+    for (int i = 0; i < n; i++) IFB_CHECK_ARG(tokens_host[i] >= 0 && tokens_host[i] < m->spec.vocab, "prefill: token %d outside the vocabulary", tokens_host[i]);
+    cudaStream_t st = (cudaStream_t)stream;
+    const auto &s = m->spec;
+    const int d = s.d_model, qd = m->q_dim_l, kvd = m->kv_dim_l, f = s.d_ffn, wdt = s.weight_dtype;
+    if (n > m->pf_cap) {
+        IFB_CUDA(cudaStreamSynchronize(st));
+        for (void **p : {&m->pf_x, &m->pf_xn, &m->pf_q, &m->pf_k, &m->pf_v, &m->pf_att, &m->pf_h1, &m->pf_h3, &m->pf_tmp, &m->pf_tok})
+            if (*p) { cudaFree(*p); *p = nullptr; }
+        const int cap = (n + 63) / 64 * 64;
+        const size_t T = (size_t)cap;
+        IFB_CUDA(cudaMalloc(&m->pf_x, T * d * 2));   IFB_CUDA(cudaMalloc(&m->pf_xn, T * d * 2));
+        IFB_CUDA(cudaMalloc(&m->pf_q, T * qd * 2));  IFB_CUDA(cudaMalloc(&m->pf_k, T * kvd * 2)); IFB_CUDA(cudaMalloc(&m->pf_v, T * kvd * 2));
+        IFB_CUDA(cudaMalloc(&m->pf_att, T * qd * 2)); IFB_CUDA(cudaMalloc(&m->pf_h1, T * f * 2)); IFB_CUDA(cudaMalloc(&m->pf_h3, T * f * 2));
+        IFB_CUDA(cudaMalloc(&m->pf_tmp, T * d * 2)); IFB_CUDA(cudaMalloc(&m->pf_tok, T * 4));
+        m->pf_cap = cap;
+    }
+    IFB_CUDA(cudaMemcpyAsync(m->pf_tok, tokens_host, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    TRY(embed_rows(m->pf_x, m->tok_emb.p, (const int32_t *)m->pf_tok, n, d, s.vocab, st));
+    for (int li = 0; li < s.layers; li++) {
+        LayerW &L = m->layers[li];
+        TRY(rmsnorm(m->pf_xn, m->pf_x, L.attn_norm.p, n, d, s.norm_eps, 0.f, st));
+        TRY(gemm_q(wdt, m->pf_q, L.wq.p, m->pf_xn, n, qd, d, nullptr, st));
+        TRY(gemm_q(wdt, m->pf_k, L.wk.p, m->pf_xn, n, kvd, d, nullptr, st));
+        TRY(gemm_q(wdt, m->pf_v, L.wv.p, m->pf_xn, n, kvd, d, nullptr, st));
+        KvAppend ka;
+        ka.kv_dtype = s.kv_dtype; ka.kv_heads = m->kv_heads_l; ka.head_dim = m->hd; ka.max_ctx = s.max_ctx; ka.pos0 = pos0; ka.n_tokens = n;
+        ka.kcache = L.kcache.p; ka.vcache = L.vcache.p; ka.k = m->pf_k; ka.v = m->pf_v;
+        ka.rope = 1; ka.rope_order = s.rope_order; ka.rope_dims = 0; ka.rope_theta = s.rope_theta; ka.q = m->pf_q; ka.q_heads = m->heads_l;
+        TRY(kv_append(ka, st));
+        TRY(attn_prefill(s.kv_dtype, m->pf_att, m->pf_q, L.kcache.p, L.vcache.p, n, pos0, m->heads_l, m->kv_heads_l, m->hd, s.max_ctx, st));
+        TRY(gemm_q(wdt, m->pf_tmp, L.wo.p, m->pf_att, n, d, qd, nullptr, st));
+        TRY(add(m->pf_x, m->pf_x, m->pf_tmp, (int64_t)n * d, st));
+        TRY(rmsnorm(m->pf_xn, m->pf_x, L.ffn_norm.p, n, d, s.norm_eps, 0.f, st));
+        TRY(gemm_q(wdt, m->pf_h1, L.w1.p, m->pf_xn, n, f, d, nullptr, st));
+        TRY(gemm_q(wdt, m->pf_h3, L.w3.p, m->pf_xn, n, f, d, nullptr, st));
+        TRY(silu_mul(m->pf_h1, m->pf_h1, m->pf_h3, (int64_t)n * f, st));
+        TRY(gemm_q(wdt, m->pf_tmp, L.w2.p, m->pf_h1, n, d, f, nullptr, st));
+        TRY(add(m->pf_x, m->pf_x, m->pf_tmp, (int64_t)n * d, st));
+    }
+    // the last row: final norm + lm_head + greedy pick, and the device-side position / token for decode_next
+    IFB_CUDA(cudaMemcpyAsync(m->x0.p, (const uint8_t *)m->pf_x + (size_t)(n - 1) * d * 2, (size_t)d * 2, cudaMemcpyDeviceToDevice, st));
+    GemvLaunch h;
+    h.w_dtype = s.lm_head_dtype; h.nseg = 1; h.w[0] = m->lm_head.p; h.rows[0] = m->vocab_l; h.cx = d;
+    h.x = m->x0.p; h.norm_w = m->out_norm.p; h.norm_eps = s.norm_eps; h.y = m->logits.p;
+    h.quantize_x = (s.lm_head_dtype != DT_F16) ? 1 : 0;
+    TRY(gemv_launch(h, st));
+    int32_t *sc = (int32_t *)m->scalars.p;
+    set_scalars_kernel<<<1, 1, 0, st>>>(sc, pos0 + n - 1, tokens_host[n - 1], nullptr);
+    IFB_LAUNCH_CHECK();
+    TRY(argmax(sc + 2, m->logits.p, s.vocab, st));
+    advance_kernel<<<1, 1, 0, st>>>(sc, 1);
+    IFB_LAUNCH_CHECK();
+    m->host_pos = pos0 + n - 1;
+    return IFB_OK;
+}
 
 extern "C" int32_t ifb_model_tp_export(ifb_model_t *m, void *host_handle) {
     IFB_CHECK_ARG(m != nullptr && host_handle != nullptr, "tp_export: null argument");

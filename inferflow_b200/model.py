@@ -120,6 +120,16 @@ class Model:
     def decode(self, token_id, pos, stream=0, token_dev=None):
         check(lib.ifb_model_decode(self._h, token_id, token_dev, pos, stream), "ifb_model_decode")
 
+    def prefill(self, tokens, pos0=0, stream=0):
+        """the prompt in one pass (ifb_model_prefill); logits / next token of the last prompt token as after decode()"""
+        import numpy as np
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        check(lib.ifb_model_prefill(self._h, t.ctypes.data, len(t), pos0, stream), "ifb_model_prefill")
+
+    @property
+    def prefill_supported(self):
+        return bool(lib.ifb_model_prefill_supported(self._h))
+
     def decode_next(self, stream=0):
         check(lib.ifb_model_decode_next(self._h, stream), "ifb_model_decode_next")
 
