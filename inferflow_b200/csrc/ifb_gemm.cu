@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(128 * RB + 64, RB == 1 ? 2 : 1) gemm_q_kernel(
                 const uint32_t m = (uint32_t)((uintptr_t)seg & 3u);       // blocks are only 2- or 4-byte aligned
                 const uint32_t *seg4 = reinterpret_cast<const uint32_t *>(seg - m);
 #pragma unroll
-                for (int i = 0; i < NRAW; i++) rw[i] = seg4[i];
+                for (int i = 0; i < NRAW; i++) rw[i] = (i * 4 < (int)m + SEG) ? seg4[i] : 0u;   // never a word past the row's bytes
             }
         };
         auto produce = [&](int kb, const uint32_t *raw) {

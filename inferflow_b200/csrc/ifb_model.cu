@@ -1010,20 +1010,10 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
     return IFB_OK;
 }
 
-extern "C" int32_t ifb_model_decode(ifb_model_t *m, int32_t token_id, const int32_t *token_dev, int32_t pos,
-                                    ifb_stream_t stream) {
-    IFB_CHECK_ARG(m != nullptr, "null model");
-    IFB_CHECK_ARG(pos >= 0 && pos < m->spec.max_ctx, "decode: position %d outside max_context_len %d", pos, m->spec.max_ctx);
-    IFB_CHECK_ARG(m->spec.tp_size == 1 || !m->peer_xchg.empty(), "decode: tensor-parallel model without imported peer buffers");
-    IFB_CHECK_ARG(token_id < m->spec.vocab, "decode: token %d outside the vocabulary (%d)", token_id, m->spec.vocab);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (pos >= 0 && (token_id >= 0 || token_dev != nullptr)) {
-        set_scalars_kernel<<<1, 1, 0, st>>>((int32_t *)m->scalars.p, pos, token_id, token_id < 0 ? token_dev : nullptr);
-        IFB_LAUNCH_CHECK();
-    }
-    m->host_pos = pos;
-    if (!m->use_graph) return issue_step(m, st, &m->launches_per_step);
-    if (!m->graph_ready) {
+// capture the step once (position and token live in device memory, so the graph replays without host data)
+static int prepare_graph(ifb_model *m, cudaStream_t st) {
+    if (!m->use_graph || m->graph_ready) return IFB_OK;
+    {
         // warm every kernel once outside capture (cudaFuncSetAttribute etc. are not capturable)
         int32_t saved[3];   // pos, token, next token -- NOT the step sequence number (sc[3]): the warm-up step was a
                             // real exchange round for the peers
@@ -1046,7 +1036,7 @@ extern "C" int32_t ifb_model_decode(ifb_model_t *m, int32_t token_id, const int3
                 if (m->graph) { cudaGraphDestroy(m->graph); m->graph = nullptr; }
                 m->graph_exec = nullptr;
                 m->use_graph = 0;
-                return issue_step(m, st, &m->launches_per_step);
+                return IFB_OK;
             }
             if (rc != IFB_OK) return rc;
             set_last_error("graph capture failed: %s", cudaGetErrorString(e));
@@ -1054,19 +1044,38 @@ extern "C" int32_t ifb_model_decode(ifb_model_t *m, int32_t token_id, const int3
         }
         m->graph_ready = true;
     }
+    return IFB_OK;
+}
+
+extern "C" int32_t ifb_model_decode(ifb_model_t *m, int32_t token_id, const int32_t *token_dev, int32_t pos,
+                                    ifb_stream_t stream) {
+    IFB_CHECK_ARG(m != nullptr, "null model");
+    IFB_CHECK_ARG(pos >= 0 && pos < m->spec.max_ctx, "decode: position %d outside max_context_len %d", pos, m->spec.max_ctx);
+    IFB_CHECK_ARG(m->spec.tp_size == 1 || !m->peer_xchg.empty(), "decode: tensor-parallel model without imported peer buffers");
+    IFB_CHECK_ARG(token_id < m->spec.vocab, "decode: token %d outside the vocabulary (%d)", token_id, m->spec.vocab);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pos >= 0 && (token_id >= 0 || token_dev != nullptr)) {
+        set_scalars_kernel<<<1, 1, 0, st>>>((int32_t *)m->scalars.p, pos, token_id, token_id < 0 ? token_dev : nullptr);
+        IFB_LAUNCH_CHECK();
+    }
+    m->host_pos = pos;
+    if (!m->use_graph) return issue_step(m, st, &m->launches_per_step);
+    TRY(prepare_graph(m, st));
+    if (!m->use_graph) return issue_step(m, st, &m->launches_per_step);   // (a driver that cannot capture the launch)
     IFB_CUDA(cudaGraphLaunch(m->graph_exec, st));
     return IFB_OK;
 }
 
 // replay without touching the scalars: continues from the position/token the previous step left
 extern "C" int32_t ifb_model_decode_next(ifb_model_t *m, ifb_stream_t stream) {
-    IFB_CHECK_ARG(m != nullptr && m->host_pos >= 0 && (m->graph_ready || !m->use_graph), "decode_next: call ifb_model_decode first");
+    IFB_CHECK_ARG(m != nullptr && m->host_pos >= 0, "decode_next: call ifb_model_decode or ifb_model_prefill first");
     if (m->host_pos + 1 >= m->spec.max_ctx) {
         set_last_error("decode_next: position %d is outside max_context_len %d", m->host_pos + 1, m->spec.max_ctx);
         return IFB_ERR_STATE;
     }
     m->host_pos++;
     cudaStream_t st = (cudaStream_t)stream;
+    TRY(prepare_graph(m, st));        // (after a prefill the step has not been captured yet)
     if (!m->use_graph) return issue_step(m, st, &m->launches_per_step);
     IFB_CUDA(cudaGraphLaunch(m->graph_exec, st));
     return IFB_OK;
