@@ -284,13 +284,21 @@ int32_t ifb_engine_add_query(ifb_engine_t *e, const int32_t *tokens, int32_t n) 
 int32_t ifb_engine_infer(ifb_engine_t *e, int32_t *next_token, float *logits_f32) {
     IFB_CHECK_ARG(e != nullptr && next_token != nullptr, "infer: null argument");
     if (!e->active || e->to_feed.empty()) { set_last_error("infer: no query is waiting for a step"); return IFB_ERR_STATE; }
-    for (size_t i = 0; i < e->to_feed.size(); i++) {
-        if (e->pos >= e->max_ctx) { set_last_error("infer: the context is full (%d tokens)", e->max_ctx); return IFB_ERR_STATE; }
-        int rc = ifb_model_decode(e->model, e->to_feed[i], nullptr, e->pos, nullptr);
-        if (rc != IFB_OK) return rc;
-        e->pos++;
+    if (e->pos + (int)e->to_feed.size() > e->max_ctx) { set_last_error("infer: the context is full (%d tokens)", e->max_ctx); return IFB_ERR_STATE; }
+    if (e->to_feed.size() > 1 && ifb_model_prefill_supported(e->model)) {
+        // the prompt as ONE step with q_tokens = n, as the reference runs it (tensor-core GEMMs + prefill attention)
+        int rc = ifb_model_prefill(e->model, e->to_feed.data(), (int32_t)e->to_feed.size(), e->pos, nullptr);
+        if (rc != IFB_OK) return rc;        // nothing was consumed: pos and to_feed unchanged, a retry repeats the same step
+        e->pos += (int)e->to_feed.size();
+        e->to_feed.clear();
+    } else {
+        while (!e->to_feed.empty()) {
+            int rc = ifb_model_decode(e->model, e->to_feed.front(), nullptr, e->pos, nullptr);
+            if (rc != IFB_OK) return rc;    // tokens already fed are gone from to_feed: a retry continues where this stopped
+            e->to_feed.erase(e->to_feed.begin());
+            e->pos++;
+        }
     }
-    e->to_feed.clear();
     int rc = ifb_device_synchronize();
     if (rc != IFB_OK) return rc;
     rc = ifb_memcpy_d2h(next_token, ifb_model_next_token(e->model), 4);

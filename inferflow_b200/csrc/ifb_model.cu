@@ -150,10 +150,10 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     const char *e2 = getenv("IFB_NO_GRAPH");
     if (e2 && atoi(e2)) m->use_graph = 0;
     // Which decode path: the persistent step kernel (one launch per token) or the multi-launch CUDA graph. Measured on
-    // B200: on one GPU the two are within ~10 % of each other (multi-launch ahead: both pay ~4 us
-    // per grid-wide dependency, the step kernel in boundaries, the graph in launch + staging); under tensor parallelism
-    // the step kernel wins clearly (per-rank streaming shrinks, launch overheads do not). IFB_STEP=0/1 overrides.
-    m->use_step = tp > 1 ? 1 : 0;
+    // B200: on one and two GPUs the graph is 5-8 % ahead (both designs pay ~4 us per grid-wide
+    // dependency: the step kernel in its op boundaries, the graph in launch + staging); from four GPUs on the step kernel
+    // wins (per-rank streaming shrinks, launch overheads do not). IFB_STEP=0/1 overrides.
+    m->use_step = tp >= 4 ? 1 : 0;       // measured crossover (7B Q4, ctx 2k): 1 GPU 556 vs 600, 2 GPUs 641 vs 675, 4 GPUs 716 vs 671 tok/s
     const char *e4 = getenv("IFB_STEP");
     if (e4) m->use_step = atoi(e4) ? 1 : 0;
 
