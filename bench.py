@@ -256,11 +256,25 @@ GEMV_TRAFFIC_PER_LAUNCH = (32 * (31.528448 + 10.557440 + 56.434944 + 28.266496 +
 STEP_TRAFFIC_PER_LAUNCH = 4881.514e6 + 29.273e6
 
 
-def workload_config(n):
-    return {"workload": "Llama-2-7B Q4 (Q4_B32T1A) weights, Q8_B32T2 KV cache, batch 1, ctx 2048, fp16 lm_head, greedy",
+# BASELINE.json's decode configurations. The default (configs[1]) is the one the metric is quoted on; the others are run
+# with --workload as parity/measurement cases (same verification, same timing rules), not as the headline line.
+WORKLOADS = {
+    "llama2_7b_q4": dict(name="Llama-2-7B Q4 (Q4_B32T1A)", w="Q4_B32T1A", dims="LLAMA2_7B"),
+    "llama2_7b_q3h": dict(name="Llama-2-7B Q3.5 (Q3H_B64T1)", w="Q3H_B64T1", dims="LLAMA2_7B"),
+    "llama2_70b_q4": dict(name="Llama-2-70B Q4 (Q4_B32T1A), GQA 64/8", w="Q4_B32T1A", dims="LLAMA2_70B"),
+}
+DEFAULT_WORKLOAD = "llama2_7b_q4"
+
+
+def workload_config(n, workload=DEFAULT_WORKLOAD):
+    import inferflow_b200.model as mdl
+    w = WORKLOADS[workload]
+    dims = getattr(mdl, w["dims"])
+    return {"workload": "%s weights, Q8_B32T2 KV cache, batch 1, ctx 2048, fp16 lm_head, greedy" % w["name"],
             "parallelism": "tp%d" % n if n > 1 else "single-gpu",
-            "l2": "inputs larger than L2 (4.3 GB of weights streamed per step vs 126 MB L2)",
-            "layers": 32, "d_model": 4096, "d_ffn": 11008, "heads": 32, "kv_heads": 32, "vocab": 32000}
+            "l2": "inputs larger than L2 (GBs of weights streamed per step vs 126 MB L2)",
+            "layers": dims["layers"], "d_model": dims["d_model"], "d_ffn": dims["d_ffn"], "heads": dims["heads"],
+            "kv_heads": dims["kv_heads"], "vocab": dims["vocab"]}
 
 
 # --------------------------------------------------------------------------- reference CUDA operators beside ours
@@ -403,8 +417,12 @@ def run_ours(args):
 
 
 def _run_ours(args, ib, np, torch, dist, rank, world, local):
-    spec = ib.ModelSpec(max_ctx=CTX, weight_dtype=ib.DT.Q4_B32T1A, kv_dtype=ib.DT.Q8_B32T2,
-                        lm_head_dtype=ib.DT.F16, tp_rank=rank, tp_size=world, **ib.LLAMA2_7B)
+    wl = WORKLOADS[args.workload]
+    default_wl = args.workload == DEFAULT_WORKLOAD
+    w_dtype = getattr(ib.DT, wl["w"])
+    dims = getattr(ib, wl["dims"])
+    spec = ib.ModelSpec(max_ctx=CTX, weight_dtype=w_dtype, kv_dtype=ib.DT.Q8_B32T2,
+                        lm_head_dtype=ib.DT.F16, tp_rank=rank, tp_size=world, **dims)
     model = ib.Model(spec)
     stream = torch.cuda.Stream()
     sh = stream.cuda_stream
@@ -428,8 +446,8 @@ def _run_ours(args, ib, np, torch, dist, rank, world, local):
         if world == 1:
             os.environ["IFB_STEP"] = "0" if uses_step else "1"
         try:
-            spec1 = ib.ModelSpec(max_ctx=CTX, weight_dtype=ib.DT.Q4_B32T1A, kv_dtype=ib.DT.Q8_B32T2,
-                                 lm_head_dtype=ib.DT.F16, **ib.LLAMA2_7B)
+            spec1 = ib.ModelSpec(max_ctx=CTX, weight_dtype=w_dtype, kv_dtype=ib.DT.Q8_B32T2,
+                                 lm_head_dtype=ib.DT.F16, **dims)
             ref = ib.Model(spec1)
         finally:
             if saved is None:
@@ -553,10 +571,10 @@ def _run_ours(args, ib, np, torch, dist, rank, world, local):
     peak = float(peaks["hbm_gbs"])
     if uses_step:
         achieved = step_bytes / (ms_per_step * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "decode_step_kernel<FmtQ4_B32T1> (one persistent launch per token: every GEMV, the attention, "
-                                              "the op boundaries)",
+        roofline = {"bound": "hbm", "kernel": "decode_step_kernel<Fmt%s> (one persistent launch per token: every GEMV, the attention, "
+                                              "the op boundaries)" % wl["w"].rstrip("A"),
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": STEP_TRAFFIC_PER_LAUNCH if world == 1 else None, "peak_kind": peak_kind,
+                    "traffic": STEP_TRAFFIC_PER_LAUNCH if world == 1 and default_wl else None, "peak_kind": peak_kind,
                     "bytes_per_launch_avg": step_bytes, "us_per_launch_avg": ms_per_step * 1e3,
                     "weights_only_run": {"ms": gemv_ms, "achieved": wbytes / (gemv_ms * 1e-3) / 1e9, "frac": wbytes / (gemv_ms * 1e-3) / 1e9 / peak,
                                          "what": "the same kernel with the attention units switched off (boundaries still run)"},
@@ -565,7 +583,8 @@ def _run_ours(args, ib, np, torch, dist, rank, world, local):
     else:
         achieved = wbytes / (gemv_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "gemv_stream_kernel (all %d GEMV launches of one token)" % nl,
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": GEMV_TRAFFIC_PER_LAUNCH,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": GEMV_TRAFFIC_PER_LAUNCH if default_wl else None,
                     "peak_kind": peak_kind, "bytes_per_launch_avg": wbytes / max(nl, 1),
                     "us_per_launch_avg": gemv_ms * 1e3 / max(nl, 1),
                     "attention": {"achieved": kvbytes / (attn_ms * 1e-3) / 1e9, "launches": na,
@@ -584,17 +603,18 @@ def _run_ours(args, ib, np, torch, dist, rank, world, local):
     if rank != 0:
         return 0
     refcuda = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and default_wl and not args.no_cpu_baseline:
         try:
             refcuda = reference_cuda_ops(ib, torch)
         except Exception as e:  # noqa: BLE001
             refcuda = {"error": repr(e)}
-    cpu = cpu_baseline_port() if world == 1 and not args.no_cpu_baseline else None
+    cpu = cpu_baseline_port() if world == 1 and default_wl and not args.no_cpu_baseline else None
     line = {
         "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "int8 x q4 (dp4a, fp32 combine); fp16 lm_head/KV math in fp32",
-        "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int8 x q4 (dp4a, fp32 combine); fp16 lm_head/KV math in fp32" if wl["w"].startswith("Q4") else
+                 "int8 x q3.5 (dp4a, fp32 combine); fp16 lm_head/KV math in fp32",
+        "data": "synthetic", "config": workload_config(world, args.workload), "clocks": clocks,
         "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 4,
                 "d2h_bytes_per_step": spec.vocab * 2 + 4},
         "gpu_launches": launches * args.steps,
@@ -617,6 +637,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS),
+                    help="BASELINE.json decode configuration (default: the one the metric is quoted on)")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON result: everything libraries print on the way (NCCL's version banner,
     # the reference engine's progress log) is sent to stderr
