@@ -370,8 +370,7 @@ __device__ __forceinline__ void stage_x_f16(const XStage &a, const void *xsrc, _
 //   y += s_x * (scale_w * sum(q_w q_x) + base_w * sum(q_x))
 template <class Fmt>
 __device__ __forceinline__ float row_dot_q8(const uint8_t *row, int nblk, const uint4 *xlo,
-                                            const uint4 *xhi, const float2 *xs, int lane) {
-    float acc = 0.f;
+                                            const uint4 *xhi, const float2 *xs, int lane, float acc = 0.f) {
     for (int b = lane; b < nblk; b += 32) {
         uint32_t codes[Fmt::NW];
         float sc, ba;
@@ -430,13 +429,16 @@ __device__ __forceinline__ float q4b32_block_dot(uint32_t hdr, uint32_t d0, uint
 
 // Q4_B32T1 rows with nblk % 4 == 0: a lane owns blocks 4*lane..4*lane+3 of each pass of 128
 // (80 contiguous bytes = 5 LDS.128, bank-conflict free across the warp). NM = 2 processes the
-// gate row of the GLU pair against the same activation registers.
-template <int NM>
+// gate row of the GLU pair against the same activation registers. ZERO = false continues the sums in acc (a row
+// taken in several K-chunks: same per-lane order of additions as the whole row at once).
+template <int NM, bool ZERO = true>
 __device__ __forceinline__ void row_dot_q4b32_vec4(const uint8_t *row, size_t mat_bytes, int nblk,
                                                    const uint4 *xlo, const uint4 *xhi,
                                                    const float2 *xs, int lane, float *acc) {
+    if (ZERO) {
 #pragma unroll
-    for (int m = 0; m < NM; m++) acc[m] = 0.f;
+        for (int m = 0; m < NM; m++) acc[m] = 0.f;
+    }
     for (int p0 = 0; p0 < nblk; p0 += 128) {
         const int b0 = p0 + 4 * lane;
         if (b0 < nblk) {
@@ -481,10 +483,9 @@ __device__ __forceinline__ float row_dot_hx(int dt, const uint8_t *row, int nblk
 // fp16 weights (GemvHalf_AX_Alg3_Kernel, gemv.h:470; used for lm_head when L > 20).
 // fp32 accumulation (the reference accumulates in half -- strictly less accurate).
 __device__ __forceinline__ float row_dot_f16(const uint8_t *row, int cx, const __half *xh,
-                                             int lane) {
+                                             int lane, float acc = 0.f) {
     const uint4 *w4 = reinterpret_cast<const uint4 *>(row);
     const uint4 *x4 = reinterpret_cast<const uint4 *>(xh);
-    float acc = 0.f;
     const int n8 = cx >> 3;
 #pragma unroll 4
     for (int i = lane; i < n8; i += 32) {

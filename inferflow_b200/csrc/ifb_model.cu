@@ -783,6 +783,12 @@ static int step_prepare(ifb_model *m) {
     P.w_dtype = s.weight_dtype;
     P.eps = s.norm_eps;
     P.softmax_scale = 1.0f / sqrtf((float)m->hd);     // alpha * kq_scale (inference_worker.cc:1666), as attn_decode
+    {
+        // warp-private pipelines (every consumer warp streams its own tasks) unless IFB_STEP_PRIV=0 or the model's
+        // chunks do not fit: step_build then falls back to the shared-ring layout and clears P.priv
+        const char *e = getenv("IFB_STEP_PRIV");
+        P.priv = e ? (atoi(e) != 0) : 0;
+    }
     if (step_build(P, s.kv_dtype, s.lm_head_dtype, sm_count()) != IFB_OK) return IFB_OK;   // not covered: reason in ifb_last_error
     if (s.rope_order != 0 && s.rope_order != 2) return IFB_OK;
     if (s.layers > 126 || s.d_model > 11520) return IFB_OK;   // word tags are 8 bits; a normalised vector is staged in one round

@@ -44,6 +44,8 @@ constexpr int STEP_CWARPS = 15;
 constexpr int STEP_CTHREADS = STEP_CWARPS * 32;
 constexpr int STEP_THREADS = STEP_CTHREADS + 32;
 constexpr int STEP_MAX_SLOTS = 16;
+constexpr int STEP_MAX_BARS = 2 * STEP_CWARPS + 2;   // warp-private pipelines: two slots (and barriers) per consumer warp
+constexpr int STEP_PRIV_CHUNK = 5120;                // payload bytes of a private slot: two Q4_B32T1 rows of 4096 columns
 constexpr int STEP_TARGET_UNIT = 20480;   // bytes per ring slot the unit sizes aim for
 
 struct FmtF16 {   // tag: fp16 weights (tensors below tensor_quant_threshold, network_builder.cc:1558)
@@ -486,21 +488,22 @@ __device__ __forceinline__ float s8f_(uint32_t w_biased, int k) {
 // lane-owns-4-dims P.V.
 template <int HD, bool Q8>
 __device__ __forceinline__ void att_task(const StepParams &P, const StepLayer &lw, const float *s_cos, const float *s_sin, uint32_t qflag,
-                                         uint8_t *slot, int tt, int kvh, int p0, int ctx, const uint8_t *xst, float *sp, int lane) {
+                                         uint8_t *kslot, uint8_t *vslot, int UP, int tt, int kvh, int p0, int ctx, const uint8_t *xst, float *sp, int lane) {
     constexpr int NB = HD / 32;
     const int pbase = p0 + tt * 32;
     if (pbase >= ctx) return;
     const AttLayout L = att_layout(P.heads, HD, Q8);
-    const int UP = P.att_pos, G = P.group;
+    const int G = P.group;
+    // kslot / vslot: UP positions of the head's K / V plane as the bulk copies left them (Q8: codes, then block scales)
     uint8_t *tK, *tKs = nullptr, *tV, *tVs = nullptr;
     if (Q8) {
-        tK = slot + tt * 32 * HD;
-        tKs = slot + UP * HD + tt * 32 * NB * 2;
-        tV = slot + UP * HD + UP * NB * 2 + tt * 32 * HD;
-        tVs = slot + 2 * UP * HD + UP * NB * 2 + tt * 32 * NB * 2;
+        tK = kslot + tt * 32 * HD;
+        tKs = kslot + UP * HD + tt * 32 * NB * 2;
+        tV = vslot + tt * 32 * HD;
+        tVs = vslot + UP * HD + tt * 32 * NB * 2;
     } else {
-        tK = slot;
-        tV = slot + 32 * HD * 2;
+        tK = kslot;
+        tV = vslot;
     }
     if (ctx - 1 >= pbase && ctx - 1 < pbase + 32) {
         // This tile holds the position being decoded. Its bulk copy was issued before this token's K/V row existed
@@ -702,13 +705,13 @@ struct RingPos {
 };
 
 __device__ __forceinline__ void att_task_any(const StepParams &P, const StepLayer &lw, const float *s_cos, const float *s_sin, uint32_t qflag,
-                                             uint8_t *slot, int tt, int kvh, int p0, int ctx, const uint8_t *xst, float *sp, int lane) {
+                                             uint8_t *kslot, uint8_t *vslot, int UP, int tt, int kvh, int p0, int ctx, const uint8_t *xst, float *sp, int lane) {
     if (P.hd == 128) {
-        if (P.kv_q8) att_task<128, true>(P, lw, s_cos, s_sin, qflag, slot, tt, kvh, p0, ctx, xst, sp, lane);
-        else att_task<128, false>(P, lw, s_cos, s_sin, qflag, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        if (P.kv_q8) att_task<128, true>(P, lw, s_cos, s_sin, qflag, kslot, vslot, UP, tt, kvh, p0, ctx, xst, sp, lane);
+        else att_task<128, false>(P, lw, s_cos, s_sin, qflag, kslot, vslot, UP, tt, kvh, p0, ctx, xst, sp, lane);
     } else {
-        if (P.kv_q8) att_task<64, true>(P, lw, s_cos, s_sin, qflag, slot, tt, kvh, p0, ctx, xst, sp, lane);
-        else att_task<64, false>(P, lw, s_cos, s_sin, qflag, slot, tt, kvh, p0, ctx, xst, sp, lane);
+        if (P.kv_q8) att_task<64, true>(P, lw, s_cos, s_sin, qflag, kslot, vslot, UP, tt, kvh, p0, ctx, xst, sp, lane);
+        else att_task<64, false>(P, lw, s_cos, s_sin, qflag, kslot, vslot, UP, tt, kvh, p0, ctx, xst, sp, lane);
     }
 }
 
@@ -811,10 +814,10 @@ __device__ __forceinline__ void dot2(const StepOpShape &s, const uint8_t *row, s
     }
 }
 
-template <class Fmt>
+template <class Fmt, bool PRIV>
 __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t full_bar[STEP_MAX_SLOTS], empty_bar[STEP_MAX_SLOTS];
+    __shared__ uint64_t full_bar[STEP_MAX_BARS], empty_bar[STEP_MAX_SLOTS];
     __shared__ int2 slot_meta[STEP_MAX_SLOTS];   // (op, unit) of what sits in each ring slot
     __shared__ float red[STEP_CWARPS];
     __shared__ unsigned long long s_key[STEP_CWARPS];
@@ -836,9 +839,13 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
 
     if (tid < 4) s_prof[tid] = 0;
     if (tid == 0) {
-        for (int i = 0; i < P.nslots; i++) {
-            mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], STEP_CWARPS);
+        if constexpr (PRIV) {
+            for (int i = 0; i < 2 * STEP_CWARPS; i++) mbar_init(&full_bar[i], 1);
+        } else {
+            for (int i = 0; i < P.nslots; i++) {
+                mbar_init(&full_bar[i], 1);
+                mbar_init(&empty_bar[i], STEP_CWARPS);
+            }
         }
         mbar_fence_init();
     }
@@ -864,6 +871,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
     const int tiles_per_head = (ctx + P.att_pos - 1) / P.att_pos;
 
     if (warp == STEP_CWARPS) {
+        if constexpr (PRIV) return;        // warp-private pipelines: every consumer warp issues its own copies
         // ===== producer: depends on nothing but free ring slots =====
         if (lane != 0) return;
         const uint64_t pol = l2_policy_evict_first();   // weights and cache tiles are read once per token
@@ -1091,6 +1099,257 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
     // the executed instructions, the generic per-slot bookkeeping ~45 %).
     float best_v = -INFINITY;
     int best_i = 0x7fffffff;
+    if constexpr (PRIV) {
+        // ===== warp-private pipelines =====
+        // Every consumer warp streams its OWN tasks through its OWN two slots: lane 0 issues the bulk copies, the warp
+        // waits on its own two barriers -- no producer warp, no unit cursors, no slot every warp has to pass. Tasks are
+        // dealt statically, round-robin over all grid x 15 warps and continuing across ops (task t of an op whose first
+        // task fell to global warp `rot` belongs to warp (rot + t) mod nwt), so every warp streams the same number of
+        // chunks +-1 per op and the ops of a layer even each other out. The copy side runs two chunks ahead of the
+        // arithmetic and does not stop at op boundaries: weights and cache tiles depend on no activation, so while the
+        // CTAs synchronise at a boundary the next op's first chunks are already on their way.
+        const int nwt = STEP_CWARPS * (int)gridDim.x;
+        const int gw = warp * (int)gridDim.x + (int)blockIdx.x;
+        const uint64_t pol = l2_policy_evict_first();
+        const uint32_t bar0 = smem_u32(full_bar) + 8u * (uint32_t)(2 * warp), ring0 = smem_u32(ring) + (uint32_t)(2 * warp) * (uint32_t)P.pslot;
+        uint8_t *myring = ring + (size_t)(2 * warp) * P.pslot;
+        const int pslot = P.pslot;
+        const bool gemv_on = (P.parts & STEP_PART_GEMV) != 0;
+        auto kind_of = [&](int o) { return o == head_op ? OPK_HEAD : o % 5; };
+        auto ntasks_of = [&](int kind) { return kind == OPK_ATT ? att_units : (gemv_on ? P.pv[kind].ntasks : 0); };
+        auto nchunks_of = [&](int kind) { return kind == OPK_ATT ? 2 : (kind == OPK_GLU ? 2 * P.pv[kind].nc : P.pv[kind].nc); };
+
+        // ---- the copy side: a cursor over this warp's chunks of the whole token
+        int i_op = 0, i_kind = OPK_QKV, i_rot = 0, i_nt = ntasks_of(OPK_QKV), i_nch = nchunks_of(OPK_QKV), i_t = gw, i_c = 0;
+        unsigned i_seq = 0;
+        auto issue_one = [&]() {
+            while (i_op < n_ops && i_t >= i_nt) {            // this warp has no (more) tasks in the op: next op
+                i_rot += i_nt % nwt; if (i_rot >= nwt) i_rot -= nwt;
+                if (++i_op >= n_ops) break;
+                i_kind = kind_of(i_op); i_nt = ntasks_of(i_kind); i_nch = nchunks_of(i_kind);
+                i_t = gw - i_rot; if (i_t < 0) i_t += nwt;
+                i_c = 0;
+            }
+            if (i_op >= n_ops) return;
+            const uint32_t sl = i_seq & 1u, fb = bar0 + 8u * sl, dst = ring0 + sl * (uint32_t)pslot;
+            if (lane == 0) {
+                const StepLayer &lw = s_layers[i_kind == OPK_HEAD ? 0 : i_op / 5];
+                if (i_kind == OPK_ATT) {
+                    const int h = i_t / tiles_per_head, tl = i_t - h * tiles_per_head;
+                    const int64_t row0 = (int64_t)h * P.max_ctx_pad + (int64_t)tl * 32;
+                    const int hd = P.hd, nb = hd >> 5;
+                    const uint8_t *plane = i_c == 0 ? lw.kcache : lw.vcache;
+                    if (P.kv_q8) {
+                        const uint32_t kb = (uint32_t)(32 * hd), sb = (uint32_t)(32 * nb * 2);
+                        const int64_t soff = (int64_t)P.kv_heads * P.max_ctx_pad * hd;
+                        mbar_arrive_expect_tx_a(fb, kb + sb);
+                        bulk_g2s_hint_a(dst, plane + row0 * hd, kb, fb, pol);
+                        bulk_g2s_hint_a(dst + kb, plane + soff + row0 * nb * 2, sb, fb, pol);
+                    } else {
+                        const uint32_t kb = (uint32_t)(32 * hd * 2);
+                        mbar_arrive_expect_tx_a(fb, kb);
+                        bulk_g2s_hint_a(dst, plane + row0 * hd * 2, kb, fb, pol);
+                    }
+                } else {
+                    const StepPrivShape &v = P.pv[i_kind];
+                    const int rb = P.op[i_kind].row_bytes;
+                    int r = i_t * v.rt, cc = i_c;
+                    const uint8_t *base;
+                    if (i_kind == OPK_QKV) {
+                        if (r < P.q_dim) base = lw.wq;
+                        else if (r < P.q_dim + P.kv_dim) { base = lw.wk; r -= P.q_dim; }
+                        else { base = lw.wv; r -= P.q_dim + P.kv_dim; }
+                    } else if (i_kind == OPK_WO) base = lw.wo;
+                    else if (i_kind == OPK_GLU) { base = cc >= v.nc ? lw.w3 : lw.w1; if (cc >= v.nc) cc -= v.nc; }
+                    else if (i_kind == OPK_W2) base = lw.w2;
+                    else base = P.lm_head;
+                    const uint8_t *src = base + (size_t)r * rb;
+                    if (v.nc == 1) {
+                        const uint32_t nb_ = (uint32_t)(v.rt * rb);
+                        mbar_arrive_expect_tx_a(fb, nb_);
+                        bulk_g2s_hint_a(dst, src, nb_, fb, pol);
+                    } else {                                    // rt == 2: the same K-segment of two rows
+                        const uint32_t off = (uint32_t)(cc * v.kc_bytes), seg = min((uint32_t)v.kc_bytes, (uint32_t)rb - off);
+                        mbar_arrive_expect_tx_a(fb, 2 * seg);
+                        bulk_g2s_hint_a(dst, src + off, seg, fb, pol);
+                        bulk_g2s_hint_a(dst + seg, src + rb + off, seg, fb, pol);
+                    }
+                }
+            }
+            i_seq++;
+            if (++i_c == i_nch) { i_c = 0; i_t += nwt; }
+        };
+        issue_one();
+        issue_one();
+
+        // ---- the arithmetic side
+        unsigned c_seq = 0;
+        // wait for this warp's chunk c_seq; returns its slot
+        auto chunk_wait = [&](int op) -> uint8_t * {
+            const uint32_t sl = c_seq & 1u;
+            mbar_wait_bounded(bar0 + 8u * sl, (c_seq >> 1) & 1u, P, op);
+            return myring + (size_t)sl * pslot;
+        };
+        // the chunk is read: its slot takes the next copy (the warp's own generic-proxy reads, then an async-proxy write)
+        auto chunk_done = [&]() {
+            c_seq++;
+            __syncwarp();
+            if (lane == 0) fence_proxy_async_smem();
+            issue_one();
+        };
+        int rot = 0;
+        for (int op = 0; op < n_ops; op++) {
+            const int kind = kind_of(op), layer = op / 5;
+            if (op > 0) {
+                // end of op - 1: the count where somebody waits for one (attention tiles -> merge, lm_head -> end of the
+                // token, row-parallel outputs that do not travel as flag-in-data words); a CTA barrier otherwise (the
+                // staging below overwrites what the slowest warp may still read)
+                const int k = op - 1, kk = kind_of(k);
+                if (kk == OPK_ATT || (!ll && (kk == OPK_WO || kk == OPK_W2))) dep_signal(&P.done[k], tid);
+                else named_bar_sync(BAR_CONSUMERS, STEP_CTHREADS);
+            }
+            stage_for(op);
+            trace_op(P, op, 3, tid);
+            const StepOpShape &s = P.op[kind];
+            const int nt = ntasks_of(kind);
+            const bool compute = (P.debug & 1) == 0;
+            const uint32_t lflag_op = (seq << 8) | (uint32_t)(layer + 1);
+            int t = gw - rot; if (t < 0) t += nwt;
+            rot += nt % nwt; if (rot >= nwt) rot -= nwt;
+            if (kind == OPK_ATT) {
+                for (; t < nt; t += nwt) {
+                    // the K tile and the V tile of the task are this warp's chunks c_seq and c_seq + 1: both slots at once
+                    const unsigned n1 = c_seq + 1u;
+                    mbar_wait_bounded(bar0 + 8u * (c_seq & 1u), (c_seq >> 1) & 1u, P, op);
+                    mbar_wait_bounded(bar0 + 8u * (n1 & 1u), (n1 >> 1) & 1u, P, op);
+                    uint8_t *kslot = myring + (size_t)(c_seq & 1u) * pslot, *vslot = myring + (size_t)(n1 & 1u) * pslot;
+                    const int h = t / tiles_per_head, tl = t - h * tiles_per_head;
+                    if (compute) att_task_any(P, s_layers[layer], s_cos, s_sin, lflag_op, kslot, vslot, 32, 0, h, tl * 32, ctx, xst, sp, lane);
+                    c_seq += 2;
+                    __syncwarp();
+                    if (lane == 0) fence_proxy_async_smem();
+                    issue_one();
+                    issue_one();
+                }
+                continue;
+            }
+            const StepPrivShape &v = P.pv[kind];
+            const int rt = v.rt, nc = v.nc, np = rt >> 1;
+            const bool f16w = is_f16_fmt<Fmt>::value || (kind == OPK_HEAD && P.head_f16 != 0);
+            // one chunk of rt rows (stride = the chunk's bytes per row) against the staged activation, sums continued in acc
+            auto chunk_dot = [&](const uint8_t *slot, int cc, float *acc) {
+                if (f16w) {
+                    const int e0 = cc * v.kc_blk, ne = nc == 1 ? s.cx : min(v.kc_blk, s.cx - e0);
+                    const size_t stride = (size_t)ne * 2;
+                    const __half *xh = reinterpret_cast<const __half *>(xst) + e0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (j < rt) acc[j] = row_dot_f16(slot + (size_t)j * stride, ne, xh, lane, acc[j]);
+                    return;
+                }
+                if constexpr (!is_f16_fmt<Fmt>::value) {
+                    const int b0 = cc * v.kc_blk, nb_ = nc == 1 ? s.nblk : min(v.kc_blk, s.nblk - b0);
+                    const size_t stride = (size_t)nb_ * Fmt::BYTES;
+                    const int xo = b0 * (Fmt::CAP / 32);
+                    const uint4 *xlo = reinterpret_cast<const uint4 *>(xst) + xo, *xhi = reinterpret_cast<const uint4 *>(xst + (size_t)s.nxb * 16) + xo;
+                    const float2 *xs = reinterpret_cast<const float2 *>(xst + (size_t)s.nxb * 32) + xo;
+                    if constexpr (is_q4b32_fmt<Fmt>::value) {
+                        if (s.vec4) {
+#pragma unroll
+                            for (int p = 0; p < 2; p++)
+                                if (p < np) row_dot_q4b32_vec4<2, false>(slot + (size_t)(2 * p) * stride, stride, nb_, xlo, xhi, xs, lane, acc + 2 * p);
+                            return;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (j < rt) acc[j] = row_dot_q8<Fmt>(slot + (size_t)j * stride, nb_, xlo, xhi, xs, lane, acc[j]);
+                }
+            };
+            if (kind == OPK_GLU) {
+                for (; t < nt; t += nwt) {
+                    float a1[4] = {0.f, 0.f, 0.f, 0.f}, a3[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int cc = 0; cc < nc; cc++) {
+                        const uint8_t *slot = chunk_wait(op);
+                        if (compute) chunk_dot(slot, cc, a1);
+                        chunk_done();
+                    }
+                    for (int cc = 0; cc < nc; cc++) {
+                        const uint8_t *slot = chunk_wait(op);
+                        if (compute) chunk_dot(slot, cc, a3);
+                        chunk_done();
+                    }
+                    if (!compute) continue;
+#pragma unroll
+                    for (int p = 0; p < 2; p++) {
+                        if (p >= np) break;
+                        float h2[2];
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            // SiluActivation_Kernel (unary_tensor_opr.h:553) then Mul, each stored as half
+                            const float v0 = round_h(warp_sum(a1[2 * p + j])), v1 = round_h(warp_sum(a3[2 * p + j]));
+                            const float g = round_h(v0 / (1.0f + expf(-v0)));
+                            h2[j] = g * v1;
+                        }
+                        if (lane == 0) {
+                            const __half2 hv = __floats2half2_rn(h2[0], h2[1]);
+                            st_relaxed_sys_v2(P.hbufw + ((t * rt) >> 1) + p, make_uint2(*reinterpret_cast<const uint32_t *>(&hv), lflag_op));
+                        }
+                    }
+                }
+                continue;
+            }
+            const bool qkv = kind == OPK_QKV, head = kind == OPK_HEAD;
+            const bool push = !qkv && !head && ll;
+            uint32_t *out32 = reinterpret_cast<uint32_t *>(P.ybuf);
+            const uint32_t xidx = kind == OPK_WO ? (uint32_t)(2 * layer + 1) : (uint32_t)(2 * layer + 2);
+            const size_t xoff = (size_t)P.x_recv + (size_t)(xidx & 1u) * P.x_recv_parity + (size_t)P.tp_rank * P.x_recv_rank;
+            for (; t < nt; t += nwt) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int cc = 0; cc < nc; cc++) {
+                    const uint8_t *slot = chunk_wait(op);
+                    if (compute) chunk_dot(slot, cc, acc);
+                    chunk_done();
+                }
+                if (!compute) continue;
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    if (p >= np) break;
+                    const float s0 = warp_sum(acc[2 * p]), s1 = warp_sum(acc[2 * p + 1]);
+                    if (lane != 0) continue;
+                    const int o = t * rt + 2 * p;
+                    if (head) {
+                        const float v0 = round_h(s0), v1 = round_h(s1);
+                        const __half2 hv = __floats2half2_rn(v0, v1);
+                        const uint32_t bits = *reinterpret_cast<const uint32_t *>(&hv);
+                        if (tp == 1) {
+                            reinterpret_cast<uint32_t *>(P.logits)[o >> 1] = bits;
+                            if (v0 == v0 && (v0 > best_v || (v0 == best_v && o < best_i))) { best_v = v0; best_i = o; }
+                            if (v1 == v1 && (v1 > best_v || (v1 == best_v && o + 1 < best_i))) { best_v = v1; best_i = o + 1; }
+                        } else {
+                            const uint2 wd = make_uint2(bits, (seq << 8) | 255u);
+                            const size_t off = (size_t)P.x_logits + ((size_t)(P.tp_rank * P.vocab_l + o) >> 1) * 8;
+                            for (int pr = 0; pr < tp; pr++) st_relaxed_sys_v2(reinterpret_cast<uint8_t *>(P.peer[pr]) + off, wd);
+                        }
+                        continue;
+                    }
+                    const __half2 hv = __floats2half2_rn(s0, s1);      // GEMV output tensors are half
+                    const uint32_t bits = *reinterpret_cast<const uint32_t *>(&hv);
+                    if (qkv) {
+                        st_relaxed_sys_v2(P.qkvw + (o >> 1), make_uint2(bits, lflag_op));   // q|k|v as {half2, flag} words
+                    } else if (!push) {
+                        out32[o >> 1] = bits;
+                    } else {
+                        const uint2 wd = make_uint2(bits, (seq << 8) | xidx);
+                        for (int pr = 0; pr < tp; pr++) st_relaxed_sys_v2(reinterpret_cast<uint8_t *>(P.peer[pr]) + xoff + (size_t)(o >> 1) * 8, wd);
+                    }
+                }
+            }
+        }
+        // end of the lm_head
+        if (tp == 1 && lane == 0 && best_i != 0x7fffffff) atomicMax(P.amax, amax_key(best_v, best_i));
+        dep_signal(&P.done[head_op], tid);
+    } else {
     int cur_op = -1;            // nothing staged yet: the first pass stages op 0 while the first units are in flight
     int next_op = 0;
     int pos = 0, tbase = 0;
@@ -1144,7 +1403,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
                 IFB_SLOT_BEGIN()
                 if (t < ntask) {
                     const int h = u / tiles_per_head, tl = u - h * tiles_per_head;
-                    for (; t < ntask; t += STEP_CWARPS) att_task_any(P, s_layers[layer], s_cos, s_sin, lflag_op, slot, t, h, tl * P.att_pos, ctx, xst, sp, lane);
+                    uint8_t *vslot = slot + (P.kv_q8 ? P.att_pos * (P.hd + (P.hd >> 5) * 2) : 32 * P.hd * 2);
+                    for (; t < ntask; t += STEP_CWARPS) att_task_any(P, s_layers[layer], s_cos, s_sin, lflag_op, slot, vslot, P.att_pos, t, h, tl * P.att_pos, ctx, xst, sp, lane);
                 }
                 IFB_SLOT_END()
             }
@@ -1244,6 +1504,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) decode_step_kernel(const __gr
     }
 #undef IFB_SLOT_BEGIN
 #undef IFB_SLOT_END
+    }   // shared ring
 
     // ===== end of the token: next token id, position += 1 =====
     if (tp > 1 && (P.parts & STEP_PART_GEMV)) {
@@ -1385,6 +1646,60 @@ int step_build(StepParams &P, int kv_dtype, int head_dtype, int sms) {
     { const int segs[1] = {P.ffn}; if ((rc = gemv_shape(OPK_GLU, segs, 1, P.d, wdt, 2)) != IFB_OK) return rc; }
     { const int segs[1] = {P.d}; if ((rc = gemv_shape(OPK_W2, segs, 1, P.ffn, wdt, 1)) != IFB_OK) return rc; }
     { const int segs[1] = {P.vocab_l}; if ((rc = gemv_shape(OPK_HEAD, segs, 1, P.d, head_dtype, 1)) != IFB_OK) return rc; }
+    // ---- warp-private pipelines (P.priv requested by the caller): eligible when every chunk fits a private slot
+    if (P.priv) {
+        const char *why = nullptr;
+        auto priv_shape = [&](int kind, const int *segs, int nseg, int dt) {
+            const StepOpShape &s = P.op[kind];
+            StepPrivShape &v = P.pv[kind];
+            v = StepPrivShape();
+            const int rb = s.row_bytes;
+            int rt = 2;
+            while (rt <= 4 && (rt * rb) % 16 != 0) rt *= 2;
+            if (rt > 4) { why = "rows are not a multiple of 4 bytes"; return; }
+            int total = 0;
+            for (int i = 0; i < nseg; i++) { total += segs[i]; if (segs[i] % rt) why = "a matrix has a row count that is no multiple of the task's rows"; }
+            v.rt = rt;
+            v.ntasks = total / rt;
+            if (rt * rb <= STEP_PRIV_CHUNK) {
+                v.nc = 1; v.kc_bytes = rb; v.kc_blk = dt == DT_F16 ? s.cx : s.nblk;
+                return;
+            }
+            if (rt != 2 || rb % 16 != 0) { why = "long rows that are no multiple of 16 bytes"; return; }
+            const int half = STEP_PRIV_CHUNK / 2;
+            if (dt == DT_F16) {
+                int nc = (rb + half - 1) / half;
+                int ke = ((s.cx + nc - 1) / nc + 7) / 8 * 8;        // halves per chunk: equal chunks, 16-byte granules
+                v.nc = (s.cx + ke - 1) / ke; v.kc_blk = ke; v.kc_bytes = ke * 2;
+            } else if (s.vec4) {
+                v.kc_blk = 128; v.kc_bytes = 128 * block_bytes(dt); v.nc = (s.nblk + 127) / 128;   // one pass of the lane-owns-4-blocks loop
+                if (v.kc_bytes > half) why = "a 128-block pass does not fit half a private slot";
+            } else {
+                const int bb = block_bytes(dt);
+                int nc = (rb + half - 1) / half, kb = 0;
+                for (;; nc++) {
+                    kb = ((s.nblk + nc - 1) / nc + 31) / 32 * 32;   // blocks per chunk: whole lane strides
+                    if (kb * bb <= half || kb <= 32) break;
+                }
+                if (kb * bb > half) { why = "32 blocks do not fit half a private slot"; return; }
+                v.kc_blk = kb; v.kc_bytes = kb * bb; v.nc = (s.nblk + kb - 1) / kb;
+            }
+        };
+        { const int segs[3] = {P.q_dim, P.kv_dim, P.kv_dim}; priv_shape(OPK_QKV, segs, 3, wdt); }
+        { const int segs[1] = {P.d}; priv_shape(OPK_WO, segs, 1, wdt); }
+        { const int segs[1] = {P.ffn}; priv_shape(OPK_GLU, segs, 1, wdt); }
+        { const int segs[1] = {P.d}; priv_shape(OPK_W2, segs, 1, wdt); }
+        { const int segs[1] = {P.vocab_l}; priv_shape(OPK_HEAD, segs, 1, head_dtype); }
+        P.pv[OPK_ATT] = StepPrivShape();
+        const int att_chunk = P.kv_q8 ? 32 * (P.hd + (P.hd / 32) * 2) : 32 * P.hd * 2;   // one plane of a 32-position tile
+        if (att_chunk > STEP_PRIV_CHUNK) why = "a 32-position cache tile does not fit a private slot";
+        if (why == nullptr) {
+            P.att_pos = 32;
+            P.pslot = (STEP_PRIV_CHUNK + 16 + 127) / 128 * 128;   // + 16: Q8_B32T2 block decode reads one word past its block
+        } else {
+            P.priv = 0;          // the shared-ring layout below takes it
+        }
+    }
     StepOpShape &a = P.op[OPK_ATT];
     a = StepOpShape();
     a.tasks = P.att_pos / 32;
@@ -1415,7 +1730,15 @@ int step_build(StepParams &P, int kv_dtype, int head_dtype, int sms) {
     const int64_t norm_b = resid_b;
     const int64_t smem_max = 232448 - 1536;     // opt-in maximum per CTA minus this kernel's static shared memory
     int64_t nslots = (smem_max - xb - resid_b - sp_b - rope_b - lay_b - norm_b) / slot;
-    if (nslots > STEP_MAX_SLOTS) nslots = STEP_MAX_SLOTS;
+    if (P.priv) {
+        if (nslots * slot >= (int64_t)2 * STEP_CWARPS * P.pslot) {
+            nslots = 2 * STEP_CWARPS;
+            slot = P.pslot;
+        } else {
+            P.priv = 0;          // the staging areas of this model leave no room for 30 private slots
+        }
+    }
+    if (!P.priv && nslots > STEP_MAX_SLOTS) nslots = STEP_MAX_SLOTS;
     IFB_CHECK_ARG(nslots >= 3, "step kernel: only %lld ring slots of %lld bytes fit beside %lld bytes of staging", (long long)nslots, (long long)slot, (long long)(xb + resid_b));
     P.nslots = (int)nslots;
     P.slot_bytes = (int)slot;
@@ -1429,9 +1752,9 @@ int step_build(StepParams &P, int kv_dtype, int head_dtype, int sms) {
     return IFB_OK;
 }
 
-template <class Fmt>
-static int launch_fmt(const StepParams &P, int grid, cudaStream_t st) {
-    auto kern = decode_step_kernel<Fmt>;
+template <class Fmt, bool PRIV>
+static int launch_fmt2(const StepParams &P, int grid, cudaStream_t st) {
+    auto kern = decode_step_kernel<Fmt, PRIV>;
     static int attr_dev = -1;   // per instantiation: the opt-in is per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1451,6 +1774,11 @@ static int launch_fmt(const StepParams &P, int grid, cudaStream_t st) {
     cfg.numAttrs = 1;
     IFB_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
     return IFB_OK;
+}
+
+template <class Fmt>
+static int launch_fmt(const StepParams &P, int grid, cudaStream_t st) {
+    return P.priv ? launch_fmt2<Fmt, true>(P, grid, st) : launch_fmt2<Fmt, false>(P, grid, st);
 }
 
 int step_launch(const StepParams &P, int grid, cudaStream_t st) {

@@ -26,6 +26,16 @@ struct StepOpShape {
     int nxb;          // staged activation blocks (cx/32; padded to a multiple of 128 for vec4)
 };
 
+// geometry of one op kind for the warp-private pipelines (decode_step_kernel<Fmt, true>): a task = rt adjacent rows,
+// streamed as nc K-chunks of kc_blk blocks (kc_bytes per row) into the warp's own two-slot ring
+struct StepPrivShape {
+    int rt;           // rows per task (2; 4 when two rows are not a multiple of the 16-byte bulk-copy granularity)
+    int nc;           // K-chunks per row
+    int kc_blk;       // weight blocks per chunk and row (fp16 weights: halves)
+    int kc_bytes;     // bytes per chunk and row
+    int ntasks;       // tasks of one instance of the op (ATT: derived on the device from the context length)
+};
+
 struct StepLayer {
     const uint8_t *wq, *wk, *wv, *wo, *w1, *w3, *w2;
     const __half *attn_norm, *ffn_norm;
@@ -59,6 +69,10 @@ struct StepParams {
     int debug;                   // measurement aid (IFB_STEP_DEBUG): bit 0 = the tasks skip their arithmetic (pure streaming + boundaries)
     int claim_batch;             // most units one cursor claim takes (guided self-scheduling)
     int max_inflight;            // bulk copies outstanding per SM (0: as many as the ring has slots)
+    // warp-private pipelines: every consumer warp streams its own, statically assigned tasks through two private slots
+    int priv;                    // 1: this layout (no producer warp, no unit cursors)
+    int pslot;                   // bytes per private slot
+    StepPrivShape pv[OPK_COUNT];
     // tensor parallelism (size 1: unused) -- exchange regions as in ifb_model.cu
     int tp_size, tp_rank;
     int local_ll;                // one GPU: wo / w2 outputs as flag-in-data words in this GPU's own exchange region
