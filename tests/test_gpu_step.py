@@ -36,16 +36,18 @@ def _read(ib, m, spec):
     return logits, int(nxt[0])
 
 
-def _model(ib, spec, step, seed=7):
-    old = os.environ.get("IFB_STEP")
+def _model(ib, spec, step, seed=7, priv=False):
+    old = {k: os.environ.get(k) for k in ("IFB_STEP", "IFB_STEP_PRIV")}
     os.environ["IFB_STEP"] = "1" if step else "0"
+    os.environ["IFB_STEP_PRIV"] = "1" if priv else "0"
     try:
         m = ib.Model(spec)
     finally:
-        if old is None:
-            del os.environ["IFB_STEP"]
-        else:
-            os.environ["IFB_STEP"] = old
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
     m.init_synthetic(seed=seed)
     return m
 
@@ -68,12 +70,15 @@ def _n(dt):
 IDS = [f"{_n(c['weight_dtype'])}-kv{_n(c['kv_dtype'])}-h{c['heads']}g{c['heads'] // c['kv_heads']}d{c['d_model']}" for c in CONFIGS]
 
 
+# both schedules of the kernel: the shared ring fed by a producer warp (default) and the warp-private pipelines
+# (IFB_STEP_PRIV=1: static task assignment, K-chunked rows; models whose chunks do not fit fall back to the ring)
+@pytest.mark.parametrize("priv", [False, True], ids=["ring", "private"])
 @pytest.mark.parametrize("cfg", CONFIGS, ids=IDS)
-def test_step_kernel_matches_oracle(cfg):
+def test_step_kernel_matches_oracle(cfg, priv):
     import inferflow_b200 as ib
     torch.zeros(1, device="cuda")
     spec = ib.ModelSpec(layers=2, vocab=512, max_ctx=128, **cfg)
-    m = _model(ib, spec, step=True)
+    m = _model(ib, spec, step=True, priv=priv)
     orcm = OracleModel(spec, _tensors(m, spec))
     tok = 5
     for pos in range(70):          # crosses the 32- and 64-position tile edges of the cache
@@ -87,6 +92,38 @@ def test_step_kernel_matches_oracle(cfg):
         err = np.abs(logits.astype(np.float64) - want).max()
         assert err <= 2 ** -7 * scale, f"pos {pos}: logits differ by {err:.3e} (range {scale:.3e})"
         assert nxt == int(np.argmax(logits.astype(np.float32))), "device argmax != argmax of device logits"
+        srt = np.sort(want)
+        if srt[-1] - srt[-2] > 4 * err:
+            assert nxt == int(np.argmax(want))
+        tok = nxt
+    m.close()
+
+
+# rows longer than a private slot: streamed as K-chunks (Q4_B32T1: 128-block passes; other formats: whole lane strides;
+# fp16: equal 16-byte-granular pieces), the per-lane sums continued from chunk to chunk
+LONG_ROWS = [
+    dict(weight_dtype=orc.Q4_B32T1A, kv_dtype=orc.Q8_B32T2, heads=4, kv_heads=4, d_model=512, d_ffn=5504),   # w2: 172 blocks = 128 + 44
+    dict(weight_dtype=orc.Q8_B32T2, kv_dtype=orc.Q8_B32T2, heads=4, kv_heads=2, d_model=512, d_ffn=5504),   # w2: 3 chunks of 64 / 64 / 44 blocks
+    dict(weight_dtype=orc.F16, kv_dtype=orc.Q8_B32T2, heads=16, kv_heads=16, d_model=2048, d_ffn=512),       # every 2048-column row: 2 chunks
+]
+
+
+@pytest.mark.parametrize("cfg", LONG_ROWS, ids=["Q4-ffn5504", "Q8-ffn5504", "F16-d2048"])
+def test_private_pipelines_k_chunked_rows(cfg):
+    import inferflow_b200 as ib
+    spec = ib.ModelSpec(layers=2, vocab=512, max_ctx=64, **cfg)
+    m = _model(ib, spec, step=True, priv=True)
+    orcm = OracleModel(spec, _tensors(m, spec))
+    tok = 9
+    for pos in range(36):
+        m.decode(tok, pos)
+        logits, nxt = _read(ib, m, spec)
+        on, rec = m.step_status()
+        assert on and rec[0] == 0, f"persistent step kernel not in use or failed: {on} {rec} {ib.lib.ifb_last_error()}"
+        want = orcm.step(tok, pos)
+        scale = np.abs(want).max()
+        err = np.abs(logits.astype(np.float64) - want).max()
+        assert err <= 2 ** -7 * scale, f"pos {pos}: logits differ by {err:.3e} (range {scale:.3e})"
         srt = np.sort(want)
         if srt[-1] - srt[-2] > 4 * err:
             assert nxt == int(np.argmax(want))
