@@ -60,6 +60,7 @@ int32_t ifb_dtype_from_name(const char *name);
 /* plumbing for bindings that hold no CUDA runtime handle of their own (blocking copies) */
 int32_t ifb_memcpy_d2h(void *host, const void *dev, int64_t bytes);
 int32_t ifb_memcpy_h2d(void *dev, const void *host, int64_t bytes);
+int32_t ifb_memcpy_d2d(void *dst_dev, const void *src_dev, int64_t bytes);   /* same device (a pipeline hand-off on one GPU) */
 int32_t ifb_memcpy_d2h_async(void *host_pinned, const void *dev, int64_t bytes, ifb_stream_t stream);
 int32_t ifb_memcpy_h2d_async(void *dev, const void *host_pinned, int64_t bytes, ifb_stream_t stream);
 int32_t ifb_device_synchronize(void);
@@ -218,6 +219,13 @@ typedef struct ifb_model_spec {
     int32_t experts, experts_top_k; /* 0 = dense FFN; else every layer's FFN is a mixture of `experts` GLU FFNs,
                                        `experts_top_k` active per token (ProcessGpuLayer_Moe, inference_worker.cc:1924-2146) */
     int32_t moe_norm_top_k_prob;    /* hparams.moe_norm_top_k_prob (model.h:66): renormalise the selected weights */
+    int32_t weight_repack;          /* 1: IFB_Q3H_B64T1 matrices are stored as IFB_Q4_B64T1 blocks holding the same codes,
+                                       base and scale (lossless; 36 instead of 32 bytes per 64 weights, decoded with an
+                                       order of magnitude fewer instructions). 0: stored as the reference stores them. */
+    int32_t layer_begin, layer_end; /* pipeline stage (BY_LAYER / HYBRID, SplitGpuLayers): this instance holds layers
+                                       [layer_begin, layer_end) only; 0, 0 = all. A stage with layer_begin > 0 takes
+                                       its input from ifb_model_hidden_ptr instead of the embedding; one with
+                                       layer_end < layers leaves its output there instead of running the lm_head. */
 } ifb_model_spec_t;
 
 typedef struct ifb_model ifb_model_t;
@@ -226,6 +234,12 @@ typedef struct ifb_model ifb_model_t;
 int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *spec);
 void ifb_model_destroy(ifb_model_t *m);
 int64_t ifb_model_weight_bytes(const ifb_model_t *m);   /* quantized bytes read per token */
+/* element type the layer matrices (which = 0) / the lm_head (which = 1) are STORED in: the spec's type unless
+ * weight_repack changed it */
+int32_t ifb_model_storage_dtype(const ifb_model_t *m, int32_t which);
+/* the fp16 hidden state [d_model] a pipeline stage reads (layer_begin > 0) and leaves (layer_end < layers): the caller
+ * hands it from stage to stage (same GPU: a device copy; another GPU: cudaMemcpyPeerAsync or a peer-mapped store) */
+void *ifb_model_hidden_ptr(ifb_model_t *m);
 int64_t ifb_model_kv_bytes_per_token(const ifb_model_t *m, int32_t ctx_len);
 /* deterministic synthetic weights generated on the device: quant blocks
  * with uniform codes and |N(0,sigma)| fp16 scales, norms 1.0 */
@@ -247,6 +261,11 @@ int32_t ifb_llama2c_probe(const char *path, int32_t header_out[7], int32_t *shar
 int32_t ifb_model_load_llama2c(ifb_model_t **out, const char *path, int32_t weight_dtype, int32_t kv_dtype,
                                int32_t max_ctx, int32_t rope_order /* qk_column_order; < 0: the format's 0 */,
                                ifb_stream_t stream);
+/* the same file, a pipeline stage of it: only layers [layer_begin, layer_end) are kept (0, 0 = all), the embedding on
+ * the first stage, the final norm and the classifier on the last (BY_LAYER device groups, network_builder.cc:2094-2145) */
+int32_t ifb_model_load_llama2c_stage(ifb_model_t **out, const char *path, int32_t weight_dtype, int32_t kv_dtype,
+                                     int32_t max_context_len, int32_t qk_column_order, int32_t layer_begin,
+                                     int32_t layer_end, ifb_stream_t stream);
 
 /* reset the KV length (and optionally fill `ctx_len` synthetic rows for benchmarking) */
 int32_t ifb_model_kv_reset(ifb_model_t *m, int32_t ctx_len, int32_t fill_synthetic, uint64_t seed,
@@ -285,6 +304,39 @@ int32_t ifb_model_step_status(ifb_model_t *m, int32_t rec[4]);
  * the host side (torch.distributed all_gather / MPI / fork) hands all handles to every rank */
 int32_t ifb_model_tp_export(ifb_model_t *m, void *host_handle_64B);
 int32_t ifb_model_tp_import(ifb_model_t *m, const void *host_handles_64B_each, int32_t n);
+
+/* ------------------------------------------------------------------ partitioner (host logic, no CUDA call)
+ * The `devices` grammar of the engine config and what follows from it. `;` or `,` separate device GROUPS (layer /
+ * pipeline split: contiguous layer ranges, the groups run one after the other), `&` or `|` join the devices INSIDE a
+ * group (tensor split). Replaces InferenceEngine::LoadDeviceGroups (inference_engine.cc:1738-1783), the strategy rule
+ * (inference_engine.cc:1509-1515), NetworkBuilder::SplitGpuLayers (network_builder.cc:2094-2117) and the tensor map
+ * of Build{Attn,Ffn,Moe}TensorIdMap / AddLayerTasks_TensorParallel (network_builder.cc:1373-1413, 1594-1688). */
+enum { IFB_STRATEGY_BY_LAYER = 0, IFB_STRATEGY_BY_TENSOR = 1, IFB_STRATEGY_HYBRID = 2 };   /* MultiGpuStrategy, network_structure.h:114 */
+enum { IFB_PART_DUP = 0, IFB_PART_BY_ROW = 1, IFB_PART_BY_COL = 2 };                       /* TensorPartitionType, tensor_common.h:103 */
+/* "0&1;2&3" -> ids_out = {0,1,2,3}, n_groups 2, group_size 2, strategy HYBRID. Ids are read with atoi, empty pieces
+ * are skipped, all groups must have the same size (IFB_ERR_ARG and the reference's message otherwise). ids_out may be
+ * NULL (sizes only). */
+int32_t ifb_device_groups_parse(const char *devices, int32_t *ids_out, int32_t capacity, int32_t *n_groups,
+                                int32_t *group_size, int32_t *strategy);
+/* layers [start_layer, end_layer) over n_groups groups: ceil(L / n_groups) contiguous layers each, the last group takes
+ * the rest, a group left without layers gets no range. ranges_out[2k], ranges_out[2k+1] = [begin, end) of range k,
+ * group_of_range[k] = its group. (As in the reference the end of a range is (g+1)*per_group, not offset by
+ * start_layer: identical for start_layer = 0, the only value the reference passes.) */
+int32_t ifb_split_layers(int32_t start_layer, int32_t end_layer, int32_t n_groups, int32_t *ranges_out,
+                         int32_t *group_of_range, int32_t *n_ranges);
+/* how a layer tensor is divided inside a tensor-parallel group, by its name ("layers.3.wq", "w2", "ffn_norm" ...):
+ * IFB_PART_BY_COL = output rows (wq wk wv qkv w1 w3 and their biases), IFB_PART_BY_ROW = contraction dimension
+ * (wo w2), IFB_PART_DUP (norms, wo_b, w2_b, the MoE gate); -1 = not a layer tensor */
+int32_t ifb_tensor_partition_type(const char *tensor_name);
+/* element type a weight matrix gets on the device: weight_dtype, or IFB_F16 when its share per device
+ * (elements / n_devices) is below tensor_quant_threshold (network_builder.cc:1558-1561, 1648-1652) */
+int32_t ifb_tensor_device_dtype(int64_t elements, int32_t n_devices, int32_t weight_dtype, int64_t tensor_quant_threshold);
+/* One process per GPU: rank r is the r-th device of the string. plan_out[IFB_PLAN_*] = its group, its rank and the size
+ * of its tensor-parallel group, its layer range (ifb_model_spec.layer_begin / layer_end), the ranks it receives the
+ * hidden state from / sends it to (-1: the embedding / the lm_head are its own), its device id, the strategy. */
+enum { IFB_PLAN_GROUP = 0, IFB_PLAN_TP_RANK = 1, IFB_PLAN_TP_SIZE = 2, IFB_PLAN_LAYER_BEGIN = 3, IFB_PLAN_LAYER_END = 4,
+       IFB_PLAN_PREV_RANK = 5, IFB_PLAN_NEXT_RANK = 6, IFB_PLAN_DEVICE = 7, IFB_PLAN_STRATEGY = 8, IFB_PLAN_FIELDS = 9 };
+int32_t ifb_rank_plan(const char *devices, int32_t rank, int32_t n_layers, int32_t plan_out[IFB_PLAN_FIELDS]);
 
 /* ------------------------------------------------------------------ engine-shaped host layer
  * The outermost seam of the reference for this path, for ONE live query and greedy decoding

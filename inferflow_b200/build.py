@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libinferflow_b200.so")
-SOURCES = ["ifb_capi.cu", "ifb_gemv.cu", "ifb_quantize.cu", "ifb_ops.cu", "ifb_attention.cu", "ifb_model.cu", "ifb_engine.cu", "ifb_step.cu", "ifb_gemm.cu", "ifb_prefill.cu"]
+SOURCES = ["ifb_capi.cu", "ifb_gemv.cu", "ifb_quantize.cu", "ifb_ops.cu", "ifb_attention.cu", "ifb_model.cu", "ifb_engine.cu", "ifb_step.cu", "ifb_gemm.cu", "ifb_prefill.cu", "ifb_partition.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-diag-suppress", "550"]

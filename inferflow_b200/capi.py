@@ -38,6 +38,7 @@ class ModelSpecC(C.Structure):
         ("rope_order", C.c_int32), ("rope_theta", C.c_float), ("norm_eps", C.c_float),
         ("kq_scale", C.c_float), ("tp_rank", C.c_int32), ("tp_size", C.c_int32),
         ("experts", C.c_int32), ("experts_top_k", C.c_int32), ("moe_norm_top_k_prob", C.c_int32),
+        ("weight_repack", C.c_int32), ("layer_begin", C.c_int32), ("layer_end", C.c_int32),
     ]
 
 
@@ -56,6 +57,7 @@ def _load():
     L.ifb_row_bytes.argtypes = [i32, i64]
     L.ifb_dtype_from_name.argtypes = [C.c_char_p]
     L.ifb_memcpy_d2h.argtypes = [vp, vp, i64]
+    L.ifb_memcpy_d2d.argtypes = [vp, vp, i64]
     L.ifb_memcpy_h2d.argtypes = [vp, vp, i64]
     L.ifb_memcpy_d2h_async.argtypes = [vp, vp, i64, vp]
     L.ifb_memcpy_h2d_async.argtypes = [vp, vp, i64, vp]
@@ -103,6 +105,14 @@ def _load():
     L.ifb_model_next_token.argtypes = [vp]
     L.ifb_model_kernel_launches_per_step.argtypes = [vp]
     L.ifb_model_step_status.argtypes = [vp, vp]
+    L.ifb_model_storage_dtype.argtypes = [vp, i32]
+    L.ifb_model_hidden_ptr.argtypes = [vp]
+    L.ifb_model_hidden_ptr.restype = vp
+    L.ifb_device_groups_parse.argtypes = [C.c_char_p, vp, i32, vp, vp, vp]
+    L.ifb_split_layers.argtypes = [i32, i32, i32, vp, vp, vp]
+    L.ifb_tensor_partition_type.argtypes = [C.c_char_p]
+    L.ifb_tensor_device_dtype.argtypes = [i64, i32, i32, i64]
+    L.ifb_rank_plan.argtypes = [C.c_char_p, i32, i32, vp]
     L.ifb_engine_resolve.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, vp, i32, vp]
     L.ifb_engine_create.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
     L.ifb_engine_destroy.argtypes = [vp]
@@ -114,6 +124,7 @@ def _load():
     L.ifb_engine_remove_query.argtypes = [vp, i32]
     L.ifb_llama2c_probe.argtypes = [C.c_char_p, vp, vp]
     L.ifb_model_load_llama2c.argtypes = [vp, C.c_char_p, i32, i32, i32, i32, vp]
+    L.ifb_model_load_llama2c_stage.argtypes = [vp, C.c_char_p, i32, i32, i32, i32, i32, i32, vp]
     L.ifb_model_tp_export.argtypes = [vp, vp]
     L.ifb_model_tp_import.argtypes = [vp, vp, i32]
     return L
@@ -128,11 +139,13 @@ DECLARED = [
     "ifb_rmsnorm", "ifb_rope", "ifb_silu_mul", "ifb_add", "ifb_argmax", "ifb_kv_cache_bytes",
     "ifb_kv_append", "ifb_kv_get_rows", "ifb_attn_workspace_bytes", "ifb_attn_decode", "ifb_attn_decode_append", "ifb_moe_topk", "ifb_moe_route", "ifb_moe_combine",
     "ifb_engine_resolve", "ifb_engine_create", "ifb_engine_destroy", "ifb_engine_vocab_size", "ifb_engine_add_query",
-    "ifb_engine_infer", "ifb_engine_commit", "ifb_engine_remove_query", "ifb_llama2c_probe", "ifb_model_load_llama2c", "ifb_model_create", "ifb_model_destroy", "ifb_model_weight_bytes", "ifb_model_kv_bytes_per_token",
+    "ifb_engine_infer", "ifb_engine_commit", "ifb_engine_remove_query", "ifb_llama2c_probe", "ifb_model_load_llama2c", "ifb_model_load_llama2c_stage", "ifb_model_create", "ifb_model_destroy", "ifb_model_weight_bytes", "ifb_model_kv_bytes_per_token",
     "ifb_model_init_synthetic", "ifb_model_load_tensor", "ifb_model_kv_reset", "ifb_model_decode",
     "ifb_model_logits", "ifb_model_next_token", "ifb_model_kernel_launches_per_step",
     "ifb_model_tp_export", "ifb_model_tp_import", "ifb_model_decode_next", "ifb_model_tensor_ptr",
-    "ifb_memcpy_d2h", "ifb_memcpy_h2d", "ifb_device_synchronize", "ifb_model_issue_parts", "ifb_memcpy_d2h_async", "ifb_memcpy_h2d_async", "ifb_model_step_status", "ifb_model_prefill", "ifb_model_prefill_supported", "ifb_attn_prefill",
+    "ifb_memcpy_d2h", "ifb_memcpy_h2d", "ifb_memcpy_d2d", "ifb_device_synchronize", "ifb_model_issue_parts", "ifb_memcpy_d2h_async", "ifb_memcpy_h2d_async", "ifb_model_step_status", "ifb_model_prefill", "ifb_model_prefill_supported", "ifb_attn_prefill",
+    "ifb_model_storage_dtype", "ifb_model_hidden_ptr", "ifb_device_groups_parse", "ifb_split_layers", "ifb_tensor_partition_type",
+    "ifb_tensor_device_dtype", "ifb_rank_plan",
 ]
 
 

@@ -62,6 +62,10 @@ int32_t ifb_memcpy_h2d(void *dev, const void *host, int64_t bytes) {
     IFB_CUDA(cudaMemcpy(dev, host, (size_t)bytes, cudaMemcpyHostToDevice));
     return IFB_OK;
 }
+int32_t ifb_memcpy_d2d(void *dst, const void *src, int64_t bytes) {
+    IFB_CUDA(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice));
+    return IFB_OK;
+}
 int32_t ifb_memcpy_d2h_async(void *host, const void *dev, int64_t bytes, ifb_stream_t st) {
     IFB_CUDA(cudaMemcpyAsync(host, dev, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)st));
     return IFB_OK;

@@ -54,12 +54,13 @@ struct Ini {
             if (s.empty() || s[0] == ';' || s[0] == '#') continue;
             if (s[0] == '[') {
                 size_t e = s.find(']');
-                if (e != std::string::npos) cur = trim(s.substr(1, e - 1));
+                if (e != std::string::npos) cur = lower(trim(s.substr(1, e - 1)));
                 continue;
             }
             size_t eq = s.find('=');
             if (eq == std::string::npos) continue;
-            sec[cur][trim(s.substr(0, eq))] = trim(s.substr(eq + 1));
+            // group and item names are case-insensitive (sslib ConfigData, 3rd_party/sslib/config_data.cc:39-121)
+            sec[cur][lower(trim(s.substr(0, eq)))] = trim(s.substr(eq + 1));
         }
         fclose(f);
         return true;
@@ -76,9 +77,9 @@ struct Ini {
         return v;
     }
     bool get(const std::string &s, const std::string &k, std::string &out) const {
-        auto i = sec.find(s);
+        auto i = sec.find(lower(s));
         if (i == sec.end()) return false;
-        auto j = i->second.find(k);
+        auto j = i->second.find(lower(k));
         if (j == i->second.end()) return false;
         out = expand(j->second);
         return true;
@@ -124,6 +125,7 @@ struct Resolved {
     std::string model_path, model_id;
     int weight_dtype = DT_F16, kv_dtype = DT_F16, max_ctx = 0, rope_order = 0, return_logits = 0;
     int tensor_quant_threshold = 2000 * 2000;   // model.h:137
+    std::string devices;                        // device groups as written ("0", "0;1", "0&1;2&3")
 };
 
 int resolve_config(const char *ini_path, const char *section, const char *data_root_dir, Resolved &r) {
@@ -164,6 +166,9 @@ int resolve_config(const char *ini_path, const char *section, const char *data_r
     if (ini.get(msec, "max_context_len", s)) r.max_ctx = atoi(s.c_str());
     if (ini.get(msec, "tensor_quant_threshold", s)) r.tensor_quant_threshold = atoi(s.c_str());
     if (ini.get(sec, "return_output_tensors", s)) r.return_logits = (lower(s) == "true" || s == "1") ? 1 : 0;
+    // engine-wide device groups; a model section may name its own (inference_engine.cc:1490-1515)
+    if (ini.get(sec, "devices", s)) r.devices = s;
+    if (ini.get(msec, "devices", s) && !trim(s).empty()) r.devices = s;
 
     // the model specification
     const std::string spec_path = dir + spec_file;
@@ -191,8 +196,16 @@ int resolve_config(const char *ini_path, const char *section, const char *data_r
 
 }  // namespace
 
-struct ifb_engine {
+// one pipeline stage of the engine: a contiguous layer range on one device (BY_LAYER, SplitGpuLayers)
+struct Stage {
     ifb_model_t *model = nullptr;
+    int device = 0, layer_begin = 0, layer_end = 0;
+};
+
+struct ifb_engine {
+    ifb_model_t *model = nullptr;      // the last stage's model (the whole model when there is one stage): logits, next token
+    std::vector<Stage> stages;
+    int d_model = 0;
     Resolved cfg;
     int vocab = 0, max_ctx = 0;
     int pos = 0;                       // tokens already in the KV cache
@@ -245,10 +258,50 @@ int32_t ifb_engine_create(ifb_engine_t **out, const char *ini_path, const char *
     e->cfg.model_path = path;
     e->cfg.weight_dtype = info[0]; e->cfg.kv_dtype = info[1]; e->cfg.max_ctx = info[2]; e->cfg.rope_order = info[3];
     e->cfg.return_logits = info[4];
-    rc = ifb_model_load_llama2c(&e->model, path, info[0], info[1], info[2], info[3], nullptr);
-    if (rc != IFB_OK) { delete e; return rc; }
     int32_t hv[7];
     ifb_llama2c_probe(path, hv, nullptr);
+    {
+        // `devices`: groups of one device each = layer parallelism, the groups run one after the other as the reference's
+        // workers do (Infer_LayerParallelism, inference_engine.cc:1185-1220). Groups of several devices (tensor / hybrid
+        // parallelism) are one PROCESS per GPU in this runtime: ifb_rank_plan + ifb_model_create + ifb_model_tp_*.
+        Resolved r;
+        resolve_config(ini_path, section, data_root_dir, r);
+        int32_t ids[64], ng = 0, gs = 0, strat = 0;
+        rc = ifb_device_groups_parse(r.devices.c_str(), ids, 64, &ng, &gs, &strat);
+        if (rc != IFB_OK) { delete e; return rc; }
+        if (ng == 0) { ids[0] = 0; ng = 1; gs = 1; }          // no `devices` item: the current device... id 0
+        if (gs > 1) {
+            set_last_error("engine: devices = '%s' asks for tensor-parallel groups of %d; this runtime runs one process per GPU for "
+                           "those (ifb_rank_plan, ifb_model_create with tp_rank/tp_size, ifb_model_tp_export/import)", r.devices.c_str(), gs);
+            delete e;
+            return IFB_ERR_ARG;
+        }
+        int32_t ranges[128], gof[64], nr = 0;
+        ifb_split_layers(0, hv[2], ng, ranges, gof, &nr);
+        int ndev = 0;
+        cudaGetDeviceCount(&ndev);
+        for (int i = 0; i < nr; i++) {
+            Stage st;
+            st.layer_begin = ranges[2 * i];
+            st.layer_end = ranges[2 * i + 1] < hv[2] ? ranges[2 * i + 1] : hv[2];
+            if (st.layer_end <= st.layer_begin) continue;
+            st.device = ids[gof[i]];
+            if (st.device < 0 || st.device >= ndev) {
+                set_last_error("engine: devices = '%s' names device %d; this process sees %d", r.devices.c_str(), st.device, ndev);
+                ifb_engine_destroy(e);
+                return IFB_ERR_ARG;
+            }
+            e->stages.push_back(st);
+        }
+        if (e->stages.size() == 1) { e->stages[0].layer_begin = 0; e->stages[0].layer_end = 0; }   // the whole model
+        for (auto &st : e->stages) {
+            cudaSetDevice(st.device);
+            rc = ifb_model_load_llama2c_stage(&st.model, path, info[0], info[1], info[2], info[3], st.layer_begin, st.layer_end, nullptr);
+            if (rc != IFB_OK) { ifb_engine_destroy(e); return rc; }
+        }
+        e->model = e->stages.back().model;
+    }
+    e->d_model = hv[0];
     e->vocab = hv[5];
     e->max_ctx = info[2];
     e->logits_h.resize((size_t)e->vocab);
@@ -258,7 +311,8 @@ int32_t ifb_engine_create(ifb_engine_t **out, const char *ini_path, const char *
 
 void ifb_engine_destroy(ifb_engine_t *e) {
     if (!e) return;
-    if (e->model) ifb_model_destroy(e->model);
+    for (auto &st : e->stages)
+        if (st.model) { cudaSetDevice(st.device); ifb_model_destroy(st.model); }
     delete e;
 }
 
@@ -271,8 +325,11 @@ int32_t ifb_engine_add_query(ifb_engine_t *e, const int32_t *tokens, int32_t n) 
     IFB_CHECK_ARG(n < e->max_ctx, "add_query: %d tokens do not fit max_context_len %d", n, e->max_ctx);
     for (int i = 0; i < n; i++)
         IFB_CHECK_ARG(tokens[i] >= 0 && tokens[i] < e->vocab, "add_query: token id %d outside the vocabulary", tokens[i]);
-    int rc = ifb_model_kv_reset(e->model, 0, 0, 0, nullptr);
-    if (rc != IFB_OK) return rc;
+    for (auto &st : e->stages) {
+        cudaSetDevice(st.device);
+        int rc = ifb_model_kv_reset(st.model, 0, 0, 0, nullptr);
+        if (rc != IFB_OK) return rc;
+    }
     e->to_feed.assign(tokens, tokens + n);
     e->pos = 0;
     e->active = true;
@@ -285,7 +342,28 @@ int32_t ifb_engine_infer(ifb_engine_t *e, int32_t *next_token, float *logits_f32
     IFB_CHECK_ARG(e != nullptr && next_token != nullptr, "infer: null argument");
     if (!e->active || e->to_feed.empty()) { set_last_error("infer: no query is waiting for a step"); return IFB_ERR_STATE; }
     if (e->pos + (int)e->to_feed.size() > e->max_ctx) { set_last_error("infer: the context is full (%d tokens)", e->max_ctx); return IFB_ERR_STATE; }
-    if (e->to_feed.size() > 1 && ifb_model_prefill_supported(e->model)) {
+    if (e->stages.size() > 1) {
+        // layer parallelism: a token passes the stages in order; the hidden state travels from one stage's buffer to the
+        // next one's (GetOutput -> SetInput of the next worker, inference_engine.cc:1196-1212)
+        while (!e->to_feed.empty()) {
+            for (size_t k = 0; k < e->stages.size(); k++) {
+                Stage &st = e->stages[k];
+                cudaSetDevice(st.device);
+                if (k > 0) {
+                    Stage &pv = e->stages[k - 1];
+                    cudaError_t ce = pv.device == st.device
+                        ? cudaMemcpy(ifb_model_hidden_ptr(st.model), ifb_model_hidden_ptr(pv.model), (size_t)e->d_model * 2, cudaMemcpyDeviceToDevice)
+                        : cudaMemcpyPeer(ifb_model_hidden_ptr(st.model), st.device, ifb_model_hidden_ptr(pv.model), pv.device, (size_t)e->d_model * 2);
+                    if (ce != cudaSuccess) { set_last_error("infer: hidden-state hand-off failed: %s", cudaGetErrorString(ce)); return IFB_ERR_CUDA; }
+                }
+                int rc = ifb_model_decode(st.model, e->to_feed.front(), nullptr, e->pos, nullptr);
+                if (rc == IFB_OK) rc = ifb_device_synchronize();      // the groups run one after the other
+                if (rc != IFB_OK) return rc;   // a retry repeats this token on every stage: each rewrites the same cache rows
+            }
+            e->to_feed.erase(e->to_feed.begin());
+            e->pos++;
+        }
+    } else if (e->to_feed.size() > 1 && ifb_model_prefill_supported(e->model)) {
         // the prompt as ONE step with q_tokens = n, as the reference runs it (tensor-core GEMMs + prefill attention)
         int rc = ifb_model_prefill(e->model, e->to_feed.data(), (int32_t)e->to_feed.size(), e->pos, nullptr);
         if (rc != IFB_OK) return rc;        // nothing was consumed: pos and to_feed unchanged, a retry repeats the same step

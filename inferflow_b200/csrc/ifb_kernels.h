@@ -75,6 +75,8 @@ int embed_rows(void *dst_f16, const void *table_f16, const int32_t *tokens_dev, 
 
 int quantize_rows(int dt, void *dst, const void *src_f16, int64_t rows, int64_t cx, cudaStream_t st);
 int dequantize_rows(int dt, void *dst_f16, const void *src, int64_t rows, int64_t cx, cudaStream_t st);
+// Q3H_B64T1 blocks -> Q4_B64T1 blocks holding the same codes, base and scale (lossless; see ifb_quantize.cu)
+int repack_q3h_q4b64(void *dst, const void *src, int64_t nblocks, cudaStream_t st);
 
 int rmsnorm(void *y, const void *x, const void *w, int64_t rows, int64_t cols, float eps,
             float multi_base, cudaStream_t st);

@@ -75,6 +75,9 @@ struct ifb_model {
     int pf_cap = 0;
     void *pf_x = nullptr, *pf_xn = nullptr, *pf_q = nullptr, *pf_k = nullptr, *pf_v = nullptr, *pf_att = nullptr, *pf_h1 = nullptr,
          *pf_h3 = nullptr, *pf_tmp = nullptr, *pf_tok = nullptr;
+    int api_wdt = 0, api_ldt = 0;   // element types the caller named (spec.weight_dtype / lm_head_dtype hold the STORAGE types)
+    int l0 = 0, nl = 0;             // pipeline stage: this instance holds the global layers [l0, l0 + nl)
+    bool first_stage = true, last_stage = true;
     int64_t smem_kb[5] = {0, 0, 0, 0, 0};   // per-CTA shared-memory budget of the QKV / wo / GLU / w2 / lm_head GEMVs (KB, 0 = kernel default)
 };
 
@@ -117,9 +120,15 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     IFB_CHECK_ARG(s.experts == 0 || s.tp_size <= 1, "MoE layers are single-GPU in this runtime (the reference cannot run MoE on several GPUs either)");
     IFB_CHECK_ARG(tp <= 8 && s.vocab % tp == 0 && (s.vocab / tp) % 8 == 0, "vocab %d cannot be sharded %d ways", s.vocab, tp);
     IFB_CHECK_ARG(tp == 1 || s.layers <= 127, "tensor parallel: at most 127 layers (exchange index is 8 bits)");
-    const int wdt = s.weight_dtype;
+    // weight_repack: 3.5-bit blocks are stored as nibble blocks with the same codes / base / scale (ifb_quantize.cu)
+    const int wdt = (s.weight_repack && s.weight_dtype == DT_Q3H_B64T1) ? DT_Q4_B64T1 : s.weight_dtype;
+    const int ldt_store = (s.weight_repack && s.lm_head_dtype == DT_Q3H_B64T1) ? DT_Q4_B64T1 : s.lm_head_dtype;
     const int wcap = block_capacity(wdt);
     IFB_CHECK_ARG(wcap > 0 && wdt != DT_F32, "unsupported device_weight_data_type %d", wdt);
+    // pipeline stage: layers [layer_begin, layer_end) of the model (0, 0 = all)
+    const int lb = s.layer_begin, le = (s.layer_begin == 0 && s.layer_end == 0) ? s.layers : s.layer_end;
+    IFB_CHECK_ARG(lb >= 0 && le > lb && le <= s.layers, "pipeline stage: layers [%d, %d) of %d", lb, le, s.layers);
+    IFB_CHECK_ARG((lb == 0 && le == s.layers) || tp == 1, "pipeline stages of a tensor-parallel group are not supported yet (stage [%d, %d), tp %d)", lb, le, tp);
     // BY_ROW split must fall on block boundaries (device_tensor_builder.cu:161-330)
     IFB_CHECK_ARG((s.d_model / tp) % (wcap > 32 ? wcap : 32) == 0 && (s.d_ffn / tp) % (wcap > 32 ? wcap : 32) == 0,
                   "BY_ROW shard (d_model/%d=%d, d_ffn/%d=%d) is not a multiple of the block capacity %d",
@@ -128,6 +137,10 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     ifb_model *m = new ifb_model();
     m->spec = s;
     m->spec.tp_size = tp;
+    m->api_wdt = s.weight_dtype; m->api_ldt = s.lm_head_dtype;
+    m->spec.weight_dtype = wdt; m->spec.lm_head_dtype = ldt_store;       // from here on: the storage types
+    m->l0 = lb; m->nl = le - lb;
+    m->first_stage = lb == 0; m->last_stage = le == s.layers;
     m->hd = s.d_model / s.heads;
     m->heads_l = s.heads / tp;
     m->kv_heads_l = s.kv_heads / tp;
@@ -153,14 +166,15 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     // B200: on one and two GPUs the graph is 5-8 % ahead (both designs pay ~4 us per grid-wide
     // dependency: the step kernel in its op boundaries, the graph in launch + staging); from four GPUs on the step kernel
     // wins (per-rank streaming shrinks, launch overheads do not). IFB_STEP=0/1 overrides.
-    m->use_step = tp >= 4 ? 1 : 0;       // measured crossover (7B Q4, ctx 2k): 1 GPU 556 vs 600, 2 GPUs 641 vs 675, 4 GPUs 716 vs 671 tok/s
+    m->use_step = (tp >= 4 && m->first_stage && m->last_stage) ? 1 : 0;       // measured crossover (7B Q4, ctx 2k): 1 GPU 556 vs 600, 2 GPUs 641 vs 675, 4 GPUs 716 vs 671 tok/s
     const char *e4 = getenv("IFB_STEP");
     if (e4) m->use_step = atoi(e4) ? 1 : 0;
+    if (!(m->first_stage && m->last_stage)) m->use_step = 0;     // a pipeline stage runs the multi-launch path
 
     int rc = IFB_OK;
     auto A = [&](DevBuf &b, size_t bytes) { if (rc == IFB_OK) rc = dev_alloc(m, b, bytes); };
     const int d = s.d_model;
-    m->layers.resize(s.layers);
+    m->layers.resize(m->nl);
     int64_t wsum = 0;
     for (auto &L : m->layers) {
         A(L.attn_norm, d * 2);
@@ -201,15 +215,15 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
         A(L.kcache, kvb);
         A(L.vcache, kvb);
     }
-    A(m->tok_emb, (size_t)s.vocab * d * 2);
+    A(m->tok_emb, m->first_stage ? (size_t)s.vocab * d * 2 : 256);      // the embedding lives on the first stage,
     A(m->out_norm, d * 2);
-    const int ldt = s.lm_head_dtype;
+    const int ldt = ldt_store;
     if (rc == IFB_OK && (block_capacity(ldt) <= 0 || ldt == DT_F32)) {
         set_last_error("unsupported lm_head type %d", ldt);
         rc = IFB_ERR_TYPE;
     }
-    A(m->lm_head, wbytes(ldt, m->vocab_l, d));
-    wsum += wbytes(ldt, m->vocab_l, d);
+    A(m->lm_head, m->last_stage ? wbytes(ldt, m->vocab_l, d) : 256);     // the lm_head on the last
+    if (m->last_stage) wsum += wbytes(ldt, m->vocab_l, d);
     {   // the exchange region: under tensor parallelism the peers store into it; on one GPU the step kernel's own
         // row-parallel GEMVs do (flag-in-data words instead of a completion count, see ifb_step.cu)
         auto up = [](int64_t v) { return (v + 255) / 256 * 256; };
@@ -237,7 +251,7 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     A(m->scalars, 256);
     {   // one 8-int cursor block per launch of a step: dense 5 per layer, MoE 6 + 2*top_k per layer, + embedding, lm_head, argmax, advance
         const size_t per_layer = s.experts > 0 ? 6 + 2 * (size_t)s.experts_top_k : 5;
-        A(m->counters, (per_layer * s.layers + 8) * 8 * sizeof(int));
+        A(m->counters, (per_layer * m->nl + 8) * 8 * sizeof(int));
     }
     A(m->ybuf, d * 2);
     A(m->qkvw, (size_t)(m->q_dim_l + 2 * m->kv_dim_l) * 4);     // {half2, flag} words
@@ -281,12 +295,17 @@ extern "C" void ifb_model_destroy(ifb_model_t *m) {
 }
 
 extern "C" int64_t ifb_model_weight_bytes(const ifb_model_t *m) { return m ? m->weight_bytes : 0; }
+extern "C" int32_t ifb_model_storage_dtype(const ifb_model_t *m, int32_t which) {
+    if (!m) return -1;
+    return which == 1 ? m->spec.lm_head_dtype : m->spec.weight_dtype;
+}
+extern "C" void *ifb_model_hidden_ptr(ifb_model_t *m) { return m ? m->x0.p : nullptr; }
 
 extern "C" int64_t ifb_model_kv_bytes_per_token(const ifb_model_t *m, int32_t ctx_len) {
     if (!m) return 0;
     // 2 * L * ctx * (g*e) * kvb   (SURVEY section 8d), this rank's shard
     double kvb = m->spec.kv_dtype == DT_F16 ? 2.0 : 34.0 / 32.0;
-    return (int64_t)(2.0 * m->spec.layers * (double)ctx_len * m->kv_dim_l * kvb);
+    return (int64_t)(2.0 * m->nl * (double)ctx_len * m->kv_dim_l * kvb);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -381,9 +400,25 @@ __global__ void synth_f16_kernel(__half *dst, int64_t n, uint64_t seed, float si
 }
 
 // this rank's [rows x cols] shard at (row0, col0) of a global tensor with gcols columns
-static int synth_tensor(void *p, int dt, int64_t rows, int64_t cols, uint64_t seed, float sigma, cudaStream_t st,
+// blocks made in the caller's element type `api_dt` by make(buffer), kept in the storage type `store_dt`
+// (the same unless weight_repack turned 3.5-bit blocks into nibble blocks)
+template <class F>
+static int produce_blocks(void *dst, int store_dt, int api_dt, int64_t rows, int64_t cols, cudaStream_t st, F make) {
+    if (store_dt == api_dt) return make(dst);
+    IFB_CHECK_ARG(api_dt == DT_Q3H_B64T1 && store_dt == DT_Q4_B64T1, "no repacking from type %d to type %d", api_dt, store_dt);
+    void *tmp = nullptr;
+    IFB_CUDA(cudaMalloc(&tmp, (size_t)(rows * row_bytes(api_dt, cols))));
+    int rc = make(tmp);
+    if (rc == IFB_OK) rc = repack_q3h_q4b64(dst, tmp, rows * (cols / 64), st);
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    return rc;
+}
+
+static int synth_tensor(void *p_store, int store_dt, int dt, int64_t rows, int64_t cols, uint64_t seed, float sigma, cudaStream_t st,
                         int64_t gcols = 0, int64_t row0 = 0, int64_t col0 = 0) {
     if (gcols == 0) gcols = cols;
+    return produce_blocks(p_store, store_dt, dt, rows, cols, st, [&](void *p) -> int {
     if (dt == DT_F16) {
         int64_t n = rows * cols;
         synth_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((__half *)p, n, seed, sigma, 0.f, 0, cols, gcols, row0, col0);
@@ -394,6 +429,7 @@ static int synth_tensor(void *p, int dt, int64_t rows, int64_t cols, uint64_t se
     }
     IFB_LAUNCH_CHECK();
     return IFB_OK;
+    });
 }
 static int const_f16(void *p, int64_t n, float v, cudaStream_t st) {
     synth_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((__half *)p, n, 0, 0.f, v, 1, n, n, 0, 0);
@@ -412,32 +448,32 @@ extern "C" int32_t ifb_model_init_synthetic(ifb_model_t *m, uint64_t seed, ifb_s
     const int64_t rk = s.tp_rank;
     const int64_t q0 = rk * m->q_dim_l, kv0 = rk * m->kv_dim_l, f0 = rk * m->ffn_l;
     const int64_t gq = (int64_t)s.heads * m->hd, gf = s.d_ffn;
-    int li = 0;
+    int li = m->l0;                  // GLOBAL layer index: a pipeline stage holds its slice of the same model
     for (auto &L : m->layers) {
         uint64_t ls = sd + 100ull * (uint64_t)(li + 1);
         TRY(const_f16(L.attn_norm.p, d, 1.0f, st));
         TRY(const_f16(L.ffn_norm.p, d, 1.0f, st));
-        TRY(synth_tensor(L.wq.p, wdt, m->q_dim_l, d, ls + 1, 0.02f, st, d, q0, 0));          // BY_COL: rows of this rank
-        TRY(synth_tensor(L.wk.p, wdt, m->kv_dim_l, d, ls + 2, 0.02f, st, d, kv0, 0));
-        TRY(synth_tensor(L.wv.p, wdt, m->kv_dim_l, d, ls + 3, 0.02f, st, d, kv0, 0));
-        TRY(synth_tensor(L.wo.p, wdt, d, m->q_dim_l, ls + 4, 0.02f, st, gq, 0, q0));          // BY_ROW: columns of this rank
+        TRY(synth_tensor(L.wq.p, wdt, m->api_wdt, m->q_dim_l, d, ls + 1, 0.02f, st, d, q0, 0));          // BY_COL: rows of this rank
+        TRY(synth_tensor(L.wk.p, wdt, m->api_wdt, m->kv_dim_l, d, ls + 2, 0.02f, st, d, kv0, 0));
+        TRY(synth_tensor(L.wv.p, wdt, m->api_wdt, m->kv_dim_l, d, ls + 3, 0.02f, st, d, kv0, 0));
+        TRY(synth_tensor(L.wo.p, wdt, m->api_wdt, d, m->q_dim_l, ls + 4, 0.02f, st, gq, 0, q0));          // BY_ROW: columns of this rank
         if (s.experts == 0) {
-            TRY(synth_tensor(L.w1.p, wdt, m->ffn_l, d, ls + 5, 0.02f, st, d, f0, 0));
-            TRY(synth_tensor(L.w3.p, wdt, m->ffn_l, d, ls + 6, 0.02f, st, d, f0, 0));
-            TRY(synth_tensor(L.w2.p, wdt, d, m->ffn_l, ls + 7, 0.02f, st, gf, 0, f0));
+            TRY(synth_tensor(L.w1.p, wdt, m->api_wdt, m->ffn_l, d, ls + 5, 0.02f, st, d, f0, 0));
+            TRY(synth_tensor(L.w3.p, wdt, m->api_wdt, m->ffn_l, d, ls + 6, 0.02f, st, d, f0, 0));
+            TRY(synth_tensor(L.w2.p, wdt, m->api_wdt, d, m->ffn_l, ls + 7, 0.02f, st, gf, 0, f0));
         } else {
-            TRY(synth_tensor(L.gate.p, DT_F16, s.experts, d, ls + 8, 0.05f, st));   // router: non-degenerate expert choice
+            TRY(synth_tensor(L.gate.p, DT_F16, DT_F16, s.experts, d, ls + 8, 0.05f, st));   // router: non-degenerate expert choice
             for (int e = 0; e < s.experts; e++) {
-                TRY(synth_tensor(L.ew1[e].p, wdt, m->ffn_l, d, ls + 20 + 3 * e, 0.02f, st));
-                TRY(synth_tensor(L.ew3[e].p, wdt, m->ffn_l, d, ls + 21 + 3 * e, 0.02f, st));
-                TRY(synth_tensor(L.ew2[e].p, wdt, d, m->ffn_l, ls + 22 + 3 * e, 0.02f, st));
+                TRY(synth_tensor(L.ew1[e].p, wdt, m->api_wdt, m->ffn_l, d, ls + 20 + 3 * e, 0.02f, st));
+                TRY(synth_tensor(L.ew3[e].p, wdt, m->api_wdt, m->ffn_l, d, ls + 21 + 3 * e, 0.02f, st));
+                TRY(synth_tensor(L.ew2[e].p, wdt, m->api_wdt, d, m->ffn_l, ls + 22 + 3 * e, 0.02f, st));
             }
         }
         li++;
     }
-    TRY(synth_tensor(m->tok_emb.p, DT_F16, s.vocab, d, seed * 1000003ull + 11, 1.0f, st));   // same on all ranks
+    if (m->first_stage) TRY(synth_tensor(m->tok_emb.p, DT_F16, DT_F16, s.vocab, d, seed * 1000003ull + 11, 1.0f, st));   // same on all ranks
     TRY(const_f16(m->out_norm.p, d, 1.0f, st));
-    TRY(synth_tensor(m->lm_head.p, s.lm_head_dtype, m->vocab_l, d, seed * 1000003ull + 13, 0.02f, st, d, rk * m->vocab_l, 0));   // vocabulary-sharded
+    if (m->last_stage) TRY(synth_tensor(m->lm_head.p, s.lm_head_dtype, m->api_ldt, m->vocab_l, d, seed * 1000003ull + 13, 0.02f, st, d, rk * m->vocab_l, 0));   // vocabulary-sharded
     return IFB_OK;
 }
 
@@ -479,7 +515,7 @@ extern "C" int32_t ifb_model_kv_reset(ifb_model_t *m, int32_t ctx_len, int32_t f
     cudaStream_t st = (cudaStream_t)stream;
     if (fill && ctx_len > 0) {
         int pad = (m->spec.max_ctx + 63) / 64 * 64;
-        int li = 0;
+        int li = m->l0;              // GLOBAL layer index
         for (auto &L : m->layers) {
             int64_t warps = (int64_t)m->kv_heads_l * ctx_len * (m->hd / 32);
             unsigned grid = (unsigned)((warps * 32 + 255) / 256);
@@ -502,11 +538,11 @@ __global__ void f32_to_f16_kernel(__half *dst, const float *src, int64_t n) {
 }
 
 // Upload rows [r0, r0+nr) x cols [c0, c0+nc) of a host [rows][cols] matrix as fp16, then quantize to dt.
-static int load_shard(DevBuf &dst, int dt, const void *host, int host_dt, int64_t rows, int64_t cols,
+static int load_shard(DevBuf &dst, int store_dt, int dt, const void *host, int host_dt, int64_t rows, int64_t cols,
                       int64_t r0, int64_t nr, int64_t c0, int64_t nc, cudaStream_t st) {
     const size_t esz = host_dt == DT_F32 ? 4 : 2;
     IFB_CHECK_ARG(host_dt == DT_F32 || host_dt == DT_F16, "load_tensor: host data must be F32 or F16");
-    IFB_CHECK_ARG(wbytes(dt, nr, nc) <= (int64_t)dst.bytes, "load_tensor: shard %lldx%lld does not fit the device tensor", (long long)nr, (long long)nc);
+    IFB_CHECK_ARG(wbytes(store_dt, nr, nc) <= (int64_t)dst.bytes, "load_tensor: shard %lldx%lld does not fit the device tensor", (long long)nr, (long long)nc);
     void *staging = nullptr, *half_buf = nullptr;
     IFB_CUDA(cudaMalloc(&staging, (size_t)nr * nc * esz));
     cudaError_t e = cudaMemcpy2DAsync(staging, nc * esz, (const uint8_t *)host + ((size_t)r0 * cols + c0) * esz,
@@ -526,7 +562,7 @@ static int load_shard(DevBuf &dst, int dt, const void *host, int host_dt, int64_
         if (dt == DT_F16) {
             if (cudaMemcpyAsync(dst.p, h16, (size_t)nr * nc * 2, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { set_last_error("D2D copy failed"); rc = IFB_ERR_CUDA; }
         } else {
-            rc = quantize_rows(dt, dst.p, h16, nr, nc, st);
+            rc = produce_blocks(dst.p, store_dt, dt, nr, nc, st, [&](void *p) -> int { return quantize_rows(dt, p, h16, nr, nc, st); });
         }
     }
     cudaStreamSynchronize(st);
@@ -543,11 +579,13 @@ extern "C" int32_t ifb_model_load_tensor(ifb_model_t *m, const char *name, const
     const int tp = s.tp_size, rk = s.tp_rank, d = s.d_model, wdt = s.weight_dtype;
     std::string n(name);
     // weights are read through fixed pointers: a captured graph stays valid
-    if (n == "tok_embeddings") return load_shard(m->tok_emb, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
-    if (n == "output_norm") return load_shard(m->out_norm, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
+    if (n == "tok_embeddings" && !m->first_stage) return IFB_OK;                       // held by the first pipeline stage
+    if ((n == "output_norm" || n == "output") && !m->last_stage) return IFB_OK;       // held by the last
+    if (n == "tok_embeddings") return load_shard(m->tok_emb, DT_F16, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
+    if (n == "output_norm") return load_shard(m->out_norm, DT_F16, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
     if (n == "output") {
         IFB_CHECK_ARG(rows == s.vocab && cols == d, "output shape");
-        return load_shard(m->lm_head, s.lm_head_dtype, host, host_dt, rows, cols, (int64_t)rk * m->vocab_l, m->vocab_l, 0, cols, st);
+        return load_shard(m->lm_head, s.lm_head_dtype, m->api_ldt, host, host_dt, rows, cols, (int64_t)rk * m->vocab_l, m->vocab_l, 0, cols, st);
     }
     int li = -1;
     char tn[64] = {0};
@@ -555,30 +593,31 @@ extern "C" int32_t ifb_model_load_tensor(ifb_model_t *m, const char *name, const
         set_last_error("load_tensor: unknown tensor '%s'", name);
         return IFB_ERR_ARG;
     }
-    LayerW &L = m->layers[li];
+    if (li < m->l0 || li >= m->l0 + m->nl) return IFB_OK;     // another pipeline stage holds this layer
+    LayerW &L = m->layers[li - m->l0];
     std::string t(tn);
     const int hd = m->hd;
     // DUP
-    if (t == "attention_norm") return load_shard(L.attn_norm, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
-    if (t == "ffn_norm") return load_shard(L.ffn_norm, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
+    if (t == "attention_norm") return load_shard(L.attn_norm, DT_F16, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
+    if (t == "ffn_norm") return load_shard(L.ffn_norm, DT_F16, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st);
     // BY_COL (split output rows; heads stay whole)
-    if (t == "wq") { IFB_CHECK_ARG(rows == (int64_t)s.heads * hd && cols == d, "wq shape"); return load_shard(L.wq, wdt, host, host_dt, rows, cols, (int64_t)rk * m->q_dim_l, m->q_dim_l, 0, cols, st); }
-    if (t == "wk") { IFB_CHECK_ARG(rows == (int64_t)s.kv_heads * hd && cols == d, "wk shape"); return load_shard(L.wk, wdt, host, host_dt, rows, cols, (int64_t)rk * m->kv_dim_l, m->kv_dim_l, 0, cols, st); }
-    if (t == "wv") { IFB_CHECK_ARG(rows == (int64_t)s.kv_heads * hd && cols == d, "wv shape"); return load_shard(L.wv, wdt, host, host_dt, rows, cols, (int64_t)rk * m->kv_dim_l, m->kv_dim_l, 0, cols, st); }
-    if (t == "w1") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "w1 shape"); return load_shard(L.w1, wdt, host, host_dt, rows, cols, (int64_t)rk * m->ffn_l, m->ffn_l, 0, cols, st); }
-    if (t == "w3") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "w3 shape"); return load_shard(L.w3, wdt, host, host_dt, rows, cols, (int64_t)rk * m->ffn_l, m->ffn_l, 0, cols, st); }
+    if (t == "wq") { IFB_CHECK_ARG(rows == (int64_t)s.heads * hd && cols == d, "wq shape"); return load_shard(L.wq, wdt, m->api_wdt, host, host_dt, rows, cols, (int64_t)rk * m->q_dim_l, m->q_dim_l, 0, cols, st); }
+    if (t == "wk") { IFB_CHECK_ARG(rows == (int64_t)s.kv_heads * hd && cols == d, "wk shape"); return load_shard(L.wk, wdt, m->api_wdt, host, host_dt, rows, cols, (int64_t)rk * m->kv_dim_l, m->kv_dim_l, 0, cols, st); }
+    if (t == "wv") { IFB_CHECK_ARG(rows == (int64_t)s.kv_heads * hd && cols == d, "wv shape"); return load_shard(L.wv, wdt, m->api_wdt, host, host_dt, rows, cols, (int64_t)rk * m->kv_dim_l, m->kv_dim_l, 0, cols, st); }
+    if (t == "w1") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "w1 shape"); return load_shard(L.w1, wdt, m->api_wdt, host, host_dt, rows, cols, (int64_t)rk * m->ffn_l, m->ffn_l, 0, cols, st); }
+    if (t == "w3") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "w3 shape"); return load_shard(L.w3, wdt, m->api_wdt, host, host_dt, rows, cols, (int64_t)rk * m->ffn_l, m->ffn_l, 0, cols, st); }
     // BY_ROW (split the contraction dimension)
-    if (t == "wo") { IFB_CHECK_ARG(rows == d && cols == (int64_t)s.heads * hd, "wo shape"); return load_shard(L.wo, wdt, host, host_dt, rows, cols, 0, rows, (int64_t)rk * m->q_dim_l, m->q_dim_l, st); }
-    if (t == "w2") { IFB_CHECK_ARG(rows == d && cols == s.d_ffn, "w2 shape"); return load_shard(L.w2, wdt, host, host_dt, rows, cols, 0, rows, (int64_t)rk * m->ffn_l, m->ffn_l, st); }
+    if (t == "wo") { IFB_CHECK_ARG(rows == d && cols == (int64_t)s.heads * hd, "wo shape"); return load_shard(L.wo, wdt, m->api_wdt, host, host_dt, rows, cols, 0, rows, (int64_t)rk * m->q_dim_l, m->q_dim_l, st); }
+    if (t == "w2") { IFB_CHECK_ARG(rows == d && cols == s.d_ffn, "w2 shape"); return load_shard(L.w2, wdt, m->api_wdt, host, host_dt, rows, cols, 0, rows, (int64_t)rk * m->ffn_l, m->ffn_l, st); }
     // mixture of experts: "gate" [experts][d] (router, kept fp16), "experts.E.w1|w2|w3"
     if (s.experts > 0) {
-        if (t == "gate") { IFB_CHECK_ARG(rows == s.experts && cols == d, "gate shape"); return load_shard(L.gate, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
+        if (t == "gate") { IFB_CHECK_ARG(rows == s.experts && cols == d, "gate shape"); return load_shard(L.gate, DT_F16, DT_F16, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
         int e = -1; char wn[16] = {0};
         if (sscanf(tn, "experts.%d.%15s", &e, wn) == 2 && e >= 0 && e < s.experts) {
             std::string w(wn);
-            if (w == "w1") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "expert w1 shape"); return load_shard(L.ew1[e], wdt, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
-            if (w == "w3") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "expert w3 shape"); return load_shard(L.ew3[e], wdt, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
-            if (w == "w2") { IFB_CHECK_ARG(rows == d && cols == s.d_ffn, "expert w2 shape"); return load_shard(L.ew2[e], wdt, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
+            if (w == "w1") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "expert w1 shape"); return load_shard(L.ew1[e], wdt, m->api_wdt, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
+            if (w == "w3") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "expert w3 shape"); return load_shard(L.ew3[e], wdt, m->api_wdt, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
+            if (w == "w2") { IFB_CHECK_ARG(rows == d && cols == s.d_ffn, "expert w2 shape"); return load_shard(L.ew2[e], wdt, m->api_wdt, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
         }
     }
     set_last_error("load_tensor: unknown tensor '%s'", name);
@@ -647,6 +686,12 @@ extern "C" int32_t ifb_llama2c_probe(const char *path, int32_t header_out[7], in
 
 extern "C" int32_t ifb_model_load_llama2c(ifb_model_t **out, const char *path, int32_t weight_dtype, int32_t kv_dtype,
                                           int32_t max_ctx, int32_t rope_order, ifb_stream_t stream) {
+    return ifb_model_load_llama2c_stage(out, path, weight_dtype, kv_dtype, max_ctx, rope_order, 0, 0, stream);
+}
+
+extern "C" int32_t ifb_model_load_llama2c_stage(ifb_model_t **out, const char *path, int32_t weight_dtype, int32_t kv_dtype,
+                                                int32_t max_ctx, int32_t rope_order, int32_t layer_begin, int32_t layer_end,
+                                                ifb_stream_t stream) {
     IFB_CHECK_ARG(out != nullptr && path != nullptr, "load_llama2c: null argument");
     int32_t hv[7];
     int32_t shared = 1;
@@ -656,7 +701,9 @@ extern "C" int32_t ifb_model_load_llama2c(ifb_model_t **out, const char *path, i
     s.max_ctx = max_ctx > 0 ? max_ctx : hv[6];
     s.weight_dtype = weight_dtype; s.kv_dtype = kv_dtype; s.lm_head_dtype = DT_F16;
     s.rope_order = rope_order >= 0 ? rope_order : 0;   // llama2.c stores q/k for interleaved rotation (qk_column_order 0)
-    s.rope_theta = 10000.0f; s.norm_eps = 1e-5f; s.kq_scale = 1.0f; s.tp_rank = 0; s.tp_size = 1;
+    s.rope_theta = 10000.0f;
+    s.layer_begin = layer_begin; s.layer_end = layer_end;
+    s.weight_repack = 1;           // 3.5-bit files are kept as nibble blocks with the same values (see ifb_model_spec_t) s.norm_eps = 1e-5f; s.kq_scale = 1.0f; s.tp_rank = 0; s.tp_size = 1;
     ifb_model_t *m = nullptr;
     TRY(ifb_model_create(&m, &s));
     FILE *f = fopen(path, "rb");
@@ -720,8 +767,8 @@ extern "C" int32_t ifb_model_tensor_ptr(ifb_model_t *m, const char *name, void *
     else if (n == "trace" && m->trace_on) b = &m->trace;
     else {
         int li = -1; char tn[64] = {0};
-        if (sscanf(name, "layers.%d.%63s", &li, tn) == 2 && li >= 0 && li < m->spec.layers) {
-            LayerW &L = m->layers[li];
+        if (sscanf(name, "layers.%d.%63s", &li, tn) == 2 && li >= m->l0 && li < m->l0 + m->nl) {
+            LayerW &L = m->layers[li - m->l0];
             std::string t(tn);
             if (t == "attention_norm") b = &L.attn_norm; else if (t == "ffn_norm") b = &L.ffn_norm;
             else if (t == "wq") b = &L.wq; else if (t == "wk") b = &L.wk; else if (t == "wv") b = &L.wv;
@@ -878,7 +925,8 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
     IFB_CUDA(cudaMemsetAsync(m->counters.p, 0, m->counters.bytes, st));
     auto CT = [&](int idx) -> void * { return (void *)((int *)m->counters.p + (size_t)idx * 8); };   // cursor + per-op completion counts
     auto TR = [&](int idx) -> void * { return (m->trace_on && idx < 512) ? (void *)((uint64_t *)m->trace.p + (size_t)idx * 160 * 8) : nullptr; };
-    if (parts & PART_MISC) { TRY(embed_row(m->x0.p, m->tok_emb.p, DT_F16, d, 0, sc + 1, st, s.vocab)); n++; }
+    // a later pipeline stage starts from the hidden state its predecessor left in x0 (ifb_model_hidden_ptr)
+    if ((parts & PART_MISC) && m->first_stage) { TRY(embed_row(m->x0.p, m->tok_emb.p, DT_F16, d, 0, sc + 1, st, s.vocab)); n++; }
     const bool q8 = true;   // enable_full_quant_gemv = true (inference_engine.cc:53-57)
     auto ax8_ok = [](int dt) {
         return dt == DT_Q8_B32T2 || dt == DT_Q6_B64T1 || dt == DT_Q5_B64T1 || dt == DT_Q4_B32T1A ||
@@ -900,7 +948,7 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
                               t.resid = resid; t.xout = xout; return t; };
     TpExchange t_head;
     // every GEMV of the step first (descriptors only), then the launches
-    const int nl = s.layers;
+    const int nl = m->nl;
     std::vector<GemvLaunch> g_qkv(nl), g_wo(nl), g_glu(nl), g_w2(nl);
     std::vector<TpExchange> t_qkv(nl), t_wo(nl), t_glu(nl), t_w2(nl);
     for (int li = 0; li < nl; li++) {
@@ -982,6 +1030,12 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
             TRY(launch(&g_glu[li]));
             TRY(launch(&g_w2[li]));
         }
+    }
+    if (!m->last_stage) {
+        // the hidden state stays in x0 for the next stage; position += 1 so that decode_next works on every stage
+        if (parts & PART_MISC) { advance_kernel<<<1, 1, 0, st>>>(sc, 1); n++; IFB_LAUNCH_CHECK(); }
+        if (launches) *launches = n;
+        return IFB_OK;
     }
     // --- final norm + lm_head (fp16 weights meet an fp16 activation: GemvHalf_AX_Alg3)
     GemvLaunch h;
@@ -1112,7 +1166,7 @@ static bool prefill_supported(const ifb_model *m) {
     const auto &s = m->spec;
     auto ok_w = [](int dt) { return dt == DT_F16 || dt == DT_Q8_B32T2 || dt == DT_Q6_B64T1 || dt == DT_Q5_B64T1 || dt == DT_Q4_B32T1A ||
                                     dt == DT_Q4_B32T1B || dt == DT_Q4_B64T1 || dt == DT_Q3H_B64T1; };
-    return s.tp_size == 1 && s.experts == 0 && ok_w(s.weight_dtype) && (m->hd == 64 || m->hd == 128) && s.d_model % 128 == 0 &&
+    return s.tp_size == 1 && s.experts == 0 && m->first_stage && m->last_stage && ok_w(s.weight_dtype) && (m->hd == 64 || m->hd == 128) && s.d_model % 128 == 0 &&
            m->q_dim_l % 128 == 0 && m->kv_dim_l % 128 == 0 && s.d_ffn % 128 == 0 && (s.rope_order == 0 || s.rope_order == 2);
 }
 

@@ -26,12 +26,16 @@ class ModelSpec:
     experts: int = 0
     experts_top_k: int = 0
     moe_norm_top_k_prob: int = 1
+    weight_repack: int = 0      # 1: Q3H_B64T1 matrices stored as Q4_B64T1 blocks with the same codes (lossless, faster to decode)
+    layer_begin: int = 0        # pipeline stage [layer_begin, layer_end); 0, 0 = the whole model
+    layer_end: int = 0
 
     def to_c(self):
         return ModelSpecC(self.layers, self.d_model, self.d_ffn, self.heads, self.kv_heads, self.vocab,
                           self.max_ctx, self.weight_dtype, self.kv_dtype, self.lm_head_dtype,
                           self.rope_order, self.rope_theta, self.norm_eps, self.kq_scale, self.tp_rank,
-                          self.tp_size, self.experts, self.experts_top_k, self.moe_norm_top_k_prob)
+                          self.tp_size, self.experts, self.experts_top_k, self.moe_norm_top_k_prob,
+                          self.weight_repack, self.layer_begin, self.layer_end)
 
 
 # shapes of SURVEY.md section 8
@@ -104,6 +108,16 @@ class Model:
         n = C.c_int64()
         check(lib.ifb_model_tensor_ptr(self._h, name.encode(), C.byref(p), C.byref(n)), "ifb_model_tensor_ptr")
         return p.value, n.value
+
+    @property
+    def storage_weight_dtype(self):
+        """element type the layer matrices are stored in (differs from spec.weight_dtype under weight_repack)"""
+        return int(lib.ifb_model_storage_dtype(self._h, 0))
+
+    @property
+    def hidden_ptr(self):
+        """device pointer of the fp16 hidden state a pipeline stage reads / leaves"""
+        return lib.ifb_model_hidden_ptr(self._h)
 
     def read_tensor(self, name, nbytes=None):
         """device bytes of a named tensor as a numpy uint8 array (blocking)"""
