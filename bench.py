@@ -421,8 +421,9 @@ def _run_ours(args, ib, np, torch, dist, rank, world, local):
     default_wl = args.workload == DEFAULT_WORKLOAD
     w_dtype = getattr(ib.DT, wl["w"])
     dims = getattr(ib, wl["dims"])
+    # weight_repack: 3.5-bit blocks are kept as nibble blocks holding the same values (lossless; no effect on other types)
     spec = ib.ModelSpec(max_ctx=CTX, weight_dtype=w_dtype, kv_dtype=ib.DT.Q8_B32T2,
-                        lm_head_dtype=ib.DT.F16, tp_rank=rank, tp_size=world, **dims)
+                        lm_head_dtype=ib.DT.F16, tp_rank=rank, tp_size=world, weight_repack=1, **dims)
     model = ib.Model(spec)
     stream = torch.cuda.Stream()
     sh = stream.cuda_stream
@@ -448,7 +449,7 @@ def _run_ours(args, ib, np, torch, dist, rank, world, local):
                 os.environ["IFB_STEP"] = "0" if uses_step else "1"
             try:
                 spec1 = ib.ModelSpec(max_ctx=CTX, weight_dtype=w_dtype, kv_dtype=ib.DT.Q8_B32T2,
-                                     lm_head_dtype=ib.DT.F16, **dims)
+                                     lm_head_dtype=ib.DT.F16, weight_repack=1, **dims)
                 ref = ib.Model(spec1)
             finally:
                 if saved is None:
@@ -578,7 +579,14 @@ def _run_ours(args, ib, np, torch, dist, rank, world, local):
         a1.record(stream)
         stream.synchronize()
         attn_ms = a0.elapsed_time(a1) / reps
-    wbytes = model.weight_bytes
+    stored_wbytes = model.weight_bytes
+    wbytes = stored_wbytes
+    store_dt = model.storage_weight_dtype
+    if store_dt != w_dtype:
+        # algorithmic bytes are those of the format the model is GIVEN in; what the kernels stream is
+        # the repacked form (reported as stored_bytes_per_token: more bytes, far fewer instructions per weight)
+        head_b = (spec.vocab // world) * spec.d_model * 2
+        wbytes = (stored_wbytes - head_b) * ib.lib.ifb_block_bytes(w_dtype) // ib.lib.ifb_block_bytes(store_dt) + head_b
     kvbytes = model.kv_bytes_per_token(CTX)
     step_bytes = wbytes + kvbytes
     peak = float(peaks["hbm_gbs"])
@@ -602,6 +610,9 @@ def _run_ours(args, ib, np, torch, dist, rank, world, local):
                     "us_per_launch_avg": gemv_ms * 1e3 / max(nl, 1),
                     "attention": {"achieved": kvbytes / (attn_ms * 1e-3) / 1e9, "launches": na,
                                   "frac": kvbytes / (attn_ms * 1e-3) / 1e9 / peak}}
+    if store_dt != w_dtype:
+        roofline["stored_bytes_per_token"] = stored_wbytes + kvbytes
+        roofline["storage"] = "Q3H_B64T1 weights kept as Q4_B64T1 nibble blocks (same codes, base, scale): 36 instead of 32 bytes per 64 weights"
     roofline["step"] = {"bytes_per_token": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                         "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
 
