@@ -224,8 +224,8 @@ typedef struct ifb_model_spec {
                                        order of magnitude fewer instructions). 0: stored as the reference stores them. */
     int32_t layer_begin, layer_end; /* pipeline stage (BY_LAYER / HYBRID, SplitGpuLayers): this instance holds layers
                                        [layer_begin, layer_end) only; 0, 0 = all. A stage with layer_begin > 0 takes
-                                       its input from ifb_model_hidden_ptr instead of the embedding; one with
-                                       layer_end < layers leaves its output there instead of running the lm_head. */
+                                       its input from ifb_model_hidden_ptr(m, 0) instead of the embedding; one with
+                                       layer_end < layers leaves its output in ifb_model_hidden_ptr(m, 1) and runs no lm_head. */
 } ifb_model_spec_t;
 
 typedef struct ifb_model ifb_model_t;
@@ -237,9 +237,10 @@ int64_t ifb_model_weight_bytes(const ifb_model_t *m);   /* quantized bytes read 
 /* element type the layer matrices (which = 0) / the lm_head (which = 1) are STORED in: the spec's type unless
  * weight_repack changed it */
 int32_t ifb_model_storage_dtype(const ifb_model_t *m, int32_t which);
-/* the fp16 hidden state [d_model] a pipeline stage reads (layer_begin > 0) and leaves (layer_end < layers): the caller
- * hands it from stage to stage (same GPU: a device copy; another GPU: cudaMemcpyPeerAsync or a peer-mapped store) */
-void *ifb_model_hidden_ptr(ifb_model_t *m);
+/* the fp16 hidden state [d_model] of a pipeline stage: which = 0 the buffer a stage with layer_begin > 0 reads its input
+ * from, which = 1 the buffer a stage leaves its output in. The caller hands it from stage to stage after the producing
+ * step has completed (same GPU: ifb_memcpy_d2d; another GPU: cudaMemcpyPeer or a peer-mapped store). */
+void *ifb_model_hidden_ptr(ifb_model_t *m, int32_t which);
 int64_t ifb_model_kv_bytes_per_token(const ifb_model_t *m, int32_t ctx_len);
 /* deterministic synthetic weights generated on the device: quant blocks
  * with uniform codes and |N(0,sigma)| fp16 scales, norms 1.0 */

@@ -106,7 +106,7 @@ def _load():
     L.ifb_model_kernel_launches_per_step.argtypes = [vp]
     L.ifb_model_step_status.argtypes = [vp, vp]
     L.ifb_model_storage_dtype.argtypes = [vp, i32]
-    L.ifb_model_hidden_ptr.argtypes = [vp]
+    L.ifb_model_hidden_ptr.argtypes = [vp, i32]
     L.ifb_model_hidden_ptr.restype = vp
     L.ifb_device_groups_parse.argtypes = [C.c_char_p, vp, i32, vp, vp, vp]
     L.ifb_split_layers.argtypes = [i32, i32, i32, vp, vp, vp]

@@ -352,8 +352,8 @@ int32_t ifb_engine_infer(ifb_engine_t *e, int32_t *next_token, float *logits_f32
                 if (k > 0) {
                     Stage &pv = e->stages[k - 1];
                     cudaError_t ce = pv.device == st.device
-                        ? cudaMemcpy(ifb_model_hidden_ptr(st.model), ifb_model_hidden_ptr(pv.model), (size_t)e->d_model * 2, cudaMemcpyDeviceToDevice)
-                        : cudaMemcpyPeer(ifb_model_hidden_ptr(st.model), st.device, ifb_model_hidden_ptr(pv.model), pv.device, (size_t)e->d_model * 2);
+                        ? cudaMemcpy(ifb_model_hidden_ptr(st.model, 0), ifb_model_hidden_ptr(pv.model, 1), (size_t)e->d_model * 2, cudaMemcpyDeviceToDevice)
+                        : cudaMemcpyPeer(ifb_model_hidden_ptr(st.model, 0), st.device, ifb_model_hidden_ptr(pv.model, 1), pv.device, (size_t)e->d_model * 2);
                     if (ce != cudaSuccess) { set_last_error("infer: hidden-state hand-off failed: %s", cudaGetErrorString(ce)); return IFB_ERR_CUDA; }
                 }
                 int rc = ifb_model_decode(st.model, e->to_feed.front(), nullptr, e->pos, nullptr);

@@ -47,6 +47,7 @@ struct ifb_model {
     std::vector<LayerW> layers;
     DevBuf tok_emb, out_norm, lm_head;
     DevBuf router, moe_ids, moe_wts, moe_y;   // MoE: router logits [experts] f16, slots' expert ids / weights, expert outputs [top_k][d]
+    DevBuf xin;            // pipeline stage with layer_begin > 0: the hidden state handed over by the previous stage
     DevBuf x0, x1, qkv, attn_out, hbuf, logits, attn_ws, scalars, trace;   // trace: [512 launches][160 CTAs][8] ns stamps
     int trace_on = 0;
     DevBuf counters;   // one work cursor per launch of a step, zeroed at the start of every step   // scalars: [0]=pos, [1]=token, [2]=next
@@ -237,6 +238,7 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     m->weight_bytes = wsum;
     A(m->x0, d * 2);
     A(m->x1, d * 2);
+    A(m->xin, d * 2);
     A(m->qkv, (size_t)(m->q_dim_l + 2 * m->kv_dim_l) * 2);
     A(m->attn_out, (size_t)m->q_dim_l * 2);
     A(m->hbuf, (size_t)m->ffn_l * 2);
@@ -299,7 +301,10 @@ extern "C" int32_t ifb_model_storage_dtype(const ifb_model_t *m, int32_t which) 
     if (!m) return -1;
     return which == 1 ? m->spec.lm_head_dtype : m->spec.weight_dtype;
 }
-extern "C" void *ifb_model_hidden_ptr(ifb_model_t *m) { return m ? m->x0.p : nullptr; }
+extern "C" void *ifb_model_hidden_ptr(ifb_model_t *m, int32_t which) {
+    if (!m) return nullptr;
+    return which == 0 ? m->xin.p : m->x0.p;      // 0: where a later stage expects its input; 1: where a stage leaves its output
+}
 
 extern "C" int64_t ifb_model_kv_bytes_per_token(const ifb_model_t *m, int32_t ctx_len) {
     if (!m) return 0;
@@ -925,8 +930,11 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
     IFB_CUDA(cudaMemsetAsync(m->counters.p, 0, m->counters.bytes, st));
     auto CT = [&](int idx) -> void * { return (void *)((int *)m->counters.p + (size_t)idx * 8); };   // cursor + per-op completion counts
     auto TR = [&](int idx) -> void * { return (m->trace_on && idx < 512) ? (void *)((uint64_t *)m->trace.p + (size_t)idx * 160 * 8) : nullptr; };
-    // a later pipeline stage starts from the hidden state its predecessor left in x0 (ifb_model_hidden_ptr)
+    // a later pipeline stage starts from the hidden state its predecessor handed over (ifb_model_hidden_ptr(m, 0))
     if ((parts & PART_MISC) && m->first_stage) { TRY(embed_row(m->x0.p, m->tok_emb.p, DT_F16, d, 0, sc + 1, st, s.vocab)); n++; }
+    // (the input has a buffer of its own: x0 is also where the step leaves its output, and a step may run twice --
+    // the warm-up before the graph capture)
+    if ((parts & PART_MISC) && !m->first_stage) IFB_CUDA(cudaMemcpyAsync(m->x0.p, m->xin.p, (size_t)d * 2, cudaMemcpyDeviceToDevice, st));
     const bool q8 = true;   // enable_full_quant_gemv = true (inference_engine.cc:53-57)
     auto ax8_ok = [](int dt) {
         return dt == DT_Q8_B32T2 || dt == DT_Q6_B64T1 || dt == DT_Q5_B64T1 || dt == DT_Q4_B32T1A ||

@@ -115,9 +115,14 @@ class Model:
         return int(lib.ifb_model_storage_dtype(self._h, 0))
 
     @property
-    def hidden_ptr(self):
-        """device pointer of the fp16 hidden state a pipeline stage reads / leaves"""
-        return lib.ifb_model_hidden_ptr(self._h)
+    def hidden_in_ptr(self):
+        """device buffer a pipeline stage with layer_begin > 0 reads its input hidden state from"""
+        return lib.ifb_model_hidden_ptr(self._h, 0)
+
+    @property
+    def hidden_out_ptr(self):
+        """device buffer a pipeline stage leaves its output hidden state in"""
+        return lib.ifb_model_hidden_ptr(self._h, 1)
 
     def read_tensor(self, name, nbytes=None):
         """device bytes of a named tensor as a numpy uint8 array (blocking)"""

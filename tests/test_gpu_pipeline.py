@@ -54,7 +54,7 @@ def test_two_pipeline_stages_equal_the_whole_model(cfg):
         want, want_tok = _logits(ib, whole, spec)
         a.decode(tok, pos)
         ib.check(ib.lib.ifb_device_synchronize(), "sync")
-        ib.check(ib.lib.ifb_memcpy_d2d(b.hidden_ptr, a.hidden_ptr, spec.d_model * 2), "hand-off")
+        ib.check(ib.lib.ifb_memcpy_d2d(b.hidden_in_ptr, a.hidden_out_ptr, spec.d_model * 2), "hand-off")
         b.decode(tok, pos)
         got, got_tok = _logits(ib, b, spec)
         assert np.array_equal(got, want), f"pos {pos}: staged logits differ from the whole model"

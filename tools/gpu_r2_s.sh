@@ -3,7 +3,5 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_pipeline.py tests/test_zzzz_gpu_engine.py tests/test_zz_gpu_load_path.py tests/test_gpu_model.py tests/test_zzz_gpu_llama2c_file.py -x -q > gpurun_out/r2s_tests.log 2>&1
 echo "tests rc=$?"; tail -12 gpurun_out/r2s_tests.log
-timeout 300 python bench.py --steps 100 --warmup 5 --workload llama2_7b_q3h > gpurun_out/r2s_bench_q3h.json 2> gpurun_out/r2s_bench_q3h.err
-echo "bench q3h rc=$?"; python -c "
-import json; d=json.load(open('gpurun_out/r2s_bench_q3h.json')); print(d['value'], d['ms_per_step'], d['decode_path'], d['verify']['ok'], d['roofline']['step'], d['roofline'].get('stored_bytes_per_token'))"
-tail -2 gpurun_out/r2s_bench_q3h.err
+true
+
