@@ -88,7 +88,9 @@ def test_engine_layer_parallel_groups_emit_the_same_tokens():
     t3, l3 = three.generate(prompt, 12, want_logits=True)
     assert t1 == t3 == g["tokens"].tolist()[:12]
     for x, y in zip(l1, l3):
-        assert np.array_equal(x, y)            # token-by-token decode on both sides: the same kernels, the same bits
+        # the one-stage engine runs the prompt as one prefill pass (tensor-core GEMMs), the staged one token by token:
+        # the same model within the model tolerance
+        assert np.abs(x - y).max() <= 2 ** -7 * np.abs(x).max()
     one.close(); three.close()
 
 
