@@ -4,8 +4,12 @@
 //
 //   nvcc -std=c++14 -DUSE_CUDA -I/root/reference/src -I/root/reference/3rd_party -Iinclude -c integration/reference_shim.cu
 //
-// A reference maintainer replaces the bodies in tensor_mul.cu / tensor_opr.cu by these (or links this object in
-// place of them); element-type ids and block bytes are the reference's, so tensors pass through untouched.
+// TensorMul::Gemv_AX and TensorOpr::Quantize below are DEFINITIONS OF THE REFERENCE'S OWN MEMBERS (same signatures):
+// oracle/Makefile (target `boundary`) links this object into the reference's CUDA engine in place of the stock
+// bodies -- the stock tensor_mul.cu / tensor_opr.cu are compiled with the two names renamed, no source is edited --
+// and tests/test_gpu_boundary.py runs that engine beside the stock one on the same config and compares the tokens.
+// The other functions (namespace ifb_shim) show the remaining operators of the path in the same style.
+// Element-type ids and block bytes are the reference's, so tensors pass through untouched.
 // tests/test_integration_shim.py compiles this file when /root/reference is present.
 #include "tensor/tensor_mul.h"
 #include "tensor/tensor_opr.h"
@@ -14,19 +18,29 @@
 
 INFER_FLOW_BEGIN
 
-namespace ifb_shim {
-
-// TensorMul::Gemv_AX (tensor_mul.h:27, tensor_mul.cu:97): y[cy] = A[cy][cx] . x[cx] (+ bias), fp16 out.
-// X is half, or Q8_B32T2 when the worker already called TensorOpr::Quantize (GetUseFullQuantGemv).
-bool Gemv_AX(DeviceTensor &Y, const DeviceTensor &A, const DeviceTensor &X, const DeviceTensor *bias)
+// TensorMul::Gemv_AX (tensor_mul.h:26-28, stock body tensor_mul.cu:97-132): y[cy] = A[cy][cx] . x[cx] (+ bias), fp16
+// out. X is half, or Q8_B32T2 when the worker already called TensorOpr::Quantize (GetUseFullQuantGemv,
+// inference_worker.cc:2385-2395). The worker passes Alg3; Alg4 (an auxiliary tensor U) has no caller on this path.
+bool TensorMul::Gemv_AX(DeviceTensor &Y, const DeviceTensor &A, const DeviceTensor &X,
+    VectorMatrixMulAlg alg, DeviceTensor *U, const DeviceTensor *bias)
 {
-    const int cx = A.ne[0], cy = A.Rows();
-    if (X.ne[0] != cx || Y.ne[0] != cy || Y.data_type != ElementType::F16) {
-        LogError("Gemv_AX: incompatible tensors");
+    (void)U;
+    const int M = A.Rows(), N = A.Columns();
+    if (X.size != N) {
+        LogError("A and X are not compatible");
+        return false;
+    }
+    if (Y.size != M) {
+        LogError("A and Y are not compatible: (%d, %d, %d) vs. (%d, %d, %d))",
+            Y.ne[0], Y.ne[1], Y.ne[2], A.ne[0], A.ne[1], A.ne[2]);
+        return false;
+    }
+    if (alg != VectorMatrixMulAlg::Alg3 || Y.data_type != ElementType::F16) {
+        LogError("Gemv_AX: Algorithm %d is not impelemtned.", (int)alg);
         return false;
     }
     int32_t rc = ifb_gemv((int32_t)A.data_type, Y.data, A.data, (int32_t)X.data_type, X.data,
-                          cy, cx, bias != nullptr ? bias->data : nullptr, /*stream=*/nullptr);
+                          M, N, bias != nullptr ? bias->data : nullptr, /*stream=*/nullptr);
     if (rc != 0) {
         LogError("Gemv_AX: %s", ifb_last_error());
         return false;
@@ -34,11 +48,16 @@ bool Gemv_AX(DeviceTensor &Y, const DeviceTensor &A, const DeviceTensor &X, cons
     return true;
 }
 
-// TensorOpr::Quantize (tensor_opr.h:130): B (any block type) <- A (half); bytes identical to the reference kernels
-bool Quantize(DeviceTensor &B, const DeviceTensor &A)
+// TensorOpr::Quantize (tensor_opr.h:130, stock body tensor_opr.cu:1623-1700): B (a block type) <- A (half); the bytes
+// are those of the reference's kernels (tests/test_gpu_vs_reference_cuda.py)
+bool TensorOpr::Quantize(DeviceTensor &B, const DeviceTensor &A)
 {
-    if (A.data_type != ElementType::F16 || A.ne[0] != B.ne[0] || A.Rows() != B.Rows()) {
-        LogError("Quantize: incompatible tensors");
+    if (A.data_type != ElementType::F16) {
+        LogError("Quantize: The data type of A should be F32 or F16");     // F32 sources: none on the decode path
+        return false;
+    }
+    if (A.ne[0] != B.ne[0] || A.Rows() != B.Rows()) {
+        LogKeyInfo("Quantize: Tensor B is not compatible with A");
         return false;
     }
     int32_t rc = ifb_quantize_rows((int32_t)B.data_type, B.data, A.data, A.Rows(), A.ne[0], nullptr);
@@ -48,6 +67,8 @@ bool Quantize(DeviceTensor &B, const DeviceTensor &A)
     }
     return true;
 }
+
+namespace ifb_shim {
 
 // TensorOpr::Dequantize (tensor_opr.h:128): B (half) <- A (block type)
 bool Dequantize(DeviceTensor &B, const DeviceTensor &A)
