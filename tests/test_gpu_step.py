@@ -131,6 +131,30 @@ def test_private_pipelines_k_chunked_rows(cfg):
     m.close()
 
 
+@pytest.mark.parametrize("step,priv", [(False, False), (True, False), (True, True)], ids=["multi-launch", "step-ring", "step-private"])
+def test_one_llama2_70b_shaped_layer_matches_oracle(step, priv):
+    """BASELINE config 4's shapes (d 8192, 64 heads / 8 kv heads = group 8, d_ffn 28672), one layer, against the oracle:
+    what the 80-layer bench verification cannot separate (rounding amplified through depth vs a shape-dependent defect)"""
+    import inferflow_b200 as ib
+    torch.zeros(1, device="cuda")
+    spec = ib.ModelSpec(layers=1, vocab=512, max_ctx=64, weight_dtype=orc.Q4_B32T1A, kv_dtype=orc.Q8_B32T2,
+                        heads=64, kv_heads=8, d_model=8192, d_ffn=28672)
+    m = _model(ib, spec, step=step, priv=priv)
+    orcm = OracleModel(spec, _tensors(m, spec))
+    tok = 5
+    for pos in range(6):
+        m.decode(tok, pos)
+        logits, nxt = _read(ib, m, spec)
+        on, rec = m.step_status()
+        assert bool(on) == step and rec[0] == 0, f"decode path: {on} {rec} {ib.lib.ifb_last_error()}"
+        want = orcm.step(tok, pos)
+        scale = np.abs(want).max()
+        err = np.abs(logits.astype(np.float64) - want).max()
+        assert err <= 2 ** -7 * scale, f"pos {pos}: logits differ by {err:.3e} (range {scale:.3e})"
+        tok = nxt
+    m.close()
+
+
 @pytest.mark.parametrize("cfg", CONFIGS[:4], ids=IDS[:4])
 def test_step_kernel_matches_multi_launch_path(cfg):
     """same weights, same synthetic 500-row cache: one persistent launch == the chain of operator kernels"""
