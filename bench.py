@@ -250,10 +250,10 @@ def run_reference_arm(args):
 # run is never a timing run; the byte counts do not depend on the clock):
 #  * multi-launch path, per GEMV launch averaged over the 129 of one token (profiles/r1_ncu.md): per layer
 #    31.53 + 10.56 + 56.44 + 28.27 MB read (+0.3 MB written), lm_head 262.1 MB; algorithmic 33.41 MB -- no re-reads
-#  * step kernel, the one launch of a token (profiles/r2_ncu.md): 4881.5 MB read + 29.3 MB written; algorithmic
-#    4880.1 MB -- no re-reads (the 29 MB written are the attention partials, the activations and the new cache rows)
+#  * step kernel, the one launch of a token (profiles/r2_ncu.md, capture r2k): 4881.4 MB read + 20.7 MB written;
+#    algorithmic 4880.1 MB -- no re-reads (the 21 MB written: attention partials, flag-in-data words, new cache rows)
 GEMV_TRAFFIC_PER_LAUNCH = (32 * (31.528448 + 10.557440 + 56.434944 + 28.266496 + 0.3) + 262.2) * 1e6 / 129
-STEP_TRAFFIC_PER_LAUNCH = 4881.514e6 + 29.273e6
+STEP_TRAFFIC_PER_LAUNCH = 4881.430e6 + 20.675e6
 
 
 # BASELINE.json's decode configurations. The default (configs[1]) is the one the metric is quoted on; the others are run
