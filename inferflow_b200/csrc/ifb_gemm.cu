@@ -7,18 +7,20 @@
 //
 //   Y[tokens][cy] = X[tokens][cx] . W[cy][cx]^T        (fp16 in, fp32 accumulate in TMEM, fp16 out)
 //
-//  * a CTA owns 128 weight rows x up to 128 tokens; the K loop walks 64 columns at a time through a 3-stage ring;
-//  * the 4 producer warps (thread = one weight row / one token) fetch their row's quantized blocks of the k-slice,
-//    decode them with the same Fmt::decode the GEMV uses, compute value = fp16(q * scale + base) -- the bytes
-//    TensorOpr::Dequantize would have written -- and store them straight into the A tile in shared memory; the same
-//    threads copy their token's 64 activations into the B tile. Both tiles are laid out as UMMA "core matrices"
-//    (8 rows x 16 bytes, contiguous), K-major, no swizzle;
+//  * a CTA owns 128 * RB weight rows x up to NTMAX tokens (two tile configurations, below); the K loop walks 64 columns
+//    at a time through a 3-stage ring of shared-memory tiles;
+//  * A tile (weights): the producer warps (thread = one weight row) keep the raw quantized blocks of their row two
+//    k-slices ahead in registers, decode them with the same Fmt::decode the GEMV uses, compute
+//    value = fp16(q * scale + base) -- the bytes TensorOpr::Dequantize would have written; int -> float through a
+//    mantissa trick, the I2F of the first version kept the XU pipe 77 % busy -- and store them straight into the tile;
+//  * B tile (activations): ONE 2-D TMA load per k-slice (cuTensorMapEncodeTiled over X, box = 8 halves x NTMAX tokens),
+//    issued by a loader warp; both tiles are UMMA "core matrices" (8 rows x 16 bytes, contiguous), K-major, no swizzle;
 //  * ONE elected thread of the MMA warp issues tcgen05.mma (M = 128, N = token tile, K = 16 per instruction) with the
 //    accumulator in tensor memory; tcgen05.commit hands the shared-memory stage back to the producers;
 //  * after the last k-slice the producer warps become the epilogue: tcgen05.ld (32 lanes x 32 bit, lane = weight row)
 //    -> fp16 -> Y. The output is written in its final [tokens][cy] orientation (no transpose pass).
-//  * two CTAs fit an SM (96 KB of shared memory, 128 TMEM columns each): one CTA's block fetch latency hides behind the
-//    other's MMAs.
+//  Measured on B200 (profiles/r2_bench.md, r2_ncu.md): 452-666 TFLOP/s at 4096 tokens, tensor pipe active 20-22 % of
+//  the cycles -- the kernel is bound by producing fp16 operands from the 4-bit blocks (ALU pipe 18-43 %).
 #include <cuda.h>      // CUtensorMap + the driver's encode function (fetched through cudaGetDriverEntryPoint: no libcuda link)
 
 #include "ifb_formats.cuh"
