@@ -732,14 +732,17 @@ static int attn_launch_t(const AttnArgs &a_in, int kv_dtype, bool pdl, cudaStrea
     }
     cfg.attrs = at;
     cfg.numAttrs = na;
-    static size_t attr_smem[2] = {0, 0};   // per <HD, G> instantiation
+    static size_t attr_smem[64][2] = {};   // per <HD, G> instantiation and device: the opt-in is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
     if (q8) {
         auto kern = attn_decode_kernel<HD, G, true>;
-        if (attr_smem[1] < smem) { IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem[1] = smem; }
+        if (attr_smem[dev][1] < smem) { IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem[dev][1] = smem; }
         IFB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     } else {
         auto kern = attn_decode_kernel<HD, G, false>;
-        if (attr_smem[0] < smem) { IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem[0] = smem; }
+        if (attr_smem[dev][0] < smem) { IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem[dev][0] = smem; }
         IFB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     }
     return IFB_OK;

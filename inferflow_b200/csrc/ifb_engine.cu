@@ -229,15 +229,26 @@ int32_t ifb_engine_resolve(const char *ini_path, const char *section, const char
     int32_t shared = 1;
     rc = ifb_llama2c_probe(r.model_path.c_str(), hv, &shared);
     if (rc != IFB_OK) return rc;
-    // load-time policy of the reference: a matrix below tensor_quant_threshold elements stays fp16
-    // (network_builder.cc:1558-1561). This runtime holds one element type for all layer matrices: quantize when the
-    // SMALLEST of them reaches the threshold, otherwise keep fp16 (exactly the reference for its tiny models, where
-    // every matrix is below the threshold).
+    // load-time policy of the reference: a matrix below tensor_quant_threshold elements stays fp16, decided PER TENSOR
+    // (network_builder.cc:1558-1561; ifb_tensor_device_dtype). This runtime holds one element type for all layer
+    // matrices: the policy is followed when it gives every matrix the same type (the reference's tiny models: all below
+    // the threshold; 7B and larger: all above). A model that splits (grouped-query models whose wk / wv alone fall below
+    // it) is refused by name rather than loaded under a different policy.
     const int64_t d = hv[0], f = hv[1], kvd = (int64_t)hv[4] * (hv[0] / hv[3]);
-    int64_t smallest = d * d;
-    if (kvd * d < smallest) smallest = kvd * d;
-    if (f * d < smallest) smallest = f * d;
-    if (smallest < r.tensor_quant_threshold) r.weight_dtype = DT_F16;
+    const struct { const char *name; int64_t elements; } mats[] = {
+        {"wq / wo", d * d}, {"wk / wv", kvd * d}, {"w1 / w3 / w2", f * d}};
+    int first = ifb_tensor_device_dtype(mats[0].elements, 1, r.weight_dtype, r.tensor_quant_threshold);
+    for (const auto &mt : mats) {
+        const int dt = ifb_tensor_device_dtype(mt.elements, 1, r.weight_dtype, r.tensor_quant_threshold);
+        if (dt != first) {
+            set_last_error("engine: tensor_quant_threshold = %d keeps %s (%lld elements) in another element type than wq (%lld): "
+                           "per-tensor weight types are not supported by this runtime; set tensor_quant_threshold so that all "
+                           "layer matrices fall on one side", r.tensor_quant_threshold, mt.name, (long long)mt.elements,
+                           (long long)mats[0].elements);
+            return IFB_ERR_TYPE;
+        }
+    }
+    r.weight_dtype = first;
     if (r.max_ctx <= 0) r.max_ctx = hv[6];            // inference_engine.cc:112-113
     else if (r.max_ctx <= 16) r.max_ctx = 4096;        // ModelSpec::DEFAULT_MAX_CONTEXT_LEN
     if (model_path_out != nullptr && path_capacity > 0) {

@@ -354,24 +354,30 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_stream_kernel(const Gemv
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-static int g_sm_count = 0;
+// per-device caches: a process may drive several GPUs (the engine's layer-parallel stages)
+static int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < 64) ? dev : 0;
+}
 int sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
+    static int counts[64] = {0};
+    const int dev = current_device();
+    if (counts[dev] == 0) {
+        cudaDeviceGetAttribute(&counts[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (counts[dev] <= 0) counts[dev] = 148;
     }
-    return g_sm_count;
+    return counts[dev];
 }
 
 template <class Fmt, int MODE, bool GLU, bool VEC4, bool TP>
 static int launch_variant_tp(const GemvArgs &a, size_t smem, int grid, bool pdl, cudaStream_t st) {
     auto kern = gemv_stream_kernel<Fmt, MODE, GLU, VEC4, TP>;
-    static bool attr_done = false;  // per instantiation
-    if (!attr_done) {
+    static unsigned long long attr_done = 0ull;  // per instantiation, one bit per device: the opt-in is per device
+    const int dev = current_device();
+    if (!((attr_done >> dev) & 1ull)) {
         IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_done = true;
+        attr_done |= 1ull << dev;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);

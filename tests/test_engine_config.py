@@ -54,6 +54,17 @@ def test_element_types_follow_the_reference_rules():
     with tempfile.TemporaryDirectory() as d:
         ini = _tree(d, hp, [("device_weight_data_type = F16", "device_weight_data_type = Q4\ntensor_quant_threshold = 0")])
         assert ib.resolve_config(ini)[1] == orc.Q4_B32T1A
+    # the rule is per tensor (network_builder.cc:1558): a grouped-query model whose wk / wv alone fall below the threshold
+    # would get mixed element types -- this runtime holds one type for all layer matrices and says so instead of
+    # loading the model under another policy; item names are case-insensitive (sslib ConfigData)
+    gqa = dict(dim=64, hidden=128, layers=1, heads=4, kv_heads=1, vocab=96, seq=32)
+    with tempfile.TemporaryDirectory() as d:
+        ini = _tree(d, gqa, [("device_weight_data_type = F16", "Device_Weight_Data_Type = Q4\nTENSOR_QUANT_THRESHOLD = 2000")])
+        with pytest.raises(ib.IfbError, match="per-tensor weight types"):      # wq 4096 >= 2000 > wk 1024 elements
+            ib.resolve_config(ini)
+    with tempfile.TemporaryDirectory() as d:
+        ini = _tree(d, gqa, [("device_weight_data_type = F16", "device_weight_data_type = Q4\ntensor_quant_threshold = 1000")])
+        assert ib.resolve_config(ini)[1] == orc.Q4_B32T1A
 
 
 def test_config_errors_are_reported():
