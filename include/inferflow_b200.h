@@ -222,6 +222,8 @@ typedef struct ifb_model_spec {
     int32_t weight_repack;          /* 1: IFB_Q3H_B64T1 matrices are stored as IFB_Q4_B64T1 blocks holding the same codes,
                                        base and scale (lossless; 36 instead of 32 bytes per 64 weights, decoded with an
                                        order of magnitude fewer instructions). 0: stored as the reference stores them. */
+    int32_t kv_slots;               /* KV caches held side by side (<= 16; 0 / 1 = one): the sequences ifb_model_decode_batch
+                                       advances together (the reference's concurrent queries, query_state_table.h) */
     int32_t layer_begin, layer_end; /* pipeline stage (BY_LAYER / HYBRID, SplitGpuLayers): this instance holds layers
                                        [layer_begin, layer_end) only; 0, 0 = all. A stage with layer_begin > 0 takes
                                        its input from ifb_model_hidden_ptr(m, 0) instead of the embedding; one with
@@ -267,6 +269,19 @@ int32_t ifb_model_load_llama2c(ifb_model_t **out, const char *path, int32_t weig
 int32_t ifb_model_load_llama2c_stage(ifb_model_t **out, const char *path, int32_t weight_dtype, int32_t kv_dtype,
                                      int32_t max_context_len, int32_t qk_column_order, int32_t layer_begin,
                                      int32_t layer_end, ifb_stream_t stream);
+
+/* Batched decode: n sequences, sequence i living in KV slot slots_host[i] at position positions_host[i], advance by
+ * one token (tokens_host[i]) in one step -- the step InferenceEngine::Infer runs over all live queries
+ * (inference_engine.cc:1054-1124). The matrix products see n rows (ifb_gemm_q: the weights are read once for all
+ * sequences), attention runs per sequence over its own cache. Results on the device: fp16 logits [n][vocab] at
+ * ifb_model_batch_logits, greedy next tokens int32 [n] at ifb_model_batch_next_tokens, rows in the order given. Needs
+ * spec.kv_slots >= n and a model ifb_model_batch_supported accepts (single GPU, dense, dimensions and vocabulary
+ * multiples of 128). Slot 0 is also the cache of ifb_model_decode / ifb_model_prefill. */
+int32_t ifb_model_batch_supported(const ifb_model_t *m);
+int32_t ifb_model_decode_batch(ifb_model_t *m, const int32_t *tokens_host, const int32_t *slots_host,
+                               const int32_t *positions_host, int32_t n, ifb_stream_t stream);
+void *ifb_model_batch_logits(ifb_model_t *m);
+void *ifb_model_batch_next_tokens(ifb_model_t *m);
 
 /* reset the KV length (and optionally fill `ctx_len` synthetic rows for benchmarking) */
 int32_t ifb_model_kv_reset(ifb_model_t *m, int32_t ctx_len, int32_t fill_synthetic, uint64_t seed,

@@ -38,7 +38,7 @@ class ModelSpecC(C.Structure):
         ("rope_order", C.c_int32), ("rope_theta", C.c_float), ("norm_eps", C.c_float),
         ("kq_scale", C.c_float), ("tp_rank", C.c_int32), ("tp_size", C.c_int32),
         ("experts", C.c_int32), ("experts_top_k", C.c_int32), ("moe_norm_top_k_prob", C.c_int32),
-        ("weight_repack", C.c_int32), ("layer_begin", C.c_int32), ("layer_end", C.c_int32),
+        ("weight_repack", C.c_int32), ("kv_slots", C.c_int32), ("layer_begin", C.c_int32), ("layer_end", C.c_int32),
     ]
 
 
@@ -106,6 +106,12 @@ def _load():
     L.ifb_model_kernel_launches_per_step.argtypes = [vp]
     L.ifb_model_step_status.argtypes = [vp, vp]
     L.ifb_model_storage_dtype.argtypes = [vp, i32]
+    L.ifb_model_batch_supported.argtypes = [vp]
+    L.ifb_model_decode_batch.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.ifb_model_batch_logits.argtypes = [vp]
+    L.ifb_model_batch_logits.restype = vp
+    L.ifb_model_batch_next_tokens.argtypes = [vp]
+    L.ifb_model_batch_next_tokens.restype = vp
     L.ifb_model_hidden_ptr.argtypes = [vp, i32]
     L.ifb_model_hidden_ptr.restype = vp
     L.ifb_device_groups_parse.argtypes = [C.c_char_p, vp, i32, vp, vp, vp]
@@ -144,7 +150,7 @@ DECLARED = [
     "ifb_model_logits", "ifb_model_next_token", "ifb_model_kernel_launches_per_step",
     "ifb_model_tp_export", "ifb_model_tp_import", "ifb_model_decode_next", "ifb_model_tensor_ptr",
     "ifb_memcpy_d2h", "ifb_memcpy_h2d", "ifb_memcpy_d2d", "ifb_device_synchronize", "ifb_model_issue_parts", "ifb_memcpy_d2h_async", "ifb_memcpy_h2d_async", "ifb_model_step_status", "ifb_model_prefill", "ifb_model_prefill_supported", "ifb_attn_prefill",
-    "ifb_model_storage_dtype", "ifb_model_hidden_ptr", "ifb_device_groups_parse", "ifb_split_layers", "ifb_tensor_partition_type",
+    "ifb_model_storage_dtype", "ifb_model_hidden_ptr", "ifb_model_batch_supported", "ifb_model_decode_batch", "ifb_model_batch_logits", "ifb_model_batch_next_tokens", "ifb_device_groups_parse", "ifb_split_layers", "ifb_tensor_partition_type",
     "ifb_tensor_device_dtype", "ifb_rank_plan",
 ]
 

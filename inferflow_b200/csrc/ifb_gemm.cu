@@ -102,6 +102,11 @@ struct GemmArgs {
     const __half *bias;      // [cy] or null
     int tokens, cy, cx, row_bytes, w_dtype;
     int nt;                  // token tile (multiple of 16)
+    // split-K (few tokens: cy / 128 CTAs would leave most SMs idle while 128 threads per CTA dequantize whole rows):
+    // blockIdx.z takes nk_per k-slices and leaves fp32 partial sums in part[z][tokens][cy]; gemm_splitk_reduce_kernel
+    // adds them in split order (deterministic) and applies the half rounding + bias of the one-pass epilogue
+    int nk_per;              // k-slices per split (0: no split)
+    float *part;
 };
 
 // element (r, k) of a tile: core matrices of 8 rows x 8 halves (128 contiguous bytes); K-adjacent core matrices 128 B
@@ -124,7 +129,9 @@ __global__ void __launch_bounds__(128 * RB + 64, RB == 1 ? 2 : 1) gemm_q_kernel(
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * (GQ_ROWS * RB), tok0 = blockIdx.y * a.nt;
-    const int nk = a.cx / GQ_BK;
+    const int nk_all = a.cx / GQ_BK;
+    const int kb0 = a.nk_per > 0 ? (int)blockIdx.z * a.nk_per : 0;            // first k-slice of this CTA
+    const int nk = a.nk_per > 0 ? min(a.nk_per, nk_all - kb0) : nk_all;
     uint8_t *strips = smem + GQ_STAGES * STAGE_BYTES;     // [NPROD][GQ_STRIP]
 
     if (tid == 0) {
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(128 * RB + 64, RB == 1 ? 2 : 1) gemm_q_kernel(
                 mbar_arrive_expect_tx(&full_bar[s], (uint32_t)B_BYTES);
 #pragma unroll
                 for (int k8 = 0; k8 < GQ_BK / 8; k8++)           // tokens beyond the input are zero-filled by the TMA unit
-                    tma_load_2d(Bt + k8 * B_LBO, &xmap, kb * GQ_BK + k8 * 8, tok0, &full_bar[s]);
+                    tma_load_2d(Bt + k8 * B_LBO, &xmap, (kb0 + kb) * GQ_BK + k8 * 8, tok0, &full_bar[s]);
             }
         }
     } else if (warp == PW) {
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(128 * RB + 64, RB == 1 ? 2 : 1) gemm_q_kernel(
         uint32_t raw0[NRAW], raw1[NRAW], raw2[NRAW];
         auto fetch = [&](int kb, uint32_t *rw) {
             if (kb >= nk) return;
-            const int k0 = kb * GQ_BK;
+            const int k0 = (kb0 + kb) * GQ_BK;
             if (F16W) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(wrow + (size_t)k0 * 2);
 #pragma unroll
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(128 * RB + 64, RB == 1 ? 2 : 1) gemm_q_kernel(
                     *reinterpret_cast<uint4 *>(arow + k8 * GQ_LBO) = make_uint4(raw[4 * k8], raw[4 * k8 + 1], raw[4 * k8 + 2], raw[4 * k8 + 3]);
             } else {
                 // raw bytes -> this thread's strip, decoded with the GEMV's Fmt::decode
-                const uint32_t mis = (uint32_t)((uintptr_t)(wrow + (size_t)(kb * GQ_BK / Fmt::CAP) * Fmt::BYTES) & 3u);
+                const uint32_t mis = (uint32_t)((uintptr_t)(wrow + (size_t)((kb0 + kb) * GQ_BK / Fmt::CAP) * Fmt::BYTES) & 3u);
                 uint32_t *strip4 = reinterpret_cast<uint32_t *>(strip);
 #pragma unroll
                 for (int i = 0; i < NRAW; i++) strip4[i] = raw[i];
@@ -278,6 +285,10 @@ __global__ void __launch_bounds__(128 * RB + 64, RB == 1 ? 2 : 1) gemm_q_kernel(
                 const int t = tok0 + c0 + c;
                 if (t < a.tokens) {
                     float f = __uint_as_float(v[c]);
+                    if (a.part != nullptr) {
+                        a.part[((size_t)blockIdx.z * a.tokens + t) * a.cy + row0 + r] = f;
+                        continue;
+                    }
                     if (a.bias != nullptr) f = __half2float(__float2half_rn(f)) + bias;     // GEMM output is half, then + bias
                     a.y[(size_t)t * a.cy + row0 + r] = __float2half_rn(f);
                 }
@@ -290,6 +301,15 @@ __global__ void __launch_bounds__(128 * RB + 64, RB == 1 ? 2 : 1) gemm_q_kernel(
         tc_fence_after();
         tmem_dealloc(tmem, TMEM_COLS);
     }
+}
+
+__global__ void gemm_splitk_reduce_kernel(__half *y, const float *part, const __half *bias, int tokens, int cy, int ksplit) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)tokens * cy) return;
+    float f = 0.f;
+    for (int s = 0; s < ksplit; s++) f += part[(size_t)s * tokens * cy + i];      // split order: the same sum every run
+    if (bias != nullptr) f = __half2float(__float2half_rn(f)) + __half2float(bias[i % cy]);
+    y[i] = __float2half_rn(f);
 }
 
 // the activation matrix [tokens][cx] fp16 as a 2-D tensor map with a box of NTMAX tokens x 8 halves (16 bytes): one
@@ -335,6 +355,29 @@ static int launch_gemm_cfg(const GemmArgs &a, cudaStream_t st) {
     int rc = make_xmap(&xmap, a.x, a.tokens, a.cx, NTMAX);
     if (rc != IFB_OK) return rc;
     dim3 grid(a.cy / (GQ_ROWS * RB), (a.tokens + a.nt - 1) / a.nt);
+    // few tokens: split K until ~two CTAs per SM are busy (each split >= 4 k-slices, at most 8 splits)
+    const int ctas = (int)(grid.x * grid.y), nk_all = a.cx / GQ_BK;
+    int ksplit = 1;
+    if (RB == 1 && a.tokens <= 32 && ctas < 2 * 148) {
+        ksplit = (2 * 148 + ctas - 1) / ctas;
+        if (ksplit > 8) ksplit = 8;
+        if (ksplit > nk_all / 4) ksplit = nk_all / 4;
+        if (ksplit < 1) ksplit = 1;
+    }
+    if (ksplit > 1) {
+        GemmArgs b = a;
+        b.nk_per = (nk_all + ksplit - 1) / ksplit;
+        ksplit = (nk_all + b.nk_per - 1) / b.nk_per;
+        // stream-ordered scratch for the partial sums (capturable, safe across streams)
+        IFB_CUDA(cudaMallocAsync((void **)&b.part, (size_t)ksplit * a.tokens * a.cy * sizeof(float), st));
+        grid.z = ksplit;
+        kern<<<grid, 128 * RB + 64, smem, st>>>(b, xmap);
+        const int64_t n = (int64_t)a.tokens * a.cy;
+        gemm_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.y, b.part, a.bias, a.tokens, a.cy, ksplit);
+        cudaFreeAsync(b.part, st);
+        IFB_LAUNCH_CHECK();
+        return IFB_OK;
+    }
     kern<<<grid, 128 * RB + 64, smem, st>>>(a, xmap);
     IFB_LAUNCH_CHECK();
     return IFB_OK;
@@ -363,7 +406,7 @@ int gemm_q(int w_dtype, void *y_f16, const void *w, const void *x_f16, int64_t t
     a.w = (const uint8_t *)w; a.x = (const __half *)x_f16; a.y = (__half *)y_f16; a.bias = (const __half *)bias_f16;
     a.tokens = (int)tokens; a.cy = (int)cy; a.cx = (int)cx; a.w_dtype = w_dtype;
     a.row_bytes = (int)(w_dtype == DT_F16 ? cx * 2 : row_bytes(w_dtype, cx));
-    a.nt = 0;
+    a.nt = 0; a.nk_per = 0; a.part = nullptr;
     switch (w_dtype) {
         case DT_F16: return launch_gemm<FmtQ4_B32T1, true>(a, st);
         case DT_Q4_B32T1A:

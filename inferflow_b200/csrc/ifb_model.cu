@@ -76,6 +76,10 @@ struct ifb_model {
     int pf_cap = 0;
     void *pf_x = nullptr, *pf_xn = nullptr, *pf_q = nullptr, *pf_k = nullptr, *pf_v = nullptr, *pf_att = nullptr, *pf_h1 = nullptr,
          *pf_h3 = nullptr, *pf_tmp = nullptr, *pf_tok = nullptr;
+    // batched decode (ifb_model_decode_batch): several sequences, each with its own KV slot, one token each per step
+    int kv_slots = 1;
+    int64_t kv_slot_bytes = 0;      // bytes of one slot of a layer's K (or V) cache
+    DevBuf bt_pos, bt_next, bt_logits;
     int api_wdt = 0, api_ldt = 0;   // element types the caller named (spec.weight_dtype / lm_head_dtype hold the STORAGE types)
     int l0 = 0, nl = 0;             // pipeline stage: this instance holds the global layers [l0, l0 + nl)
     bool first_stage = true, last_stage = true;
@@ -129,6 +133,7 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     // pipeline stage: layers [layer_begin, layer_end) of the model (0, 0 = all)
     const int lb = s.layer_begin, le = (s.layer_begin == 0 && s.layer_end == 0) ? s.layers : s.layer_end;
     IFB_CHECK_ARG(lb >= 0 && le > lb && le <= s.layers, "pipeline stage: layers [%d, %d) of %d", lb, le, s.layers);
+    IFB_CHECK_ARG(s.kv_slots >= 0 && s.kv_slots <= 16, "kv_slots %d (at most 16 concurrent sequences, query_state_table.h)", s.kv_slots);
     IFB_CHECK_ARG((lb == 0 && le == s.layers) || tp == 1, "pipeline stages of a tensor-parallel group are not supported yet (stage [%d, %d), tp %d)", lb, le, tp);
     // BY_ROW split must fall on block boundaries (device_tensor_builder.cu:161-330)
     IFB_CHECK_ARG((s.d_model / tp) % (wcap > 32 ? wcap : 32) == 0 && (s.d_ffn / tp) % (wcap > 32 ? wcap : 32) == 0,
@@ -140,6 +145,7 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     m->spec.tp_size = tp;
     m->api_wdt = s.weight_dtype; m->api_ldt = s.lm_head_dtype;
     m->spec.weight_dtype = wdt; m->spec.lm_head_dtype = ldt_store;       // from here on: the storage types
+    m->kv_slots = s.kv_slots > 1 ? s.kv_slots : 1;
     m->l0 = lb; m->nl = le - lb;
     m->first_stage = lb == 0; m->last_stage = le == s.layers;
     m->hd = s.d_model / s.heads;
@@ -213,8 +219,10 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
         wsum += wbytes(wdt, m->q_dim_l, d) + 2 * wbytes(wdt, m->kv_dim_l, d) + wbytes(wdt, d, m->q_dim_l);
         int64_t kvb = kv_cache_bytes(s.kv_dtype, m->kv_heads_l, m->hd, s.max_ctx);
         if (kvb < 0 && rc == IFB_OK) { set_last_error("unsupported kv cache type %d", s.kv_dtype); rc = IFB_ERR_TYPE; }
-        A(L.kcache, kvb);
-        A(L.vcache, kvb);
+        kvb = (kvb + 255) / 256 * 256;
+        m->kv_slot_bytes = kvb;
+        A(L.kcache, kvb * m->kv_slots);      // slot 0 is the cache of the single-sequence paths
+        A(L.vcache, kvb * m->kv_slots);
     }
     A(m->tok_emb, m->first_stage ? (size_t)s.vocab * d * 2 : 256);      // the embedding lives on the first stage,
     A(m->out_norm, d * 2);
@@ -249,6 +257,11 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
         A(m->moe_y, (size_t)s.experts_top_k * d * 2);
     }
     A(m->logits, (size_t)s.vocab * 2);
+    if (m->kv_slots > 1) {
+        A(m->bt_pos, 16 * 4);
+        A(m->bt_next, 16 * 4);
+        A(m->bt_logits, (size_t)m->kv_slots * s.vocab * 2);
+    }
     A(m->attn_ws, attn_workspace_bytes(m->heads_l, m->hd));
     A(m->scalars, 256);
     {   // one 8-int cursor block per launch of a step: dense 5 per layer, MoE 6 + 2*top_k per layer, + embedding, lm_head, argmax, advance
@@ -1178,6 +1191,24 @@ static bool prefill_supported(const ifb_model *m) {
            m->q_dim_l % 128 == 0 && m->kv_dim_l % 128 == 0 && s.d_ffn % 128 == 0 && (s.rope_order == 0 || s.rope_order == 2);
 }
 
+// activations of up to n rows (prompt tokens / batched sequences), grown on demand
+static int prefill_reserve(ifb_model *m, int n, cudaStream_t st) {
+    if (n <= m->pf_cap) return IFB_OK;
+    const auto &s = m->spec;
+    const int d = s.d_model, qd = m->q_dim_l, kvd = m->kv_dim_l, f = s.d_ffn;
+    IFB_CUDA(cudaStreamSynchronize(st));
+    for (void **p : {&m->pf_x, &m->pf_xn, &m->pf_q, &m->pf_k, &m->pf_v, &m->pf_att, &m->pf_h1, &m->pf_h3, &m->pf_tmp, &m->pf_tok})
+        if (*p) { cudaFree(*p); *p = nullptr; }
+    const int cap = (n + 63) / 64 * 64;
+    const size_t T = (size_t)cap;
+    IFB_CUDA(cudaMalloc(&m->pf_x, T * d * 2));   IFB_CUDA(cudaMalloc(&m->pf_xn, T * d * 2));
+    IFB_CUDA(cudaMalloc(&m->pf_q, T * qd * 2));  IFB_CUDA(cudaMalloc(&m->pf_k, T * kvd * 2)); IFB_CUDA(cudaMalloc(&m->pf_v, T * kvd * 2));
+    IFB_CUDA(cudaMalloc(&m->pf_att, T * qd * 2)); IFB_CUDA(cudaMalloc(&m->pf_h1, T * f * 2)); IFB_CUDA(cudaMalloc(&m->pf_h3, T * f * 2));
+    IFB_CUDA(cudaMalloc(&m->pf_tmp, T * d * 2)); IFB_CUDA(cudaMalloc(&m->pf_tok, T * 4));
+    m->pf_cap = cap;
+    return IFB_OK;
+}
+
 extern "C" int32_t ifb_model_prefill_supported(const ifb_model_t *m) { return (m != nullptr && prefill_supported(m)) ? 1 : 0; }
 
 extern "C" int32_t ifb_model_prefill(ifb_model_t *m, const int32_t *tokens_host, int32_t n, int32_t pos0, ifb_stream_t stream) {
@@ -1189,18 +1220,7 @@ extern "C" int32_t ifb_model_prefill(ifb_model_t *m, const int32_t *tokens_host,
     cudaStream_t st = (cudaStream_t)stream;
     const auto &s = m->spec;
     const int d = s.d_model, qd = m->q_dim_l, kvd = m->kv_dim_l, f = s.d_ffn, wdt = s.weight_dtype;
-    if (n > m->pf_cap) {
-        IFB_CUDA(cudaStreamSynchronize(st));
-        for (void **p : {&m->pf_x, &m->pf_xn, &m->pf_q, &m->pf_k, &m->pf_v, &m->pf_att, &m->pf_h1, &m->pf_h3, &m->pf_tmp, &m->pf_tok})
-            if (*p) { cudaFree(*p); *p = nullptr; }
-        const int cap = (n + 63) / 64 * 64;
-        const size_t T = (size_t)cap;
-        IFB_CUDA(cudaMalloc(&m->pf_x, T * d * 2));   IFB_CUDA(cudaMalloc(&m->pf_xn, T * d * 2));
-        IFB_CUDA(cudaMalloc(&m->pf_q, T * qd * 2));  IFB_CUDA(cudaMalloc(&m->pf_k, T * kvd * 2)); IFB_CUDA(cudaMalloc(&m->pf_v, T * kvd * 2));
-        IFB_CUDA(cudaMalloc(&m->pf_att, T * qd * 2)); IFB_CUDA(cudaMalloc(&m->pf_h1, T * f * 2)); IFB_CUDA(cudaMalloc(&m->pf_h3, T * f * 2));
-        IFB_CUDA(cudaMalloc(&m->pf_tmp, T * d * 2)); IFB_CUDA(cudaMalloc(&m->pf_tok, T * 4));
-        m->pf_cap = cap;
-    }
+    TRY(prefill_reserve(m, n, st));
     IFB_CUDA(cudaMemcpyAsync(m->pf_tok, tokens_host, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     TRY(embed_rows(m->pf_x, m->tok_emb.p, (const int32_t *)m->pf_tok, n, d, s.vocab, st));
     for (int li = 0; li < s.layers; li++) {
@@ -1238,6 +1258,76 @@ extern "C" int32_t ifb_model_prefill(ifb_model_t *m, const int32_t *tokens_host,
     advance_kernel<<<1, 1, 0, st>>>(sc, 1);
     IFB_LAUNCH_CHECK();
     m->host_pos = pos0 + n - 1;
+    return IFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// batched decode: n sequences (each in its own KV slot, at its own position) advance by one token in ONE step.
+// The reference batches the live queries of an engine the same way (max_concurrent_queries, query_state_table.h;
+// inference_engine.cc:1054-1124: one Infer over all queries with q_tokens = sum of their new tokens): the matrix
+// products see n rows -- here the dequant-fused tensor-core GEMM with split-K, the weights are read once for all
+// sequences -- and attention runs per sequence over its own cache.
+// ---------------------------------------------------------------------------------------
+static bool batch_supported(const ifb_model *m) { return prefill_supported(m) && m->kv_slots > 1 && m->spec.vocab % 128 == 0; }
+
+extern "C" int32_t ifb_model_batch_supported(const ifb_model_t *m) { return (m != nullptr && batch_supported(m)) ? 1 : 0; }
+extern "C" void *ifb_model_batch_logits(ifb_model_t *m) { return m ? m->bt_logits.p : nullptr; }
+extern "C" void *ifb_model_batch_next_tokens(ifb_model_t *m) { return m ? m->bt_next.p : nullptr; }
+
+extern "C" int32_t ifb_model_decode_batch(ifb_model_t *m, const int32_t *tokens_host, const int32_t *slots_host,
+                                          const int32_t *positions_host, int32_t n, ifb_stream_t stream) {
+    IFB_CHECK_ARG(m != nullptr && tokens_host != nullptr && slots_host != nullptr && positions_host != nullptr, "decode_batch: null argument");
+    IFB_CHECK_ARG(batch_supported(m), "decode_batch: needs kv_slots > 1 and a model the tensor-core path covers (single GPU, dense, "
+                  "dimensions and vocabulary multiples of 128)");
+    IFB_CHECK_ARG(n >= 1 && n <= m->kv_slots, "decode_batch: %d sequences, %d KV slots", n, m->kv_slots);
+    unsigned seen = 0;
+    for (int i = 0; i < n; i++) {
+        IFB_CHECK_ARG(tokens_host[i] >= 0 && tokens_host[i] < m->spec.vocab, "decode_batch: token %d outside the vocabulary", tokens_host[i]);
+        IFB_CHECK_ARG(slots_host[i] >= 0 && slots_host[i] < m->kv_slots && !((seen >> slots_host[i]) & 1u), "decode_batch: slot %d is out of range or named twice", slots_host[i]);
+        IFB_CHECK_ARG(positions_host[i] >= 0 && positions_host[i] < m->spec.max_ctx, "decode_batch: position %d outside max_context_len %d", positions_host[i], m->spec.max_ctx);
+        seen |= 1u << slots_host[i];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const auto &s = m->spec;
+    const int d = s.d_model, qd = m->q_dim_l, kvd = m->kv_dim_l, f = s.d_ffn, wdt = s.weight_dtype;
+    TRY(prefill_reserve(m, n, st));
+    IFB_CUDA(cudaMemcpyAsync(m->pf_tok, tokens_host, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    IFB_CUDA(cudaMemcpyAsync(m->bt_pos.p, positions_host, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    TRY(embed_rows(m->pf_x, m->tok_emb.p, (const int32_t *)m->pf_tok, n, d, s.vocab, st));
+    for (int li = 0; li < s.layers; li++) {
+        LayerW &L = m->layers[li];
+        TRY(rmsnorm(m->pf_xn, m->pf_x, L.attn_norm.p, n, d, s.norm_eps, 0.f, st));
+        TRY(gemm_q(wdt, m->pf_q, L.wq.p, m->pf_xn, n, qd, d, nullptr, st));
+        TRY(gemm_q(wdt, m->pf_k, L.wk.p, m->pf_xn, n, kvd, d, nullptr, st));
+        TRY(gemm_q(wdt, m->pf_v, L.wv.p, m->pf_xn, n, kvd, d, nullptr, st));
+        for (int b = 0; b < n; b++) {
+            // RoPE(q, k) + append the new K/V row to the sequence's own cache + attention over it: the decode kernel
+            AttnDecode ad;
+            ad.q = (const __half *)m->pf_q + (size_t)b * qd;
+            ad.k_new = (const __half *)m->pf_k + (size_t)b * kvd; ad.v_new = (const __half *)m->pf_v + (size_t)b * kvd;
+            ad.rope = 1; ad.rope_order = s.rope_order; ad.rope_dims = 0; ad.rope_theta = s.rope_theta;
+            ad.kv_dtype = s.kv_dtype; ad.heads = m->heads_l; ad.kv_heads = m->kv_heads_l; ad.head_dim = m->hd;
+            ad.max_ctx = s.max_ctx; ad.ctx_len = 0; ad.kq_scale = s.kq_scale;
+            ad.out = (__half *)m->pf_att + (size_t)b * qd;
+            ad.kcache = (uint8_t *)L.kcache.p + (size_t)slots_host[b] * m->kv_slot_bytes;
+            ad.vcache = (uint8_t *)L.vcache.p + (size_t)slots_host[b] * m->kv_slot_bytes;
+            ad.workspace = m->attn_ws.p; ad.pos_dev = (const int32_t *)m->bt_pos.p + b; ad.pdl = 0;
+            TRY(attn_decode(ad, st));
+        }
+        TRY(gemm_q(wdt, m->pf_tmp, L.wo.p, m->pf_att, n, d, qd, nullptr, st));
+        TRY(add(m->pf_x, m->pf_x, m->pf_tmp, (int64_t)n * d, st));
+        TRY(rmsnorm(m->pf_xn, m->pf_x, L.ffn_norm.p, n, d, s.norm_eps, 0.f, st));
+        TRY(gemm_q(wdt, m->pf_h1, L.w1.p, m->pf_xn, n, f, d, nullptr, st));
+        TRY(gemm_q(wdt, m->pf_h3, L.w3.p, m->pf_xn, n, f, d, nullptr, st));
+        TRY(silu_mul(m->pf_h1, m->pf_h1, m->pf_h3, (int64_t)n * f, st));
+        TRY(gemm_q(wdt, m->pf_tmp, L.w2.p, m->pf_h1, n, d, f, nullptr, st));
+        TRY(add(m->pf_x, m->pf_x, m->pf_tmp, (int64_t)n * d, st));
+    }
+    // every row: final norm + lm_head + greedy pick
+    TRY(rmsnorm(m->pf_xn, m->pf_x, m->out_norm.p, n, d, s.norm_eps, 0.f, st));
+    TRY(gemm_q(s.lm_head_dtype, m->bt_logits.p, m->lm_head.p, m->pf_xn, n, s.vocab, d, nullptr, st));
+    for (int b = 0; b < n; b++)
+        TRY(argmax((int32_t *)m->bt_next.p + b, (const __half *)m->bt_logits.p + (size_t)b * s.vocab, s.vocab, st));
     return IFB_OK;
 }
 

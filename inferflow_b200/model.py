@@ -27,6 +27,7 @@ class ModelSpec:
     experts_top_k: int = 0
     moe_norm_top_k_prob: int = 1
     weight_repack: int = 0      # 1: Q3H_B64T1 matrices stored as Q4_B64T1 blocks with the same codes (lossless, faster to decode)
+    kv_slots: int = 0           # KV caches side by side (<= 16): the sequences decode_batch advances together
     layer_begin: int = 0        # pipeline stage [layer_begin, layer_end); 0, 0 = the whole model
     layer_end: int = 0
 
@@ -35,7 +36,7 @@ class ModelSpec:
                           self.max_ctx, self.weight_dtype, self.kv_dtype, self.lm_head_dtype,
                           self.rope_order, self.rope_theta, self.norm_eps, self.kq_scale, self.tp_rank,
                           self.tp_size, self.experts, self.experts_top_k, self.moe_norm_top_k_prob,
-                          self.weight_repack, self.layer_begin, self.layer_end)
+                          self.weight_repack, self.kv_slots, self.layer_begin, self.layer_end)
 
 
 # shapes of SURVEY.md section 8
@@ -144,6 +145,25 @@ class Model:
         import numpy as np
         t = np.ascontiguousarray(tokens, dtype=np.int32)
         check(lib.ifb_model_prefill(self._h, t.ctypes.data, len(t), pos0, stream), "ifb_model_prefill")
+
+    def decode_batch(self, tokens, slots, positions, stream=0):
+        """one token for each of n sequences (KV slot, position); returns (logits fp16 [n][vocab], next tokens [n])"""
+        import numpy as np
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        ps = np.ascontiguousarray(positions, dtype=np.int32)
+        n = len(t)
+        check(lib.ifb_model_decode_batch(self._h, t.ctypes.data, sl.ctypes.data, ps.ctypes.data, n, stream), "ifb_model_decode_batch")
+        check(lib.ifb_device_synchronize(), "sync")
+        logits = np.empty((n, self.spec.vocab), dtype=np.float16)
+        check(lib.ifb_memcpy_d2h(logits.ctypes.data, lib.ifb_model_batch_logits(self._h), logits.nbytes), "d2h")
+        nxt = np.empty(n, dtype=np.int32)
+        check(lib.ifb_memcpy_d2h(nxt.ctypes.data, lib.ifb_model_batch_next_tokens(self._h), 4 * n), "d2h")
+        return logits, nxt
+
+    @property
+    def batch_supported(self):
+        return bool(lib.ifb_model_batch_supported(self._h))
 
     @property
     def prefill_supported(self):
