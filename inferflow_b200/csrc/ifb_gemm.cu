@@ -21,6 +21,10 @@
 //    -> fp16 -> Y. The output is written in its final [tokens][cy] orientation (no transpose pass).
 //  Measured on B200 (profiles/r2_bench.md, r2_ncu.md): 452-666 TFLOP/s at 4096 tokens, tensor pipe active 20-22 % of
 //  the cycles -- the kernel is bound by producing fp16 operands from the 4-bit blocks (ALU pipe 18-43 %).
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include <cuda.h>      // CUtensorMap + the driver's encode function (fetched through cudaGetDriverEntryPoint: no libcuda link)
 
 #include "ifb_formats.cuh"
@@ -340,6 +344,24 @@ static int make_xmap(CUtensorMap *map, const void *x, int64_t tokens, int64_t cx
     return IFB_OK;
 }
 
+static int splitk_scratch(cudaStream_t st, size_t need, float **out) {
+    struct Buf { void *p; size_t bytes; };
+    static std::map<std::pair<int, cudaStream_t>, Buf> bufs;
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    Buf &b = bufs[std::make_pair(dev, st)];
+    if (b.bytes < need) {
+        if (b.p != nullptr) { cudaStreamSynchronize(st); cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+        const size_t bytes = (need + ((size_t)1 << 20) - 1) >> 20 << 20;
+        IFB_CUDA(cudaMalloc(&b.p, bytes));
+        b.bytes = bytes;
+    }
+    *out = (float *)b.p;
+    return IFB_OK;
+}
+
 template <class Fmt, bool F16W, int RB, int NTMAX>
 static int launch_gemm_cfg(const GemmArgs &a, cudaStream_t st) {
     auto kern = gemm_q_kernel<Fmt, F16W, RB, NTMAX>;
@@ -368,13 +390,16 @@ static int launch_gemm_cfg(const GemmArgs &a, cudaStream_t st) {
         GemmArgs b = a;
         b.nk_per = (nk_all + ksplit - 1) / ksplit;
         ksplit = (nk_all + b.nk_per - 1) / b.nk_per;
-        // stream-ordered scratch for the partial sums (capturable, safe across streams)
-        IFB_CUDA(cudaMallocAsync((void **)&b.part, (size_t)ksplit * a.tokens * a.cy * sizeof(float), st));
+        // scratch for the partial sums: one buffer per (device, stream), grown when a larger product comes (the first
+        // version asked the stream-ordered allocator per call: with its default release threshold every call paid a
+        // real cudaMalloc -- 0.5-1.4 ms against 25 us of work)
+        const size_t need = (size_t)ksplit * a.tokens * a.cy * sizeof(float);
+        rc = splitk_scratch(st, need, &b.part);
+        if (rc != IFB_OK) return rc;
         grid.z = ksplit;
         kern<<<grid, 128 * RB + 64, smem, st>>>(b, xmap);
         const int64_t n = (int64_t)a.tokens * a.cy;
         gemm_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.y, b.part, a.bias, a.tokens, a.cy, ksplit);
-        cudaFreeAsync(b.part, st);
         IFB_LAUNCH_CHECK();
         return IFB_OK;
     }
