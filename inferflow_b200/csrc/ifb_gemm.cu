@@ -381,7 +381,7 @@ static int launch_gemm_cfg(const GemmArgs &a, cudaStream_t st) {
     const int ctas = (int)(grid.x * grid.y), nk_all = a.cx / GQ_BK;
     int ksplit = 1;
     if (RB == 1 && a.tokens <= 32 && ctas < 2 * 148) {
-        ksplit = (2 * 148 + ctas - 1) / ctas;
+        ksplit = (4 * 148 + ctas - 1) / ctas;
         if (ksplit > 8) ksplit = 8;
         if (ksplit > nk_all / 4) ksplit = nk_all / 4;
         if (ksplit < 1) ksplit = 1;
