@@ -129,8 +129,9 @@ int attn_decode(const AttnDecode &a, cudaStream_t st);
 // ascending expert order as ProcessGpuLayer_Moe walks them; ids[top_k] (-1 = unused), weights as half
 int moe_route(int32_t *ids, void *weights_f16, const void *logits_f16, int experts, int top_k, int norm, cudaStream_t st);
 // x_out = x_res + sum_k w_k * y_k with the reference's fp16 FMA chain (AddByRowIdx_Kernel, binary_tensor_opr.h:81)
+// tp (optional, tp->push): y holds this rank's partial sums; the folded vector goes to every rank's exchange region
 int moe_combine(void *x_out, const void *x_res, const void *y, const int32_t *ids, const void *weights_f16, int top_k,
-                int64_t d, cudaStream_t st);
+                int64_t d, cudaStream_t st, const TpExchange *tp = nullptr);
 
 int moe_topk(int32_t *ids, float *weights, int32_t *counts, const void *scores, int rows,
              int experts, int top_k, int norm, cudaStream_t st);

@@ -122,7 +122,8 @@ extern "C" int32_t ifb_model_create(ifb_model_t **out, const ifb_model_spec_t *s
     IFB_CHECK_ARG(s.experts >= 0 && s.experts <= 32, "experts %d (the routing kernel handles up to 32)", s.experts);
     IFB_CHECK_ARG(s.experts == 0 || (s.experts_top_k >= 1 && s.experts_top_k <= 8 && s.experts_top_k <= s.experts),
                   "experts_top_k %d (RowItemForMoe::MAX_SIZE is 8)", s.experts_top_k);
-    IFB_CHECK_ARG(s.experts == 0 || s.tp_size <= 1, "MoE layers are single-GPU in this runtime (the reference cannot run MoE on several GPUs either)");
+    // MoE under tensor parallelism (the reference cannot: its expert tensors reach one device only): every
+    // expert is split like the dense FFN -- w1 / w3 BY_COL, w2 BY_ROW -- the gate is duplicated
     IFB_CHECK_ARG(tp <= 8 && s.vocab % tp == 0 && (s.vocab / tp) % 8 == 0, "vocab %d cannot be sharded %d ways", s.vocab, tp);
     IFB_CHECK_ARG(tp == 1 || s.layers <= 127, "tensor parallel: at most 127 layers (exchange index is 8 bits)");
     // weight_repack: 3.5-bit blocks are stored as nibble blocks with the same codes / base / scale (ifb_quantize.cu)
@@ -482,9 +483,9 @@ extern "C" int32_t ifb_model_init_synthetic(ifb_model_t *m, uint64_t seed, ifb_s
         } else {
             TRY(synth_tensor(L.gate.p, DT_F16, DT_F16, s.experts, d, ls + 8, 0.05f, st));   // router: non-degenerate expert choice
             for (int e = 0; e < s.experts; e++) {
-                TRY(synth_tensor(L.ew1[e].p, wdt, m->api_wdt, m->ffn_l, d, ls + 20 + 3 * e, 0.02f, st));
-                TRY(synth_tensor(L.ew3[e].p, wdt, m->api_wdt, m->ffn_l, d, ls + 21 + 3 * e, 0.02f, st));
-                TRY(synth_tensor(L.ew2[e].p, wdt, m->api_wdt, d, m->ffn_l, ls + 22 + 3 * e, 0.02f, st));
+                TRY(synth_tensor(L.ew1[e].p, wdt, m->api_wdt, m->ffn_l, d, ls + 20 + 3 * e, 0.02f, st, d, f0, 0));
+                TRY(synth_tensor(L.ew3[e].p, wdt, m->api_wdt, m->ffn_l, d, ls + 21 + 3 * e, 0.02f, st, d, f0, 0));
+                TRY(synth_tensor(L.ew2[e].p, wdt, m->api_wdt, d, m->ffn_l, ls + 22 + 3 * e, 0.02f, st, gf, 0, f0));
             }
         }
         li++;
@@ -633,9 +634,9 @@ extern "C" int32_t ifb_model_load_tensor(ifb_model_t *m, const char *name, const
         int e = -1; char wn[16] = {0};
         if (sscanf(tn, "experts.%d.%15s", &e, wn) == 2 && e >= 0 && e < s.experts) {
             std::string w(wn);
-            if (w == "w1") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "expert w1 shape"); return load_shard(L.ew1[e], wdt, m->api_wdt, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
-            if (w == "w3") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "expert w3 shape"); return load_shard(L.ew3[e], wdt, m->api_wdt, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
-            if (w == "w2") { IFB_CHECK_ARG(rows == d && cols == s.d_ffn, "expert w2 shape"); return load_shard(L.ew2[e], wdt, m->api_wdt, host, host_dt, rows, cols, 0, rows, 0, cols, st); }
+            if (w == "w1") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "expert w1 shape"); return load_shard(L.ew1[e], wdt, m->api_wdt, host, host_dt, rows, cols, (int64_t)rk * m->ffn_l, m->ffn_l, 0, cols, st); }
+            if (w == "w3") { IFB_CHECK_ARG(rows == s.d_ffn && cols == d, "expert w3 shape"); return load_shard(L.ew3[e], wdt, m->api_wdt, host, host_dt, rows, cols, (int64_t)rk * m->ffn_l, m->ffn_l, 0, cols, st); }
+            if (w == "w2") { IFB_CHECK_ARG(rows == d && cols == s.d_ffn, "expert w2 shape"); return load_shard(L.ew2[e], wdt, m->api_wdt, host, host_dt, rows, cols, 0, rows, (int64_t)rk * m->ffn_l, m->ffn_l, st); }
         }
     }
     set_last_error("load_tensor: unknown tensor '%s'", name);
@@ -1026,6 +1027,9 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
             GemvLaunch r;
             r.w_dtype = DT_F16; r.nseg = 1; r.w[0] = L.gate.p; r.rows[0] = s.experts; r.cx = d;
             r.x = m->x1.p; r.norm_w = L.ffn_norm.p; r.norm_eps = s.norm_eps; r.y = m->router.p; r.quantize_x = 0; r.pdl = pdl;
+            // tensor parallel: the router is the first reader of x1 = x0 + sum(wo partials) -- it gathers (and leaves x1
+            // for the expert launches); the gate is duplicated, so every rank routes alike
+            if (tp > 1) r.tp = &t_glu[li];
             TRY(launch(&r));
             if (parts & PART_GEMV) {
                 TRY(moe_route((int32_t *)m->moe_ids.p, m->moe_wts.p, m->router.p, s.experts, s.experts_top_k,
@@ -1034,6 +1038,7 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
             }
             for (int k = 0; k < s.experts_top_k; k++) {
                 GemvLaunch f = g_glu[li], w2 = g_w2[li];
+                f.tp = nullptr; w2.tp = nullptr;        // x1 is in place; the slots' partial outputs stay local until the combine
                 f.w_table = (const void *const *)L.tbl_w1.p; f.wg_table = (const void *const *)L.tbl_w3.p;
                 f.moe_id = (const int32_t *)m->moe_ids.p + k;
                 w2.w_table = (const void *const *)L.tbl_w2.p; w2.moe_id = (const int32_t *)m->moe_ids.p + k;
@@ -1042,8 +1047,10 @@ static int issue_step(ifb_model *m, cudaStream_t st, int *launches, int parts = 
                 TRY(launch(&w2));
             }
             if (parts & PART_GEMV) {
+                // tensor parallel: this rank's folded partial sums go to every rank (exchange 2l+2, where the dense w2 pushes);
+                // the next layer's QKV GEMV (or the lm_head) adds them to x1
                 TRY(moe_combine(m->x0.p, m->x1.p, m->moe_y.p, (const int32_t *)m->moe_ids.p, m->moe_wts.p,
-                                s.experts_top_k, d, st));
+                                s.experts_top_k, d, st, tp > 1 ? &t_w2[li] : nullptr));
                 n++;
             }
         } else {

@@ -327,8 +327,26 @@ __global__ void moe_combine_kernel(__half *x_out, const __half *x_res, const __h
         x_out[i] = __hadd(x_res[i], out);                        // the layer's residual Add
     }
 }
+// tensor-parallel form: the experts' w2 are row-parallel, so y holds this rank's PARTIAL sums; the weighted combination
+// is linear, each rank folds its partials and pushes the result into every rank's exchange region as flag-in-data words
+// {half2, flag}; the next GEMV's prologue adds the ranks' vectors in rank order and the residual last (tp_gather8).
+__global__ void moe_combine_push_kernel(const __half *y, const int32_t *ids, const __half *wts, int top_k, int64_t d,
+                                        TpExchange tp) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t flag = ((uint32_t)*reinterpret_cast<const volatile int32_t *>(tp.seq) << 8) | tp.push_idx;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < d / 2; w += (int64_t)gridDim.x * blockDim.x) {
+        __half2 out = __floats2half2_rn(0.f, 0.f);
+        for (int k = 0; k < top_k; k++)
+            if (ids[k] >= 0) out = __hfma2(reinterpret_cast<const __half2 *>(y + (int64_t)k * d)[w], __half2half2(wts[k]), out);
+        const uint2 word = make_uint2(*reinterpret_cast<const uint32_t *>(&out), flag);
+        for (int p = 0; p < tp.size; p++)
+            asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(reinterpret_cast<uint8_t *>(tp.peer[p]) + tp.dst_off + w * 8),
+                         "r"(word.x), "r"(word.y) : "memory");
+    }
+}
 int moe_combine(void *x_out, const void *x_res, const void *y, const int32_t *ids, const void *weights_f16, int top_k,
-                int64_t d, cudaStream_t st) {
+                int64_t d, cudaStream_t st, const TpExchange *tp) {
     IFB_CHECK_ARG(top_k >= 1 && top_k <= 8 && d > 0, "moe_combine: bad sizes");
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((d + 255) / 256)); cfg.blockDim = dim3(256); cfg.stream = st;
@@ -336,6 +354,11 @@ int moe_combine(void *x_out, const void *x_res, const void *y, const int32_t *id
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    if (tp != nullptr && tp->push) {
+        IFB_CHECK_ARG(d % 2 == 0, "moe_combine: odd vector length");
+        IFB_CUDA(cudaLaunchKernelEx(&cfg, moe_combine_push_kernel, (const __half *)y, ids, (const __half *)weights_f16, top_k, d, *tp));
+        return IFB_OK;
+    }
     IFB_CUDA(cudaLaunchKernelEx(&cfg, moe_combine_kernel, (__half *)x_out, (const __half *)x_res, (const __half *)y, ids,
                                 (const __half *)weights_f16, top_k, d));
     return IFB_OK;

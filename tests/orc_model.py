@@ -53,6 +53,19 @@ class OracleModel:
             acc = part if acc is None else orc.f16(acc + part)
         return orc.f16(acc + resid)
 
+    def _rowpar_shard(self, name, dt, x, rows, cols, r):
+        """rank r's partial product of a row-parallel matrix: round_h(W[:, shard r] x[shard r])"""
+        rb = orc.row_bytes(dt, cols) if dt != orc.F16 else cols * 2
+        w = self.t[name][: rb * rows].reshape(rows, rb)
+        nc, sb = cols // self.tp, rb // self.tp
+        shard = np.ascontiguousarray(w[:, r * sb:(r + 1) * sb]).reshape(-1)
+        xs = np.ascontiguousarray(x[r * nc:(r + 1) * nc])
+        if dt == orc.F16:
+            return orc.f16(self.o.gemv_f16(shard.view(np.float16).reshape(rows, nc), xs, rows, nc))
+        if dt in AX8:
+            return orc.f16(self.o.gemv_ax8(dt, shard, self.o.quantize(orc.Q8_B32T2, xs[None, :]), rows, nc))
+        return orc.f16(self.o.gemv_half(dt, shard, xs, rows, nc))
+
     def _ffn(self, prefix, wdt, xn, d, f):
         """GLU FFN on an already normalised input: silu(w1 x) * (w3 x) -> w2, every tensor stored as half"""
         g = orc.f16(self._gemv(prefix + "w1", wdt, xn, f, d))
@@ -86,6 +99,22 @@ class OracleModel:
         ids, wts, cnt = o.moe_topk(probs.astype(np.float32)[None, :], s.experts_top_k, bool(s.moe_norm_top_k_prob))
         sel = sorted((int(ids[0, j]), float(wts[0, j])) for j in range(int(cnt[0])))     # ascending expert id
         self.last_route = sel
+        if self.tp > 1:
+            # tensor parallel (ours; the reference cannot): the experts' w2 are row-parallel, rank r folds ITS partial
+            # outputs with the same half FMA chain, the ranks' vectors are added in rank order, the residual last
+            acc = None
+            for r in range(self.tp):
+                out = np.zeros(d, dtype=np.float16)
+                for e, w in sel:
+                    pre = f"{p}experts.{e}."
+                    g = orc.f16(self._gemv(pre + "w1", wdt, x1n, f, d))
+                    u = orc.f16(self._gemv(pre + "w3", wdt, x1n, f, d))
+                    h = orc.f16(orc.f16(g / (1.0 + np.exp(-g.astype(np.float64)))) * u)
+                    y = self._rowpar_shard(pre + "w2", wdt, h, d, f, r)
+                    out = (y.astype(np.float64) * np.float64(np.float16(w)) + out.astype(np.float64)).astype(np.float16)
+                part = out.astype(np.float32)
+                acc = part if acc is None else orc.f16(acc + part)
+            return orc.f16(acc + x1)
         out = np.zeros(d, dtype=np.float16)
         for e, w in sel:
             y = self._ffn(f"{p}experts.{e}.", wdt, x1n, d, f)

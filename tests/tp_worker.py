@@ -80,6 +80,54 @@ CONFIGS = [
 ]
 
 
+def moe_check(rank, world):
+    """mixture of experts under tensor parallelism (experts split like the dense FFN, gate duplicated): the TP group
+    against the oracle computing the same shard sums, and against the single-GPU model of the same seed"""
+    if world > 4:
+        return
+    base = dict(layers=2, vocab=512, max_ctx=64, weight_dtype=orc.Q4_B32T1A, kv_dtype=orc.Q8_B32T2, heads=4, kv_heads=4,
+                d_model=512, d_ffn=1024, experts=4, experts_top_k=2)
+    spec = ib.ModelSpec(tp_rank=rank, tp_size=world, **base)
+    m = ib.Model(spec)
+    m.init_synthetic(seed=55)            # a function of seed and GLOBAL position: the shards are the single-GPU model
+    m.tp_connect(dist)
+    ref = orcm = None
+    if rank == 0:
+        spec1 = ib.ModelSpec(**base)
+        ref = ib.Model(spec1)
+        ref.init_synthetic(seed=55)
+        t = {n: ref.read_tensor(n) for n in ("tok_embeddings", "output_norm", "output")}
+        for l in range(spec1.layers):
+            for n in ("attention_norm", "ffn_norm", "wq", "wk", "wv", "wo", "gate"):
+                t[f"layers.{l}.{n}"] = ref.read_tensor(f"layers.{l}.{n}")
+            for e in range(spec1.experts):
+                for n in ("w1", "w2", "w3"):
+                    t[f"layers.{l}.experts.{e}.{n}"] = ref.read_tensor(f"layers.{l}.experts.{e}.{n}")
+        orcm = OracleModel(spec1, t, tp=world)
+    tok = 5
+    for pos in range(6):
+        m.decode(tok, pos)
+        logits, nxt = read(m, spec)
+        same_on_all_ranks(logits, f"moe pos {pos} logits")
+        if rank == 0:
+            want = orcm.step(tok, pos)
+            scale = np.abs(want).max()
+            err = np.abs(logits.astype(np.float64) - want).max()
+            ref.decode(tok, pos)
+            l1, _ = read(ref, spec)
+            e1 = np.abs(l1.astype(np.float64) - logits.astype(np.float64)).max()
+            print(f"moe pos {pos}: |tp - tp oracle| {err:.3e}  |tp - single GPU| {e1:.3e}  range {scale:.3e}  experts {orcm.last_route}", flush=True)
+            assert err <= 2 ** -7 * scale, f"moe pos {pos}: TP logits differ from the TP oracle by {err:.3e} (range {scale:.3e})"
+            assert e1 <= 2 ** -4 * scale, f"moe pos {pos}: TP vs single-GPU logits differ by {e1:.3e}"
+        tok = nxt
+    dist.barrier()
+    m.close()
+    if ref is not None:
+        ref.close()
+    if rank == 0:
+        print(f"tp{world} mixture of experts (4 experts, top-2, Q4): ok", flush=True)
+
+
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
@@ -91,6 +139,7 @@ def main():
         # the per-rank shapes of the benchmark model: ONE Llama-2-7B layer (d 4096, f 11008, 32 heads), fp16 lm_head
         configs.append(dict(weight_dtype=orc.Q4_B32T1A, kv_dtype=orc.Q8_B32T2, heads=32, kv_heads=32, d_model=4096, d_ffn=11008,
                             layers=1, vocab=4096, max_ctx=64))
+    moe_check(rank, world)
     for ci, cfg in enumerate(configs):
         cfg = dict(cfg)
         if cfg["kv_heads"] % world or cfg["heads"] % world:
