@@ -16,6 +16,7 @@
 #include "tensor/host_tensor_opr.h"   // HostTensorOpr::BuildRowsForMoE
 #include "tensor/tensor_common.h"
 #include "transformer/inference_engine.h"
+#include "transformer/network_builder.h"
 
 using namespace inferflow;
 using namespace inferflow::transformer;
@@ -191,6 +192,44 @@ int ifref_engine_generate(void *h, const int32_t *prompt, int prompt_len, int ma
     }
     if (seconds_decode) *seconds_decode = decode_s;
     return n;
+}
+
+// ---------------------------------------------------------------------------
+// the partitioner's host logic, as the reference computes it (pins csrc/ifb_partition.cu)
+// ---------------------------------------------------------------------------
+// InferenceEngine::LoadDeviceGroups (inference_engine.cc:1738) on item `devices` of `section` of a REAL .ini file read
+// by the reference's own ConfigData. sizes_out[g] = devices in group g, ids_out = all ids in order.
+// returns the number of groups, -1 when LoadDeviceGroups refuses the string, -2 when the file cannot be read.
+int ifref_load_device_groups(const char *ini_path, const char *section, int32_t *ids_out, int ids_cap,
+                             int32_t *sizes_out, int sizes_cap) {
+    sslib::ConfigData cfg;
+    if (!cfg.Load(ini_path)) return -2;
+    std::vector<std::vector<int>> groups;
+    if (!InferenceEngine::LoadDeviceGroups(groups, cfg, section, "devices")) return -1;
+    int k = 0;
+    for (int g = 0; g < (int)groups.size(); g++) {
+        if (g < sizes_cap) sizes_out[g] = (int32_t)groups[g].size();
+        for (int id : groups[g]) if (k < ids_cap) ids_out[k++] = id;
+    }
+    return (int)groups.size();
+}
+
+// NetworkBuilder::SplitGpuLayers (network_builder.cc:2094) for n_groups groups of one device each.
+// ranges_out[3k..3k+2] = {start_layer, end_layer, group}; returns the number of assignments.
+int ifref_split_gpu_layers(int start_layer, int end_layer, int n_groups, int32_t *ranges_out, int cap) {
+    ModelSpec spec;
+    for (int g = 0; g < n_groups; g++) spec.device_groups.push_back(std::vector<int>(1, g));
+    std::vector<LayerAssignment> la;
+    NetworkBuilder::SplitGpuLayers(la, start_layer, end_layer, spec);
+    int k = 0;
+    for (const auto &a : la) {
+        if (k >= cap) break;
+        ranges_out[3 * k] = a.start_layer;
+        ranges_out[3 * k + 1] = a.end_layer;
+        ranges_out[3 * k + 2] = (int32_t)(a.devices - &spec.device_groups[0]);
+        k++;
+    }
+    return k;
 }
 
 }  // extern "C"

@@ -1,15 +1,24 @@
-"""Host logic of the partitioner (csrc/ifb_partition.cu) against fixtures traced by hand through the reference's code
-(no GPU, no reference at run time):
+"""Host logic of the partitioner (csrc/ifb_partition.cu) against (1) fixtures traced by hand through the reference's code,
+(2) fixtures PRODUCED BY THE COMPILED REFERENCE (tests/golden/partition.json) and (3), where oracle/_ref is present, the
+compiled reference itself on 300 random device strings (through its own .ini reader) and 300 random layer splits
+(no GPU; nothing under /root/reference is read at run time):
   * InferenceEngine::LoadDeviceGroups, inference_engine.cc:1738-1783 -- the `devices` grammar;
   * the strategy rule, inference_engine.cc:1509-1515;
   * NetworkBuilder::SplitGpuLayers, network_builder.cc:2094-2117 -- layer ranges of the groups;
   * Build{Attn,Ffn,Moe}TensorIdMap + AddLayerTasks_TensorParallel, network_builder.cc:1373-1413, 1594-1688 --
     BY_COL / BY_ROW / DUP per tensor and the per-tensor tensor_quant_threshold rule."""
 import ctypes as C
+import json
+import os
+import random
+import sys
+import tempfile
 
 import pytest
 
 import orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 BY_LAYER, BY_TENSOR, HYBRID = 0, 1, 2
 DUP, BY_ROW, BY_COL = 0, 1, 2
@@ -119,3 +128,41 @@ def test_tensor_quant_threshold_rule():
     assert f(288 * 288, 1, orc.Q8_B32T2, thr) == orc.F16               # the reference's tiny models stay fp16
     assert f(288 * 288, 1, orc.Q8_B32T2, 0) == orc.Q8_B32T2            # tensor_quant_threshold = 0: always quantize
     assert f(100, 1, orc.F16, thr) == orc.F16
+
+
+# ---- against the COMPILED reference: committed fixtures (tests/golden/partition.json, made by
+# tests/golden/make_golden_partition.py from oracle/_ref/libifref_cpu.so) and, where that library is present, live
+def _ours_groups(text):
+    r = _parse(text)
+    if isinstance(r[0], int):
+        return {"error": -1}
+    return {"groups": r[0]}
+
+
+def test_grammar_and_layer_split_match_the_compiled_reference_fixtures():
+    gold = json.load(open(os.path.join(HERE, "golden", "partition.json")))
+    assert len(gold["grammar"]) >= 30 and len(gold["splits"]) >= 16
+    for case in gold["grammar"]:
+        want = {k: case[k] for k in ("groups", "error") if k in case}
+        assert _ours_groups(case["devices"]) == want, repr(case["devices"])
+    for case in gold["splits"]:
+        got = [[a, b, g] for a, b, g in _split(case["start"], case["end"], case["groups"])]
+        assert got == case["ranges"], case
+
+
+@pytest.mark.skipif(not os.path.exists(orc.ref_cpu_path()), reason="oracle/_ref/libifref_cpu.so not built (needs /root/reference)")
+def test_grammar_and_layer_split_match_the_compiled_reference_live():
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden_partition as G
+    lib = G.ref_lib()
+    rnd = random.Random(11)
+    alphabet = "0123456789  &|;,;&x-"
+    with tempfile.TemporaryDirectory() as d:
+        for _ in range(300):
+            text = "".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 14))).strip()
+            if "=" in text or "\n" in text or text.startswith(("#", ";", "[")):
+                continue                     # not an item VALUE of an .ini line any more
+            assert _ours_groups(text) == G.ref_groups(lib, text, d), repr(text)
+    for _ in range(300):
+        a, b, n = 0, rnd.randint(0, 130), rnd.randint(0, 9)
+        assert [[x, y, g] for x, y, g in _split(a, b, n)] == G.ref_split(lib, a, b, n), (a, b, n)
