@@ -166,3 +166,23 @@ def test_grammar_and_layer_split_match_the_compiled_reference_live():
     for _ in range(300):
         a, b, n = 0, rnd.randint(0, 130), rnd.randint(0, 9)
         assert [[x, y, g] for x, y, g in _split(a, b, n)] == G.ref_split(lib, a, b, n), (a, b, n)
+
+
+@pytest.mark.skipif(not os.path.exists(orc.ref_cpu_path()), reason="oracle/_ref/libifref_cpu.so not built (needs /root/reference)")
+def test_ini_names_are_case_insensitive_in_the_reference_as_in_the_engine():
+    """sslib ConfigData finds [Transformer_Engine] / DEVICES under the names transformer_engine / devices: the engine's
+    .ini reader (csrc/ifb_engine.cu) lower-cases section and item names for the same reason"""
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden_partition as G
+    lib = G.ref_lib()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "g.ini")
+        for text, want in (("[transformer_engine]\nDEVICES = 0;1\n", [[0], [1]]), ("[Transformer_Engine]\nDevices = 0&1\n", [[0, 1]])):
+            open(path, "w").write(text)
+            ids, sizes = (C.c_int32 * 16)(), (C.c_int32 * 8)()
+            n = lib.ifref_load_device_groups(path.encode(), b"transformer_engine", ids, 16, sizes, 8)
+            got, k = [], 0
+            for g in range(n):
+                got.append([ids[k + i] for i in range(sizes[g])])
+                k += sizes[g]
+            assert got == want
