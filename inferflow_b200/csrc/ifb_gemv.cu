@@ -430,24 +430,7 @@ static bool is_ax8_type(int dt) {
     }
 }
 
-static int *g_scratch_counter = nullptr;
-
-// Several GEMVs in one call. A fused "chain" kernel (one persistent launch walking all ops, grid-wide completion
-// counters between them) was built and measured in round 1 -- experiments/gemv_chain/ -- and lost to separate
-// launches of this kernel (507 vs 595 tok/s): here the ops simply go out one after the other.
-int gemv_chain_launch(const GemvLaunch *ops, int nops, cudaStream_t st) {
-    IFB_CHECK_ARG(ops != nullptr && nops >= 1 && nops <= 4, "gemv: a chain holds 1..4 ops");
-    for (int k = 0; k < nops; k++) {
-        GemvLaunch g = ops[k];
-        if (k > 0) {
-            g.trace = nullptr;
-            g.counter = ops[0].counter ? (void *)((int *)ops[0].counter + k) : nullptr;
-        }
-        int rc = gemv_launch(g, st);
-        if (rc != IFB_OK) return rc;
-    }
-    return IFB_OK;
-}
+static int *g_scratch_counter[64] = {nullptr};   // per device (a process may drive several GPUs)
 
 int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     const int dt = g.w_dtype;
@@ -603,9 +586,10 @@ int gemv_launch(const GemvLaunch &g, cudaStream_t st) {
     int grid = sm_count();
     if (grid > units) grid = units;
     if (a.counter == nullptr) {   // stand-alone call: a library-owned cursor, zeroed on the caller's stream
-        if (g_scratch_counter == nullptr) IFB_CUDA(cudaMalloc((void **)&g_scratch_counter, 256));
-        IFB_CUDA(cudaMemsetAsync(g_scratch_counter, 0, sizeof(int), st));
-        a.counter = g_scratch_counter;
+        int *&sc = g_scratch_counter[current_device()];
+        if (sc == nullptr) IFB_CUDA(cudaMalloc((void **)&sc, 256));
+        IFB_CUDA(cudaMemsetAsync(sc, 0, sizeof(int), st));
+        a.counter = sc;
     }
 
     if (g.w_gate) return dispatch<true>(a, mode, vec4, smem, grid, g.pdl, st);

@@ -62,7 +62,6 @@ struct GemvLaunch {
 };
 int gemv_launch(const GemvLaunch &g, cudaStream_t st);
 // up to 4 GEMVs in ONE launch; op k+1 reads what op k wrote (counter: 8 ints, zero before the launch)
-int gemv_chain_launch(const GemvLaunch *ops, int nops, cudaStream_t st);
 
 // rows > 1: Y[tokens][cy] = X[tokens][cx] . W[cy][cx]^T on the tensor cores, W dequantized tile by tile in shared memory
 int gemm_q(int w_dtype, void *y_f16, const void *w, const void *x_f16, int64_t tokens, int64_t cy, int64_t cx,
