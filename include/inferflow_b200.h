@@ -270,6 +270,14 @@ int32_t ifb_model_load_llama2c_stage(ifb_model_t **out, const char *path, int32_
                                      int32_t max_context_len, int32_t qk_column_order, int32_t layer_begin,
                                      int32_t layer_end, ifb_stream_t stream);
 
+/* The work plan of the persistent decode-step kernel for `spec`, computed on the host (no GPU needed): for each of the
+ * 6 op kinds (wq|wk|wv, attention, wo, w1|w3, w2, lm_head) 13 ints {units, tasks, rows per unit, cx, blocks per row,
+ * row bytes, unit bytes, vec4 | rows per task, K-chunks per row, blocks per chunk, bytes per chunk and row, tasks}
+ * (the last five for the warp-private schedule, 0 otherwise), then {private schedule used, ring slots, slot bytes,
+ * shared memory bytes, positions per attention unit, private slot bytes}. IFB_E_ARG when the kernel does not cover the
+ * model (the runtime then decodes with the multi-launch path). Used by the CPU tests of the plan's invariants. */
+int32_t ifb_step_plan(const ifb_model_spec_t *spec, int32_t want_private_schedule, int32_t *out, int32_t capacity);
+
 /* Batched decode: n sequences, sequence i living in KV slot slots_host[i] at position positions_host[i], advance by
  * one token (tokens_host[i]) in one step -- the step InferenceEngine::Infer runs over all live queries
  * (inference_engine.cc:1054-1124). The matrix products see n rows (ifb_gemm_q: the weights are read once for all

@@ -106,6 +106,7 @@ def _load():
     L.ifb_model_kernel_launches_per_step.argtypes = [vp]
     L.ifb_model_step_status.argtypes = [vp, vp]
     L.ifb_model_storage_dtype.argtypes = [vp, i32]
+    L.ifb_step_plan.argtypes = [vp, i32, vp, i32]
     L.ifb_model_batch_supported.argtypes = [vp]
     L.ifb_model_decode_batch.argtypes = [vp, vp, vp, vp, i32, vp]
     L.ifb_model_batch_logits.argtypes = [vp]
@@ -150,7 +151,7 @@ DECLARED = [
     "ifb_model_logits", "ifb_model_next_token", "ifb_model_kernel_launches_per_step",
     "ifb_model_tp_export", "ifb_model_tp_import", "ifb_model_decode_next", "ifb_model_tensor_ptr",
     "ifb_memcpy_d2h", "ifb_memcpy_h2d", "ifb_memcpy_d2d", "ifb_device_synchronize", "ifb_model_issue_parts", "ifb_memcpy_d2h_async", "ifb_memcpy_h2d_async", "ifb_model_step_status", "ifb_model_prefill", "ifb_model_prefill_supported", "ifb_attn_prefill",
-    "ifb_model_storage_dtype", "ifb_model_hidden_ptr", "ifb_model_batch_supported", "ifb_model_decode_batch", "ifb_model_batch_logits", "ifb_model_batch_next_tokens", "ifb_device_groups_parse", "ifb_split_layers", "ifb_tensor_partition_type",
+    "ifb_model_storage_dtype", "ifb_model_hidden_ptr", "ifb_step_plan", "ifb_model_batch_supported", "ifb_model_decode_batch", "ifb_model_batch_logits", "ifb_model_batch_next_tokens", "ifb_device_groups_parse", "ifb_split_layers", "ifb_tensor_partition_type",
     "ifb_tensor_device_dtype", "ifb_rank_plan",
 ]
 

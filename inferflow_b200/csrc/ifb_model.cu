@@ -1366,6 +1366,40 @@ extern "C" int32_t ifb_model_tp_import(ifb_model_t *m, const void *handles, int3
     return IFB_OK;
 }
 
+// The plan the persistent step kernel would run `spec` with, computed on the host alone (no device needed: sm_count
+// falls back to 148): per op kind {units, tasks, R, cx, nblk, row_bytes, unit_bytes, vec4} and, for the warp-private
+// schedule, {rt, nc, kc_blk, kc_bytes, ntasks}; then {priv, nslots, slot_bytes, smem_bytes, att_pos, pslot}. Lets the CPU
+// tests check the geometry invariants (every row covered once, chunks within a slot, 16-byte bulk-copy granules).
+extern "C" int32_t ifb_step_plan(const ifb_model_spec_t *spec, int32_t want_priv, int32_t *out, int32_t capacity) {
+    IFB_CHECK_ARG(spec != nullptr && out != nullptr && capacity >= OPK_COUNT * 13 + 6, "step_plan: null argument or a buffer below %d ints", OPK_COUNT * 13 + 6);
+    const ifb_model_spec_t &s = *spec;
+    IFB_CHECK_ARG(s.heads > 0 && s.kv_heads > 0 && s.d_model % s.heads == 0, "step_plan: bad hyper-parameters");
+    const int tp = s.tp_size > 0 ? s.tp_size : 1;
+    StepParams P = StepParams();
+    P.n_layers = s.layers;
+    P.hd = s.d_model / s.heads;
+    P.heads = s.heads / tp; P.kv_heads = s.kv_heads / tp; P.group = P.heads / (P.kv_heads > 0 ? P.kv_heads : 1);
+    P.d = s.d_model; P.q_dim = P.heads * P.hd; P.kv_dim = P.kv_heads * P.hd; P.ffn = s.d_ffn / tp;
+    P.vocab = s.vocab; P.vocab_l = s.vocab / tp;
+    P.max_ctx = s.max_ctx; P.max_ctx_pad = (s.max_ctx + 63) / 64 * 64;
+    P.w_dtype = (s.weight_repack && s.weight_dtype == DT_Q3H_B64T1) ? DT_Q4_B64T1 : s.weight_dtype;
+    P.priv = want_priv ? 1 : 0;
+    const int ldt = (s.weight_repack && s.lm_head_dtype == DT_Q3H_B64T1) ? DT_Q4_B64T1 : s.lm_head_dtype;
+    const int rc = step_build(P, s.kv_dtype, ldt, 148);
+    if (rc != IFB_OK) return rc;
+    int k = 0;
+    for (int kind = 0; kind < OPK_COUNT; kind++) {
+        const StepOpShape &o = P.op[kind];
+        const int v[8] = {o.units, o.tasks, o.R, o.cx, o.nblk, o.row_bytes, o.unit_bytes, o.vec4};
+        for (int i = 0; i < 8; i++) out[k++] = v[i];
+        const StepPrivShape &pv = P.pv[kind];
+        const int w[5] = {pv.rt, pv.nc, pv.kc_blk, pv.kc_bytes, pv.ntasks};
+        for (int i = 0; i < 5; i++) out[k++] = P.priv ? w[i] : 0;
+    }
+    out[k++] = P.priv; out[k++] = P.nslots; out[k++] = P.slot_bytes; out[k++] = P.smem_bytes; out[k++] = P.att_pos; out[k++] = P.pslot;
+    return IFB_OK;
+}
+
 // 1 when the model decodes with the persistent step kernel, 0 for the multi-launch path; rec[4] (optional) receives
 // the error record {code, op, detail, cta} a step kernel left before it trapped on a missed deadline (code 0: none)
 extern "C" int32_t ifb_model_step_status(ifb_model_t *m, int32_t rec[4]) {
