@@ -9,17 +9,22 @@
 // takes 1.6-8.6 us. Here the launch boundaries are gone:
 //
 //  * grid = one CTA per SM, resident for the whole token: 15 consumer warps + 1 producer warp;
-//  * the PRODUCER (one elected thread) walks every op of the token in order -- per layer wq|wk|wv, the KV cache,
-//    wo, w1|w3, w2, then the lm_head -- claiming units from per-op global cursors and streaming them with 1-D TMA
-//    bulk copies into a shared-memory ring. It never waits for an activation: while the consumers of all SMs
-//    synchronise at an op boundary, the HBM pipe keeps filling the rings with the NEXT op's weights (the rings of
-//    148 SMs hold ~27 MB = 4 us of HBM time; a boundary costs ~1 us);
-//  * the CONSUMERS take ring slots in order; a slot's tasks (2 adjacent rows / one w1,w3 row pair / 32 cache
-//    positions) are dealt round-robin to the 15 warps. When the next slot belongs to a new op, the CTA signals
-//    "my part of op k is stored" (one release add on a global counter), waits until all CTAs have, and stages the
-//    new op's input into shared memory: residual add (fp16, the reference's order), RMSNorm, Q8_B32T2
-//    quantization (the reference's alg-2 arithmetic), or RoPE + two-term int8 q + the new K/V cache row for
-//    attention;
+//  * the PRODUCER (one elected thread; shared-ring schedule, PRIV = false) walks every op of the token in order --
+//    per layer wq|wk|wv, the KV cache, wo, w1|w3, w2, then the lm_head -- claiming units from per-op global cursors
+//    and streaming them with 1-D TMA bulk copies into a shared-memory ring. It never waits for an activation: while
+//    the consumers of all SMs synchronise at an op boundary, the HBM pipe keeps filling the rings with the NEXT op's
+//    weights (the rings of 148 SMs hold ~27 MB = 4 us of HBM time);
+//  * the CONSUMERS take ring slots in order; a slot's tasks (2 adjacent rows / two w1,w3 row pairs / 32 cache
+//    positions) are dealt round-robin to the 15 warps. At an op boundary every CTA stages the new op's input into
+//    shared memory itself: gather of what the previous op left -- as FLAG-IN-DATA WORDS {half2, flag} that the reader
+//    polls (q|k|v, attention output, h, the wo / w2 outputs; no fence, no atomic), or behind a completion count where
+//    a reduction needs one (attention tiles -> merge) -- then residual add (fp16, the reference's order), RMSNorm,
+//    Q8_B32T2 quantization (the reference's alg-2 arithmetic), or RoPE + two-term int8 q for attention;
+//  * PRIV = true (IFB_STEP_PRIV=1): no producer warp -- every consumer warp streams its own statically assigned tasks
+//    through two private slots (see the kernel body);
+//  * MEASURED (profiles/r2_ncu.md): a boundary costs ~4 us, not the ~1 us this design assumed (tail of the
+//    producing op + store -> poll round trip under streaming load + staging with two CTA barriers + first task): 5 per
+//    layer are 22 us beside 34 us of streaming on the 7B model; neither schedule is instruction-bound;
 //  * attention is flash-decoding over the cache as stored: a task is one 32-position tile of one kv head, its
 //    (m, l, acc) partial goes to an L2-resident workspace, one CTA per head merges them (log-sum-exp) before wo;
 //  * tensor parallelism: the row-parallel GEMVs (wo, w2) store their partial sums straight into every peer's
