@@ -7,10 +7,10 @@
 // 1555-1571,1726-1900).
 //
 // Design (HBM-bound streaming kernel; DESIGN.md "gemv"):
-//  * ONE persistent CTA per SM using at most half of the SM's shared memory, so that under
-//    programmatic dependent launch the NEXT kernel's CTA is co-resident: its producer warp asks the
-//    L2 to prefetch that kernel's weights (cp.async.bulk.prefetch.L2) and fills its own ring while
-//    this kernel is still computing -- the HBM pipe does not drain at kernel boundaries;
+//  * ONE persistent CTA per SM whose weight ring takes (almost) the whole SM's shared memory (216 KB; measured: bytes
+//    in flight per SM matter more than a co-resident successor -- 110 KB 512 tok/s, 150 KB 559, 216 KB 586). Only the
+//    wq|wk|wv launch keeps 150 KB so that the attention kernel's CTAs fit beside it and prefetch the KV cache early.
+//    Under programmatic dependent launch the NEXT kernel's producer warp fills its ring as soon as an SM has room;
 //  * 1 producer warp + 16 consumer warps. The weight matrix is streamed in the reference's own
 //    AoS block layout: a "unit" is R whole rows = one contiguous byte range, moved
 //    global->shared by ONE 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) into a ring of
